@@ -1,0 +1,73 @@
+"""Synthetic Pb+Pb-like single-species samples.
+
+Per event: event-plane angle Psi ~ U[0,2pi); p_x', p_y' ~ N(0,0.37), N(0,0.33) GeV rotated by
+Psi; y ~ U(-0.45,0.45) (inside HBTrap = +-0.5, so every particle survives the rapidity cut);
+m_T = sqrt(m^2+p_T^2), p_z = m_T sinh y, E = m_T cosh y; source x', y' ~ N(0, 4 fm) rotated by
+Psi; tau ~ Gamma(k=4, theta=2.5 fm); eta_s = y + N(0,0.3); t = tau cosh eta_s, z = tau sinh eta_s.
+Fixed multiplicity per event, so ``event_buffer_size = oversample * M`` yields groups of
+exactly ``oversample`` events (reader rule, ``src/particleSamples.cpp:1256-1284``).
+
+Groups are generated independently (Philox keyed by seed and group index), so any rank can
+build just its own shard.
+"""
+from __future__ import annotations
+
+import gzip
+from typing import List
+
+import numpy as np
+
+from .hbtio import Batch
+from .params import EVENT_MULTIPLICITY, PION_MASS
+
+
+def make_group(seed: int, group: int, n_events: int, mass: float = PION_MASS,
+               multiplicity: int = EVENT_MULTIPLICITY) -> np.ndarray:
+    """One oversample group as a float64 array [n_events, multiplicity, 8] (px,py,pz,E,x,y,z,t)."""
+    rng = np.random.Generator(np.random.Philox(key=[seed, group]))
+    shp = (n_events, multiplicity)
+    psi = rng.uniform(0.0, 2.0 * np.pi, size=(n_events, 1))
+    c, s = np.cos(psi), np.sin(psi)
+    pxp = rng.normal(0.0, 0.37, shp)
+    pyp = rng.normal(0.0, 0.33, shp)
+    y = rng.uniform(-0.45, 0.45, shp)
+    xp = rng.normal(0.0, 4.0, shp)
+    yp = rng.normal(0.0, 4.0, shp)
+    tau = rng.gamma(4.0, 2.5, shp)
+    eta = y + rng.normal(0.0, 0.3, shp)
+    out = np.empty(shp + (8,), dtype=np.float64)
+    px = pxp * c - pyp * s
+    py = pxp * s + pyp * c
+    mT = np.sqrt(mass * mass + px * px + py * py)
+    out[..., 0] = px
+    out[..., 1] = py
+    out[..., 2] = mT * np.sinh(y)
+    out[..., 3] = mT * np.cosh(y)
+    out[..., 4] = xp * c - yp * s
+    out[..., 5] = xp * s + yp * c
+    out[..., 6] = tau * np.sinh(eta)
+    out[..., 7] = tau * np.cosh(eta)
+    return out
+
+
+def make_batches(seed: int, n_groups: int, oversample: int, mass: float = PION_MASS,
+                 multiplicity: int = EVENT_MULTIPLICITY, first_group: int = 0) -> List[Batch]:
+    out = []
+    for g in range(first_group, first_group + n_groups):
+        arr = make_group(seed, g, oversample, mass, multiplicity)
+        out.append(Batch([arr[e] for e in range(oversample)]))
+    return out
+
+
+def write_iss_gz(path: str, batches: List[Batch], monval: int = 211, mass: float = PION_MASS) -> None:
+    """Write events as the reference's read_in_mode=10 text (``particle_samples.gz``): per event
+    a line with the particle count, then ``monval mass t x y z E px py pz`` per particle
+    (field order of ``src/particleSamples.cpp:1247-1286``), %.17g so the reader's text parse
+    returns the same doubles."""
+    with gzip.open(path, "wt", compresslevel=1) as f:
+        for b in batches:
+            for ev in b.same:
+                f.write(f"{len(ev)}\n")
+                for p in ev:
+                    f.write("%d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n"
+                            % (monval, mass, p[7], p[4], p[5], p[6], p[3], p[0], p[1], p[2]))
