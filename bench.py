@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — HBT pairs/sec (same+mixed) on N B200s, with the FP64 roofline and the reference's
+own CPU implementation timed beside it.
+
+    python bench.py [--gpus N --steps K --warmup W]            our arm (libhbt_b200.so via the C ABI)
+    python bench.py --impl reference [...]                      the reference's CPU path (oracle/_ref)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): oversample groups of BASELINE.json's config 5 shape —
+`--events-per-group` (100) synthetic central events x 1500 pi+, 41^3 q grid, 4 K_T bins,
+same-event + mixed-event pairs; ONE STEP = `--groups-per-gpu` such groups on every GPU (weak
+scaling: each rank owns distinct groups, exactly how config 5 shards its 200 groups; no
+data-path collective) followed by the single NCCL all-reduce of the histograms.
+
+`value`  = pairs of all ranks / max-over-ranks device time of the step, particles already in HBM.
+`e2e`    = same metric through the reference-facing host call (hbt_accumulate_batch) with the
+           particles in pinned HOST memory: staging copy, H2D, mixed-event plan (RNG draws),
+           kernels, all-reduce and the D2H read of the per-K_T pair counters inside the timing.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from hadronic_afterburner_toolkit_b200 import hbtio, synth  # noqa: E402
+from hadronic_afterburner_toolkit_b200.params import C5, EVENT_MULTIPLICITY, PION_MASS  # noqa: E402
+
+METRIC = "HBT pairs/sec (same+mixed)"
+UNIT = "pairs/s"
+SEED = 20260005
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--groups-per-gpu", type=int, default=2)
+    ap.add_argument("--events-per-group", type=int, default=100)
+    ap.add_argument("--multiplicity", type=int, default=EVENT_MULTIPLICITY)
+    ap.add_argument("--cpu-events", type=int, default=10, help="events in the CPU baseline's bounded sample group")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {
+        "workload": f"config-5-shape oversample groups: {a.events_per_group} events x {a.multiplicity} pi+ "
+                    f"per group, same+mixed pairs, 41^3 q grid x 4 K_T bins; {a.groups_per_gpu} groups/GPU/step",
+        "groups_per_gpu_per_step": a.groups_per_gpu, "events_per_group": a.events_per_group,
+        "multiplicity": a.multiplicity, "qnpts": C5.qnpts, "n_KT": C5.n_KT,
+        "needed_number_of_pairs": C5.needed_number_of_pairs,
+        "sharding": f"event groups over {world} rank(s), one NCCL all-reduce of the histograms per step",
+        "l2": "flushed between timed steps (256 MiB write); accumulators stay resident by design",
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU implementation on the host cores
+def run_cpu_reference(n_events, multiplicity, cores, repeats=1):
+    """One process per core, each pushing one group of n_events x multiplicity pi+ through the
+    UNMODIFIED reference (oracle/_ref/ref_driver mem).  Returns (pairs/s aggregate, pairs per
+    process, kind).  Falls back to the C oracle port if the compiled reference is absent."""
+    from oracle import oracle_py as O
+
+    P = C5
+    nmix = n_events // 2 + 1
+    n = n_events * multiplicity
+    pairs = n * (n - 1) // 2 + n_events * multiplicity * nmix * multiplicity
+    if O.have_reference():
+        with tempfile.TemporaryDirectory() as td:
+            fpar = os.path.join(td, "parameters.dat")
+            with open(fpar, "w") as f:
+                f.write(P.parameters_dat())
+            fins = []
+            for c in range(cores):
+                fin = os.path.join(td, f"in{c}.bin")
+                hbtio.write_batches(fin, synth.make_batches(SEED, 1, n_events, PION_MASS, multiplicity, first_group=1000 + c))
+                fins.append(fin)
+            best = 0.0
+            for _ in range(repeats):
+                t0 = time.perf_counter()
+                procs = [subprocess.Popen([O.REF_DRIVER, "mem", fpar, fins[c], os.path.join(td, f"out{c}.bin")],
+                                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for c in range(cores)]
+                rcs = [p.wait() for p in procs]
+                wall = time.perf_counter() - t0
+                assert all(r == 0 for r in rcs), "ref_driver failed"
+                # time inside the reference's two loop functions, slowest process
+                t_loop = max(hbtio.read_accumulators(os.path.join(td, f"out{c}.bin")).t_total for c in range(cores))
+                best = max(best, cores * pairs / t_loop)
+            return best, pairs, "reference", wall
+    # port: the C restatement, single-threaded per process (run in-process, one core)
+    o = O.Oracle(P)
+    b = synth.make_batches(SEED, 1, n_events, PION_MASS, multiplicity, first_group=1000)[0]
+    t0 = time.perf_counter()
+    o.process_batch(b)
+    wall = time.perf_counter() - t0
+    ts, tm = o.times()
+    return pairs / (ts + tm), pairs, "port", wall
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_arm(a, rank, world):
+    if rank != 0:
+        return
+    cores = host_cores()
+    vals, walls = [], []
+    for i in range(a.warmup + a.steps):
+        v, pairs, kind, wall = run_cpu_reference(a.cpu_events, a.multiplicity, cores)
+        if i >= a.warmup:
+            vals.append(v)
+            walls.append(wall)
+    value = float(np.mean(vals))
+    sample = (f"per step: {cores} processes x 1 group of {a.cpu_events} events x {a.multiplicity} pi+ "
+              f"({pairs:.3e} pairs each), time inside the reference's two pair-loop functions")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except FileNotFoundError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, power, reasons = [], 0.0, [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2])); power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.strip().lower().startswith("active"):
+                    reasons.add(name)
+        # "under load" = samples in the upper half of the observed power range
+        if power:
+            thr = 0.5 * (min(power) + max(power))
+            load = [s for s, w in zip(sm, power) if w >= thr] or sm
+        else:
+            load = sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx or None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_ops(stage, boost=True, az=False):
+    """lazily-evaluated FP64 operation count from the stage populations."""
+    d = 17 if boost else 2
+    e_extra = 3 if az else 0
+    s, m = stage[:6].astype(np.float64), stage[6:].astype(np.float64)
+    same = 7 * s[0] + 10 * s[1] + 5 * s[2] + d * s[3] + (20 + e_extra) * s[4]
+    mixed = 7 * m[0] + 10 * m[1] + 5 * m[2] + d * m[3] + (3 + e_extra) * m[4]
+    return same, mixed
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if a.impl == "reference":
+        reference_arm(a, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from hadronic_afterburner_toolkit_b200 import capi
+    from hadronic_afterburner_toolkit_b200.hbt_correlation import HBT_correlation, Random, _check, gather_rapidity
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU path"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = capi.lib()
+    P = C5
+    eng = HBT_correlation(P, device=local)
+    h = eng._h
+    if world > 1:  # NCCL communicator of the library itself; torch only ferries the 128-byte id
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            _check(None, L.hbt_comm_unique_id(buf))
+            uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().numpy().tobytes())
+        _check(h, L.hbt_comm_init_rank(h, world, rank, ctypes.create_string_buffer(raw, 128)))
+
+    # ---- synthetic input: this rank's groups, pinned host copies and HBM-resident copies
+    G, nev, mult = a.groups_per_gpu, a.events_per_group, a.multiplicity
+    host, dev, offs = [], [], []
+    for g in range(G):
+        arr = synth.make_group(SEED, rank * G + g, nev, PION_MASS, mult).reshape(nev * mult, 8)
+        flat = np.ascontiguousarray(np.concatenate([gather_rapidity(P, arr[e * mult:(e + 1) * mult]) for e in range(nev)]))
+        assert flat.shape[0] == nev * mult  # |y| < 0.45 < HBTrap: the cut keeps everything
+        t = torch.from_numpy(flat).pin_memory()
+        host.append(t)
+        dev.append(t.cuda())
+        offs.append(np.arange(nev + 1, dtype=np.int64) * mult)
+    n = nev * mult
+    nmix = nev // 2 + 1
+    pairs_step_rank = G * (n * (n - 1) // 2 + nev * mult * nmix * mult)
+    rng = Random(P.randomSeed)
+    plans = [rng.mixed_plan(nev, nev) for _ in range(G)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        for g in range(G):
+            ids, cs = plans[g]
+            _check(h, L.hbt_accumulate_same_dev(h, dev[g].data_ptr(), n, 0.0))
+            _check(h, L.hbt_accumulate_mixed_dev(h, dev[g].data_ptr(), offs[g].ctypes.data, nev, None, None, 0,
+                                                 ids.ctypes.data, cs.ctypes.data, nmix, 0.0))
+        if world > 1:
+            _check(h, L.hbt_allreduce(h))
+
+    kcount = np.zeros(2 * P.n_slabs, dtype=np.uint64)
+
+    def step_e2e():
+        for g in range(G):
+            ids, cs = rng.mixed_plan(nev, nev)  # fresh draws, as the host loop would make them
+            _check(h, L.hbt_accumulate_batch(h, host[g].data_ptr(), offs[g].ctypes.data, nev, None, None, 0,
+                                             ids.ctypes.data, cs.ctypes.data, nmix, 0.0, 1, 1))
+        if world > 1:
+            _check(h, L.hbt_allreduce(h))
+        # the step's result: per-K_T accepted-pair counters, device -> host
+        _check(h, L.hbt_read(h, None, None, None, None, None, None, kcount.ctypes.data, kcount[P.n_slabs:].ctypes.data))
+
+    def timed(step_fn, steps, device_timer):
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            barrier()
+            if device_timer:
+                _check(h, L.hbt_timer_start(h))
+                step_fn()
+                ms = ctypes.c_double()
+                _check(h, L.hbt_timer_stop(h, ctypes.byref(ms)))
+                _check(h, L.hbt_synchronize(h))
+                total += ms.value * 1e-3
+            else:
+                t0 = time.perf_counter()
+                step_fn()
+                _check(h, L.hbt_synchronize(h))
+                torch.cuda.synchronize()
+                total += time.perf_counter() - t0
+        t = torch.tensor([total], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def launches():
+        c = ctypes.c_uint64()
+        _check(h, L.hbt_get_launch_count(h, ctypes.byref(c)))
+        return c.value
+
+    # ---- resident-input measurement (value) ---------------------------------------------
+    timed(step_resident, a.warmup, True)
+    st0 = eng.stage_counters()
+    tm0, l0 = eng.timers(), launches()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_value = timed(step_resident, a.steps, True)
+    clocks = sampler.stop() if sampler else None
+    st1 = eng.stage_counters()
+    tm1, l1 = eng.timers(), launches()
+    pairs_total = world * pairs_step_rank * a.steps
+    value = pairs_total / t_value
+
+    # ---- end-to-end measurement (host buffers through the reference-facing call) ----------
+    e2e = None
+    if not a.no_e2e:
+        timed(step_e2e, max(1, a.warmup - 1), False)
+        t_e2e = timed(step_e2e, a.steps, False)
+        e2e = {"value": pairs_total / t_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": int(G * (n * 64 + nev * nmix * 48)),
+               "d2h_bytes_per_step": int(kcount.nbytes),
+               "ms_per_step": 1e3 * t_e2e / a.steps}
+
+    # ---- roofline of the pair kernels (rank 0's device) -------------------------------------
+    peak = ctypes.c_double()
+    _check(None, L.hbt_measure_fp64_peak(local, 300.0, ctypes.byref(peak)))
+    dst = (st1 - st0).astype(np.uint64)
+    ops_same, ops_mixed = algorithmic_ops(dst, boost=P.long_comoving_boost == 1, az=P.azimuthal_flag == 1)
+    ks = (tm1["same_ms"] - tm0["same_ms"]) * 1e-3
+    km = (tm1["mixed_ms"] - tm0["mixed_ms"]) * 1e-3
+    ach = (ops_same + ops_mixed) / (ks + km) / 1e12
+    roofline = {
+        "bound": "fp64", "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
+        "traffic": None,
+        "peak_source": "measured on this device: DFMA dependent-chain microbenchmark (hbt_measure_fp64_peak); "
+                       "FP64 is not in MEASURED_PEAKS.json",
+        "definition": "algorithmic FP64 ops (SURVEY.md 8d: 7nA+10nB+5nC+17nD+20nE same, ...+3nE mixed, from device stage "
+                      "counters) / CUDA-event time of the pair kernels on the launching stream",
+        "kernels": {
+            "same": {"ms_per_launch": 1e3 * ks / max(1, tm1["same_launches"] - tm0["same_launches"]),
+                     "pairs_per_s": float(dst[0]) / ks, "tflops": ops_same / ks / 1e12, "frac": ops_same / ks / 1e12 / peak.value,
+                     "ops_per_pair": ops_same / float(dst[0])},
+            "mixed": {"ms_per_launch": 1e3 * km / max(1, tm1["mixed_launches"] - tm0["mixed_launches"]),
+                      "pairs_per_s": float(dst[6]) / km, "tflops": ops_mixed / km / 1e12, "frac": ops_mixed / km / 1e12 / peak.value,
+                      "ops_per_pair": ops_mixed / float(dst[6])},
+        },
+        "stage_fractions_same": [float(x) / float(dst[0]) for x in dst[:6]],
+        "kernel_share_of_step": (ks + km) / (t_value if world == 1 else max(t_value, 1e-12)),
+    }
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = host_cores()
+        v, pairs, kind, wall = run_cpu_reference(a.cpu_events, mult, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{cores} processes x 1 group of {a.cpu_events} events x {mult} pi+ ({pairs:.3e} pairs each), "
+                         f"time inside the reference's two pair-loop functions; wall {wall:.1f} s",
+               "per_core": v / cores}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * t_value / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(a, world), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(l1 - l0), "roofline": roofline, "cpu_baseline": cpu,
+            "pairs_per_step": world * pairs_step_rank, "kernel": os.environ.get("HBT_B200_KERNEL", "default"),
+            "deferred_pairs": eng.deferred_pairs(),
+        }
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,844 @@
+// libhbt_b200: context, staging, launches and the C ABI (include/hbt_b200.h).
+//
+// One context = one B200.  Per batch ("oversample group") the host hands in the
+// rapidity-cut particle lists and the mixed-event plan; particles go through a ring of
+// pinned staging slots to HBM on a copy stream while the previous batch's pair kernels
+// run on the compute stream; histograms live in HBM (L2-resident at the benchmark sizes)
+// for the whole analysis and are read back once.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hbt_common.h"
+#include "hbt_kernels_v1.cuh"
+#ifdef HBT_HAVE_V2
+#include "hbt_kernels_v2.cuh"
+#else
+#define HBT_V2_TILE_I 128
+#define HBT_V2_TILE_J 128
+#endif
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kSlots = 3;
+constexpr unsigned kDeferredCapacity = 1u << 16;
+constexpr int kTileV1 = 128;
+
+struct Slot {
+    double *h_p = nullptr, *d_p = nullptr;  // pinned staging / device copy of the particle lists
+    size_t cap = 0;                         // particles
+    HbtMixSeg *h_seg = nullptr, *d_seg = nullptr;
+    size_t cap_seg = 0;
+    cudaEvent_t uploaded = nullptr, done = nullptr;
+    bool in_flight = false;
+};
+
+struct TimerRec {
+    cudaEvent_t start, stop;
+    int kind;  // 0 same, 1 mixed
+};
+
+// ---- NCCL, loaded lazily so that the library itself has no link-time dependency ----------
+struct NcclApi {
+    void *handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    std::string error;
+    bool load() {
+        if (handle) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) {
+            error = std::string("cannot load libnccl.so.2: ") + dlerror();
+            return false;
+        }
+#define HBT_SYM(field, sym)                                                        \
+    field = reinterpret_cast<decltype(field)>(dlsym(handle, sym));                 \
+    if (!field) {                                                                  \
+        error = std::string("libnccl lacks ") + sym;                               \
+        return false;                                                              \
+    }
+        HBT_SYM(GetUniqueId, "ncclGetUniqueId")
+        HBT_SYM(CommInitRank, "ncclCommInitRank")
+        HBT_SYM(CommInitAll, "ncclCommInitAll")
+        HBT_SYM(CommDestroy, "ncclCommDestroy")
+        HBT_SYM(AllReduce, "ncclAllReduce")
+        HBT_SYM(GroupStart, "ncclGroupStart")
+        HBT_SYM(GroupEnd, "ncclGroupEnd")
+        HBT_SYM(GetErrorString, "ncclGetErrorString")
+#undef HBT_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+}  // namespace
+
+struct hbt_ctx {
+    int device = 0;
+    hbt_params params{};
+    HbtGrid grid{};
+    HbtAccum acc{};
+    unsigned long long *blob_u64 = nullptr;  // all integer accumulators, contiguous
+    double *blob_f64 = nullptr;              // all floating sums, contiguous
+    unsigned long long *red_u64 = nullptr;   // all-reduced copies (allocated on first use)
+    double *red_f64 = nullptr;
+    bool reduced = false;                    // red_* hold the sum over ranks of the current state
+    size_t n_u64 = 0, n_f64 = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    Slot slots[kSlots];
+    int next_slot = 0;
+    std::vector<TimerRec> timers;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
+    double same_ms = 0., mixed_ms = 0.;
+    uint64_t same_launches = 0, mixed_launches = 0, kernel_launches = 0;
+    HbtDeferred *h_deferred = nullptr;  // pinned
+    unsigned *h_defcount = nullptr;     // pinned [2]
+    HbtCorrection *d_corr = nullptr;
+    uint64_t deferred_total = 0;
+    cudaEvent_t sw0 = nullptr, sw1 = nullptr;  // hbt_timer_start / hbt_timer_stop
+    int kernel_version = 2;
+    ncclComm_t comm = nullptr;
+    int nranks = 1;
+    std::string err;
+};
+
+namespace {
+
+int fail(hbt_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(ctx, HBT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+int ensure_slot(hbt_ctx *ctx, Slot &s, size_t particles, size_t segs) {
+    if (particles > s.cap) {
+        if (s.h_p) cudaFreeHost(s.h_p);
+        if (s.d_p) cudaFree(s.d_p);
+        s.h_p = nullptr; s.d_p = nullptr;
+        size_t cap = std::max<size_t>(particles + particles / 4, 4096);
+        CU(ctx, cudaMallocHost(&s.h_p, cap * 64));
+        CU(ctx, cudaMalloc(&s.d_p, cap * 64));
+        s.cap = cap;
+    }
+    if (segs > s.cap_seg) {
+        if (s.h_seg) cudaFreeHost(s.h_seg);
+        if (s.d_seg) cudaFree(s.d_seg);
+        s.h_seg = nullptr; s.d_seg = nullptr;
+        size_t cap = std::max<size_t>(segs + segs / 4, 256);
+        CU(ctx, cudaMallocHost(&s.h_seg, cap * sizeof(HbtMixSeg)));
+        CU(ctx, cudaMalloc(&s.d_seg, cap * sizeof(HbtMixSeg)));
+        s.cap_seg = cap;
+    }
+    return HBT_OK;
+}
+
+// take the next staging slot; waits (host side) until its previous batch has finished
+int acquire_slot(hbt_ctx *ctx, Slot **out) {
+    Slot &s = ctx->slots[ctx->next_slot];
+    ctx->next_slot = (ctx->next_slot + 1) % kSlots;
+    if (s.in_flight) {
+        CU(ctx, cudaEventSynchronize(s.done));
+        s.in_flight = false;
+    }
+    *out = &s;
+    return HBT_OK;
+}
+
+int get_event_pair(hbt_ctx *ctx, cudaEvent_t *a, cudaEvent_t *b) {
+    if (!ctx->event_pool.empty()) {
+        *a = ctx->event_pool.back().first;
+        *b = ctx->event_pool.back().second;
+        ctx->event_pool.pop_back();
+        return HBT_OK;
+    }
+    CU(ctx, cudaEventCreate(a));
+    CU(ctx, cudaEventCreate(b));
+    return HBT_OK;
+}
+
+// fold finished timer records into the totals (all of them when `all`, which requires the
+// stream to be idle or blocks until each stop event has fired)
+int drain_timers(hbt_ctx *ctx, bool all) {
+    size_t keep = all ? 0 : 64;
+    while (ctx->timers.size() > keep) {
+        TimerRec r = ctx->timers.front();
+        CU(ctx, cudaEventSynchronize(r.stop));
+        float ms = 0.f;
+        CU(ctx, cudaEventElapsedTime(&ms, r.start, r.stop));
+        (r.kind == 0 ? ctx->same_ms : ctx->mixed_ms) += ms;
+        ctx->event_pool.emplace_back(r.start, r.stop);
+        ctx->timers.erase(ctx->timers.begin());
+    }
+    return HBT_OK;
+}
+
+size_t dyn_smem_bytes(const HbtGrid &g) {
+    const size_t nslab_pad = (g.nslab + 1) & ~1;
+    const size_t nqi = g.qinv ? static_cast<size_t>(g.nKT) * g.nq : 0;
+    return nslab_pad * 4 + nqi * (8 + 8 + 4) + (g.qinv ? g.nKT * 4 : 0) + 16;
+}
+
+// ---- launches ------------------------------------------------------------------------
+int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref) {
+    if (n < 2) return HBT_OK;
+    ctx->reduced = false;
+    cudaEvent_t e0, e1;
+    int rc = get_event_pair(ctx, &e0, &e1);
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(e0, ctx->compute));
+    const unsigned long long npairs = static_cast<unsigned long long>(n) * (n - 1) / 2;
+    if (ctx->kernel_version == 1) {
+        const long long T = (n + kTileV1 - 1) / kTileV1;
+        const long long blocks = T * (T + 1) / 2;
+        if (blocks > 0x7fffffffLL) return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld tiles", blocks);
+        hbt_add_stage_a<<<1, 1, 0, ctx->compute>>>(ctx->acc, 0, npairs);
+        ctx->kernel_launches += 2;
+        hbt_pairs_v1<kTileV1, false><<<static_cast<unsigned>(blocks), kTileV1, dyn_smem_bytes(ctx->grid), ctx->compute>>>(
+            d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref);
+    } else {
+#ifdef HBT_HAVE_V2
+        rc = hbt_v2_launch_same(ctx->compute, d_p, n, ctx->grid, ctx->acc, psi_ref, npairs);
+        if (rc) return fail(ctx, rc, "v2 same-event launch failed");
+#endif
+    }
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaEventRecord(e1, ctx->compute));
+    ctx->timers.push_back({e0, e1, 0});
+    ctx->same_launches++;
+    return drain_timers(ctx, false);
+}
+
+// builds the (event, partner) segments of one batch into seg[]; returns their number
+size_t build_segments(const int64_t *off1, int32_t nev1, const int64_t *off2, int64_t base2,
+                      const int32_t *ids, const double *cs, int32_t nmix, int tile_i, int tile_j,
+                      HbtMixSeg *seg, unsigned long long *npairs, long long *nblocks) {
+    size_t ns = 0;
+    long long block0 = 0;
+    unsigned long long pairs = 0;
+    for (int iev = 0; iev < nev1; iev++) {
+        const int64_t i0 = off1[iev], ni = off1[iev + 1] - off1[iev];
+        for (int c = 0; c < nmix; c++) {
+            const size_t k = static_cast<size_t>(iev) * nmix + c;
+            const int id = ids[k];
+            const int64_t j0 = off2[id], nj = off2[id + 1] - off2[id];
+            if (ni <= 0 || nj <= 0) continue;
+            HbtMixSeg &s = seg[ns++];
+            s.i0 = i0; s.ni = static_cast<int32_t>(ni);
+            s.j0 = base2 + j0; s.nj = static_cast<int32_t>(nj);
+            s.c = cs[2 * k]; s.s = cs[2 * k + 1];
+            s.tiles_j = static_cast<int32_t>((nj + tile_j - 1) / tile_j);
+            const int32_t tiles_i = static_cast<int32_t>((ni + tile_i - 1) / tile_i);
+            s.block0 = block0;
+            block0 += static_cast<long long>(tiles_i) * s.tiles_j;
+            pairs += static_cast<unsigned long long>(ni) * nj;
+        }
+    }
+    *npairs = pairs;
+    *nblocks = block0;
+    return ns;
+}
+
+int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg, size_t nseg,
+                 long long nblocks, unsigned long long npairs, double psi_ref) {
+    if (nseg == 0 || nblocks == 0) return HBT_OK;
+    ctx->reduced = false;
+    cudaEvent_t e0, e1;
+    int rc = get_event_pair(ctx, &e0, &e1);
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(e0, ctx->compute));
+    if (nblocks > 0x7fffffffLL) return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld tiles", nblocks);
+    if (ctx->kernel_version == 1) {
+        hbt_add_stage_a<<<1, 1, 0, ctx->compute>>>(ctx->acc, 6, npairs);
+        ctx->kernel_launches += 2;
+        hbt_pairs_v1<kTileV1, true><<<static_cast<unsigned>(nblocks), kTileV1, dyn_smem_bytes(ctx->grid), ctx->compute>>>(
+            d_p1, d_p2, static_cast<long long>(nseg), d_seg, ctx->grid, ctx->acc, psi_ref);
+    } else {
+#ifdef HBT_HAVE_V2
+        rc = hbt_v2_launch_mixed(ctx->compute, d_p1, d_p2, d_seg, nseg, nblocks, ctx->grid, ctx->acc, psi_ref, npairs);
+        if (rc) return fail(ctx, rc, "v2 mixed-event launch failed");
+#endif
+    }
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaEventRecord(e1, ctx->compute));
+    ctx->timers.push_back({e0, e1, 1});
+    ctx->mixed_launches++;
+    return drain_timers(ctx, false);
+}
+
+int tile_i(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V2_TILE_I; }
+int tile_j(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V2_TILE_J; }
+
+// host literal evaluation of the pairs the device deferred; leaves the stream idle
+int resolve_deferred(hbt_ctx *ctx) {
+    CU(ctx, cudaMemcpyAsync(ctx->h_defcount, ctx->acc.deferred_count, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    if (ctx->h_defcount[1]) return fail(ctx, HBT_ERR_OVERFLOW, "deferred-pair list overflowed (%u entries)", kDeferredCapacity);
+    const unsigned n = ctx->h_defcount[0];
+    if (n == 0) return HBT_OK;
+    CU(ctx, cudaMemcpyAsync(ctx->h_deferred, ctx->acc.deferred, static_cast<size_t>(n) * sizeof(HbtDeferred),
+                            cudaMemcpyDeviceToHost, ctx->compute));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    std::vector<HbtCorrection> corr;
+    HbtStageDelta delta{};
+    for (unsigned k = 0; k < n; k++) {
+        const HbtDeferred &d = ctx->h_deferred[k];
+        HbtCorrection c;
+        uint64_t st[6] = {0, 0, 0, 0, 0, 0};
+        if (hbt_host_pair_literal(&ctx->grid, d.a, d.b, d.mixed, d.psi_ref, &c, st)) corr.push_back(c);
+        for (int s = 1; s < 6; s++) delta.v[(d.mixed ? 6 : 0) + s] += st[s];
+    }
+    ctx->deferred_total += n;
+    if (!corr.empty())
+        CU(ctx, cudaMemcpyAsync(ctx->d_corr, corr.data(), corr.size() * sizeof(HbtCorrection), cudaMemcpyHostToDevice, ctx->compute));
+    hbt_apply_corrections<<<(static_cast<int>(corr.size()) + 127) / 128 + 1, 128, 0, ctx->compute>>>(
+        ctx->d_corr, static_cast<int>(corr.size()), ctx->acc, delta);
+    ctx->kernel_launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemsetAsync(ctx->acc.deferred_count, 0, 8, ctx->compute));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    return HBT_OK;
+}
+
+// the accumulators a reader sees: the all-reduced copies while they are current
+HbtAccum view(const hbt_ctx *ctx) {
+    HbtAccum a = ctx->acc;
+    if (!ctx->reduced) return a;
+    const ptrdiff_t du = ctx->red_u64 - ctx->blob_u64;
+    const ptrdiff_t df = ctx->red_f64 - ctx->blob_f64;
+    a.num_count += du; a.den_count += du; a.npairs_num += du; a.npairs_den += du; a.stage += du;
+    a.qinv_count += du; a.qinv_den += du; a.npairs_num_qinv += du; a.npairs_den_qinv += du;
+    a.num_cos += df; a.sum_qo += df; a.sum_qs += df; a.sum_ql += df; a.qinv_sum += df; a.qinv_cos += df;
+    return a;
+}
+
+int check_cap(hbt_ctx *ctx, const uint64_t *num, const uint64_t *den, const uint64_t *qn, const uint64_t *qd) {
+    // The reference stops accepting pairs into a (K_T[,K_phi]) slab once its counter
+    // exceeds needed_number_of_pairs (src/HBT_correlation.cpp:402-406, :651-655), in pair
+    // order.  A slab counter <= needed+1 proves the cap never engaged.
+    const uint64_t lim = ctx->grid.needed + 1;
+    for (int k = 0; k < ctx->grid.nslab; k++)
+        if ((num && num[k] > lim) || (den && den[k] > lim))
+            return fail(ctx, HBT_ERR_CAP,
+                        "needed_number_of_pairs=%llu was exceeded in slab %d: the ordered pair cap is not "
+                        "implemented on the device path; raise needed_number_of_pairs",
+                        static_cast<unsigned long long>(ctx->grid.needed), k);
+    if (ctx->grid.qinv)
+        for (int k = 0; k < ctx->grid.nKT; k++)
+            if ((qn && qn[k] > 50 * ctx->grid.needed) || (qd && qd[k] > 50 * ctx->grid.needed))
+                return fail(ctx, HBT_ERR_CAP, "50*needed_number_of_pairs was exceeded in the q_inv histogram, K_T bin %d", k);
+    return HBT_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" const char *hbt_version(void) { return "hbt_b200 0.1 sm_100a"; }
+
+extern "C" const char *hbt_last_error(const hbt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **out) {
+    if (!params || !out) return fail(nullptr, HBT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, HBT_ERR_NO_DEVICE, "no CUDA device available (%s); libhbt_b200 has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, HBT_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    hbt_ctx *ctx = new hbt_ctx;
+    ctx->device = device;
+    ctx->params = *params;
+    char msg[256];
+    int rc = hbt_host_derive_grid(params, &ctx->grid, msg, sizeof(msg));
+    if (rc) {
+        delete ctx;
+        return fail(nullptr, rc, "%s", msg);
+    }
+    if (const char *v = getenv("HBT_B200_KERNEL")) ctx->kernel_version = atoi(v) == 1 ? 1 : 2;
+#define CUC(call)                                                                              \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            fail(nullptr, HBT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));       \
+            hbt_destroy(ctx);                                                                  \
+            return HBT_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        fail(nullptr, HBT_ERR_NO_DEVICE, "device %d is sm_%d%d; libhbt_b200 is built for sm_100a only", device, prop.major, prop.minor);
+        hbt_destroy(ctx);
+        return HBT_ERR_NO_DEVICE;
+    }
+    CUC(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+    const HbtGrid &g = ctx->grid;
+    const size_t nb = static_cast<size_t>(g.nbins), ns = g.nslab, nqi = static_cast<size_t>(g.nKT) * g.nq;
+    ctx->n_u64 = 2 * nb + 2 * ns + 12 + 2 * nqi + 2 * g.nKT;
+    ctx->n_f64 = 4 * nb + 2 * nqi;
+    CUC(cudaMalloc(&ctx->blob_u64, ctx->n_u64 * 8));
+    CUC(cudaMalloc(&ctx->blob_f64, ctx->n_f64 * 8));
+    CUC(cudaMemset(ctx->blob_u64, 0, ctx->n_u64 * 8));
+    CUC(cudaMemset(ctx->blob_f64, 0, ctx->n_f64 * 8));
+    HbtAccum &a = ctx->acc;
+    unsigned long long *u = ctx->blob_u64;
+    a.num_count = u; u += nb;
+    a.den_count = u; u += nb;
+    a.npairs_num = u; u += ns;
+    a.npairs_den = u; u += ns;
+    a.stage = u; u += 12;
+    a.qinv_count = u; u += nqi;
+    a.qinv_den = u; u += nqi;
+    a.npairs_num_qinv = u; u += g.nKT;
+    a.npairs_den_qinv = u; u += g.nKT;
+    double *f = ctx->blob_f64;
+    a.num_cos = f; f += nb;
+    a.sum_qo = f; f += nb;
+    a.sum_qs = f; f += nb;
+    a.sum_ql = f; f += nb;
+    a.qinv_sum = f; f += nqi;
+    a.qinv_cos = f; f += nqi;
+    CUC(cudaMalloc(&a.deferred, sizeof(HbtDeferred) * kDeferredCapacity));
+    CUC(cudaMalloc(&a.deferred_count, 8));
+    CUC(cudaMemset(a.deferred_count, 0, 8));
+    a.deferred_capacity = kDeferredCapacity;
+    CUC(cudaMallocHost(&ctx->h_deferred, sizeof(HbtDeferred) * kDeferredCapacity));
+    CUC(cudaMallocHost(&ctx->h_defcount, 8));
+    CUC(cudaMalloc(&ctx->d_corr, sizeof(HbtCorrection) * kDeferredCapacity));
+    for (Slot &s : ctx->slots) {
+        CUC(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+#ifdef HBT_HAVE_V2
+    rc = hbt_v2_configure(g);
+    if (rc) {
+        fail(nullptr, rc, "kernel configuration failed: %s", cudaGetErrorString(cudaGetLastError()));
+        hbt_destroy(ctx);
+        return rc;
+    }
+#else
+    ctx->kernel_version = 1;
+#endif
+    CUC(cudaDeviceSynchronize());
+#undef CUC
+    *out = ctx;
+    return HBT_OK;
+}
+
+extern "C" void hbt_destroy(hbt_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->compute) cudaStreamSynchronize(ctx->compute);
+    if (ctx->copy) cudaStreamSynchronize(ctx->copy);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    for (Slot &s : ctx->slots) {
+        if (s.h_p) cudaFreeHost(s.h_p);
+        if (s.d_p) cudaFree(s.d_p);
+        if (s.h_seg) cudaFreeHost(s.h_seg);
+        if (s.d_seg) cudaFree(s.d_seg);
+        if (s.uploaded) cudaEventDestroy(s.uploaded);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    for (auto &r : ctx->timers) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+    for (auto &r : ctx->event_pool) { cudaEventDestroy(r.first); cudaEventDestroy(r.second); }
+    if (ctx->blob_u64) cudaFree(ctx->blob_u64);
+    if (ctx->blob_f64) cudaFree(ctx->blob_f64);
+    if (ctx->red_u64) cudaFree(ctx->red_u64);
+    if (ctx->red_f64) cudaFree(ctx->red_f64);
+    if (ctx->acc.deferred) cudaFree(ctx->acc.deferred);
+    if (ctx->acc.deferred_count) cudaFree(ctx->acc.deferred_count);
+    if (ctx->h_deferred) cudaFreeHost(ctx->h_deferred);
+    if (ctx->h_defcount) cudaFreeHost(ctx->h_defcount);
+    if (ctx->d_corr) cudaFree(ctx->d_corr);
+    if (ctx->sw0) cudaEventDestroy(ctx->sw0);
+    if (ctx->sw1) cudaEventDestroy(ctx->sw1);
+    if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    if (ctx->copy) cudaStreamDestroy(ctx->copy);
+    delete ctx;
+}
+
+extern "C" int64_t hbt_num_bins(const hbt_ctx *ctx) { return ctx ? ctx->grid.nbins : 0; }
+extern "C" int32_t hbt_num_slabs(const hbt_ctx *ctx) { return ctx ? ctx->grid.nslab : 0; }
+
+extern "C" int hbt_reset(hbt_ctx *ctx) {
+    if (!ctx) return HBT_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = hbt_synchronize(ctx);
+    if (rc) return rc;
+    CU(ctx, cudaMemsetAsync(ctx->blob_u64, 0, ctx->n_u64 * 8, ctx->compute));
+    CU(ctx, cudaMemsetAsync(ctx->blob_f64, 0, ctx->n_f64 * 8, ctx->compute));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    ctx->same_ms = ctx->mixed_ms = 0.;
+    ctx->same_launches = ctx->mixed_launches = 0;
+    ctx->deferred_total = 0;
+    ctx->reduced = false;
+    return HBT_OK;
+}
+
+extern "C" int hbt_synchronize(hbt_ctx *ctx) {
+    if (!ctx) return HBT_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->copy));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    for (Slot &s : ctx->slots) s.in_flight = false;
+    int rc = drain_timers(ctx, true);
+    if (rc) return rc;
+    return resolve_deferred(ctx);
+}
+
+// ---- device-resident entry points --------------------------------------------------------
+extern "C" int hbt_accumulate_same_dev(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref) {
+    if (!ctx || (n > 0 && !d_p) || n < 0) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_same_dev: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    return launch_same(ctx, d_p, n, psi_ref);
+}
+
+extern "C" int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const int64_t *off1, int32_t nev1,
+                                        const double *d_p2, const int64_t *off2, int32_t nev2,
+                                        const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
+                                        double psi_ref) {
+    if (!ctx || nev1 < 0 || nmix < 0) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_mixed_dev: bad argument");
+    if (nev1 == 0 || nmix == 0) return HBT_OK;
+    if (!d_p1 || !off1 || !partner_ids || !cos_sin) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_mixed_dev: null argument");
+    if (!d_p2) { d_p2 = d_p1; off2 = off1; nev2 = nev1; }
+    for (size_t k = 0; k < static_cast<size_t>(nev1) * nmix; k++)
+        if (partner_ids[k] < 0 || partner_ids[k] >= nev2) return fail(ctx, HBT_ERR_INVALID, "partner id %d out of range", partner_ids[k]);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot *s;
+    int rc = acquire_slot(ctx, &s);
+    if (rc) return rc;
+    rc = ensure_slot(ctx, *s, 0, static_cast<size_t>(nev1) * nmix);
+    if (rc) return rc;
+    unsigned long long npairs;
+    long long nblocks;
+    const size_t nseg = build_segments(off1, nev1, off2, 0, partner_ids, cos_sin, nmix, tile_i(ctx), tile_j(ctx), s->h_seg, &npairs, &nblocks);
+    if (nseg) CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, ctx->compute));
+    rc = launch_mixed(ctx, d_p1, d_p2, s->d_seg, nseg, nblocks, npairs, psi_ref);
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(s->done, ctx->compute));
+    s->in_flight = true;
+    return HBT_OK;
+}
+
+// ---- host-buffer entry points ------------------------------------------------------------
+extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_t *off1, int32_t nev1,
+                                    const double *p2, const int64_t *off2, int32_t nev2,
+                                    const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
+                                    double psi_ref, int32_t do_same, int32_t do_mixed) {
+    if (!ctx || nev1 < 0) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_batch: bad argument");
+    if (nev1 == 0) return HBT_OK;  // the reader's trailing empty batch (src/Analysis.cpp:821)
+    if (!off1) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_batch: null offsets");
+    const int64_t n1 = off1[nev1];
+    if (n1 > 0 && !p1) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_batch: null particles");
+    const bool alias = (p2 == nullptr);
+    if (alias) { off2 = off1; nev2 = nev1; }
+    const int64_t n2 = alias ? 0 : off2[nev2];
+    do_mixed = do_mixed && nmix > 0;
+    if (do_mixed) {
+        if (!partner_ids || !cos_sin) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_batch: null mixed-event plan");
+        for (size_t k = 0; k < static_cast<size_t>(nev1) * nmix; k++)
+            if (partner_ids[k] < 0 || partner_ids[k] >= nev2) return fail(ctx, HBT_ERR_INVALID, "partner id %d out of range", partner_ids[k]);
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot *s;
+    int rc = acquire_slot(ctx, &s);
+    if (rc) return rc;
+    rc = ensure_slot(ctx, *s, static_cast<size_t>(n1 + n2), do_mixed ? static_cast<size_t>(nev1) * nmix : 0);
+    if (rc) return rc;
+    // the device buffers of this slot may still be read by the compute stream's previous
+    // use; acquire_slot already waited on `done`.  Stage and upload on the copy stream.
+    if (n1) std::memcpy(s->h_p, p1, static_cast<size_t>(n1) * 64);
+    if (n2) std::memcpy(s->h_p + 8 * n1, p2, static_cast<size_t>(n2) * 64);
+    if (n1 + n2) CU(ctx, cudaMemcpyAsync(s->d_p, s->h_p, static_cast<size_t>(n1 + n2) * 64, cudaMemcpyHostToDevice, ctx->copy));
+    size_t nseg = 0;
+    unsigned long long npairs = 0;
+    long long nblocks = 0;
+    if (do_mixed) {
+        nseg = build_segments(off1, nev1, off2, alias ? 0 : n1, partner_ids, cos_sin, nmix, tile_i(ctx), tile_j(ctx), s->h_seg, &npairs, &nblocks);
+        if (nseg) CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, ctx->copy));
+    }
+    CU(ctx, cudaEventRecord(s->uploaded, ctx->copy));
+    CU(ctx, cudaStreamWaitEvent(ctx->compute, s->uploaded, 0));
+    if (do_same) {
+        rc = launch_same(ctx, s->d_p, n1, psi_ref);
+        if (rc) return rc;
+    }
+    if (do_mixed) {
+        rc = launch_mixed(ctx, s->d_p, s->d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
+        if (rc) return rc;
+    }
+    CU(ctx, cudaEventRecord(s->done, ctx->compute));
+    s->in_flight = true;
+    return HBT_OK;
+}
+
+extern "C" int hbt_accumulate_same(hbt_ctx *ctx, const double *p, int64_t n, double psi_ref) {
+    if (!ctx || n < 0) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_same: bad argument");
+    if (n == 0) return HBT_OK;
+    const int64_t off[2] = {0, n};
+    return hbt_accumulate_batch(ctx, p, off, 1, nullptr, nullptr, 0, nullptr, nullptr, 0, psi_ref, 1, 0);
+}
+
+extern "C" int hbt_accumulate_mixed(hbt_ctx *ctx, const double *p1, const int64_t *off1, int32_t nev1,
+                                    const double *p2, const int64_t *off2, int32_t nev2,
+                                    const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
+                                    double psi_ref) {
+    return hbt_accumulate_batch(ctx, p1, off1, nev1, p2, off2, nev2, partner_ids, cos_sin, nmix, psi_ref, 0, 1);
+}
+
+// ---- results -----------------------------------------------------------------------------
+extern "C" int hbt_read(hbt_ctx *ctx, uint64_t *num_count, double *num_cos, double *sum_qo, double *sum_qs,
+                        double *sum_ql, uint64_t *den_count, uint64_t *npairs_num, uint64_t *npairs_den) {
+    if (!ctx) return HBT_ERR_INVALID;
+    int rc = hbt_synchronize(ctx);
+    if (rc) return rc;
+    const size_t nb = static_cast<size_t>(ctx->grid.nbins) * 8, ns = static_cast<size_t>(ctx->grid.nslab) * 8;
+    const HbtAccum a = view(ctx);
+    if (num_count) CU(ctx, cudaMemcpy(num_count, a.num_count, nb, cudaMemcpyDeviceToHost));
+    if (num_cos) CU(ctx, cudaMemcpy(num_cos, a.num_cos, nb, cudaMemcpyDeviceToHost));
+    if (sum_qo) CU(ctx, cudaMemcpy(sum_qo, a.sum_qo, nb, cudaMemcpyDeviceToHost));
+    if (sum_qs) CU(ctx, cudaMemcpy(sum_qs, a.sum_qs, nb, cudaMemcpyDeviceToHost));
+    if (sum_ql) CU(ctx, cudaMemcpy(sum_ql, a.sum_ql, nb, cudaMemcpyDeviceToHost));
+    if (den_count) CU(ctx, cudaMemcpy(den_count, a.den_count, nb, cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> kn(ctx->grid.nslab), kd(ctx->grid.nslab), qn(ctx->grid.nKT), qd(ctx->grid.nKT);
+    CU(ctx, cudaMemcpy(kn.data(), a.npairs_num, ns, cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemcpy(kd.data(), a.npairs_den, ns, cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemcpy(qn.data(), a.npairs_num_qinv, ctx->grid.nKT * 8, cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemcpy(qd.data(), a.npairs_den_qinv, ctx->grid.nKT * 8, cudaMemcpyDeviceToHost));
+    if (npairs_num) std::memcpy(npairs_num, kn.data(), ns);
+    if (npairs_den) std::memcpy(npairs_den, kd.data(), ns);
+    return check_cap(ctx, kn.data(), kd.data(), qn.data(), qd.data());
+}
+
+extern "C" int hbt_read_qinv(hbt_ctx *ctx, uint64_t *count, double *sum_qinv, double *sum_cos, uint64_t *den,
+                             uint64_t *npairs_num, uint64_t *npairs_den) {
+    if (!ctx) return HBT_ERR_INVALID;
+    if (!ctx->grid.qinv) return fail(ctx, HBT_ERR_STATE, "invariant_radius_flag is 0");
+    int rc = hbt_synchronize(ctx);
+    if (rc) return rc;
+    const size_t n = static_cast<size_t>(ctx->grid.nKT) * ctx->grid.nq * 8, nk = ctx->grid.nKT * 8;
+    const HbtAccum a = view(ctx);
+    if (count) CU(ctx, cudaMemcpy(count, a.qinv_count, n, cudaMemcpyDeviceToHost));
+    if (sum_qinv) CU(ctx, cudaMemcpy(sum_qinv, a.qinv_sum, n, cudaMemcpyDeviceToHost));
+    if (sum_cos) CU(ctx, cudaMemcpy(sum_cos, a.qinv_cos, n, cudaMemcpyDeviceToHost));
+    if (den) CU(ctx, cudaMemcpy(den, a.qinv_den, n, cudaMemcpyDeviceToHost));
+    if (npairs_num) CU(ctx, cudaMemcpy(npairs_num, a.npairs_num_qinv, nk, cudaMemcpyDeviceToHost));
+    if (npairs_den) CU(ctx, cudaMemcpy(npairs_den, a.npairs_den_qinv, nk, cudaMemcpyDeviceToHost));
+    return HBT_OK;
+}
+
+extern "C" int hbt_get_stage_counters(hbt_ctx *ctx, uint64_t same[6], uint64_t mixed[6]) {
+    if (!ctx) return HBT_ERR_INVALID;
+    int rc = hbt_synchronize(ctx);
+    if (rc) return rc;
+    uint64_t st[12];
+    CU(ctx, cudaMemcpy(st, view(ctx).stage, sizeof(st), cudaMemcpyDeviceToHost));
+    if (same) std::memcpy(same, st, 48);
+    if (mixed) std::memcpy(mixed, st + 6, 48);
+    return HBT_OK;
+}
+
+extern "C" int hbt_get_timers(hbt_ctx *ctx, double *same_ms, double *mixed_ms, uint64_t *same_launches,
+                              uint64_t *mixed_launches) {
+    if (!ctx) return HBT_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = drain_timers(ctx, true);
+    if (rc) return rc;
+    if (same_ms) *same_ms = ctx->same_ms;
+    if (mixed_ms) *mixed_ms = ctx->mixed_ms;
+    if (same_launches) *same_launches = ctx->same_launches;
+    if (mixed_launches) *mixed_launches = ctx->mixed_launches;
+    return HBT_OK;
+}
+
+extern "C" int hbt_timer_start(hbt_ctx *ctx) {
+    if (!ctx) return HBT_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->sw0) {
+        CU(ctx, cudaEventCreate(&ctx->sw0));
+        CU(ctx, cudaEventCreate(&ctx->sw1));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->copy));
+    CU(ctx, cudaEventRecord(ctx->sw0, ctx->compute));
+    return HBT_OK;
+}
+
+extern "C" int hbt_timer_stop(hbt_ctx *ctx, double *ms) {
+    if (!ctx || !ms || !ctx->sw0) return HBT_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->copy));  // everything uploaded has been handed to compute
+    CU(ctx, cudaEventRecord(ctx->sw1, ctx->compute));
+    CU(ctx, cudaEventSynchronize(ctx->sw1));
+    float t = 0.f;
+    CU(ctx, cudaEventElapsedTime(&t, ctx->sw0, ctx->sw1));
+    *ms = t;
+    return HBT_OK;
+}
+
+extern "C" int hbt_get_launch_count(hbt_ctx *ctx, uint64_t *n) {
+    if (!ctx || !n) return HBT_ERR_INVALID;
+    *n = ctx->kernel_launches;
+    return HBT_OK;
+}
+
+extern "C" int hbt_get_deferred_pairs(hbt_ctx *ctx, uint64_t *n) {
+    if (!ctx || !n) return HBT_ERR_INVALID;
+    *n = ctx->deferred_total;
+    return HBT_OK;
+}
+
+// ---- FP64 roofline denominator ---------------------------------------------------------
+namespace {
+// 8 independent DFMA chains per thread; every result feeds the final store so nothing is
+// eliminated.  2 flops per DFMA.
+__global__ void __launch_bounds__(256) hbt_dfma_chain(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int hbt_measure_fp64_peak(int32_t device, double ms, double *tflops) {
+    if (!tflops) return HBT_ERR_INVALID;
+    hbt_ctx *ctx = nullptr;
+    CU(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(ctx, cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    double *out = nullptr;
+    CU(ctx, cudaMalloc(&out, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CU(ctx, cudaEventCreate(&e0));
+    CU(ctx, cudaEventCreate(&e1));
+    int iters = 1 << 14;
+    double best = 0.0, spent = 0.0;
+    for (int rep = 0; rep < 64 && (spent < ms || rep < 3); rep++) {
+        CU(ctx, cudaEventRecord(e0, 0));
+        hbt_dfma_chain<<<blocks, threads>>>(out, iters, 0.9999999, 1e-9);
+        CU(ctx, cudaEventRecord(e1, 0));
+        CU(ctx, cudaEventSynchronize(e1));
+        float t = 0.f;
+        CU(ctx, cudaEventElapsedTime(&t, e0, e1));
+        const double flops = 2.0 * 8.0 * iters * static_cast<double>(blocks) * threads;
+        if (rep > 0) best = std::max(best, flops / (t * 1e-3) / 1e12);  // rep 0 = warm-up
+        spent += t;
+        if (t < 5.f && iters < (1 << 20)) iters *= 2;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return HBT_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------
+#define NC(ctx, call)                                                                          \
+    do {                                                                                       \
+        ncclResult_t r_ = (call);                                                              \
+        if (r_ != ncclSuccess)                                                                 \
+            return fail(ctx, HBT_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+extern "C" int hbt_comm_unique_id(char id[128]) {
+    if (!g_nccl.load()) return fail(nullptr, HBT_ERR_NCCL, "%s", g_nccl.error.c_str());
+    ncclUniqueId uid;
+    NC(nullptr, g_nccl.GetUniqueId(&uid));
+    std::memcpy(id, uid.internal, 128);
+    return HBT_OK;
+}
+
+extern "C" int hbt_comm_init_rank(hbt_ctx *ctx, int32_t nranks, int32_t rank, const char id[128]) {
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, HBT_ERR_INVALID, "hbt_comm_init_rank: bad argument");
+    if (!g_nccl.load()) return fail(ctx, HBT_ERR_NCCL, "%s", g_nccl.error.c_str());
+    CU(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    std::memcpy(uid.internal, id, 128);
+    NC(ctx, g_nccl.CommInitRank(&ctx->comm, nranks, uid, rank));
+    ctx->nranks = nranks;
+    return HBT_OK;
+}
+
+extern "C" int hbt_comm_init_all(hbt_ctx **ctxs, int32_t n) {
+    if (!ctxs || n < 1) return HBT_ERR_INVALID;
+    if (!g_nccl.load()) return fail(ctxs[0], HBT_ERR_NCCL, "%s", g_nccl.error.c_str());
+    std::vector<int> devs(n);
+    std::vector<ncclComm_t> comms(n);
+    for (int i = 0; i < n; i++) devs[i] = ctxs[i]->device;
+    NC(ctxs[0], g_nccl.CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; i++) { ctxs[i]->comm = comms[i]; ctxs[i]->nranks = n; }
+    return HBT_OK;
+}
+
+extern "C" int hbt_allreduce_all(hbt_ctx **ctxs, int32_t n) {
+    if (!ctxs || n < 1) return HBT_ERR_INVALID;
+    for (int i = 0; i < n; i++) {
+        int rc = hbt_synchronize(ctxs[i]);  // deferred pairs are folded in before the sum
+        if (rc) return rc;
+    }
+    if (n == 1 && !ctxs[0]->comm) return HBT_OK;  // a single GPU is its own sum
+    for (int i = 0; i < n; i++)
+        if (!ctxs[i]->comm) return fail(ctxs[i], HBT_ERR_STATE, "hbt_allreduce: no communicator (call hbt_comm_init_*)");
+    for (int i = 0; i < n; i++) {
+        hbt_ctx *c = ctxs[i];
+        CU(c, cudaSetDevice(c->device));
+        if (!c->red_u64) {
+            CU(c, cudaMalloc(&c->red_u64, c->n_u64 * 8));
+            CU(c, cudaMalloc(&c->red_f64, c->n_f64 * 8));
+        }
+    }
+    // the local accumulators stay local (more batches may follow); the sums over ranks land
+    // in red_*, which hbt_read / hbt_get_stage_counters return until the next accumulate
+    NC(ctxs[0], g_nccl.GroupStart());
+    for (int i = 0; i < n; i++) {
+        hbt_ctx *c = ctxs[i];
+        NC(c, g_nccl.AllReduce(c->blob_u64, c->red_u64, c->n_u64, ncclUint64, ncclSum, c->comm, c->compute));
+        NC(c, g_nccl.AllReduce(c->blob_f64, c->red_f64, c->n_f64, ncclFloat64, ncclSum, c->comm, c->compute));
+    }
+    NC(ctxs[0], g_nccl.GroupEnd());
+    for (int i = 0; i < n; i++) {
+        CU(ctxs[i], cudaSetDevice(ctxs[i]->device));
+        CU(ctxs[i], cudaStreamSynchronize(ctxs[i]->compute));
+        ctxs[i]->reduced = true;
+    }
+    return HBT_OK;
+}
+
+extern "C" int hbt_allreduce(hbt_ctx *ctx) { return hbt_allreduce_all(&ctx, 1); }

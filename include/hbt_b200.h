@@ -1,0 +1,202 @@
+/* hbt_b200 — C ABI of the B200-native HBT pair-correlation engine (libhbt_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of chunshen1987/hadronic_afterburner_toolkit:
+ * the same-event and mixed-event pair loops of class HBT_correlation.  Everything the
+ * reference does around those loops (parameters.dat, the particleSamples reader, the RNG
+ * stream, the output files) stays on the host side of this boundary.  Citations are
+ * relative to the reference tree.
+ *
+ *   reference                                                 replaced by
+ *   ---------------------------------------------------------  ------------------------------
+ *   HBT_correlation ctor, histogram allocation                 hbt_create
+ *     (src/HBT_correlation.cpp:16-143)
+ *   ~HBT_correlation (:145-175)                                hbt_destroy
+ *   gather + rapidity cut (:255-281, :468-489, :499-511)       hbt_gather_rapidity (host helper)
+ *   calculate_flow_event_plane_angle (:233-249)                hbt_psi_ref        (host helper)
+ *   partner draw + rotation angles (:206-215, :495-497)        hbt_rng_mixed_plan (host helper;
+ *                                                              the C++ class uses the reference's
+ *                                                              own RandomUtil::Random instead)
+ *   combine_and_bin_particle_pairs pair loop (:291-460)        hbt_accumulate_same[_dev]
+ *   combine_and_bin_particle_pairs_mixed_events loop (:563-689) hbt_accumulate_mixed[_dev]
+ *   one whole batch of calculate_HBT_correlation_function      hbt_accumulate_batch
+ *     (:177-218)
+ *   reading the accumulators for output_* (:694-855)           hbt_read, hbt_read_qinv
+ *
+ * Conventions: plain C types only; every function returns 0 (HBT_OK) or a negative
+ * error code, the message is available from hbt_last_error; no C++ exceptions cross the
+ * ABI.  Calls on one context must come from one host thread at a time, in batch order.
+ * Work is asynchronous on the context's CUDA stream; hbt_synchronize / hbt_read wait.
+ * There is NO CPU fallback: without a usable CUDA device hbt_create fails.
+ *
+ * Particle layout everywhere: 8 doubles per particle, px,py,pz,E,x,y,z,t — the 64 hot
+ * bytes of particle_info (src/particle_info.h:5-12) in the order the loops read them.
+ * Histogram layout: flat [slab][q_out][q_side][q_long], slab = K_T index
+ * (azimuthal_flag = 0, n_KT slabs) or K_T index * n_Kphi + K_phi index (azimuthal_flag = 1).
+ * As in the reference, n_KT counts K_T EDGES and the slab n_KT-1 exists (it receives pairs
+ * with K_T == KT_max exactly) but is never written to a file.
+ */
+#ifndef HBT_B200_H_
+#define HBT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HBT_OK 0
+#define HBT_ERR_INVALID (-1)     /* bad argument / parameter */
+#define HBT_ERR_CUDA (-2)        /* CUDA runtime or kernel failure */
+#define HBT_ERR_NO_DEVICE (-3)   /* no usable CUDA device: there is no CPU path */
+#define HBT_ERR_CAP (-4)         /* needed_number_of_pairs was reached in a mode that
+                                    does not implement the ordered cap */
+#define HBT_ERR_OVERFLOW (-5)    /* a device-side side list overflowed */
+#define HBT_ERR_NCCL (-6)
+#define HBT_ERR_STATE (-7)
+
+/* The parameters.dat switches of the path (src/HBT_correlation.cpp:22-46), verbatim.
+ * All grid constants (delta_q, window edges, dKT, dKphi, KT^2 cuts, tanh rapidity cuts)
+ * are derived inside hbt_create with the reference's own expressions (:28, :48-49,
+ * :255-256, :289-290, :363-364). */
+typedef struct hbt_params {
+    int32_t qnpts;
+    int32_t n_KT;
+    int32_t n_Kphi;
+    int32_t azimuthal_flag;
+    int32_t invariant_radius_flag;
+    int32_t long_comoving_boost;
+    double q_min, q_max;
+    double KT_min, KT_max;
+    double HBTrap_min, HBTrap_max;
+    double needed_number_of_pairs;
+} hbt_params;
+
+typedef struct hbt_ctx hbt_ctx;
+typedef struct hbt_rng hbt_rng;
+
+/* ---- lifetime -------------------------------------------------------------------- */
+/* replaces HBT_correlation::HBT_correlation (src/HBT_correlation.cpp:16-143):
+ * allocates and zeroes every accumulator in the HBM of CUDA device `device`. */
+int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **out);
+/* replaces HBT_correlation::~HBT_correlation (:145-175) */
+void hbt_destroy(hbt_ctx *ctx);
+/* message of the last failure on ctx (ctx == NULL: of the last failed hbt_create) */
+const char *hbt_last_error(const hbt_ctx *ctx);
+int64_t hbt_num_bins(const hbt_ctx *ctx);
+int32_t hbt_num_slabs(const hbt_ctx *ctx);
+int hbt_reset(hbt_ctx *ctx); /* zero all accumulators (a new analysis, same grid) */
+
+/* ---- host helpers (reference-identical host arithmetic, glibc libm) --------------- */
+/* single-particle rapidity cut tanh(HBTrap_min) < pz/E < tanh(HBTrap_max) of the gathers
+ * (src/HBT_correlation.cpp:255-266, :468-476, :509-511).  Copies the accepted particles of
+ * `in` (n x 8) to `out` in order and returns how many were kept. */
+int64_t hbt_gather_rapidity(const hbt_params *params, const double *in, int64_t n, double *out);
+/* HBT_correlation::calculate_flow_event_plane_angle (:233-249) over n particles */
+double hbt_psi_ref(const double *p, int64_t n, int32_t n_order);
+/* The RNG stream of the mixed-event step.  hbt_rng is std::mt19937 with the same
+ * distribution objects as RandomUtil::Random (src/Random.h:15-22, src/Random.cpp:7-14). */
+int hbt_rng_create(int32_t seed, hbt_rng **out);
+void hbt_rng_destroy(hbt_rng *rng);
+int32_t hbt_rng_int_uniform(hbt_rng *rng);
+double hbt_rng_uniform(hbt_rng *rng);
+/* One batch worth of draws in the reference's order (src/HBT_correlation.cpp:202-217 and
+ * :493-497): for each of the nev events, nmix = nev_mixed/2+1 partner ids
+ * (rand_int_uniform() % nev_mixed, redrawn while == iev unless nev_mixed == 1), then nmix
+ * rotation angles rand_uniform()*2*M_PI.  Outputs (any may be NULL): partner_ids
+ * [nev*nmix], cos_sin [nev*nmix*2] = glibc cos/sin of the angle, angles [nev*nmix].
+ * With all outputs NULL this just fast-forwards the stream past the batch (sharded runs).
+ * Returns nmix. */
+int32_t hbt_rng_mixed_plan(hbt_rng *rng, int32_t nev, int32_t nev_mixed, int32_t *partner_ids,
+                           double *cos_sin, double *angles);
+
+/* ---- the hot path: HOST buffers in (copies are part of the call) ------------------ */
+/* Same-event pair loop (src/HBT_correlation.cpp:291-460) over the merged, rapidity-cut
+ * particle list `p` (n x 8, reference gather order).  psi_ref is only read when
+ * azimuthal_flag = 1. */
+int hbt_accumulate_same(hbt_ctx *ctx, const double *p, int64_t n, double psi_ref);
+/* Mixed-event pair loops (:563-689) for ALL events of a batch in one submission.
+ * p1/off1: rapidity-cut particles of the batch's events, flat, with nev1+1 offsets (list 1
+ * of each call of the reference routine, :471-489).  p2/off2: rapidity-cut particles of the
+ * mixed-event lists (NULL/0: they alias p1/off1, src/particleSamples.cpp:528-530).
+ * partner_ids [nev1*nmix] index events of list 2; cos_sin [nev1*nmix*2] are the
+ * host-computed cos and sin of each partner's rotation angle; the rotation (:522-523) is
+ * applied on the device with the reference's two-multiply-one-add rounding. */
+int hbt_accumulate_mixed(hbt_ctx *ctx, const double *p1, const int64_t *off1, int32_t nev1,
+                         const double *p2, const int64_t *off2, int32_t nev2,
+                         const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
+                         double psi_ref);
+/* One whole batch = body of calculate_HBT_correlation_function (:177-218): same-event loop
+ * over the concatenation of the events of list 1, then the mixed-event loops; list 1 is
+ * uploaded once.  do_same / do_mixed select the halves. */
+int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_t *off1, int32_t nev1,
+                         const double *p2, const int64_t *off2, int32_t nev2,
+                         const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
+                         double psi_ref, int32_t do_same, int32_t do_mixed);
+
+/* ---- the hot path: particles already resident in HBM ------------------------------ */
+/* Same contracts, but d_p / d_p1 / d_p2 are DEVICE pointers on the context's device
+ * (offsets, ids and cos_sin stay host pointers: they are the host-side plan).  The
+ * device buffers must stay valid until hbt_synchronize. */
+int hbt_accumulate_same_dev(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref);
+int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const int64_t *off1, int32_t nev1,
+                             const double *d_p2, const int64_t *off2, int32_t nev2,
+                             const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
+                             double psi_ref);
+
+/* ---- results ---------------------------------------------------------------------- */
+int hbt_synchronize(hbt_ctx *ctx);
+/* Copies the accumulators out (any pointer may be NULL).  Sizes: hbt_num_bins for the six
+ * histograms, hbt_num_slabs for the two accepted-pair counters — the reference's
+ * correl_3d_num_count / correl_3d_num / q_out_mean / q_side_mean / q_long_mean /
+ * correl_3d_denorm (or the *_Kphi_diff_* set) and number_of_pairs_numerator_KTdiff /
+ * number_of_pairs_denormenator_KTdiff (or the *_KTKphidiff set)
+ * (src/HBT_correlation.h:42-61).  Counts are exact integers (the reference keeps them in
+ * doubles).  After hbt_allreduce every rank reads the global sums. */
+int hbt_read(hbt_ctx *ctx, uint64_t *num_count, double *num_cos, double *sum_qo, double *sum_qs,
+             double *sum_ql, uint64_t *den_count, uint64_t *npairs_num, uint64_t *npairs_den);
+/* invariant_radius_flag = 1 accumulators, each [n_KT][qnpts] (+ [n_KT] counters):
+ * correl_1d_inv_num_count, q_inv_mean, correl_1d_inv_num, correl_1d_inv_denorm,
+ * number_of_pairs_{numerator,denormenator}_KTdiff_qinv_ */
+int hbt_read_qinv(hbt_ctx *ctx, uint64_t *count, double *sum_qinv, double *sum_cos, uint64_t *den,
+                  uint64_t *npairs_num, uint64_t *npairs_den);
+/* stage populations {all pairs, passed K_T cut, passed q_out, passed q_side, passed q_long,
+ * accepted}: the n_A..n_E of the roofline formula */
+int hbt_get_stage_counters(hbt_ctx *ctx, uint64_t same[6], uint64_t mixed[6]);
+/* device time of the pair kernels so far, measured with CUDA events on the context's
+ * stream, and the number of kernel launches */
+int hbt_get_timers(hbt_ctx *ctx, double *same_ms, double *mixed_ms, uint64_t *same_launches,
+                   uint64_t *mixed_launches);
+/* Device-side stopwatch on the context's compute stream (CUDA events): everything the
+ * context enqueues between start and stop — copies it waits for, pair kernels, the NCCL
+ * all-reduce — is inside.  hbt_timer_stop waits for the stream and returns milliseconds. */
+int hbt_timer_start(hbt_ctx *ctx);
+int hbt_timer_stop(hbt_ctx *ctx, double *ms);
+/* number of CUDA kernels this context has launched so far (pair kernels + bookkeeping) */
+int hbt_get_launch_count(hbt_ctx *ctx, uint64_t *n);
+/* pairs that the device deferred to the host's literal re-evaluation so far (K_phi bin
+ * decisions within 1e-9 of an edge: CUDA atan2 vs glibc atan2) */
+int hbt_get_deferred_pairs(hbt_ctx *ctx, uint64_t *n);
+
+/* ---- multi-GPU: one context per GPU, one NCCL all-reduce of the histograms -------- */
+/* multi-process (one rank per GPU): rank 0 makes an id, every rank joins */
+int hbt_comm_unique_id(char id[128]);
+int hbt_comm_init_rank(hbt_ctx *ctx, int32_t nranks, int32_t rank, const char id[128]);
+/* single-process: ctxs[0..n) on distinct devices become one communicator */
+int hbt_comm_init_all(hbt_ctx **ctxs, int32_t n);
+/* sum all accumulators (u64 counts, f64 sums, counters) across the communicator over
+ * NVLink; for a single-process group call it once with all contexts via hbt_allreduce_all */
+int hbt_allreduce(hbt_ctx *ctx);
+int hbt_allreduce_all(hbt_ctx **ctxs, int32_t n);
+
+/* FP64-pipe roofline denominator: runs a dependent-chain DFMA microbenchmark on `device`
+ * for about `ms` milliseconds and returns the sustained rate in TFLOP/s (2 flops per DFMA).
+ * Measurement aid for bench.py; not part of the reference's interface. */
+int hbt_measure_fp64_peak(int32_t device, double ms, double *tflops);
+
+/* library self-description: "hbt_b200 <version> sm_100a" */
+const char *hbt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBT_B200_H_ */
