@@ -115,6 +115,10 @@ struct hbt_ctx {
     HbtCorrection *d_corr = nullptr;
     uint64_t deferred_total = 0;
     cudaEvent_t sw0 = nullptr, sw1 = nullptr;  // hbt_timer_start / hbt_timer_stop
+#ifdef HBT_HAVE_V2
+    V2Const v2c{};
+    V2Dev *d_dv = nullptr;  // global-memory copy for the non-inlined device functions
+#endif
     int kernel_version = 2;
     ncclComm_t comm = nullptr;
     int nranks = 1;
@@ -228,7 +232,8 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref) {
             d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref);
     } else {
 #ifdef HBT_HAVE_V2
-        rc = hbt_v2_launch_same(ctx->compute, d_p, n, ctx->grid, ctx->acc, psi_ref, npairs);
+        rc = hbt_v2_launch_same(ctx->compute, d_p, n, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs);
+        ctx->kernel_launches++;
         if (rc) return fail(ctx, rc, "v2 same-event launch failed");
 #endif
     }
@@ -285,7 +290,8 @@ int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const Hbt
             d_p1, d_p2, static_cast<long long>(nseg), d_seg, ctx->grid, ctx->acc, psi_ref);
     } else {
 #ifdef HBT_HAVE_V2
-        rc = hbt_v2_launch_mixed(ctx->compute, d_p1, d_p2, d_seg, nseg, nblocks, ctx->grid, ctx->acc, psi_ref, npairs);
+        rc = hbt_v2_launch_mixed(ctx->compute, d_p1, d_p2, d_seg, nseg, nblocks, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs);
+        ctx->kernel_launches++;
         if (rc) return fail(ctx, rc, "v2 mixed-event launch failed");
 #endif
     }
@@ -443,11 +449,15 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
         CUC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
 #ifdef HBT_HAVE_V2
-    rc = hbt_v2_configure(g);
-    if (rc) {
-        fail(nullptr, rc, "kernel configuration failed: %s", cudaGetErrorString(cudaGetLastError()));
-        hbt_destroy(ctx);
-        return rc;
+    ctx->v2c = hbt_v2_consts(g);
+    if (!hbt_v2_supported(g)) ctx->kernel_version = 1;  // q_inv mode, one-sided q windows: literal kernels
+    {
+        V2Dev dv;
+        dv.g = ctx->grid;
+        dv.c = ctx->v2c;
+        dv.acc = ctx->acc;
+        CUC(cudaMalloc(&ctx->d_dv, sizeof(V2Dev)));
+        CUC(cudaMemcpy(ctx->d_dv, &dv, sizeof(V2Dev), cudaMemcpyHostToDevice));
     }
 #else
     ctx->kernel_version = 1;
@@ -483,6 +493,9 @@ extern "C" void hbt_destroy(hbt_ctx *ctx) {
     if (ctx->h_deferred) cudaFreeHost(ctx->h_deferred);
     if (ctx->h_defcount) cudaFreeHost(ctx->h_defcount);
     if (ctx->d_corr) cudaFree(ctx->d_corr);
+#ifdef HBT_HAVE_V2
+    if (ctx->d_dv) cudaFree(ctx->d_dv);
+#endif
     if (ctx->sw0) cudaEventDestroy(ctx->sw0);
     if (ctx->sw1) cudaEventDestroy(ctx->sw1);
     if (ctx->compute) cudaStreamDestroy(ctx->compute);

@@ -44,7 +44,7 @@ CASES = {
     "unit_iss_gz_inv": ("test_gzip_reader", 10, UNIT.with_(invariant_radius_flag=1), {}),
     "unit_iss_gz_az": ("test_gzip_reader", 10, UNIT.with_(azimuthal_flag=1, n_Kphi=4, n_KT=3, qnpts=21), {}),
     "unit_iss_gz_noboost": ("test_gzip_reader", 10, UNIT.with_(long_comoving_boost=0), {}),
-    "unit_iss_gz_cap": ("test_gzip_reader", 10, UNIT.with_(needed_number_of_pairs=500.0), {}),
+    "unit_iss_gz_cap": ("test_gzip_reader", 10, UNIT.with_(needed_number_of_pairs=50.0), {}),
     "unit_iss_gz_realmixed": ("test_gzip_reader", 10, UNIT, {"read_in_real_mixed_events": 1}),
     "unit_urqmd_txt": ("test_reader_files", 1, UNIT.with_(HBTrap_min=-10.0, HBTrap_max=10.0), {}),
     "unit_oscar_kplus": ("test_reader_files", 0, UNIT.with_(particle_monval=321, HBTrap_min=-10.0, HBTrap_max=10.0), {}),
