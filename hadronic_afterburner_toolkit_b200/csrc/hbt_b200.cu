@@ -451,6 +451,11 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
 #ifdef HBT_HAVE_V2
     ctx->v2c = hbt_v2_consts(g);
     if (!hbt_v2_supported(g)) ctx->kernel_version = 1;  // q_inv mode, one-sided q windows: literal kernels
+    if (hbt_v2_configure() != HBT_OK) {
+        fail(nullptr, HBT_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+        hbt_destroy(ctx);
+        return HBT_ERR_CUDA;
+    }
     {
         V2Dev dv;
         dv.g = ctx->grid;
@@ -529,7 +534,17 @@ extern "C" int hbt_synchronize(hbt_ctx *ctx) {
     for (Slot &s : ctx->slots) s.in_flight = false;
     int rc = drain_timers(ctx, true);
     if (rc) return rc;
-    return resolve_deferred(ctx);
+    rc = resolve_deferred(ctx);
+    if (rc) return rc;
+    // accepted-pair counters per slab = sum of the slab's bin counts (every accepted pair
+    // increments exactly one bin, src/HBT_correlation.cpp:406/437 and :655/682)
+    const long long q3 = static_cast<long long>(ctx->grid.nq) * ctx->grid.nq * ctx->grid.nq;
+    hbt_reduce_slabs<<<2 * ctx->grid.nslab, 256, 0, ctx->compute>>>(ctx->acc, ctx->grid.nslab, q3);
+    hbt_finish_stage<<<1, 32, 0, ctx->compute>>>(ctx->acc, ctx->grid.nslab);
+    ctx->kernel_launches += 2;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    return HBT_OK;
 }
 
 // ---- device-resident entry points --------------------------------------------------------

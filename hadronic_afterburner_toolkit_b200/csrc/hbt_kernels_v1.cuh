@@ -75,7 +75,6 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
         diag = (ti == tj);
     }
 
-    for (int k = t; k < g.nslab; k += TILE) s_slab[k] = 0;
     for (int k = t; k < nqi; k += TILE) { s_qsum[k] = 0.0; s_qcos[k] = 0.0; s_qcnt[k] = 0; }
     if (g.qinv) for (int k = t; k < g.nKT; k += TILE) s_qpairs[k] = 0;
     if (t < 6) s_stage[t] = 0;
@@ -100,7 +99,7 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
     }
     __syncthreads();
 
-    unsigned nB = 0, nC = 0, nD = 0, nE = 0, nAcc = 0;
+    unsigned nB = 0, nC = 0, nD = 0, nE = 0;
     if (t < ni) {
         double a[8];
         {
@@ -163,8 +162,6 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
                 defer_pair(acc, a, b8, psi_ref, MIXED ? 1 : 0);
                 continue;
             }
-            nAcc++;
-            atomicAdd(&s_slab[pb.slab], 1u);
             const long long bin = bin_index(g, pb);
             if (MIXED) {
                 atomicAdd(&acc.den_count[bin], 1ull);
@@ -180,17 +177,15 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
         }
     }
     // block-level merge of the counters, then one global atomic per non-zero entry
-    nB = warp_sum(nB); nC = warp_sum(nC); nD = warp_sum(nD); nE = warp_sum(nE); nAcc = warp_sum(nAcc);
+    // (accepted pairs per slab and in total are derived from the bin counts at synchronize)
+    nB = warp_sum(nB); nC = warp_sum(nC); nD = warp_sum(nD); nE = warp_sum(nE);
     if ((t & 31) == 0) {
         atomicAdd(&s_stage[1], nB); atomicAdd(&s_stage[2], nC); atomicAdd(&s_stage[3], nD);
-        atomicAdd(&s_stage[4], nE); atomicAdd(&s_stage[5], nAcc);
+        atomicAdd(&s_stage[4], nE);
     }
     __syncthreads();
     unsigned long long *stage = acc.stage + (MIXED ? 6 : 0);
-    if (t >= 1 && t < 6 && s_stage[t]) atomicAdd(&stage[t], static_cast<unsigned long long>(s_stage[t]));
-    unsigned long long *npairs = MIXED ? acc.npairs_den : acc.npairs_num;
-    for (int k = t; k < g.nslab; k += TILE)
-        if (s_slab[k]) atomicAdd(&npairs[k], static_cast<unsigned long long>(s_slab[k]));
+    if (t >= 1 && t < 5 && s_stage[t]) atomicAdd(&stage[t], static_cast<unsigned long long>(s_stage[t]));
     if (g.qinv) {
         for (int k = t; k < nqi; k += TILE) {
             if (!s_qcnt[k]) continue;
@@ -208,6 +203,33 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
     }
 }
 
+// npairs_num[slab] / npairs_den[slab] = sum over the slab's q^3 bins of num_count / den_count.
+// grid = 2*nslab blocks: block b < nslab reduces the numerator slab b, the others the denominator.
+__global__ void __launch_bounds__(256) hbt_reduce_slabs(const HbtAccum acc, int nslab, long long q3) {
+    __shared__ unsigned long long part[256];
+    const bool den = static_cast<int>(blockIdx.x) >= nslab;
+    const int slab = den ? blockIdx.x - nslab : blockIdx.x;
+    const unsigned long long *src = (den ? acc.den_count : acc.num_count) + slab * q3;
+    unsigned long long s = 0;
+    for (long long k = threadIdx.x; k < q3; k += 256) s += src[k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (static_cast<int>(threadIdx.x) < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) (den ? acc.npairs_den : acc.npairs_num)[slab] = part[0];
+}
+
+// stage[5] / stage[11] (accepted pairs) = sum of the per-slab counters
+__global__ void hbt_finish_stage(const HbtAccum acc, int nslab) {
+    if (threadIdx.x >= 2) return;
+    const unsigned long long *src = threadIdx.x ? acc.npairs_den : acc.npairs_num;
+    unsigned long long s = 0;
+    for (int k = 0; k < nslab; k++) s += src[k];
+    acc.stage[threadIdx.x ? 11 : 5] = s;
+}
+
 // total pair count of a launch (stage A is known analytically on the host)
 __global__ void hbt_add_stage_a(const HbtAccum acc, int slot, unsigned long long npairs) {
     atomicAdd(&acc.stage[slot], npairs);
@@ -217,19 +239,17 @@ __global__ void hbt_add_stage_a(const HbtAccum acc, int slot, unsigned long long
 __global__ void hbt_apply_corrections(const HbtCorrection *__restrict__ c, int n, const HbtAccum acc,
                                       const HbtStageDelta delta) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < 12 && delta.v[k]) atomicAdd(&acc.stage[k], delta.v[k]);
+    if (k < 12 && k != 5 && k != 11 && delta.v[k]) atomicAdd(&acc.stage[k], delta.v[k]);
     if (k >= n) return;
     const HbtCorrection x = c[k];
     if (x.mixed) {
         atomicAdd(&acc.den_count[x.bin], 1ull);
-        atomicAdd(&acc.npairs_den[x.slab], 1ull);
     } else {
         atomicAdd(&acc.num_count[x.bin], 1ull);
         atomicAdd(&acc.sum_qo[x.bin], x.qo);
         atomicAdd(&acc.sum_qs[x.bin], x.qs);
         atomicAdd(&acc.sum_ql[x.bin], x.ql);
         atomicAdd(&acc.num_cos[x.bin], x.cosv);
-        atomicAdd(&acc.npairs_num[x.slab], 1ull);
     }
 }
 

@@ -4,20 +4,22 @@
 // its lanes idle (ncu: 10.5 of 32 threads active per instruction), because 93 % of the
 // pairs leave the chain early at different stages.  v2 splits the work in two:
 //
-//  1. PREFILTER, every pair, no divergence, ~14 FP64-pipe instructions.  Uses only
+//  1. PREFILTER, every pair, no divergence, 13 FP64-pipe instructions.  Uses only
 //     (px, py, pT^2) of the two particles:
 //        s = p_i + p_j           k2 = rn(rn(sx^2) + rn(sy^2))  ( = 4 K_perp_sq, bit-exact: the
 //                                      reference's 0.5 factors are exact power-of-two scalings)
 //        d = pT_i^2 - pT_j^2     ( = q.s = 2 K_perp q_out )
 //        x = pxj*pyi - pxi*pyj   ( 2x = q x s = 2 K_perp q_side )
-//     K_T cut: exact compare of k2.  q_out / q_side windows: d^2 and x^2 against W^2 k2 with a
-//     relative band of ~3e-6 (high-word integer compare); a pair is dropped only when it
-//     CERTAINLY fails; anything inside a band goes on.  ~92 % of the pairs end here.
-//  2. DRAIN.  Survivors are pushed as (i,j) into a per-warp shared-memory queue; whenever 32
-//     are queued the warp processes them with all lanes busy: K_T bin by exact thresholds in
-//     k2 space (no sqrt/divide), q_out/q_side/q_long from FMA arithmetic and rsqrt (a few ulp
-//     from the reference's values), each compared against the window edges and bin edges with
-//     a guard band that bounds the distance to the reference's own rounding.  Inside the guard
+//     K_T cut: exact compare of k2.  q_out / q_side windows: d^2 and 4x^2 against W^2 k2 with a
+//     relative band of ~3e-6 (integer compare of the high words); a pair is dropped only when
+//     it CERTAINLY fails; anything inside a band goes on.  ~92 % of the pairs end here.
+//  2. DRAIN.  Each lane appends its survivors (i,j) to a private shared-memory list (one
+//     predicated store, no cross-lane traffic in the hot loop).  When a list is about to
+//     fill, the warp compacts all lists into a linear queue (one prefix sum) and processes it
+//     32 pairs at a time with all lanes busy: K_T bin by exact thresholds in k2 space (no
+//     sqrt/divide), q_out/q_side/q_long from FMA arithmetic and rsqrt (a few ulp from the
+//     reference's values), each compared against the window and bin edges with a guard band
+//     that bounds the distance to the reference's own rounding.  Inside the guard
 //     (probability ~1e-12 per pair) the pair is re-evaluated with the literal chain of
 //     hbt_pair.cuh, so every bin decision equals the reference's.  Accepted pairs add
 //     cos(q.dx/hbarc) and the q sums with global atomics (histograms are L2 resident).
@@ -30,17 +32,18 @@
 #include "hbt_kernels_v1.cuh"
 
 #define HBT_V2_WARPS 4
-#define HBT_V2_IPL 2  // list-1 particles per lane
-#define HBT_V2_TILE_I (32 * HBT_V2_IPL * HBT_V2_WARPS)
-#define HBT_V2_TILE_J 256
-#define HBT_V2_QCAP 96
+#define HBT_V2_IPL 4  // list-1 particles per lane
+#define HBT_V2_TILE_I (32 * HBT_V2_IPL * HBT_V2_WARPS)  // 512
+#define HBT_V2_TILE_J 128
+#define HBT_V2_SUB (HBT_V2_TILE_I / HBT_V2_TILE_J)  // list-2 sub-tiles per 512 x 512 super-tile
+#define HBT_V2_LCAP 8                                // per-lane survivor list capacity
+#define HBT_V2_QCAP (32 + 32 * HBT_V2_LCAP)          // linear warp queue capacity
 
 // constants of the fast path, derived on the host from HbtGrid
 struct V2Const {
     double k2lo, k2hi;        // 4*KT_min_sq, 4*KT_max_sq (exact scalings)
     double kt4[HBT_MAX_KT];   // 4*kt_thr_sq[k]
     double W2;                // max(q_lo^2, q_hi^2)
-    double W2q;               // W2 / 4
     double g_abs;             // absolute part of the guard band
     double inv_dq;
     int symmetric;            // |q_lo| == |q_hi| up to 2^-24 relative
@@ -53,7 +56,6 @@ __host__ inline V2Const hbt_v2_consts(const HbtGrid &g) {
     for (int k = 0; k < HBT_MAX_KT; k++) c.kt4[k] = 4.0 * g.kt_thr_sq[k];
     const double a = g.q_lo * g.q_lo, b = g.q_hi * g.q_hi;
     c.W2 = a > b ? a : b;
-    c.W2q = 0.25 * c.W2;
     const double m = fabs(g.q_lo) > fabs(g.q_hi) ? fabs(g.q_lo) : fabs(g.q_hi);
     c.g_abs = m * 5.7e-14;  // 2^-44
     c.inv_dq = g.inv_dq;
@@ -66,6 +68,18 @@ __host__ inline V2Const hbt_v2_consts(const HbtGrid &g) {
 __host__ inline bool hbt_v2_supported(const HbtGrid &g) {
     return !g.qinv && hbt_v2_consts(g).symmetric;
 }
+
+// global-memory copy of everything the non-inlined device functions need (passing the
+// kernel's by-value parameter structs by reference would copy them to each thread's stack)
+struct V2Dev {
+    HbtGrid g;
+    V2Const c;
+    HbtAccum acc;
+};
+
+struct V2Counters {
+    unsigned nB, nC, nD, nE;
+};
 
 // outcome of a guarded comparison of a fast-path q against the window and the bin grid
 enum : int { Q_REJECT = 0, Q_OK = 1, Q_UNSURE = 2 };
@@ -82,22 +96,10 @@ __device__ __forceinline__ int classify_q(const HbtGrid &g, const V2Const &c, do
     return (idx >= 0 && idx < g.nq) ? Q_OK : Q_UNSURE;
 }
 
-// global-memory copy of everything the non-inlined device functions need (passing the
-// kernel's by-value parameter structs by reference would copy them to each thread's stack)
-struct V2Dev {
-    HbtGrid g;
-    V2Const c;
-    HbtAccum acc;
-};
-
-struct V2Counters {
-    unsigned nB, nC, nD, nE, nAcc;
-};
-
 // the literal chain for a pair the fast path could not decide; counts and accumulates
 template <bool MIXED>
 __device__ __noinline__ void v2_slow_pair(const V2Dev *__restrict__ dv, const double *a, const double *b,
-                                          double psi_ref, V2Counters &n, unsigned *s_slab) {
+                                          double psi_ref, V2Counters &n) {
     const HbtGrid &g = dv->g;
     const HbtAccum &acc = dv->acc;
     PairBin pb;
@@ -112,8 +114,6 @@ __device__ __noinline__ void v2_slow_pair(const V2Dev *__restrict__ dv, const do
     if (st == PAIR_REJ_QL) return;
     n.nE++;
     if (st == PAIR_REJ_PHI) return;
-    n.nAcc++;
-    atomicAdd(&s_slab[pb.slab], 1u);
     const long long bin = bin_index(g, pb);
     if (MIXED) {
         atomicAdd(&acc.den_count[bin], 1ull);
@@ -128,27 +128,29 @@ __device__ __noinline__ void v2_slow_pair(const V2Dev *__restrict__ dv, const do
     }
 }
 
+// one queued survivor through the guarded fast path.  si/sj are the SoA tiles in shared memory
+// (component stride TI / TJ doubles).
 template <bool MIXED, int NC>
-__device__ __noinline__ void v2_drain_pair(const V2Dev *__restrict__ dv, const double (*si)[HBT_V2_TILE_I],
-                                           const double (*sj)[HBT_V2_TILE_J], int il, int jl, double psi_ref,
-                                           V2Counters &n, unsigned *s_slab) {
-    const HbtGrid &g = dv->g;
-    const V2Const &c = dv->c;
-    const HbtAccum &acc = dv->acc;
-    const double ax = si[0][il], ay = si[1][il], bx = sj[0][jl], by = sj[1][jl];
+__device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
+                                              const V2Dev *__restrict__ dv, const double *__restrict__ si,
+                                              const double *__restrict__ sj, int il, int jl, double psi_ref,
+                                              V2Counters &n) {
+    constexpr int TI = HBT_V2_TILE_I, TJ = HBT_V2_TILE_J;
+    const double ax = si[il], ay = si[TI + il], bx = sj[jl], by = sj[TJ + jl];
     const double sx = __dadd_rn(ax, bx), sy = __dadd_rn(ay, by);
     const double k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
-    if (!(k2 >= c.k2lo && k2 <= c.k2hi)) return;  // only pairs routed here by the tiny-k2 floor
+    if (!(k2 >= c.k2lo && k2 <= c.k2hi)) return;  // cannot happen: the prefilter's K_T test is exact
     bool unsure = false;
     int iK = 0;
     for (int k = 1; k < g.nKT; k++) iK += (k2 >= c.kt4[k]) ? 1 : 0;
 
     const double qx = ax - bx, qy = ay - by;
-    const double d = fma(qx, sx, qy * sy);   // 2 K_perp q_out
+    const double d = fma(qx, sx, qy * sy);     // 2 K_perp q_out
     const double e = fma(qy, sx, -(qx * sy));  // 2 K_perp q_side
-    const double r = rsqrt(k2);              // 1 / (2 K_perp)
+    const double r = rsqrt(k2);                // 1 / (2 K_perp)
     const double qo = d * r, qs = e * r;
-    const double gt = fma(fabs(qx) + fabs(qy), 1.5e-14, c.g_abs);  // 2^-46 relative + absolute
+    // |fast - reference| <= ~8 ulp of (|qx|+|qy|); guard = 2^-46 relative + 2^-44 |window|
+    const double gt = fma(fabs(qx) + fabs(qy), 1.5e-14, c.g_abs);
     int io = 0, is = 0, il_ = 0;
     int stage = 1;  // passed K_T
     double ql = 0.0;
@@ -161,7 +163,7 @@ __device__ __noinline__ void v2_drain_pair(const V2Dev *__restrict__ dv, const d
         if (cs == Q_UNSURE) unsure = true;
         if (cs == Q_OK) {
             stage = 3;
-            az = si[2][il]; aE = si[3][il]; bz = sj[2][jl]; bE = sj[3][jl];
+            az = si[2 * TI + il]; aE = si[3 * TI + il]; bz = sj[2 * TJ + jl]; bE = sj[3 * TJ + jl];
             const double qz = az - bz;
             if (g.boost) {
                 // q_long = gamma (q_z - beta q_E) = (K_E q_z - K_z q_E) / Mt, src :383-390
@@ -193,7 +195,7 @@ __device__ __noinline__ void v2_drain_pair(const V2Dev *__restrict__ dv, const d
         while (dphi > g.two_pi) dphi = __dsub_rn(dphi, g.two_pi);
         const double u = __ddiv_rn(dphi, g.dKphi);
         const int iphi = __double2int_rz(u);
-        if (fabs(u - rint(u)) < 1e-9) unsure = true;  // literal path defers it to the host
+        if (fabs(u - rint(u)) < 1e-9) unsure = true;  // the literal path defers it to the host
         else if (iphi < 0 || iphi >= g.nKphi) stage = 5;  // counted through q_long, then dropped
         else slab = iK * g.nKphi + iphi;
     }
@@ -201,10 +203,10 @@ __device__ __noinline__ void v2_drain_pair(const V2Dev *__restrict__ dv, const d
         double a8[8], b8[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            a8[k] = k < NC ? si[k < NC ? k : 0][il] : 0.0;
-            b8[k] = k < NC ? sj[k < NC ? k : 0][jl] : 0.0;
+            a8[k] = k < NC ? si[(k < NC ? k : 0) * TI + il] : 0.0;
+            b8[k] = k < NC ? sj[(k < NC ? k : 0) * TJ + jl] : 0.0;
         }
-        v2_slow_pair<MIXED>(dv, a8, b8, psi_ref, n, s_slab);
+        v2_slow_pair<MIXED>(dv, a8, b8, psi_ref, n);
         return;
     }
     n.nB++;
@@ -212,20 +214,122 @@ __device__ __noinline__ void v2_drain_pair(const V2Dev *__restrict__ dv, const d
     if (stage >= 3) n.nD++;
     if (stage >= 4) n.nE++;
     if (stage != 4) return;
-    n.nAcc++;
-    atomicAdd(&s_slab[slab], 1u);
     const long long bin = ((static_cast<long long>(slab) * g.nq + io) * g.nq + is) * g.nq + il_;
     if (MIXED) {
         atomicAdd(&acc.den_count[bin], 1ull);
     } else {
-        const double xd = si[4 % NC][il] - sj[4 % NC][jl], yd = si[5 % NC][il] - sj[5 % NC][jl];
-        const double zd = si[6 % NC][il] - sj[6 % NC][jl], td = si[7 % NC][il] - sj[7 % NC][jl];
+        const double xd = si[(4 % NC) * TI + il] - sj[(4 % NC) * TJ + jl];
+        const double yd = si[(5 % NC) * TI + il] - sj[(5 % NC) * TJ + jl];
+        const double zd = si[(6 % NC) * TI + il] - sj[(6 % NC) * TJ + jl];
+        const double td = si[(7 % NC) * TI + il] - sj[(7 % NC) * TJ + jl];
         const double cv = pair_cos(g, qx, qy, az - bz, aE - bE, xd, yd, zd, td);
         atomicAdd(&acc.num_count[bin], 1ull);
         atomicAdd(&acc.sum_qo[bin], qo);
         atomicAdd(&acc.sum_qs[bin], qs);
         atomicAdd(&acc.sum_ql[bin], ql);
         atomicAdd(&acc.num_cos[bin], cv);
+    }
+}
+
+// state of one warp's survivor bookkeeping
+struct V2Queue {
+    unsigned *lane_list;  // this lane's private list: entry m at lane_list[32*m]
+    unsigned *cur;        // next free slot of the private list
+    unsigned *wq;         // the warp's linear queue
+    int qcount;           // entries in wq (warp-uniform)
+    unsigned kept;        // survivors queued so far (warp-uniform)
+};
+
+// The hot loop over one list-2 tile.  DIAG: same-event tile that touches the diagonal (only
+// j > i pairs count, src :301).  FLOOR: tile pair in which the prefilter's error bound is not
+// negligible against the smallest K_T (KT_min ~ 0 or huge momenta): pairs below k2_floor skip
+// the window prefilter.
+template <bool MIXED, bool DIAG, bool FLOOR>
+__device__ __forceinline__ void v2_tile_loop(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
+                                             const V2Dev *__restrict__ dv, const double *__restrict__ si,
+                                             const double *__restrict__ sj, const double *__restrict__ sjt, int nj,
+                                             long long i0, long long j0, int lane, int warp, double k2_floor,
+                                             double psi_ref, V2Queue &Q, V2Counters &n, unsigned &cntKT,
+                                             unsigned &cntRS) {
+    constexpr int NC = MIXED ? 4 : 8;
+    constexpr int TI = HBT_V2_TILE_I, TJ = HBT_V2_TILE_J, IPL = HBT_V2_IPL;
+    double ax[IPL], ay[IPL], at[IPL];
+    unsigned ent[IPL];
+    long long ig[IPL];
+#pragma unroll
+    for (int s = 0; s < IPL; s++) {
+        const int il = warp * (32 * IPL) + s * 32 + lane;
+        ax[s] = si[il];
+        ay[s] = si[TI + il];
+        at[s] = fma(ax[s], ax[s], ay[s] * ay[s]);
+        ent[s] = static_cast<unsigned>(il) << 16;
+        ig[s] = i0 + il;
+    }
+    const double k2lo = c.k2lo, k2hi = c.k2hi, W2 = c.W2;
+    unsigned *const lim = Q.lane_list + 32 * (HBT_V2_LCAP - IPL);
+
+    auto flush_and_drain = [&](bool final) {
+        // compact the per-lane lists into the linear queue (one warp prefix sum)
+        const int cnt = static_cast<int>(Q.cur - Q.lane_list) >> 5;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned *dst = Q.wq + Q.qcount + (incl - cnt);
+        for (int m = 0; m < cnt; m++) dst[m] = Q.lane_list[32 * m];
+        Q.cur = Q.lane_list;
+        Q.qcount += total;
+        Q.kept += static_cast<unsigned>(total);
+        __syncwarp();
+        while (Q.qcount >= 32 || (final && Q.qcount > 0)) {
+            const int take = min(32, Q.qcount);
+            const int base = Q.qcount - take;
+            if (lane < take) {
+                const unsigned e = Q.wq[base + lane];
+                v2_drain_pair<MIXED, NC>(g, c, acc, dv, si, sj, static_cast<int>(e >> 16), static_cast<int>(e & 0xffffu),
+                                         psi_ref, n);
+            }
+            Q.qcount = base;
+            __syncwarp();
+        }
+    };
+
+    for (int j = 0; j <= nj; j++) {  // one extra trip: the final flush shares the call site
+      if (j < nj) {
+        const double bx = sj[j], by = sj[TJ + j], bt = sjt[j];
+#pragma unroll
+        for (int s = 0; s < IPL; s++) {
+            const double sx = __dadd_rn(ax[s], bx), sy = __dadd_rn(ay[s], by);
+            const double k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+            bool kt = (k2 >= k2lo) && (k2 <= k2hi);  // exact K_T cut (NaN padding rows fail)
+            if (DIAG) kt = kt && (j0 + j > ig[s]);
+            const double d = at[s] - bt;
+            const double x = fma(bx, ay[s], -(ax[s] * by));
+            const double d2 = d * d, x2 = x * x, w = W2 * k2;
+            const int hw = __double2hiint(w);
+            const int dd = __double2hiint(d2) - hw;               // d^2   vs W^2 k2
+            const int dx = __double2hiint(x2) + 0x00200000 - hw;  // 4 x^2 vs W^2 k2
+            bool rej_o = dd > 1;                 // q_out certainly outside the window
+            bool rej_s = (dd < -1) && (dx > 1);  // q_out certainly inside, q_side certainly outside
+            if (FLOOR) {
+                const bool tiny = k2 < k2_floor;
+                rej_o = rej_o && !tiny;
+                rej_s = rej_s && !tiny;
+            }
+            const bool keep = kt && !(rej_o || rej_s);
+            cntKT += kt ? 1u : 0u;
+            cntRS += (kt && rej_s) ? 1u : 0u;
+            if (keep) {
+                *Q.cur = ent[s] | static_cast<unsigned>(j);
+                Q.cur += 32;
+            }
+        }
+      }
+        const bool final = (j == nj);
+        if (final || __any_sync(0xffffffffu, Q.cur > lim)) flush_and_drain(final);
     }
 }
 
@@ -237,14 +341,13 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
              const unsigned long long total_pairs) {
     constexpr int NC = MIXED ? 4 : 8;
     constexpr int TI = HBT_V2_TILE_I, TJ = HBT_V2_TILE_J, NT = 32 * HBT_V2_WARPS;
-    __shared__ double si[NC][TI];
-    __shared__ double sj[NC][TJ];
-    __shared__ double sjt[TJ];  // pT^2 of the list-2 tile
-    __shared__ unsigned queue[HBT_V2_WARPS][HBT_V2_QCAP];
-    __shared__ double s_max[2 * HBT_V2_WARPS];
-    __shared__ unsigned s_stage[6];
     extern __shared__ __align__(16) unsigned char dyn[];
-    unsigned *s_slab = reinterpret_cast<unsigned *>(dyn);
+    double *si = reinterpret_cast<double *>(dyn);  // [NC][TI]
+    double *sj = si + NC * TI;                      // [NC][TJ]
+    double *sjt = sj + NC * TJ;                     // [TJ] pT^2 of the list-2 tile
+    double *s_max = sjt + TJ;                       // [2*WARPS]
+    unsigned *lq = reinterpret_cast<unsigned *>(s_max + 2 * HBT_V2_WARPS);  // [WARPS][LCAP][32]
+    unsigned *wq = lq + HBT_V2_WARPS * HBT_V2_LCAP * 32;                    // [WARPS][QCAP]
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     long long i0, j0;
@@ -261,40 +364,41 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
         nj = min(TJ, sg.nj - tj * TJ);
         rc = sg.c; rs = sg.s;
     } else {
-        // square tiling of the upper triangle in units of TJ (= TI) particles
+        // upper triangle in 512 x 512 super-tiles, each split into HBT_V2_SUB list-2 sub-tiles
         const long long T = (n_same + TI - 1) / TI;
+        const long long super = blockIdx.x / HBT_V2_SUB;
+        const int sub = static_cast<int>(blockIdx.x - super * HBT_V2_SUB);
         int ti, tj;
-        tri_decode(blockIdx.x, T, ti, tj);
+        tri_decode(super, T, ti, tj);
         i0 = static_cast<long long>(ti) * TI;
-        j0 = static_cast<long long>(tj) * TJ;
+        j0 = static_cast<long long>(tj) * TI + static_cast<long long>(sub) * TJ;
         ni = static_cast<int>(min(static_cast<long long>(TI), n_same - i0));
         nj = static_cast<int>(min(static_cast<long long>(TJ), n_same - j0));
         diag = (ti == tj);
+        if (diag && j0 + nj - 1 <= i0) nj = 0;  // sub-tile entirely at or below the diagonal
     }
     if (blockIdx.x == 0 && t == 0) atomicAdd(&acc.stage[MIXED ? 6 : 0], total_pairs);
-
-    for (int k = t; k < g.nslab; k += NT) s_slab[k] = 0;
-    if (t < 6) s_stage[t] = 0;
+    if (nj <= 0 || ni <= 0) return;
 
     // ---- stage both tiles (SoA).  Rows beyond the tile end are NaN: they fail the K_T cut.
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
-    double tmax = 0.0;
+    double tmax = 0.0, tmaxj = 0.0;
     for (int k = t; k < TI; k += NT) {
         if (k < ni) {
             const double2 *src = reinterpret_cast<const double2 *>(p1 + 8 * (i0 + k));
             const double2 v0 = src[0], v1 = src[1];
-            si[0][k] = v0.x; si[1][k] = v0.y; si[2][k] = v1.x; si[3][k] = v1.y;
+            si[k] = v0.x; si[TI + k] = v0.y; si[2 * TI + k] = v1.x; si[3 * TI + k] = v1.y;
             tmax = fmax(tmax, fma(v0.x, v0.x, v0.y * v0.y));
             if (!MIXED) {
                 const double2 v2 = src[2], v3 = src[3];
-                si[4 % NC][k] = v2.x; si[5 % NC][k] = v2.y; si[6 % NC][k] = v3.x; si[7 % NC][k] = v3.y;
+                si[(4 % NC) * TI + k] = v2.x; si[(5 % NC) * TI + k] = v2.y;
+                si[(6 % NC) * TI + k] = v3.x; si[(7 % NC) * TI + k] = v3.y;
             }
         } else {
 #pragma unroll
-            for (int q = 0; q < NC; q++) si[q][k] = nan;
+            for (int q = 0; q < NC; q++) si[q * TI + k] = nan;
         }
     }
-    double tmaxj = 0.0;
     for (int k = t; k < TJ; k += NT) {
         if (k < nj) {
             const double2 *src = reinterpret_cast<const double2 *>(p2 + 8 * (j0 + k));
@@ -304,28 +408,24 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
                 x = __dsub_rn(__dmul_rn(v0.x, rc), __dmul_rn(v0.y, rs));
                 y = __dadd_rn(__dmul_rn(v0.x, rs), __dmul_rn(v0.y, rc));
             }
-            sj[0][k] = x; sj[1][k] = y; sj[2][k] = v1.x; sj[3][k] = v1.y;
+            sj[k] = x; sj[TJ + k] = y; sj[2 * TJ + k] = v1.x; sj[3 * TJ + k] = v1.y;
             const double pt2 = fma(x, x, y * y);
             sjt[k] = pt2;
             tmaxj = fmax(tmaxj, pt2);
             if (!MIXED) {
                 const double2 v2 = src[2], v3 = src[3];
-                sj[4 % NC][k] = v2.x; sj[5 % NC][k] = v2.y; sj[6 % NC][k] = v3.x; sj[7 % NC][k] = v3.y;
+                sj[(4 % NC) * TJ + k] = v2.x; sj[(5 % NC) * TJ + k] = v2.y;
+                sj[(6 % NC) * TJ + k] = v3.x; sj[(7 % NC) * TJ + k] = v3.y;
             }
-        } else {
-#pragma unroll
-            for (int q = 0; q < NC; q++) sj[q][k] = nan;
-            sjt[k] = nan;
         }
     }
     // S = max pT^2 (list 1) + max pT^2 (list 2) bounds the rounding error of d and x
-    double m1 = tmax, m2 = tmaxj;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-        m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        tmaxj = fmax(tmaxj, __shfl_xor_sync(0xffffffffu, tmaxj, o));
     }
-    if (lane == 0) { s_max[warp] = m1; s_max[HBT_V2_WARPS + warp] = m2; }
+    if (lane == 0) { s_max[warp] = tmax; s_max[HBT_V2_WARPS + warp] = tmaxj; }
     __syncthreads();  // also publishes the tiles
     double S1 = 0.0, S2 = 0.0;
 #pragma unroll
@@ -335,99 +435,68 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
     // W*sqrt(k2) could exceed the 2^-21 band of the high-word compare: such pairs are not
     // prefiltered.  (k2_floor = 2^-54 S^2 / W2; far below 4*KT_min_sq unless KT_min ~ 0.)
     const double k2_floor = (5.6e-17 * S) * S / c.W2;
-    const bool use_floor = k2_floor > c.k2lo;
+    const bool use_floor = !(k2_floor <= c.k2lo);
 
-    // ---- prefilter loop ---------------------------------------------------------------
-    const int ia = warp * 64 + lane, ib = ia + 32;
-    const double axa = si[0][ia], aya = si[1][ia], axb = si[0][ib], ayb = si[1][ib];
-    const double ata = fma(axa, axa, aya * aya), atb = fma(axb, axb, ayb * ayb);
-    V2Counters n = {0, 0, 0, 0, 0};  // drain-side counters (may live in local memory)
-    unsigned preB = 0, preC = 0;      // prefilter-side counters (registers)
-    unsigned *q = queue[warp];
-    int qcount = 0;
-    const unsigned lt_mask = (1u << lane) - 1u;
-
-    auto prefilter = [&](double ax, double ay, double at, double bx, double by, double bt, bool valid) -> bool {
-        const double sx = __dadd_rn(ax, bx), sy = __dadd_rn(ay, by);
-        const double k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
-        const bool kt = valid && (k2 >= c.k2lo) && (k2 <= c.k2hi);
-        const double d = at - bt;
-        const double x = fma(bx, ay, -(ax * by));
-        const double d2 = d * d, x2 = x * x;
-        const double w = c.W2 * k2, wq = c.W2q * k2;
-        const int dd = __double2hiint(d2) - __double2hiint(w);
-        const int dx = __double2hiint(x2) - __double2hiint(wq);
-        const bool fail_o = dd > 1, pass_o = dd < -1, fail_s = dx > 1;
-        const bool tiny = use_floor && (k2 < k2_floor);
-        const bool rej_o = kt && !tiny && fail_o;
-        const bool rej_s = kt && !tiny && pass_o && fail_s;
-        preB += (rej_o || rej_s) ? 1u : 0u;
-        preC += rej_s ? 1u : 0u;
-        return kt && !(rej_o || rej_s);
-    };
-
-    auto push = [&](bool keep, int il, int jl) {
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m) {
-            if (keep) q[qcount + __popc(m & lt_mask)] = (static_cast<unsigned>(il) << 16) | static_cast<unsigned>(jl);
-            qcount += __popc(m);
-        }
-    };
-
-    auto drain = [&](int count) {  // processes the newest `count` (<= 32) entries
-        __syncwarp();
-        const int base = qcount - count;
-        if (lane < count) {
-            const unsigned e = q[base + lane];
-            v2_drain_pair<MIXED, NC>(dv, si, sj, static_cast<int>(e >> 16), static_cast<int>(e & 0xffffu),
-                                     psi_ref, n, s_slab);
-        }
-        qcount = base;
-        __syncwarp();
-    };
-
-    for (int j = 0; j < nj; j++) {
-        const double bx = sj[0][j], by = sj[1][j], bt = sjt[j];
-        const bool va = !diag || (j > ia), vb = !diag || (j > ib);
-        const bool ka = prefilter(axa, aya, ata, bx, by, bt, va);
-        const bool kb = prefilter(axb, ayb, atb, bx, by, bt, vb);
-        push(ka, ia, j);
-        push(kb, ib, j);
-        while (qcount >= 32) drain(32);
+    V2Queue Q;
+    Q.lane_list = lq + warp * (HBT_V2_LCAP * 32) + lane;
+    Q.cur = Q.lane_list;
+    Q.wq = wq + warp * HBT_V2_QCAP;
+    Q.qcount = 0;
+    Q.kept = 0;
+    V2Counters n = {0, 0, 0, 0};
+    unsigned cntKT = 0, cntRS = 0;
+    if (use_floor) {
+        if (diag) v2_tile_loop<MIXED, true, true>(g, c, acc, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+        else v2_tile_loop<MIXED, false, true>(g, c, acc, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+    } else {
+        if (diag) v2_tile_loop<MIXED, true, false>(g, c, acc, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+        else v2_tile_loop<MIXED, false, false>(g, c, acc, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
     }
-    if (qcount > 0) drain(qcount);
 
-    // ---- merge counters ---------------------------------------------------------------
-    const unsigned nB = warp_sum(n.nB + preB), nC = warp_sum(n.nC + preC), nD = warp_sum(n.nD), nE = warp_sum(n.nE),
-                   nA = warp_sum(n.nAcc);
-    if (lane == 0) {
-        atomicAdd(&s_stage[1], nB); atomicAdd(&s_stage[2], nC); atomicAdd(&s_stage[3], nD);
-        atomicAdd(&s_stage[4], nE); atomicAdd(&s_stage[5], nA);
-    }
-    __syncthreads();
+    // ---- merge counters: pairs dropped by the prefilter passed K_T (cntKT) minus those queued;
+    // those dropped at q_side passed q_out as well (cntRS); queued pairs are counted by the drain
+    unsigned nB = warp_sum(cntKT + n.nB), nC = warp_sum(cntRS + n.nC);
+    const unsigned nD = warp_sum(n.nD), nE = warp_sum(n.nE);
+    nB -= Q.kept;
     unsigned long long *stage = acc.stage + (MIXED ? 6 : 0);
-    if (t >= 1 && t < 6 && s_stage[t]) atomicAdd(&stage[t], static_cast<unsigned long long>(s_stage[t]));
-    unsigned long long *npairs = MIXED ? acc.npairs_den : acc.npairs_num;
-    for (int k = t; k < g.nslab; k += NT)
-        if (s_slab[k]) atomicAdd(&npairs[k], static_cast<unsigned long long>(s_slab[k]));
+    if (lane == 0) {
+        if (nB) atomicAdd(&stage[1], static_cast<unsigned long long>(nB));
+        if (nC) atomicAdd(&stage[2], static_cast<unsigned long long>(nC));
+        if (nD) atomicAdd(&stage[3], static_cast<unsigned long long>(nD));
+        if (nE) atomicAdd(&stage[4], static_cast<unsigned long long>(nE));
+    }
 }
 
 // ---- host-side launch helpers ------------------------------------------------------------
+inline size_t hbt_v2_smem_bytes(bool mixed) {
+    const int NC = mixed ? 4 : 8;
+    return sizeof(double) * (NC * HBT_V2_TILE_I + NC * HBT_V2_TILE_J + HBT_V2_TILE_J + 2 * HBT_V2_WARPS)
+           + sizeof(unsigned) * (HBT_V2_WARPS * HBT_V2_LCAP * 32 + HBT_V2_WARPS * HBT_V2_QCAP + 8);
+}
 
-inline int hbt_v2_launch_same(cudaStream_t st, const double *d_p, long long n, const HbtGrid &g, const V2Const &c,
-                              const V2Dev *d_dv, const HbtAccum &acc, double psi_ref, unsigned long long npairs) {
+inline int hbt_v2_configure() {
+    cudaError_t e = cudaFuncSetAttribute(hbt_pairs_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(hbt_v2_smem_bytes(false)));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(hbt_pairs_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(hbt_v2_smem_bytes(true)));
+    return e == cudaSuccess ? HBT_OK : HBT_ERR_CUDA;
+}
+
+inline int hbt_v2_launch_same(cudaStream_t st, const double *d_p, long long n, const HbtGrid &g, const V2Const &c, const V2Dev *d_dv,
+                              const HbtAccum &acc, double psi_ref, unsigned long long npairs) {
     const long long T = (n + HBT_V2_TILE_I - 1) / HBT_V2_TILE_I;
-    const long long blocks = T * (T + 1) / 2;
+    const long long blocks = T * (T + 1) / 2 * HBT_V2_SUB;
     if (blocks > 0x7fffffffLL) return HBT_ERR_INVALID;
-    hbt_pairs_v2<false><<<static_cast<unsigned>(blocks), 32 * HBT_V2_WARPS, ((g.nslab + 3) & ~3) * 4, st>>>(
+    hbt_pairs_v2<false><<<static_cast<unsigned>(blocks), 32 * HBT_V2_WARPS, hbt_v2_smem_bytes(false), st>>>(
         d_p, d_p, n, nullptr, g, c, d_dv, acc, psi_ref, npairs);
     return HBT_OK;
 }
 
 inline int hbt_v2_launch_mixed(cudaStream_t st, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg,
-                               size_t nseg, long long nblocks, const HbtGrid &g, const V2Const &c, const V2Dev *d_dv,
-                               const HbtAccum &acc, double psi_ref, unsigned long long npairs) {
-    hbt_pairs_v2<true><<<static_cast<unsigned>(nblocks), 32 * HBT_V2_WARPS, ((g.nslab + 3) & ~3) * 4, st>>>(
+                               size_t nseg, long long nblocks, const HbtGrid &g, const V2Const &c, const V2Dev *d_dv, const HbtAccum &acc,
+                               double psi_ref, unsigned long long npairs) {
+    hbt_pairs_v2<true><<<static_cast<unsigned>(nblocks), 32 * HBT_V2_WARPS, hbt_v2_smem_bytes(true), st>>>(
         d_p1, d_p2, static_cast<long long>(nseg), d_seg, g, c, d_dv, acc, psi_ref, npairs);
     return HBT_OK;
 }

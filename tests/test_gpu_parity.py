@@ -86,17 +86,21 @@ def test_seeded_against_oracle(name):
 
 def test_empty_and_tiny_batches():
     P = HBTParams(qnpts=11)
+    batches = [hbtio.Batch([]),                        # the reader's trailing empty batch
+               hbtio.Batch([np.zeros((0, 8))]),        # one event, no particle of the species
+               synth.make_batches(1, 1, 1, multiplicity=1)[0],  # one particle: no same-event pair, but
+                                                                # mixed_nev == 1 pairs it with its own rotated copy
+               synth.make_batches(2, 1, 3, multiplicity=2)[0]]
     h = HBT_correlation(P)
-    h.calculate_HBT_correlation_function(hbtio.Batch([]))            # reader's trailing empty batch
-    h.calculate_HBT_correlation_function(hbtio.Batch([np.zeros((0, 8))]))  # one empty event
-    one = synth.make_batches(1, 1, 1, multiplicity=1)[0]
-    h.calculate_HBT_correlation_function(one)                        # a single particle: no pairs
+    o = O.Oracle(P)
+    for b in batches:
+        h.calculate_HBT_correlation_function(b)
+        o.process_batch(b)
     acc = h.accumulators()
-    assert not acc.num_count.any() and not acc.den_count.any()
-    # an empty batch consumes no random numbers; a 1-event batch consumes 1 int + 1 real draw
-    r = Random(P.randomSeed)
-    r.mixed_plan(1, 1), r.mixed_plan(1, 1)
-    assert h.ran_gen.rand_int_uniform() == r.rand_int_uniform()
+    hbtio.compare(o.accumulators(), acc, rtol=RTOL, check_stage=True)
+    assert int(acc.stage[0]) == 15 and int(acc.stage[6]) == 1 + 3 * 2 * 2 * 2
+    # the RNG stream advanced exactly like the oracle's (an empty batch draws nothing)
+    assert h.ran_gen.rand_int_uniform() == o.rand_int_uniform()
 
 
 def test_rapidity_cut_applied():
