@@ -46,6 +46,8 @@ struct V2Const {
     double W2;                // max(q_lo^2, q_hi^2)
     double g_abs;             // absolute part of the guard band
     double inv_dq;
+    double gb_min;            // minimum guard in bin units: 2e-8/delta_q (twice the window inset)
+    double nq_d;              // qnpts as a double
     int symmetric;            // |q_lo| == |q_hi| up to 2^-24 relative
 };
 
@@ -59,6 +61,8 @@ __host__ inline V2Const hbt_v2_consts(const HbtGrid &g) {
     const double m = fabs(g.q_lo) > fabs(g.q_hi) ? fabs(g.q_lo) : fabs(g.q_hi);
     c.g_abs = m * 5.7e-14;  // 2^-44
     c.inv_dq = g.inv_dq;
+    c.gb_min = 2e-8 * g.inv_dq;
+    c.nq_d = static_cast<double>(g.nq);
     c.symmetric = (g.q_lo < 0.0 && g.q_hi > 0.0 && fabs(a - b) <= 5.9e-8 * c.W2) ? 1 : 0;
     return c;
 }
@@ -66,7 +70,7 @@ __host__ inline V2Const hbt_v2_consts(const HbtGrid &g) {
 // v2 handles the 3-D histograms with a window that is symmetric about zero; everything else
 // (q_inv mode, one-sided windows) runs on the literal v1 kernels
 __host__ inline bool hbt_v2_supported(const HbtGrid &g) {
-    return !g.qinv && hbt_v2_consts(g).symmetric;
+    return !g.qinv && hbt_v2_consts(g).symmetric && g.dq > 1e-6;
 }
 
 // global-memory copy of everything the non-inlined device functions need (passing the
@@ -84,16 +88,19 @@ struct V2Counters {
 // outcome of a guarded comparison of a fast-path q against the window and the bin grid
 enum : int { Q_REJECT = 0, Q_OK = 1, Q_UNSURE = 2 };
 
-__device__ __forceinline__ int classify_q(const HbtGrid &g, const V2Const &c, double q, double guard, int &idx) {
-    if (!(q >= g.q_lo - guard && q <= g.q_hi + guard)) return Q_REJECT;  // NaN is rejected
-    if (q < g.q_lo + guard || q > g.q_hi - guard) return Q_UNSURE;
+// In units of bins, u = (q - q_base)/delta_q, the reference's window is [eps, nq - eps] with
+// eps = 1e-8/delta_q (src :363-364) and its bin edges are the integers.  A pair is decided on
+// the fast path only when u is farther than gb from every integer, gb >= 2 eps: that single
+// test covers the bin edges, both window edges and their '>' / '>=' distinction.  Everything
+// within gb of an integer (a ~1e-5 fraction of the survivors) takes the literal chain.
+__device__ __forceinline__ int classify_q(const HbtGrid &g, const V2Const &c, double q, double gb, int &idx) {
     const double u = (q - g.q_base) * c.inv_dq;
+    if (!(u > -gb && u < c.nq_d + gb)) return Q_REJECT;  // certainly outside (NaN too)
     const double fl = floor(u);
     const double fr = u - fl;
-    const double gu = guard * c.inv_dq;
-    if (fr < gu || fr > 1.0 - gu) return Q_UNSURE;
+    if (fr < gb || fr > 1.0 - gb) return Q_UNSURE;
     idx = __double2int_rz(fl);
-    return (idx >= 0 && idx < g.nq) ? Q_OK : Q_UNSURE;
+    return Q_OK;
 }
 
 // the literal chain for a pair the fast path could not decide; counts and accumulates
@@ -139,18 +146,16 @@ __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c
     const double ax = si[il], ay = si[TI + il], bx = sj[jl], by = sj[TJ + jl];
     const double sx = __dadd_rn(ax, bx), sy = __dadd_rn(ay, by);
     const double k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
-    if (!(k2 >= c.k2lo && k2 <= c.k2hi)) return;  // cannot happen: the prefilter's K_T test is exact
-    bool unsure = false;
-    int iK = 0;
-    for (int k = 1; k < g.nKT; k++) iK += (k2 >= c.kt4[k]) ? 1 : 0;
+    bool unsure = false;  // (the K_T cut was decided exactly by the prefilter)
 
     const double qx = ax - bx, qy = ay - by;
     const double d = fma(qx, sx, qy * sy);     // 2 K_perp q_out
     const double e = fma(qy, sx, -(qx * sy));  // 2 K_perp q_side
     const double r = rsqrt(k2);                // 1 / (2 K_perp)
     const double qo = d * r, qs = e * r;
-    // |fast - reference| <= ~8 ulp of (|qx|+|qy|); guard = 2^-46 relative + 2^-44 |window|
-    const double gt = fma(fabs(qx) + fabs(qy), 1.5e-14, c.g_abs);
+    // |fast - reference| <= ~8 ulp of (|qx|+|qy|); guard = 2^-46 relative + 2^-44 |window|,
+    // in bin units and never below gb_min
+    const double gt = fmax(c.gb_min, fma(fabs(qx) + fabs(qy), 1.5e-14, c.g_abs) * c.inv_dq);
     int io = 0, is = 0, il_ = 0;
     int stage = 1;  // passed K_T
     double ql = 0.0;
@@ -173,7 +178,7 @@ __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c
                 const double t1 = sE * qz, t2 = sz * qE;
                 ql = (t1 - t2) * r2;
                 const double ch = sE * r2;  // cosh of the pair rapidity: error amplification
-                const double gl = fma((fabs(t1) + fabs(t2)) * r2 * fma(2.0 * ch, ch, 1.0), 2.9e-14, c.g_abs);
+                const double gl = fmax(c.gb_min, fma((fabs(t1) + fabs(t2)) * r2 * fma(2.0 * ch, ch, 1.0), 2.9e-14, c.g_abs) * c.inv_dq);
                 const int cl = (m2 > 0.0) ? classify_q(g, c, ql, gl, il_) : Q_UNSURE;
                 if (cl == Q_UNSURE) unsure = true;
                 if (cl == Q_OK) stage = 4;
@@ -187,6 +192,9 @@ __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c
             }
         }
     }
+    int iK = 0;  // exact K_T bin: thresholds of int((sqrt(K_perp_sq)-KT_min)/dKT) in k2 space
+    if (stage == 4)
+        for (int k = 1; k < g.nKT; k++) iK += (k2 >= c.kt4[k]) ? 1 : 0;
     int slab = iK;
     if (!unsure && stage == 4 && g.az) {
         const double Kx = 0.5 * sx, Ky = 0.5 * sy;
@@ -206,7 +214,9 @@ __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c
             a8[k] = k < NC ? si[(k < NC ? k : 0) * TI + il] : 0.0;
             b8[k] = k < NC ? sj[(k < NC ? k : 0) * TJ + jl] : 0.0;
         }
-        v2_slow_pair<MIXED>(dv, a8, b8, psi_ref, n);
+        V2Counters tmp = {0, 0, 0, 0};  // keeps n itself out of local memory
+        v2_slow_pair<MIXED>(dv, a8, b8, psi_ref, tmp);
+        n.nB += tmp.nB; n.nC += tmp.nC; n.nD += tmp.nD; n.nE += tmp.nE;
         return;
     }
     n.nB++;
@@ -234,11 +244,73 @@ __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c
 // state of one warp's survivor bookkeeping
 struct V2Queue {
     unsigned *lane_list;  // this lane's private list: entry m at lane_list[32*m]
-    unsigned *cur;        // next free slot of the private list
+    unsigned list_addr;   // its 32-bit shared-memory address
+    unsigned cur;         // shared-memory address of the next free slot (advances by 128 bytes)
     unsigned *wq;         // the warp's linear queue
     int qcount;           // entries in wq (warp-uniform)
     unsigned kept;        // survivors queued so far (warp-uniform)
 };
+
+__device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// cnt += 1 when flag: one predicated add
+__device__ __forceinline__ void inc_if(unsigned &cnt, bool flag) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(cnt) : "r"(static_cast<int>(flag)));
+}
+
+// non-inlined twin of v2_drain_pair for the once-per-tile final flush (keeps one inlined copy
+// of the drain per kernel variant); reads its constants from the global-memory copy
+template <bool MIXED, int NC>
+__device__ __noinline__ void v2_drain_pair_cold(const V2Dev *__restrict__ dv, const double *__restrict__ si,
+                                                const double *__restrict__ sj, int il, int jl, double psi_ref,
+                                                V2Counters &n) {
+    V2Counters tmp = {0, 0, 0, 0};
+    v2_drain_pair<MIXED, NC>(dv->g, dv->c, dv->acc, dv, si, sj, il, jl, psi_ref, tmp);
+    n.nB += tmp.nB; n.nC += tmp.nC; n.nD += tmp.nD; n.nE += tmp.nE;
+}
+
+// Compact the per-lane lists into the warp's linear queue (one prefix sum) and process it 32
+// survivors at a time; FINAL also processes the last partial batch.
+template <bool MIXED, bool FINAL>
+__device__ __forceinline__ void v2_flush(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
+                                         const V2Dev *__restrict__ dv, const double *__restrict__ si,
+                                         const double *__restrict__ sj, int lane, double psi_ref, V2Queue &Q,
+                                         V2Counters &n) {
+    constexpr int NC = MIXED ? 4 : 8;
+    const int cnt = static_cast<int>(Q.cur - Q.list_addr) >> 7;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned *dst = Q.wq + Q.qcount + (incl - cnt);
+    for (int m = 0; m < cnt; m++) dst[m] = Q.lane_list[32 * m];
+    Q.cur = Q.list_addr;
+    Q.qcount += total;
+    Q.kept += static_cast<unsigned>(total);
+    __syncwarp();
+    while (Q.qcount >= 32 || (FINAL && Q.qcount > 0)) {
+        const int take = min(32, Q.qcount);
+        const int base = Q.qcount - take;
+        if (lane < take) {
+            const unsigned e = Q.wq[base + lane];
+            const int il = static_cast<int>(e >> 16), jl = static_cast<int>(e & 0xffffu);
+            if (FINAL) {
+                V2Counters tmp = {0, 0, 0, 0};
+                v2_drain_pair_cold<MIXED, NC>(dv, si, sj, il, jl, psi_ref, tmp);
+                n.nB += tmp.nB; n.nC += tmp.nC; n.nD += tmp.nD; n.nE += tmp.nE;
+            } else {
+                v2_drain_pair<MIXED, NC>(g, c, acc, dv, si, sj, il, jl, psi_ref, n);
+            }
+        }
+        Q.qcount = base;
+        __syncwarp();
+    }
+}
 
 // The hot loop over one list-2 tile.  DIAG: same-event tile that touches the diagonal (only
 // j > i pairs count, src :301).  FLOOR: tile pair in which the prefilter's error bound is not
@@ -266,39 +338,9 @@ __device__ __forceinline__ void v2_tile_loop(const HbtGrid &g, const V2Const &c,
         ig[s] = i0 + il;
     }
     const double k2lo = c.k2lo, k2hi = c.k2hi, W2 = c.W2;
-    unsigned *const lim = Q.lane_list + 32 * (HBT_V2_LCAP - IPL);
+    const unsigned lim = Q.list_addr + 128u * (HBT_V2_LCAP - IPL);
 
-    auto flush_and_drain = [&](bool final) {
-        // compact the per-lane lists into the linear queue (one warp prefix sum)
-        const int cnt = static_cast<int>(Q.cur - Q.lane_list) >> 5;
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned *dst = Q.wq + Q.qcount + (incl - cnt);
-        for (int m = 0; m < cnt; m++) dst[m] = Q.lane_list[32 * m];
-        Q.cur = Q.lane_list;
-        Q.qcount += total;
-        Q.kept += static_cast<unsigned>(total);
-        __syncwarp();
-        while (Q.qcount >= 32 || (final && Q.qcount > 0)) {
-            const int take = min(32, Q.qcount);
-            const int base = Q.qcount - take;
-            if (lane < take) {
-                const unsigned e = Q.wq[base + lane];
-                v2_drain_pair<MIXED, NC>(g, c, acc, dv, si, sj, static_cast<int>(e >> 16), static_cast<int>(e & 0xffffu),
-                                         psi_ref, n);
-            }
-            Q.qcount = base;
-            __syncwarp();
-        }
-    };
-
-    for (int j = 0; j <= nj; j++) {  // one extra trip: the final flush shares the call site
-      if (j < nj) {
+    for (int j = 0; j < nj; j++) {
         const double bx = sj[j], by = sj[TJ + j], bt = sjt[j];
 #pragma unroll
         for (int s = 0; s < IPL; s++) {
@@ -320,17 +362,16 @@ __device__ __forceinline__ void v2_tile_loop(const HbtGrid &g, const V2Const &c,
                 rej_s = rej_s && !tiny;
             }
             const bool keep = kt && !(rej_o || rej_s);
-            cntKT += kt ? 1u : 0u;
-            cntRS += (kt && rej_s) ? 1u : 0u;
+            inc_if(cntKT, kt);
+            inc_if(cntRS, kt && rej_s);
             if (keep) {
-                *Q.cur = ent[s] | static_cast<unsigned>(j);
-                Q.cur += 32;
+                sts_u32(Q.cur, ent[s] | static_cast<unsigned>(j));
+                Q.cur += 128u;
             }
         }
-      }
-        const bool final = (j == nj);
-        if (final || __any_sync(0xffffffffu, Q.cur > lim)) flush_and_drain(final);
+        if (__any_sync(0xffffffffu, Q.cur > lim)) v2_flush<MIXED, false>(g, c, acc, dv, si, sj, lane, psi_ref, Q, n);
     }
+    v2_flush<MIXED, true>(g, c, acc, dv, si, sj, lane, psi_ref, Q, n);
 }
 
 template <bool MIXED>
@@ -439,7 +480,8 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
 
     V2Queue Q;
     Q.lane_list = lq + warp * (HBT_V2_LCAP * 32) + lane;
-    Q.cur = Q.lane_list;
+    Q.list_addr = static_cast<unsigned>(__cvta_generic_to_shared(Q.lane_list));
+    Q.cur = Q.list_addr;
     Q.wq = wq + warp * HBT_V2_QCAP;
     Q.qcount = 0;
     Q.kept = 0;
