@@ -24,7 +24,7 @@ EXPORTS = (
     "hbt_read", "hbt_read_qinv", "hbt_get_stage_counters", "hbt_get_timers", "hbt_get_deferred_pairs",
     "hbt_get_launch_count", "hbt_measure_fp64_peak", "hbt_timer_start", "hbt_timer_stop",
     "hbt_comm_unique_id", "hbt_comm_init_rank", "hbt_comm_init_all", "hbt_allreduce", "hbt_allreduce_all",
-    "hbt_version",
+    "hbt_version", "hbt_device_count",
 )
 
 HBT_OK = 0
@@ -95,6 +95,7 @@ def lib() -> ctypes.CDLL:
         "hbt_allreduce": (ctypes.c_int, [vp]),
         "hbt_allreduce_all": (ctypes.c_int, [vp, i32]),
         "hbt_version": (ctypes.c_char_p, []),
+        "hbt_device_count": (i32, []),
     }
     for name in EXPORTS:
         f = getattr(L, name)  # AttributeError if the library lacks a declared symbol

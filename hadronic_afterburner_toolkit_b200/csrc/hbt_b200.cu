@@ -369,6 +369,11 @@ int check_cap(hbt_ctx *ctx, const uint64_t *num, const uint64_t *den, const uint
 }  // namespace
 
 // =========================================================================================
+extern "C" int32_t hbt_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 extern "C" const char *hbt_version(void) { return "hbt_b200 0.1 sm_100a"; }
 
 extern "C" const char *hbt_last_error(const hbt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }

@@ -1,0 +1,392 @@
+// Host side of the drop-in HBT_correlation class: parameters, gathers, RNG replay, logging and
+// the output writers stay on the CPU and produce the same doubles / the same files as the
+// reference (/root/reference/src/HBT_correlation.cpp); the two pair loops are submitted to
+// libhbt_b200.so.  There is no CPU implementation of the pair loops here: if the library
+// reports an error the program stops with a message, like the reference does for its own
+// fatal conditions (message + exit(1)).
+#include "HBT_correlation.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+
+#include "../../include/hbt_b200.h"
+
+namespace {
+
+// glibc / iostream print a NaN produced by 0.0/0.0 as "-nan"; nothing to do, ostream<<double
+// does the same here because the same expressions are evaluated.
+
+int device_count_from_env() {
+    const char *e = std::getenv("HBT_B200_DEVICES");
+    if (!e || !*e) return 1;
+    if (std::string(e) == "all") return hbt_device_count();
+    const int n = std::atoi(e);
+    return n < 1 ? 1 : n;
+}
+
+}  // namespace
+
+HBT_correlation::HBT_correlation(ParameterReader &paraRdr, std::string path,
+                                 std::shared_ptr<RandomUtil::Random> ran_gen)
+    : paraRdr_(paraRdr), path_(path), next_ctx_(0), reduced_(false) {
+    ran_gen_ptr_ = ran_gen;
+
+    // same keys, same order as src/HBT_correlation.cpp:22-46 (a missing key exits in getVal)
+    long_comoving_boost = (paraRdr_.getVal("long_comoving_boost") == 1);
+    qnpts = paraRdr_.getVal("qnpts");
+    q_min = paraRdr_.getVal("q_min");
+    q_max = paraRdr_.getVal("q_max");
+    delta_q = (q_max - q_min) / (qnpts - 1);
+    for (int i = 0; i < qnpts; i++) {
+        const double q = q_min + i * delta_q;
+        q_out.push_back(q);
+        q_side.push_back(q);
+        q_long.push_back(q);
+    }
+    needed_number_of_pairs = paraRdr_.getVal("needed_number_of_pairs");
+    azimuthal_flag_ = paraRdr_.getVal("azimuthal_flag");
+    invariant_radius_flag_ = paraRdr_.getVal("invariant_radius_flag");
+    n_KT = paraRdr_.getVal("n_KT");
+    n_Kphi = paraRdr_.getVal("n_Kphi");
+    KT_min = paraRdr_.getVal("KT_min");
+    KT_max = paraRdr_.getVal("KT_max");
+    Krap_min_ = paraRdr_.getVal("HBTrap_min");
+    Krap_max_ = paraRdr_.getVal("HBTrap_max");
+    dKT = (KT_max - KT_min) / (n_KT - 1);
+    dKphi = 2 * M_PI / n_Kphi;
+    for (int i = 0; i < n_KT; i++) KT_array_.push_back(KT_min + i * dKT);
+    for (int i = 0; i < n_Kphi; i++) Kphi_array_.push_back(i * dKphi);
+    psi_ref = 0.;
+    number_of_mixed_events_ = 0;
+    number_of_oversample_events_ = 0;
+
+    hbt_params p;
+    p.qnpts = qnpts;
+    p.n_KT = n_KT;
+    p.n_Kphi = n_Kphi;
+    p.azimuthal_flag = azimuthal_flag_;
+    p.invariant_radius_flag = invariant_radius_flag_;
+    p.long_comoving_boost = long_comoving_boost ? 1 : 0;
+    p.q_min = q_min;
+    p.q_max = q_max;
+    p.KT_min = KT_min;
+    p.KT_max = KT_max;
+    p.HBTrap_min = Krap_min_;
+    p.HBTrap_max = Krap_max_;
+    p.needed_number_of_pairs = paraRdr_.getVal("needed_number_of_pairs");
+
+    const int ndev = device_count_from_env();
+    for (int d = 0; d < ndev; d++) {
+        hbt_ctx *c = nullptr;
+        const int rc = hbt_create(&p, d, &c);
+        if (rc != HBT_OK) {
+            messager << "HBT_correlation: cannot create the GPU engine on device " << d << ": "
+                     << hbt_last_error(nullptr);
+            messager.flush("error");
+            exit(1);
+        }
+        ctx_.push_back(c);
+    }
+    if (ndev > 1) check(ctx_[0], hbt_comm_init_all(ctx_.data(), ndev), "hbt_comm_init_all");
+    messager << "HBT pair loops run on " << ndev << " GPU(s) [" << hbt_version() << "]";
+    messager.flush("info");
+}
+
+HBT_correlation::~HBT_correlation() {
+    for (hbt_ctx *c : ctx_) hbt_destroy(c);
+}
+
+void HBT_correlation::check(hbt_ctx *ctx, int rc, const char *what) {
+    if (rc == HBT_OK) return;
+    messager << "HBT_correlation: " << what << " failed: " << hbt_last_error(ctx);
+    messager.flush("error");
+    exit(1);
+}
+
+hbt_ctx *HBT_correlation::pick_context() {
+    hbt_ctx *c = ctx_[next_ctx_];
+    next_ctx_ = (next_ctx_ + 1) % ctx_.size();
+    reduced_ = false;
+    return c;
+}
+
+//! Psi_n of the batch, src/HBT_correlation.cpp:233-249 (all filtered particles, no rapidity cut)
+void HBT_correlation::calculate_flow_event_plane_angle(int n_order) {
+    const int nev = particle_list->get_number_of_events();
+    double vn_real = 0.0;
+    double vn_imag = 0.0;
+    for (int iev = 0; iev < nev; iev++) {
+        const int npart = particle_list->get_number_of_particles(iev);
+        for (int i = 0; i < npart; i++) {
+            const particle_info part = particle_list->get_particle(iev, i);
+            const double phi = atan2(part.py, part.px);
+            vn_real += cos(n_order * phi);
+            vn_imag += sin(n_order * phi);
+        }
+    }
+    psi_ref = atan2(vn_imag, vn_real) / n_order;
+}
+
+//! Rapidity-cut copy of the listed events (src/HBT_correlation.cpp:255-281, :468-489,
+//! :499-511) as 8 doubles per particle (px,py,pz,E,x,y,z,t) plus per-event offsets.
+long long HBT_correlation::gather_events(bool mixed_list, const std::vector<int> &events,
+                                         std::vector<double> &out, std::vector<long long> &offsets) {
+    const double cut_max = tanh(Krap_max_);
+    const double cut_min = tanh(Krap_min_);
+    out.clear();
+    offsets.assign(1, 0);
+    for (int ev : events) {
+        const int npart = mixed_list ? particle_list->get_number_of_particles_mixed_event(ev)
+                                     : particle_list->get_number_of_particles(ev);
+        for (int i = 0; i < npart; i++) {
+            const particle_info part = mixed_list ? particle_list->get_particle_from_mixed_event(ev, i)
+                                                  : particle_list->get_particle(ev, i);
+            const double ratio = part.pz / part.E;
+            if (ratio > cut_min && ratio < cut_max) {
+                const double rec[8] = {part.px, part.py, part.pz, part.E, part.x, part.y, part.z, part.t};
+                out.insert(out.end(), rec, rec + 8);
+            }
+        }
+        offsets.push_back(static_cast<long long>(out.size() / 8));
+    }
+    return offsets.back();
+}
+
+//! One batch: src/HBT_correlation.cpp:177-218, submitted as one library call
+void HBT_correlation::calculate_HBT_correlation_function(std::shared_ptr<particleSamples> particle_list_in) {
+    set_particle_list(particle_list_in);
+    const int nev = particle_list->get_number_of_events();
+    if (azimuthal_flag_ == 1) calculate_flow_event_plane_angle(2);
+
+    number_of_oversample_events_ = nev;
+    messager.info("Compute pairs from the same event ...");
+    std::vector<int> all(nev);
+    for (int i = 0; i < nev; i++) all[i] = i;
+    const long long n1 = gather_events(false, all, gather1_, off1_);
+    const unsigned long long same_pairs = n1 > 0 ? static_cast<unsigned long long>(n1) * (n1 - 1) / 2 : 0;
+    messager << "number of pairs: " << same_pairs;
+    messager.flush("info");
+
+    const int mixed_nev = particle_list->get_number_of_mixed_events();
+    messager << "nev_mixed = " << mixed_nev;
+    messager.flush("info");
+    number_of_mixed_events_ = static_cast<int>(mixed_nev / 2) + 1;
+    messager.info("Compute pairs from the mixed event ...");
+
+    const bool real_mixed = (paraRdr_.getVal("read_in_real_mixed_events") == 1);
+    const double *p2 = nullptr;
+    const long long *o2 = nullptr;
+    if (real_mixed) {
+        std::vector<int> allm(mixed_nev);
+        for (int i = 0; i < mixed_nev; i++) allm[i] = i;
+        gather_events(true, allm, gather2_, off2_);
+        p2 = gather2_.data();
+        o2 = off2_.data();
+    }
+    const std::vector<long long> &offm = real_mixed ? off2_ : off1_;
+
+    // the reference's draws, in its order: per event the partner ids (:206-215), then one
+    // rotation angle per partner inside the mixed routine (:493-497)
+    const int nmix = number_of_mixed_events_;
+    std::vector<int> ids(static_cast<size_t>(nev) * nmix);
+    std::vector<double> cs(static_cast<size_t>(nev) * nmix * 2);
+    const bool do_mixed = nev > 0 && mixed_nev > 0;
+    if (do_mixed) {
+        for (int iev = 0; iev < nev; iev++) {
+            messager << "progess: " << iev << "/" << nev;
+            messager.flush("info");
+            for (int c = 0; c < nmix; c++) {
+                int id = (ran_gen_ptr_->rand_int_uniform() % mixed_nev);
+                while (iev == id && mixed_nev != 1) id = (ran_gen_ptr_->rand_int_uniform() % mixed_nev);
+                ids[static_cast<size_t>(iev) * nmix + c] = id;
+            }
+            unsigned long long pairs = 0;
+            for (int c = 0; c < nmix; c++) {
+                const double random_rotation = ran_gen_ptr_->rand_uniform() * 2 * M_PI;
+                const size_t k = static_cast<size_t>(iev) * nmix + c;
+                cs[2 * k] = cos(random_rotation);
+                cs[2 * k + 1] = sin(random_rotation);
+                const int id = ids[k];
+                pairs += static_cast<unsigned long long>(off1_[iev + 1] - off1_[iev]) * (offm[id + 1] - offm[id]);
+            }
+            messager << "number of mixed pairs: " << pairs;
+            messager.flush("info");
+        }
+    }
+    if (nev == 0) return;  // the reader's trailing empty batch: nothing to do, no draws
+    hbt_ctx *c = pick_context();
+    check(c,
+          hbt_accumulate_batch(c, gather1_.data(), reinterpret_cast<const int64_t *>(off1_.data()), nev, p2,
+                               reinterpret_cast<const int64_t *>(o2), real_mixed ? mixed_nev : 0, ids.data(), cs.data(),
+                               do_mixed ? nmix : 0, psi_ref, 1, do_mixed ? 1 : 0),
+          "hbt_accumulate_batch");
+}
+
+//! Same-event pairs of the listed events merged into one list, src/HBT_correlation.cpp:251-462
+void HBT_correlation::combine_and_bin_particle_pairs(std::vector<int> event_list) {
+    const long long n = gather_events(false, event_list, gather1_, off1_);
+    messager << "number of pairs: " << (n > 0 ? static_cast<unsigned long long>(n) * (n - 1) / 2 : 0);
+    messager.flush("info");
+    hbt_ctx *c = pick_context();
+    check(c, hbt_accumulate_same(c, gather1_.data(), n, psi_ref), "hbt_accumulate_same");
+}
+
+//! One event against the listed partner events, each rotated by a fresh random angle,
+//! src/HBT_correlation.cpp:464-692
+void HBT_correlation::combine_and_bin_particle_pairs_mixed_events(int event_id1, std::vector<int> mixed_event_list) {
+    number_of_mixed_events_ = static_cast<int>(mixed_event_list.size());
+    const long long n1 = gather_events(false, std::vector<int>(1, event_id1), gather1_, off1_);
+    // list 2 is gathered in partner order, one segment per partner (duplicates allowed)
+    gather_events(true, mixed_event_list, gather2_, off2_);
+    const int nmix = number_of_mixed_events_;
+    std::vector<int> ids(nmix);
+    std::vector<double> cs(static_cast<size_t>(nmix) * 2);
+    for (int c = 0; c < nmix; c++) {
+        const double random_rotation = ran_gen_ptr_->rand_uniform() * 2 * M_PI;
+        cs[2 * c] = cos(random_rotation);
+        cs[2 * c + 1] = sin(random_rotation);
+        ids[c] = c;
+    }
+    messager << "number of mixed pairs: " << static_cast<unsigned long long>(n1) * off2_.back();
+    messager.flush("info");
+    hbt_ctx *c = pick_context();
+    check(c,
+          hbt_accumulate_mixed(c, gather1_.data(), reinterpret_cast<const int64_t *>(off1_.data()), 1, gather2_.data(),
+                               reinterpret_cast<const int64_t *>(off2_.data()), nmix, ids.data(), cs.data(), nmix,
+                               psi_ref),
+          "hbt_accumulate_mixed");
+}
+
+void HBT_correlation::fetch_results() {
+    if (ctx_.size() > 1 && !reduced_) check(ctx_[0], hbt_allreduce_all(ctx_.data(), static_cast<int>(ctx_.size())), "hbt_allreduce_all");
+    reduced_ = true;
+    hbt_ctx *c = ctx_[0];
+    const size_t nb = hbt_num_bins(c), ns = hbt_num_slabs(c);
+    num_count_.resize(nb); den_count_.resize(nb); num_cos_.resize(nb);
+    sum_qo_.resize(nb); sum_qs_.resize(nb); sum_ql_.resize(nb);
+    npairs_num_.resize(ns); npairs_den_.resize(ns);
+    check(c,
+          hbt_read(c, reinterpret_cast<uint64_t *>(num_count_.data()), num_cos_.data(), sum_qo_.data(), sum_qs_.data(),
+                   sum_ql_.data(), reinterpret_cast<uint64_t *>(den_count_.data()),
+                   reinterpret_cast<uint64_t *>(npairs_num_.data()), reinterpret_cast<uint64_t *>(npairs_den_.data())),
+          "hbt_read");
+    if (invariant_radius_flag_ == 1) {
+        const size_t n1 = static_cast<size_t>(n_KT) * qnpts;
+        inv_count_.resize(n1); inv_den_.resize(n1); inv_sum_.resize(n1); inv_cos_.resize(n1);
+        npairs_num_inv_.resize(n_KT); npairs_den_inv_.resize(n_KT);
+        check(c,
+              hbt_read_qinv(c, reinterpret_cast<uint64_t *>(inv_count_.data()), inv_sum_.data(), inv_cos_.data(),
+                            reinterpret_cast<uint64_t *>(inv_den_.data()),
+                            reinterpret_cast<uint64_t *>(npairs_num_inv_.data()),
+                            reinterpret_cast<uint64_t *>(npairs_den_inv_.data())),
+              "hbt_read_qinv");
+    }
+}
+
+void HBT_correlation::output_HBTcorrelation() {
+    fetch_results();
+    if (invariant_radius_flag_ == 1) output_correlation_function_inv();
+    if (azimuthal_flag_ == 0) {
+        output_correlation_function();
+    } else {
+        output_correlation_function_Kphi_differential();
+    }
+}
+
+//! src/HBT_correlation.cpp:694-724
+void HBT_correlation::output_correlation_function_inv() {
+    if (inv_count_.empty()) fetch_results();
+    const bool eco = (paraRdr_.getVal("ecoOutput", 0) == 1);
+    for (int iK = 0; iK < n_KT - 1; iK++) {
+        const double npair_ratio =
+            (static_cast<double>(npairs_num_inv_[iK]) / static_cast<double>(npairs_den_inv_[iK]));
+        std::ostringstream filename;
+        filename << path_ << "/HBT_correlation_function_inv_KT_" << KT_array_[iK] << "_" << KT_array_[iK + 1] << ".dat";
+        std::ofstream output(filename.str().c_str());
+        for (int iq = 0; iq < qnpts; iq++) {
+            const size_t k = static_cast<size_t>(iK) * qnpts + iq;
+            const double count = static_cast<double>(inv_count_[k]);
+            const double q_inv_local = inv_sum_[k] / count;
+            const double correl_fun_num = inv_cos_[k];
+            const double correl_fun_denorm = static_cast<double>(inv_den_[k]) * npair_ratio;
+            output << std::scientific << std::setw(18) << std::setprecision(8);
+            if (eco) {
+                output << correl_fun_num << "    " << correl_fun_denorm << std::endl;
+            } else {
+                output << q_inv_local << "    " << correl_fun_num << "    " << correl_fun_denorm << std::endl;
+            }
+        }
+        output.close();
+    }
+}
+
+//! one (K_T[, K_phi]) slab: rows in the order q_long outer, q_out middle, q_side inner and the
+//! column layout of src/HBT_correlation.cpp:735-777
+void HBT_correlation::write_3d_file(const std::string &filename, size_t slab, double npair_ratio) {
+    const bool eco = (paraRdr_.getVal("ecoOutput", 0) == 1);
+    std::ofstream output(filename.c_str());
+    const size_t q3 = static_cast<size_t>(qnpts) * qnpts * qnpts;
+    for (int iqlong = 0; iqlong < qnpts; iqlong++) {
+        for (int iqout = 0; iqout < qnpts; iqout++) {
+            for (int iqside = 0; iqside < qnpts; iqside++) {
+                const size_t bin = slab * q3 + (static_cast<size_t>(iqout) * qnpts + iqside) * qnpts + iqlong;
+                // the reference keeps the counts in doubles and truncates them to int here
+                const int npart_num = static_cast<int>(static_cast<double>(num_count_[bin]));
+                const int npart_denorm = static_cast<int>(static_cast<double>(den_count_[bin]));
+                double q_out_local, q_side_local, q_long_local, correl_fun_num, correl_fun_denorm;
+                if (npart_num < 2 || npart_denorm < 2) {
+                    q_out_local = q_out[iqout];
+                    q_side_local = q_side[iqside];
+                    q_long_local = q_long[iqlong];
+                    correl_fun_num = 0.0;
+                    correl_fun_denorm = npart_denorm;
+                } else {
+                    q_out_local = sum_qo_[bin] / npart_num;
+                    q_side_local = sum_qs_[bin] / npart_num;
+                    q_long_local = sum_ql_[bin] / npart_num;
+                    correl_fun_num = num_cos_[bin];
+                    correl_fun_denorm = npair_ratio * static_cast<double>(den_count_[bin]);
+                }
+                output << std::scientific << std::setw(18) << std::setprecision(8);
+                if (eco) {
+                    output << correl_fun_num << "    " << correl_fun_denorm << std::endl;
+                } else {
+                    output << q_out_local << "    " << q_side_local << "    " << q_long_local << "    "
+                           << correl_fun_num << "    " << correl_fun_denorm << std::endl;
+                }
+            }
+        }
+    }
+    output.close();
+}
+
+//! src/HBT_correlation.cpp:726-783
+void HBT_correlation::output_correlation_function() {
+    if (num_count_.empty()) fetch_results();
+    for (int iK = 0; iK < n_KT - 1; iK++) {
+        const double npair_ratio = (static_cast<double>(npairs_num_[iK]) / static_cast<double>(npairs_den_[iK]));
+        std::ostringstream filename;
+        filename << path_ << "/HBT_correlation_function_KT_" << KT_array_[iK] << "_" << KT_array_[iK + 1] << ".dat";
+        write_3d_file(filename.str(), iK, npair_ratio);
+    }
+}
+
+//! src/HBT_correlation.cpp:785-855
+void HBT_correlation::output_correlation_function_Kphi_differential() {
+    if (num_count_.empty()) fetch_results();
+    for (int iK = 0; iK < n_KT - 1; iK++) {
+        for (int iKphi = 0; iKphi < n_Kphi; iKphi++) {
+            const size_t slab = static_cast<size_t>(iK) * n_Kphi + iKphi;
+            const double npair_ratio =
+                (static_cast<double>(npairs_num_[slab]) / static_cast<double>(npairs_den_[slab]));
+            std::ostringstream filename;
+            filename << path_ << "/HBT_correlation_function_KT_" << KT_array_[iK] << "_" << KT_array_[iK + 1]
+                     << "_Kphi_" << Kphi_array_[iKphi] << ".dat";
+            write_3d_file(filename.str(), slab, npair_ratio);
+        }
+    }
+}

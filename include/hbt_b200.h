@@ -193,6 +193,9 @@ int hbt_allreduce_all(hbt_ctx **ctxs, int32_t n);
  * Measurement aid for bench.py; not part of the reference's interface. */
 int hbt_measure_fp64_peak(int32_t device, double ms, double *tflops);
 
+/* number of CUDA devices visible to the process (0 when there is none) */
+int32_t hbt_device_count(void);
+
 /* library self-description: "hbt_b200 <version> sm_100a" */
 const char *hbt_version(void);
 

@@ -1,0 +1,89 @@
+"""End-to-end drop-in check: the reference's own command-line binary and the SAME binary with
+the B200 HBT_correlation class inside (hadronic_afterburner_toolkit_b200/host) read the same
+particle_samples.gz through the reference's unchanged reader, with the same parameters.dat and
+randomSeed, and must write the same HBT_correlation_function_*.dat files."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from hadronic_afterburner_toolkit_b200 import synth
+from hadronic_afterburner_toolkit_b200.params import C3, C4, HBTParams
+
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "hadronic_afterburner_tools.e")
+OUR_EXE = os.path.join(ROOT, "hadronic_afterburner_toolkit_b200", "host", "build", "hadronic_afterburner_tools_b200.e")
+PDG = os.path.join(ROOT, "oracle", "_ref", "EOS", "pdg.dat")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (os.path.exists(REF_EXE) and os.path.exists(OUR_EXE)),
+                                 reason="compiled reference / drop-in binary not present")]
+
+
+def run_binary(exe, workdir, params_text, gz_src, env=None):
+    os.makedirs(os.path.join(workdir, "EOS"))
+    os.makedirs(os.path.join(workdir, "results"))
+    shutil.copy(PDG, os.path.join(workdir, "EOS", "pdg.dat"))
+    shutil.copy(gz_src, os.path.join(workdir, "results", "particle_samples.gz"))
+    with open(os.path.join(workdir, "parameters.dat"), "w") as f:
+        f.write(params_text)
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([exe], cwd=workdir, capture_output=True, text=True, env=e)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = os.path.join(workdir, "results")
+    return {fn: open(os.path.join(res, fn)).read().splitlines() for fn in sorted(os.listdir(res))
+            if fn.startswith("HBT_correlation_function")}, r.stdout
+
+
+def same_text(want, got):
+    assert sorted(want) == sorted(got)
+    for fn in want:
+        a, b = want[fn], got[fn]
+        assert len(a) == len(b), fn
+        for la, lb in zip(a, b):
+            if la == lb:
+                continue
+            assert len(la) == len(lb), (fn, la, lb)
+            for x, y in zip(la.split(), lb.split()):
+                if x != y:  # a <=1e-10 difference straddling the 9th digit
+                    assert abs(float(x) - float(y)) <= 2e-8 * max(abs(float(x)), 1e-300), (fn, la, lb)
+
+
+CASES = {
+    "c3_shape": (C3.with_(qnpts=15), 3, 5, 300),
+    "c4_shape_az": (C4.with_(qnpts=9, n_KT=4, n_Kphi=4), 2, 4, 300),
+    "qinv": (HBTParams(qnpts=21, invariant_radius_flag=1), 2, 4, 200),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_same_files_as_reference_binary(name, tmp_path):
+    P, ngrp, nev, mult = CASES[name]
+    batches = synth.make_batches(41, ngrp, nev, multiplicity=mult)
+    gz = str(tmp_path / "input.gz")
+    synth.write_iss_gz(gz, batches)
+    text = P.parameters_dat(event_buffer_size=nev * mult)  # groups of exactly nev events
+    want, _ = run_binary(REF_EXE, str(tmp_path / "ref"), text, gz)
+    got, out = run_binary(OUR_EXE, str(tmp_path / "ours"), text, gz)
+    assert "HBT pair loops run on 1 GPU(s)" in out
+    same_text(want, got)
+    assert len(want) == (P.n_KT - 1) * (P.n_Kphi if P.azimuthal_flag else 1) * (2 if P.invariant_radius_flag else 1)
+
+
+def test_groups_sharded_over_all_gpus_of_the_box(tmp_path):
+    from hadronic_afterburner_toolkit_b200 import capi
+
+    ndev = capi.lib().hbt_device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    P, ngrp, nev, mult = C3.with_(qnpts=15), 5, 4, 300
+    batches = synth.make_batches(43, ngrp, nev, multiplicity=mult)
+    gz = str(tmp_path / "input.gz")
+    synth.write_iss_gz(gz, batches)
+    text = P.parameters_dat(event_buffer_size=nev * mult)
+    want, _ = run_binary(REF_EXE, str(tmp_path / "ref"), text, gz)
+    got, out = run_binary(OUR_EXE, str(tmp_path / "ours"), text, gz, env={"HBT_B200_DEVICES": "all"})
+    assert f"HBT pair loops run on {ndev} GPU(s)" in out
+    same_text(want, got)
