@@ -332,6 +332,18 @@ void oracle_process_batch(oracle_state *s, const double *same, const int64_t *sa
     free(l2);
 }
 
+void oracle_skip_batch(oracle_state *s, int32_t nev, int32_t nev_mixed) {
+    if (nev_mixed <= 0) return;
+    int nmix = nev_mixed / 2 + 1;
+    for (int iev = 0; iev < nev; iev++) {
+        for (int c = 0; c < nmix; c++) { /* src/HBT_correlation.cpp:208-215 */
+            int id = oracle_rand_int_uniform(s) % nev_mixed;
+            while (iev == id && nev_mixed != 1) id = oracle_rand_int_uniform(s) % nev_mixed;
+        }
+        for (int c = 0; c < nmix; c++) (void)oracle_rand_uniform(s); /* :495 */
+    }
+}
+
 int64_t oracle_nbins(const oracle_state *s) { return s->nbins; }
 const double *oracle_num_count(const oracle_state *s) { return s->num_count; }
 const double *oracle_num_cos(const oracle_state *s) { return s->num_cos; }

@@ -56,6 +56,9 @@ void oracle_process_batch(oracle_state *s, const double *same, const int64_t *sa
                           int32_t nev, const double *mixed, const int64_t *mixed_off,
                           int32_t nev_mixed, int32_t do_mixed);
 
+/* consume the draws of a batch another rank owns (same rejection loop, no pair work) */
+void oracle_skip_batch(oracle_state *s, int32_t nev, int32_t nev_mixed);
+
 /* raw accumulators; 3-D histograms are flat [(K*(az?n_Kphi:1)+phi)][o][s][l] */
 int64_t oracle_nbins(const oracle_state *s);
 const double *oracle_num_count(const oracle_state *s);

@@ -62,6 +62,7 @@ def _load():
     L.oracle_psi_ref.restype = dbl
     L.oracle_psi_ref.argtypes = [vp, i64, i32]
     L.oracle_process_batch.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32]
+    L.oracle_skip_batch.argtypes = [vp, i32, i32]
     L.oracle_nbins.restype = i64
     L.oracle_nbins.argtypes = [vp]
     for name in ("num_count", "num_cos", "sum_qo", "sum_qs", "sum_ql", "den_count", "npairs_num",
@@ -130,6 +131,9 @@ class Oracle:
                                         None, None, 0, int(do_mixed))
         self.last_nev = len(batch.same)
         self.psi_refs.append(self.L.oracle_last_psi_ref(self.h))
+
+    def skip_batch(self, nev: int, nev_mixed: int) -> None:
+        self.L.oracle_skip_batch(self.h, nev, nev_mixed)
 
     def last_plan(self):
         nmix = self.L.oracle_last_nmix(self.h)
