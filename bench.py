@@ -324,7 +324,9 @@ def main():
     # ---- roofline of the pair kernels (rank 0's device) -------------------------------------
     peak = ctypes.c_double()
     _check(None, L.hbt_measure_fp64_peak(local, 300.0, ctypes.byref(peak)))
-    dst = (st1 - st0).astype(np.uint64)
+    # after an all-reduce the library returns the GLOBAL stage counters; every rank does the
+    # same amount of work here, so this rank's share is 1/world of the difference
+    dst = ((st1 - st0) // np.uint64(world)).astype(np.uint64)
     ops_same, ops_mixed = algorithmic_ops(dst, boost=P.long_comoving_boost == 1, az=P.azimuthal_flag == 1)
     ks = (tm1["same_ms"] - tm0["same_ms"]) * 1e-3
     km = (tm1["mixed_ms"] - tm0["mixed_ms"]) * 1e-3
