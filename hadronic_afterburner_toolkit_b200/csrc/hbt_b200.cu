@@ -122,6 +122,14 @@ struct hbt_ctx {
     int kernel_version = 2;
     ncclComm_t comm = nullptr;
     int nranks = 1;
+    // needed_number_of_pairs bookkeeping (ordered cap)
+    std::vector<uint64_t> exact_num, exact_den;  // per-slab accepted pairs as of the last refresh
+    uint64_t pending_num = 0, pending_den = 0;   // pairs submitted since (upper bound of what they add)
+    std::vector<unsigned char> closed;           // [2*nslab] slabs whose counter exceeds the cap
+    unsigned char *d_closed = nullptr;
+    bool any_closed = false;
+    unsigned long long *snap_u64 = nullptr;      // rollback copies of the accumulators
+    double *snap_f64 = nullptr;
     std::string err;
 };
 
@@ -214,7 +222,11 @@ size_t dyn_smem_bytes(const HbtGrid &g) {
 }
 
 // ---- launches ------------------------------------------------------------------------
-int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref) {
+const unsigned char *closed_ptr(const hbt_ctx *ctx) { return ctx->any_closed ? ctx->d_closed : nullptr; }
+
+// mode 0: the production kernels (v2 unless the grid needs v1); mode 1 / 2: the two ordered-cap
+// passes, always on the literal v1 kernels
+int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int mode = 0, const HbtCap *capin = nullptr) {
     if (n < 2) return HBT_OK;
     ctx->reduced = false;
     cudaEvent_t e0, e1;
@@ -222,17 +234,26 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref) {
     if (rc) return rc;
     CU(ctx, cudaEventRecord(e0, ctx->compute));
     const unsigned long long npairs = static_cast<unsigned long long>(n) * (n - 1) / 2;
-    if (ctx->kernel_version == 1) {
+    HbtCap cap{};
+    if (capin) cap = *capin;
+    cap.closed = closed_ptr(ctx);
+    if (ctx->kernel_version == 1 || mode != 0) {
         const long long T = (n + kTileV1 - 1) / kTileV1;
         const long long blocks = T * (T + 1) / 2;
         if (blocks > 0x7fffffffLL) return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld tiles", blocks);
-        hbt_add_stage_a<<<1, 1, 0, ctx->compute>>>(ctx->acc, 0, npairs);
-        ctx->kernel_launches += 2;
-        hbt_pairs_v1<kTileV1, false><<<static_cast<unsigned>(blocks), kTileV1, dyn_smem_bytes(ctx->grid), ctx->compute>>>(
-            d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref);
+        const unsigned nb = static_cast<unsigned>(blocks);
+        const size_t sm = dyn_smem_bytes(ctx->grid);
+        if (mode != 1) {
+            hbt_add_stage_a<<<1, 1, 0, ctx->compute>>>(ctx->acc, 0, npairs);
+            ctx->kernel_launches++;
+        }
+        if (mode == 0) hbt_pairs_v1<kTileV1, false, 0><<<nb, kTileV1, sm, ctx->compute>>>(d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref, cap);
+        else if (mode == 1) hbt_pairs_v1<kTileV1, false, 1><<<nb, kTileV1, sm, ctx->compute>>>(d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref, cap);
+        else hbt_pairs_v1<kTileV1, false, 2><<<nb, kTileV1, sm, ctx->compute>>>(d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref, cap);
+        ctx->kernel_launches++;
     } else {
 #ifdef HBT_HAVE_V2
-        rc = hbt_v2_launch_same(ctx->compute, d_p, n, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs);
+        rc = hbt_v2_launch_same(ctx->compute, d_p, n, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed);
         ctx->kernel_launches++;
         if (rc) return fail(ctx, rc, "v2 same-event launch failed");
 #endif
@@ -241,6 +262,7 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref) {
     CU(ctx, cudaEventRecord(e1, ctx->compute));
     ctx->timers.push_back({e0, e1, 0});
     ctx->same_launches++;
+    ctx->pending_num += npairs;
     return drain_timers(ctx, false);
 }
 
@@ -253,6 +275,7 @@ size_t build_segments(const int64_t *off1, int32_t nev1, const int64_t *off2, in
     unsigned long long pairs = 0;
     for (int iev = 0; iev < nev1; iev++) {
         const int64_t i0 = off1[iev], ni = off1[iev + 1] - off1[iev];
+        int64_t pos0 = 0;  // position inside the row's concatenated partner list (src :493-552)
         for (int c = 0; c < nmix; c++) {
             const size_t k = static_cast<size_t>(iev) * nmix + c;
             const int id = ids[k];
@@ -265,8 +288,11 @@ size_t build_segments(const int64_t *off1, int32_t nev1, const int64_t *off2, in
             s.tiles_j = static_cast<int32_t>((nj + tile_j - 1) / tile_j);
             const int32_t tiles_i = static_cast<int32_t>((ni + tile_i - 1) / tile_i);
             s.block0 = block0;
+            s.pos0 = pos0;
+            s.pad = 0;
             block0 += static_cast<long long>(tiles_i) * s.tiles_j;
             pairs += static_cast<unsigned long long>(ni) * nj;
+            pos0 += nj;
         }
     }
     *npairs = pairs;
@@ -275,7 +301,7 @@ size_t build_segments(const int64_t *off1, int32_t nev1, const int64_t *off2, in
 }
 
 int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg, size_t nseg,
-                 long long nblocks, unsigned long long npairs, double psi_ref) {
+                 long long nblocks, unsigned long long npairs, double psi_ref, int mode = 0, const HbtCap *capin = nullptr) {
     if (nseg == 0 || nblocks == 0) return HBT_OK;
     ctx->reduced = false;
     cudaEvent_t e0, e1;
@@ -283,14 +309,24 @@ int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const Hbt
     if (rc) return rc;
     CU(ctx, cudaEventRecord(e0, ctx->compute));
     if (nblocks > 0x7fffffffLL) return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld tiles", nblocks);
-    if (ctx->kernel_version == 1) {
-        hbt_add_stage_a<<<1, 1, 0, ctx->compute>>>(ctx->acc, 6, npairs);
-        ctx->kernel_launches += 2;
-        hbt_pairs_v1<kTileV1, true><<<static_cast<unsigned>(nblocks), kTileV1, dyn_smem_bytes(ctx->grid), ctx->compute>>>(
-            d_p1, d_p2, static_cast<long long>(nseg), d_seg, ctx->grid, ctx->acc, psi_ref);
+    HbtCap cap{};
+    if (capin) cap = *capin;
+    cap.closed = closed_ptr(ctx);
+    if (ctx->kernel_version == 1 || mode != 0) {
+        const unsigned nb = static_cast<unsigned>(nblocks);
+        const size_t sm = dyn_smem_bytes(ctx->grid);
+        const long long ns = static_cast<long long>(nseg);
+        if (mode != 1) {
+            hbt_add_stage_a<<<1, 1, 0, ctx->compute>>>(ctx->acc, 6, npairs);
+            ctx->kernel_launches++;
+        }
+        if (mode == 0) hbt_pairs_v1<kTileV1, true, 0><<<nb, kTileV1, sm, ctx->compute>>>(d_p1, d_p2, ns, d_seg, ctx->grid, ctx->acc, psi_ref, cap);
+        else if (mode == 1) hbt_pairs_v1<kTileV1, true, 1><<<nb, kTileV1, sm, ctx->compute>>>(d_p1, d_p2, ns, d_seg, ctx->grid, ctx->acc, psi_ref, cap);
+        else hbt_pairs_v1<kTileV1, true, 2><<<nb, kTileV1, sm, ctx->compute>>>(d_p1, d_p2, ns, d_seg, ctx->grid, ctx->acc, psi_ref, cap);
+        ctx->kernel_launches++;
     } else {
 #ifdef HBT_HAVE_V2
-        rc = hbt_v2_launch_mixed(ctx->compute, d_p1, d_p2, d_seg, nseg, nblocks, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs);
+        rc = hbt_v2_launch_mixed(ctx->compute, d_p1, d_p2, d_seg, nseg, nblocks, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed);
         ctx->kernel_launches++;
         if (rc) return fail(ctx, rc, "v2 mixed-event launch failed");
 #endif
@@ -299,6 +335,7 @@ int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const Hbt
     CU(ctx, cudaEventRecord(e1, ctx->compute));
     ctx->timers.push_back({e0, e1, 1});
     ctx->mixed_launches++;
+    ctx->pending_den += npairs;
     return drain_timers(ctx, false);
 }
 
@@ -306,23 +343,47 @@ int tile_i(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT
 int tile_j(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V2_TILE_J; }
 
 // host literal evaluation of the pairs the device deferred; leaves the stream idle
-int resolve_deferred(hbt_ctx *ctx) {
+// position filter of the ordered cap for host-evaluated pairs
+struct CapFilter {
+    const std::vector<int64_t> *cut_row = nullptr, *cut_pos = nullptr;  // per slab; null: no cut
+};
+
+// copies the device's deferred-pair list to the host (pinned buffer) and clears it
+int fetch_deferred(hbt_ctx *ctx, unsigned *n_out) {
     CU(ctx, cudaMemcpyAsync(ctx->h_defcount, ctx->acc.deferred_count, 8, cudaMemcpyDeviceToHost, ctx->compute));
     CU(ctx, cudaStreamSynchronize(ctx->compute));
     if (ctx->h_defcount[1]) return fail(ctx, HBT_ERR_OVERFLOW, "deferred-pair list overflowed (%u entries)", kDeferredCapacity);
     const unsigned n = ctx->h_defcount[0];
+    *n_out = n;
     if (n == 0) return HBT_OK;
     CU(ctx, cudaMemcpyAsync(ctx->h_deferred, ctx->acc.deferred, static_cast<size_t>(n) * sizeof(HbtDeferred),
                             cudaMemcpyDeviceToHost, ctx->compute));
+    CU(ctx, cudaMemsetAsync(ctx->acc.deferred_count, 0, 8, ctx->compute));
     CU(ctx, cudaStreamSynchronize(ctx->compute));
+    return HBT_OK;
+}
+
+// host literal evaluation of the pairs the device deferred; leaves the stream idle
+int resolve_deferred(hbt_ctx *ctx, const CapFilter *f = nullptr) {
+    unsigned n = 0;
+    int rc = fetch_deferred(ctx, &n);
+    if (rc || n == 0) return rc;
     std::vector<HbtCorrection> corr;
     HbtStageDelta delta{};
+    const int ns = ctx->grid.nslab;
     for (unsigned k = 0; k < n; k++) {
         const HbtDeferred &d = ctx->h_deferred[k];
         HbtCorrection c;
         uint64_t st[6] = {0, 0, 0, 0, 0, 0};
-        if (hbt_host_pair_literal(&ctx->grid, d.a, d.b, d.mixed, d.psi_ref, &c, st)) corr.push_back(c);
+        const int ok = hbt_host_pair_literal(&ctx->grid, d.a, d.b, d.mixed, d.psi_ref, &c, st);
         for (int s = 1; s < 6; s++) delta.v[(d.mixed ? 6 : 0) + s] += st[s];
+        if (!ok) continue;
+        if (!ctx->closed.empty() && ctx->closed[c.slab + (d.mixed ? ns : 0)]) continue;
+        if (f && f->cut_row) {
+            const int64_t cr = (*f->cut_row)[c.slab];
+            if (d.row > cr || (d.row == cr && d.pos > (*f->cut_pos)[c.slab])) continue;
+        }
+        corr.push_back(c);
     }
     ctx->deferred_total += n;
     if (!corr.empty())
@@ -331,9 +392,221 @@ int resolve_deferred(hbt_ctx *ctx) {
         ctx->d_corr, static_cast<int>(corr.size()), ctx->acc, delta);
     ctx->kernel_launches++;
     CU(ctx, cudaGetLastError());
-    CU(ctx, cudaMemsetAsync(ctx->acc.deferred_count, 0, 8, ctx->compute));
     CU(ctx, cudaStreamSynchronize(ctx->compute));
     return HBT_OK;
+}
+
+// per-slab accepted-pair counters = sums of the bin counts; refreshes the host copies
+int refresh_counts(hbt_ctx *ctx) {
+    const long long q3 = static_cast<long long>(ctx->grid.nq) * ctx->grid.nq * ctx->grid.nq;
+    hbt_reduce_slabs<<<2 * ctx->grid.nslab, 256, 0, ctx->compute>>>(ctx->acc, ctx->grid.nslab, q3);
+    hbt_finish_stage<<<1, 32, 0, ctx->compute>>>(ctx->acc, ctx->grid.nslab);
+    ctx->kernel_launches += 2;
+    CU(ctx, cudaGetLastError());
+    const size_t ns = ctx->grid.nslab;
+    ctx->exact_num.resize(ns);
+    ctx->exact_den.resize(ns);
+    CU(ctx, cudaMemcpyAsync(ctx->exact_num.data(), ctx->acc.npairs_num, ns * 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(ctx, cudaMemcpyAsync(ctx->exact_den.data(), ctx->acc.npairs_den, ns * 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    ctx->pending_num = ctx->pending_den = 0;
+    return HBT_OK;
+}
+
+
+// ==== needed_number_of_pairs: the ordered cap ==============================================
+// The reference accepts a pair into slab K only while the slab's counter is <= needed
+// (src/HBT_correlation.cpp:402-406, :651-655), in loop order, cumulatively over the batches: a
+// slab takes exactly the first needed+1 pairs that reach it.  Far from the cap nothing special
+// happens (cap_may_engage is false, batches stay asynchronous).  Near it each phase (the
+// same-event loop, then the mixed-event loops) runs optimistically with a rollback copy; if no
+// open slab crossed the cap the result stands, otherwise the phase is replayed in order:
+// pass 1 counts the accepted pairs per row (list-1 particle) of the crossing slabs, the host
+// finds the row where the quota runs out and evaluates that row literally to get the exact
+// position, pass 2 accumulates only pairs at or before it.
+struct PhaseInput {
+    bool mixed = false;
+    const double *h1 = nullptr, *h2 = nullptr;  // host copies of list 1 / list 2
+    const double *d1 = nullptr, *d2 = nullptr;  // device copies
+    int64_t n1 = 0;
+    const int64_t *off1 = nullptr, *off2 = nullptr;
+    int32_t nev1 = 0, nmix = 0;
+    const int32_t *ids = nullptr;
+    const double *cs = nullptr;
+    double psi_ref = 0.;
+};
+
+bool cap_may_engage(const hbt_ctx *ctx, bool mixed, unsigned long long pairs) {
+    const uint64_t lim = ctx->grid.needed + 1;
+    if (lim >= (1ull << 62)) return false;
+    const std::vector<uint64_t> &ex = mixed ? ctx->exact_den : ctx->exact_num;
+    const uint64_t pend = (mixed ? ctx->pending_den : ctx->pending_num) + pairs;
+    const int ns = ctx->grid.nslab;
+    for (int k = 0; k < ns; k++) {
+        if (ctx->closed[k + (mixed ? ns : 0)]) continue;
+        const uint64_t have = ex.empty() ? 0 : ex[k];
+        if (have + pend > lim) return true;
+    }
+    return false;
+}
+
+int sync_closed(hbt_ctx *ctx, bool mixed) {
+    const uint64_t needed = ctx->grid.needed;
+    const int ns = ctx->grid.nslab;
+    const std::vector<uint64_t> &ex = mixed ? ctx->exact_den : ctx->exact_num;
+    bool changed = false;
+    for (int k = 0; k < ns; k++)
+        if (ex[k] > needed && !ctx->closed[k + (mixed ? ns : 0)]) { ctx->closed[k + (mixed ? ns : 0)] = 1; changed = true; }
+    if (changed) {
+        ctx->any_closed = true;
+        CU(ctx, cudaMemcpyAsync(ctx->d_closed, ctx->closed.data(), ctx->closed.size(), cudaMemcpyHostToDevice, ctx->compute));
+        CU(ctx, cudaStreamSynchronize(ctx->compute));
+    }
+    return HBT_OK;
+}
+
+// position of the m-th pair (m >= 1) of row `row` that the reference accepts into slab K
+int64_t resolve_row(const hbt_ctx *ctx, const PhaseInput &in, int K, int64_t row, uint64_t m) {
+    const double *a = in.h1 + 8 * row;
+    HbtCorrection c;
+    uint64_t st[6];
+    if (!in.mixed) {
+        for (int64_t j = row + 1; j < in.n1; j++)
+            if (hbt_host_pair_literal(&ctx->grid, a, in.h1 + 8 * j, 0, in.psi_ref, &c, st) && c.slab == K && --m == 0) return j;
+        return -1;
+    }
+    const int iev = static_cast<int>(std::upper_bound(in.off1, in.off1 + in.nev1 + 1, row) - in.off1) - 1;
+    int64_t pos = 0;
+    for (int s = 0; s < in.nmix; s++) {
+        const size_t k = static_cast<size_t>(iev) * in.nmix + s;
+        const int id = in.ids[k];
+        const double cphi = in.cs[2 * k], sphi = in.cs[2 * k + 1];
+        for (int64_t j = in.off2[id]; j < in.off2[id + 1]; j++, pos++) {
+            const double *q = in.h2 + 8 * j;
+            double b[8] = {0., 0., q[2], q[3], 0., 0., 0., 0.};
+            const double t1 = q[0] * cphi, t2 = q[1] * sphi, t3 = q[0] * sphi, t4 = q[1] * cphi;  // :522-523
+            b[0] = t1 - t2;
+            b[1] = t3 + t4;
+            if (hbt_host_pair_literal(&ctx->grid, a, b, 1, in.psi_ref, &c, st) && c.slab == K && --m == 0) return pos;
+        }
+    }
+    return -1;
+}
+
+int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, size_t nseg, long long nblocks,
+                 unsigned long long npairs) {
+    const int ns = ctx->grid.nslab;
+    const uint64_t lim = ctx->grid.needed + 1;
+    // exact counters before the phase
+    int rc = hbt_synchronize(ctx);
+    if (rc) return rc;
+    if (!ctx->snap_u64) {
+        CU(ctx, cudaMalloc(&ctx->snap_u64, ctx->n_u64 * 8));
+        CU(ctx, cudaMalloc(&ctx->snap_f64, ctx->n_f64 * 8));
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->snap_u64, ctx->blob_u64, ctx->n_u64 * 8, cudaMemcpyDeviceToDevice, ctx->compute));
+    CU(ctx, cudaMemcpyAsync(ctx->snap_f64, ctx->blob_f64, ctx->n_f64 * 8, cudaMemcpyDeviceToDevice, ctx->compute));
+    const std::vector<uint64_t> before = in.mixed ? ctx->exact_den : ctx->exact_num;
+    // optimistic pass
+    rc = in.mixed ? launch_mixed(ctx, in.d1, in.d2, d_seg, nseg, nblocks, npairs, in.psi_ref)
+                  : launch_same(ctx, in.d1, in.n1, in.psi_ref);
+    if (rc) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    // deferred pairs of this pass (K_phi edge cases) count too: fold them in before looking
+    rc = resolve_deferred(ctx);
+    if (rc) return rc;
+    rc = refresh_counts(ctx);
+    if (rc) return rc;
+    const std::vector<uint64_t> &after = in.mixed ? ctx->exact_den : ctx->exact_num;
+    std::vector<int32_t> xidx(ns, -1);
+    std::vector<int> crossing;
+    for (int k = 0; k < ns; k++)
+        if (!ctx->closed[k + (in.mixed ? ns : 0)] && after[k] > lim) { xidx[k] = static_cast<int32_t>(crossing.size()); crossing.push_back(k); }
+    if (crossing.empty()) return sync_closed(ctx, in.mixed);
+
+    // ---- roll back and replay in order ----------------------------------------------------
+    CU(ctx, cudaMemcpyAsync(ctx->blob_u64, ctx->snap_u64, ctx->n_u64 * 8, cudaMemcpyDeviceToDevice, ctx->compute));
+    CU(ctx, cudaMemcpyAsync(ctx->blob_f64, ctx->snap_f64, ctx->n_f64 * 8, cudaMemcpyDeviceToDevice, ctx->compute));
+    (in.mixed ? ctx->exact_den : ctx->exact_num) = before;
+    const size_t nx = crossing.size();
+    const int64_t nrows = in.n1;
+    int32_t *d_xidx = nullptr;
+    unsigned *d_rowcnt = nullptr;
+    int64_t *d_cut = nullptr;
+    HbtMixSeg *d_seg1 = nullptr;
+    std::vector<HbtMixSeg> seg1;
+    unsigned long long np1 = npairs;
+    long long nb1 = 0;
+    size_t nseg1 = 0;
+    CU(ctx, cudaMalloc(&d_xidx, ns * sizeof(int32_t)));
+    CU(ctx, cudaMalloc(&d_rowcnt, nx * nrows * sizeof(unsigned)));
+    CU(ctx, cudaMalloc(&d_cut, 2 * ns * sizeof(int64_t)));
+    CU(ctx, cudaMemcpyAsync(d_xidx, xidx.data(), ns * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->compute));
+    CU(ctx, cudaMemsetAsync(d_rowcnt, 0, nx * nrows * sizeof(unsigned), ctx->compute));
+    if (in.mixed) {  // the literal kernels tile differently: rebuild the segments for them
+        seg1.resize(static_cast<size_t>(in.nev1) * in.nmix);
+        nseg1 = build_segments(in.off1, in.nev1, in.off2, in.d2 == in.d1 ? 0 : in.n1, in.ids, in.cs, in.nmix, kTileV1, kTileV1,
+                               seg1.data(), &np1, &nb1);
+        CU(ctx, cudaMalloc(&d_seg1, std::max<size_t>(nseg1, 1) * sizeof(HbtMixSeg)));
+        CU(ctx, cudaMemcpyAsync(d_seg1, seg1.data(), nseg1 * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, ctx->compute));
+    }
+    HbtCap cap{};
+    cap.xidx = d_xidx;
+    cap.rowcnt = d_rowcnt;
+    cap.nrows = nrows;
+    cap.cut_row = d_cut;
+    cap.cut_pos = d_cut + ns;
+    // pass 1: per-row counts of the crossing slabs
+    rc = in.mixed ? launch_mixed(ctx, in.d1, in.d2, d_seg1, nseg1, nb1, np1, in.psi_ref, 1, &cap)
+                  : launch_same(ctx, in.d1, in.n1, in.psi_ref, 1, &cap);
+    if (rc) return rc;
+    std::vector<unsigned> rowcnt(nx * nrows);
+    CU(ctx, cudaMemcpyAsync(rowcnt.data(), d_rowcnt, rowcnt.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->compute));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    {   // pairs the device could not decide (K_phi edge): the host's literal verdict joins the counts
+        unsigned nd = 0;
+        rc = fetch_deferred(ctx, &nd);
+        if (rc) return rc;
+        for (unsigned k = 0; k < nd; k++) {
+            const HbtDeferred &d = ctx->h_deferred[k];
+            HbtCorrection c;
+            uint64_t st[6];
+            if (hbt_host_pair_literal(&ctx->grid, d.a, d.b, d.mixed, d.psi_ref, &c, st) && xidx[c.slab] >= 0 && d.row >= 0)
+                rowcnt[static_cast<size_t>(xidx[c.slab]) * nrows + d.row]++;
+        }
+    }
+    std::vector<int64_t> cut_row(ns, INT64_MAX), cut_pos(ns, INT64_MAX);
+    for (size_t x = 0; x < nx; x++) {
+        const int K = crossing[x];
+        uint64_t quota = lim - before[K];  // >= 1: the slab was open
+        int64_t row = 0;
+        const unsigned *rc_x = rowcnt.data() + x * nrows;
+        while (row < nrows && rc_x[row] < quota) { quota -= rc_x[row]; row++; }
+        if (row >= nrows) return fail(ctx, HBT_ERR_STATE, "ordered cap: quota not reached in the replay (slab %d)", K);
+        const int64_t pos = resolve_row(ctx, in, K, row, quota);
+        if (pos < 0) return fail(ctx, HBT_ERR_STATE, "ordered cap: host and device disagree on row %lld of slab %d", static_cast<long long>(row), K);
+        cut_row[K] = row;
+        cut_pos[K] = pos;
+    }
+    CU(ctx, cudaMemcpyAsync(d_cut, cut_row.data(), ns * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->compute));
+    CU(ctx, cudaMemcpyAsync(d_cut + ns, cut_pos.data(), ns * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->compute));
+    // pass 2: accumulate up to the cuts
+    rc = in.mixed ? launch_mixed(ctx, in.d1, in.d2, d_seg1, nseg1, nb1, np1, in.psi_ref, 2, &cap)
+                  : launch_same(ctx, in.d1, in.n1, in.psi_ref, 2, &cap);
+    if (rc) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    CapFilter f;
+    f.cut_row = &cut_row;
+    f.cut_pos = &cut_pos;
+    rc = resolve_deferred(ctx, &f);
+    if (rc) return rc;
+    rc = refresh_counts(ctx);
+    cudaFree(d_xidx);
+    cudaFree(d_rowcnt);
+    cudaFree(d_cut);
+    if (d_seg1) cudaFree(d_seg1);
+    if (rc) return rc;
+    return sync_closed(ctx, in.mixed);
 }
 
 // the accumulators a reader sees: the all-reduced copies while they are current
@@ -449,6 +722,9 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     CUC(cudaMallocHost(&ctx->h_deferred, sizeof(HbtDeferred) * kDeferredCapacity));
     CUC(cudaMallocHost(&ctx->h_defcount, 8));
     CUC(cudaMalloc(&ctx->d_corr, sizeof(HbtCorrection) * kDeferredCapacity));
+    ctx->closed.assign(2 * ns, 0);
+    CUC(cudaMalloc(&ctx->d_closed, 2 * ns));
+    CUC(cudaMemset(ctx->d_closed, 0, 2 * ns));
     for (Slot &s : ctx->slots) {
         CUC(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -466,6 +742,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
         dv.g = ctx->grid;
         dv.c = ctx->v2c;
         dv.acc = ctx->acc;
+        dv.closed = ctx->d_closed;
         CUC(cudaMalloc(&ctx->d_dv, sizeof(V2Dev)));
         CUC(cudaMemcpy(ctx->d_dv, &dv, sizeof(V2Dev), cudaMemcpyHostToDevice));
     }
@@ -503,6 +780,9 @@ extern "C" void hbt_destroy(hbt_ctx *ctx) {
     if (ctx->h_deferred) cudaFreeHost(ctx->h_deferred);
     if (ctx->h_defcount) cudaFreeHost(ctx->h_defcount);
     if (ctx->d_corr) cudaFree(ctx->d_corr);
+    if (ctx->d_closed) cudaFree(ctx->d_closed);
+    if (ctx->snap_u64) cudaFree(ctx->snap_u64);
+    if (ctx->snap_f64) cudaFree(ctx->snap_f64);
 #ifdef HBT_HAVE_V2
     if (ctx->d_dv) cudaFree(ctx->d_dv);
 #endif
@@ -528,6 +808,12 @@ extern "C" int hbt_reset(hbt_ctx *ctx) {
     ctx->same_launches = ctx->mixed_launches = 0;
     ctx->deferred_total = 0;
     ctx->reduced = false;
+    ctx->exact_num.clear();
+    ctx->exact_den.clear();
+    ctx->pending_num = ctx->pending_den = 0;
+    std::fill(ctx->closed.begin(), ctx->closed.end(), 0);
+    ctx->any_closed = false;
+    CU(ctx, cudaMemset(ctx->d_closed, 0, ctx->closed.size()));
     return HBT_OK;
 }
 
@@ -543,19 +829,15 @@ extern "C" int hbt_synchronize(hbt_ctx *ctx) {
     if (rc) return rc;
     // accepted-pair counters per slab = sum of the slab's bin counts (every accepted pair
     // increments exactly one bin, src/HBT_correlation.cpp:406/437 and :655/682)
-    const long long q3 = static_cast<long long>(ctx->grid.nq) * ctx->grid.nq * ctx->grid.nq;
-    hbt_reduce_slabs<<<2 * ctx->grid.nslab, 256, 0, ctx->compute>>>(ctx->acc, ctx->grid.nslab, q3);
-    hbt_finish_stage<<<1, 32, 0, ctx->compute>>>(ctx->acc, ctx->grid.nslab);
-    ctx->kernel_launches += 2;
-    CU(ctx, cudaGetLastError());
-    CU(ctx, cudaStreamSynchronize(ctx->compute));
-    return HBT_OK;
+    return refresh_counts(ctx);
 }
 
 // ---- device-resident entry points --------------------------------------------------------
 extern "C" int hbt_accumulate_same_dev(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref) {
     if (!ctx || (n > 0 && !d_p) || n < 0) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_same_dev: bad argument");
     CU(ctx, cudaSetDevice(ctx->device));
+    if (cap_may_engage(ctx, false, n > 1 ? static_cast<unsigned long long>(n) * (n - 1) / 2 : 0))
+        return fail(ctx, HBT_ERR_CAP, "needed_number_of_pairs may be reached: use the host-buffer entry points, which replay the cap in order");
     return launch_same(ctx, d_p, n, psi_ref);
 }
 
@@ -578,6 +860,8 @@ extern "C" int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const 
     unsigned long long npairs;
     long long nblocks;
     const size_t nseg = build_segments(off1, nev1, off2, 0, partner_ids, cos_sin, nmix, tile_i(ctx), tile_j(ctx), s->h_seg, &npairs, &nblocks);
+    if (cap_may_engage(ctx, true, npairs))
+        return fail(ctx, HBT_ERR_CAP, "needed_number_of_pairs may be reached: use the host-buffer entry points, which replay the cap in order");
     if (nseg) CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, ctx->compute));
     rc = launch_mixed(ctx, d_p1, d_p2, s->d_seg, nseg, nblocks, npairs, psi_ref);
     if (rc) return rc;
@@ -625,12 +909,29 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
     }
     CU(ctx, cudaEventRecord(s->uploaded, ctx->copy));
     CU(ctx, cudaStreamWaitEvent(ctx->compute, s->uploaded, 0));
+    PhaseInput in;
+    in.h1 = s->h_p;
+    in.h2 = alias ? s->h_p : s->h_p + 8 * n1;
+    in.d1 = s->d_p;
+    in.d2 = s->d_p;  // segments carry the list-2 base offset
+    in.n1 = n1;
+    in.off1 = off1;
+    in.off2 = off2;
+    in.nev1 = nev1;
+    in.nmix = nmix;
+    in.ids = partner_ids;
+    in.cs = cos_sin;
+    in.psi_ref = psi_ref;
     if (do_same) {
-        rc = launch_same(ctx, s->d_p, n1, psi_ref);
+        const unsigned long long sp = n1 > 1 ? static_cast<unsigned long long>(n1) * (n1 - 1) / 2 : 0;
+        in.mixed = false;
+        rc = cap_may_engage(ctx, false, sp) ? capped_phase(ctx, in, nullptr, 0, 0, sp) : launch_same(ctx, s->d_p, n1, psi_ref);
         if (rc) return rc;
     }
     if (do_mixed) {
-        rc = launch_mixed(ctx, s->d_p, s->d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
+        in.mixed = true;
+        rc = cap_may_engage(ctx, true, npairs) ? capped_phase(ctx, in, s->d_seg, nseg, nblocks, npairs)
+                                               : launch_mixed(ctx, s->d_p, s->d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
         if (rc) return rc;
     }
     CU(ctx, cudaEventRecord(s->done, ctx->compute));

@@ -55,8 +55,23 @@ struct HbtDeferred {
     double a[8];
     double b[8];  // partner, already rotated for mixed events
     double psi_ref;
+    int64_t row, pos;  // position of the pair in the reference's loop order (ordered-cap mode)
     int32_t mixed;
     int32_t pad;
+};
+
+// needed_number_of_pairs support (src/HBT_correlation.cpp:402-406, :651-655).  `closed` marks
+// slabs whose counter already exceeds the cap (numerator slabs, then denominator slabs).  The
+// batch in which a slab crosses the cap is replayed in order: pass 1 counts accepted pairs per
+// row (list-1 particle) for the crossing slabs, the host locates the last accepted pair, pass 2
+// accumulates only pairs at or before that position.
+struct HbtCap {
+    const unsigned char *closed;  // [2*nslab] or null
+    const int32_t *xidx;          // pass 1: slab -> index among the crossing slabs, or -1
+    unsigned int *rowcnt;         // pass 1: [n_crossing][nrows]
+    int64_t nrows;
+    const int64_t *cut_row;       // pass 2: [nslab] last accepted row ...
+    const int64_t *cut_pos;       // ... and position inside that row
 };
 
 // one (event, partner) segment of mixed-event work: rows [i0, i0+ni) of list 1 against rows
@@ -67,6 +82,7 @@ struct HbtMixSeg {
     int32_t ni, nj;
     double c, s;
     int64_t block0;
+    int64_t pos0;  // position of the segment's first partner particle inside the row (loop order)
     int32_t tiles_j;
     int32_t pad;
 };

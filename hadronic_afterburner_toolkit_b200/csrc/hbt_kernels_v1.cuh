@@ -32,11 +32,14 @@ __device__ __forceinline__ int find_segment(const HbtMixSeg *__restrict__ segs, 
 
 __device__ __forceinline__ unsigned warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
 
-template <int TILE, bool MIXED>
+// MODE 0: accumulate (closed slabs skipped); MODE 1: ordered-cap pass 1 (count accepted pairs
+// per row for the crossing slabs, nothing else is touched); MODE 2: ordered-cap pass 2
+// (accumulate only up to the per-slab cut position).
+template <int TILE, bool MIXED, int MODE>
 __global__ void __launch_bounds__(TILE)
 hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long long n_same,
              const HbtMixSeg *__restrict__ segs, const HbtGrid g, const HbtAccum acc,
-             const double psi_ref) {
+             const double psi_ref, const HbtCap cap) {
     // same-event: n_same = particles in the merged list; mixed: n_same = number of segments
     constexpr int NC = MIXED ? 4 : 8;
     __shared__ double sj[NC][TILE];
@@ -55,6 +58,7 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
     int ni, nj;
     bool diag = false;
     double rc = 1.0, rs = 0.0;
+    long long pos_base;  // loop-order position of the tile's first list-2 particle inside a row
     if (MIXED) {
         const HbtMixSeg sg = segs[find_segment(segs, static_cast<int>(n_same), blockIdx.x)];
         const int local = static_cast<int>(blockIdx.x - sg.block0);
@@ -64,6 +68,7 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
         ni = min(TILE, sg.ni - ti * TILE);
         nj = min(TILE, sg.nj - tj * TILE);
         rc = sg.c; rs = sg.s;
+        pos_base = sg.pos0 + static_cast<long long>(tj) * TILE;
     } else {
         const long long T = (n_same + TILE - 1) / TILE;
         int ti, tj;
@@ -73,6 +78,7 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
         ni = static_cast<int>(min(static_cast<long long>(TILE), n_same - i0));
         nj = static_cast<int>(min(static_cast<long long>(TILE), n_same - j0));
         diag = (ti == tj);
+        pos_base = j0;
     }
 
     for (int k = t; k < nqi; k += TILE) { s_qsum[k] = 0.0; s_qcos[k] = 0.0; s_qcnt[k] = 0; }
@@ -116,7 +122,7 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
         const int jstart = diag ? t + 1 : 0;  // same-event: j > i only (:301)
         for (int j = jstart; j < nj; j++) {
             const double bx = sj[0][j], by = sj[1][j], bz = sj[2][j], bE = sj[3][j];
-            if (g.qinv) {
+            if (g.qinv && MODE == 0) {
                 // q_inv branch (:339-356 / :595-607); needs the K_T bin, so the cut first
                 const double Kx = __dmul_rn(0.5, __dadd_rn(a[0], bx));
                 const double Ky = __dmul_rn(0.5, __dadd_rn(a[1], by));
@@ -159,8 +165,18 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
                 nB--; nC--; nD--; nE--;
                 double b8[8] = {bx, by, bz, bE, 0., 0., 0., 0.};
                 if (!MIXED) { b8[4] = sj[4][j]; b8[5] = sj[5][j]; b8[6] = sj[6][j]; b8[7] = sj[7][j]; }
-                defer_pair(acc, a, b8, psi_ref, MIXED ? 1 : 0);
+                defer_pair(acc, a, b8, psi_ref, MIXED ? 1 : 0, i0 + t, pos_base + j);
                 continue;
+            }
+            if (cap.closed && cap.closed[pb.slab + (MIXED ? g.nslab : 0)]) continue;  // cap reached earlier
+            if (MODE == 1) {
+                const int x = cap.xidx[pb.slab];
+                if (x >= 0) atomicAdd(&cap.rowcnt[x * cap.nrows + (i0 + t)], 1u);
+                continue;
+            }
+            if (MODE == 2) {
+                const long long row = i0 + t, cr = cap.cut_row[pb.slab];
+                if (row > cr || (row == cr && pos_base + j > cap.cut_pos[pb.slab])) continue;
             }
             const long long bin = bin_index(g, pb);
             if (MIXED) {
@@ -178,6 +194,7 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
     }
     // block-level merge of the counters, then one global atomic per non-zero entry
     // (accepted pairs per slab and in total are derived from the bin counts at synchronize)
+    if (MODE == 1) return;  // pass 1 only counts rows
     nB = warp_sum(nB); nC = warp_sum(nC); nD = warp_sum(nD); nE = warp_sum(nE);
     if ((t & 31) == 0) {
         atomicAdd(&s_stage[1], nB); atomicAdd(&s_stage[2], nC); atomicAdd(&s_stage[3], nD);

@@ -79,6 +79,7 @@ struct V2Dev {
     HbtGrid g;
     V2Const c;
     HbtAccum acc;
+    const unsigned char *closed;  // [2*nslab], always allocated (all zero while no cap was reached)
 };
 
 struct V2Counters {
@@ -121,6 +122,7 @@ __device__ __noinline__ void v2_slow_pair(const V2Dev *__restrict__ dv, const do
     if (st == PAIR_REJ_QL) return;
     n.nE++;
     if (st == PAIR_REJ_PHI) return;
+    if (dv->closed[pb.slab + (MIXED ? g.nslab : 0)]) return;
     const long long bin = bin_index(g, pb);
     if (MIXED) {
         atomicAdd(&acc.den_count[bin], 1ull);
@@ -139,6 +141,7 @@ __device__ __noinline__ void v2_slow_pair(const V2Dev *__restrict__ dv, const do
 // (component stride TI / TJ doubles).
 template <bool MIXED, int NC>
 __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
+                                              const unsigned char *__restrict__ closed,
                                               const V2Dev *__restrict__ dv, const double *__restrict__ si,
                                               const double *__restrict__ sj, int il, int jl, double psi_ref,
                                               V2Counters &n) {
@@ -224,6 +227,7 @@ __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c
     if (stage >= 3) n.nD++;
     if (stage >= 4) n.nE++;
     if (stage != 4) return;
+    if (closed && closed[slab + (MIXED ? g.nslab : 0)]) return;  // needed_number_of_pairs reached earlier
     const long long bin = ((static_cast<long long>(slab) * g.nq + io) * g.nq + is) * g.nq + il_;
     if (MIXED) {
         atomicAdd(&acc.den_count[bin], 1ull);
@@ -267,7 +271,7 @@ __device__ __noinline__ void v2_drain_pair_cold(const V2Dev *__restrict__ dv, co
                                                 const double *__restrict__ sj, int il, int jl, double psi_ref,
                                                 V2Counters &n) {
     V2Counters tmp = {0, 0, 0, 0};
-    v2_drain_pair<MIXED, NC>(dv->g, dv->c, dv->acc, dv, si, sj, il, jl, psi_ref, tmp);
+    v2_drain_pair<MIXED, NC>(dv->g, dv->c, dv->acc, dv->closed, dv, si, sj, il, jl, psi_ref, tmp);
     n.nB += tmp.nB; n.nC += tmp.nC; n.nD += tmp.nD; n.nE += tmp.nE;
 }
 
@@ -275,7 +279,7 @@ __device__ __noinline__ void v2_drain_pair_cold(const V2Dev *__restrict__ dv, co
 // survivors at a time; FINAL also processes the last partial batch.
 template <bool MIXED, bool FINAL>
 __device__ __forceinline__ void v2_flush(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
-                                         const V2Dev *__restrict__ dv, const double *__restrict__ si,
+                                         const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv, const double *__restrict__ si,
                                          const double *__restrict__ sj, int lane, double psi_ref, V2Queue &Q,
                                          V2Counters &n) {
     constexpr int NC = MIXED ? 4 : 8;
@@ -304,7 +308,7 @@ __device__ __forceinline__ void v2_flush(const HbtGrid &g, const V2Const &c, con
                 v2_drain_pair_cold<MIXED, NC>(dv, si, sj, il, jl, psi_ref, tmp);
                 n.nB += tmp.nB; n.nC += tmp.nC; n.nD += tmp.nD; n.nE += tmp.nE;
             } else {
-                v2_drain_pair<MIXED, NC>(g, c, acc, dv, si, sj, il, jl, psi_ref, n);
+                v2_drain_pair<MIXED, NC>(g, c, acc, closed, dv, si, sj, il, jl, psi_ref, n);
             }
         }
         Q.qcount = base;
@@ -318,7 +322,7 @@ __device__ __forceinline__ void v2_flush(const HbtGrid &g, const V2Const &c, con
 // the window prefilter.
 template <bool MIXED, bool DIAG, bool FLOOR>
 __device__ __forceinline__ void v2_tile_loop(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
-                                             const V2Dev *__restrict__ dv, const double *__restrict__ si,
+                                             const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv, const double *__restrict__ si,
                                              const double *__restrict__ sj, const double *__restrict__ sjt, int nj,
                                              long long i0, long long j0, int lane, int warp, double k2_floor,
                                              double psi_ref, V2Queue &Q, V2Counters &n, unsigned &cntKT,
@@ -369,9 +373,9 @@ __device__ __forceinline__ void v2_tile_loop(const HbtGrid &g, const V2Const &c,
                 Q.cur += 128u;
             }
         }
-        if (__any_sync(0xffffffffu, Q.cur > lim)) v2_flush<MIXED, false>(g, c, acc, dv, si, sj, lane, psi_ref, Q, n);
+        if (__any_sync(0xffffffffu, Q.cur > lim)) v2_flush<MIXED, false>(g, c, acc, closed, dv, si, sj, lane, psi_ref, Q, n);
     }
-    v2_flush<MIXED, true>(g, c, acc, dv, si, sj, lane, psi_ref, Q, n);
+    v2_flush<MIXED, true>(g, c, acc, closed, dv, si, sj, lane, psi_ref, Q, n);
 }
 
 template <bool MIXED>
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(32 * HBT_V2_WARPS, 4)
 hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long long n_same,
              const HbtMixSeg *__restrict__ segs, const HbtGrid g, const V2Const c,
              const V2Dev *__restrict__ dv, const HbtAccum acc, const double psi_ref,
-             const unsigned long long total_pairs) {
+             const unsigned long long total_pairs, const unsigned char *__restrict__ closed) {
     constexpr int NC = MIXED ? 4 : 8;
     constexpr int TI = HBT_V2_TILE_I, TJ = HBT_V2_TILE_J, NT = 32 * HBT_V2_WARPS;
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -488,11 +492,11 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
     V2Counters n = {0, 0, 0, 0};
     unsigned cntKT = 0, cntRS = 0;
     if (use_floor) {
-        if (diag) v2_tile_loop<MIXED, true, true>(g, c, acc, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
-        else v2_tile_loop<MIXED, false, true>(g, c, acc, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+        if (diag) v2_tile_loop<MIXED, true, true>(g, c, acc, closed, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+        else v2_tile_loop<MIXED, false, true>(g, c, acc, closed, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
     } else {
-        if (diag) v2_tile_loop<MIXED, true, false>(g, c, acc, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
-        else v2_tile_loop<MIXED, false, false>(g, c, acc, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+        if (diag) v2_tile_loop<MIXED, true, false>(g, c, acc, closed, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+        else v2_tile_loop<MIXED, false, false>(g, c, acc, closed, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
     }
 
     // ---- merge counters: pairs dropped by the prefilter passed K_T (cntKT) minus those queued;
@@ -526,20 +530,21 @@ inline int hbt_v2_configure() {
 }
 
 inline int hbt_v2_launch_same(cudaStream_t st, const double *d_p, long long n, const HbtGrid &g, const V2Const &c, const V2Dev *d_dv,
-                              const HbtAccum &acc, double psi_ref, unsigned long long npairs) {
+                              const HbtAccum &acc, double psi_ref, unsigned long long npairs,
+                              const unsigned char *closed) {
     const long long T = (n + HBT_V2_TILE_I - 1) / HBT_V2_TILE_I;
     const long long blocks = T * (T + 1) / 2 * HBT_V2_SUB;
     if (blocks > 0x7fffffffLL) return HBT_ERR_INVALID;
     hbt_pairs_v2<false><<<static_cast<unsigned>(blocks), 32 * HBT_V2_WARPS, hbt_v2_smem_bytes(false), st>>>(
-        d_p, d_p, n, nullptr, g, c, d_dv, acc, psi_ref, npairs);
+        d_p, d_p, n, nullptr, g, c, d_dv, acc, psi_ref, npairs, closed);
     return HBT_OK;
 }
 
 inline int hbt_v2_launch_mixed(cudaStream_t st, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg,
                                size_t nseg, long long nblocks, const HbtGrid &g, const V2Const &c, const V2Dev *d_dv, const HbtAccum &acc,
-                               double psi_ref, unsigned long long npairs) {
+                               double psi_ref, unsigned long long npairs, const unsigned char *closed) {
     hbt_pairs_v2<true><<<static_cast<unsigned>(nblocks), 32 * HBT_V2_WARPS, hbt_v2_smem_bytes(true), st>>>(
-        d_p1, d_p2, static_cast<long long>(nseg), d_seg, g, c, d_dv, acc, psi_ref, npairs);
+        d_p1, d_p2, static_cast<long long>(nseg), d_seg, g, c, d_dv, acc, psi_ref, npairs, closed);
     return HBT_OK;
 }
 

@@ -108,7 +108,7 @@ __device__ __forceinline__ long long bin_index(const HbtGrid &g, const PairBin &
 }
 
 __device__ __forceinline__ void defer_pair(const HbtAccum &acc, const double *a, const double *b,
-                                           double psi_ref, int mixed) {
+                                           double psi_ref, int mixed, long long row = -1, long long pos = -1) {
     const unsigned slot = atomicAdd(&acc.deferred_count[0], 1u);
     if (slot >= acc.deferred_capacity) {
         acc.deferred_count[1] = 1u;  // overflow: reported as HBT_ERR_OVERFLOW at sync
@@ -121,6 +121,8 @@ __device__ __forceinline__ void defer_pair(const HbtAccum &acc, const double *a,
         d.b[k] = b[k];
     }
     d.psi_ref = psi_ref;
+    d.row = row;
+    d.pos = pos;
     d.mixed = mixed;
     d.pad = 0;
 }

@@ -55,6 +55,7 @@ CASES = {
     "c3_shape": (C3.with_(qnpts=15), 3, 5, 300),
     "c4_shape_az": (C4.with_(qnpts=9, n_KT=4, n_Kphi=4), 2, 4, 300),
     "qinv": (HBTParams(qnpts=21, invariant_radius_flag=1), 2, 4, 200),
+    "cap_reached": (C3.with_(qnpts=15, needed_number_of_pairs=2500.0), 4, 4, 300),
 }
 
 

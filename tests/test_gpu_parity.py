@@ -17,7 +17,6 @@ from oracle import oracle_py as O
 pytestmark = pytest.mark.gpu
 RTOL = 1e-10
 
-CAP_CASES = {"unit_iss_gz_cap", "synth_c3_cap"}
 
 
 def run_product(P, batches, do_mixed=True):
@@ -35,8 +34,11 @@ def run_oracle(P, batches, do_mixed=True):
     return o.accumulators()
 
 
-@pytest.mark.parametrize("name", [n for n in GOLDEN_NAMES if n not in CAP_CASES])
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
 def test_golden_reference_vectors(name):
+    """Includes the cases in which needed_number_of_pairs is reached (unit_iss_gz_cap,
+    synth_c3_cap): the ordered cap must reproduce the reference's first-come-first-served
+    acceptance exactly."""
     P, batches, ref, meta = load_golden(name)
     h, acc = run_product(P, batches)
     hbtio.compare(ref, acc, rtol=RTOL)
@@ -44,17 +46,37 @@ def test_golden_reference_vectors(name):
     assert h.pairs_same == meta["pairs_same"] == int(acc.stage[0])
 
 
-@pytest.mark.parametrize("name", sorted(CAP_CASES))
-def test_cap_reached_is_reported_not_silently_wrong(name):
-    """needed_number_of_pairs engaged: the order-dependent cap is not on the device path yet;
-    the library must refuse rather than return uncapped histograms."""
-    P, batches, ref, meta = load_golden(name)
+CAPPED = {
+    # needed_number_of_pairs small enough to close slabs at different batches / phases
+    "cap_az0": (HBTParams(qnpts=21, needed_number_of_pairs=4000.0), 4, 4, 400),
+    "cap_az0_tiny": (HBTParams(qnpts=11, needed_number_of_pairs=7.0), 3, 3, 150),
+    "cap_zero": (HBTParams(qnpts=11, needed_number_of_pairs=0.0), 2, 3, 150),
+    "cap_az1": (C4.with_(qnpts=11, n_KT=4, n_Kphi=4, needed_number_of_pairs=900.0), 3, 4, 400),
+    "cap_first_batch_only": (HBTParams(qnpts=21, needed_number_of_pairs=50000.0), 3, 4, 500),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CAPPED))
+def test_ordered_cap_against_oracle(name):
+    P, ngrp, nev, mult = CAPPED[name]
+    batches = synth.make_batches(20260007, ngrp, nev, multiplicity=mult)
+    ref = run_oracle(P, batches)
+    h, acc = run_product(P, batches)
+    hbtio.compare(ref, acc, rtol=RTOL, check_stage=True)
+    lim = int(P.needed_number_of_pairs) + 1
+    assert int(acc.npairs_num.max()) <= lim and int(acc.npairs_den.max()) <= lim
+    if name != "cap_first_batch_only":
+        assert int(acc.npairs_num.max()) == lim  # the cap really engaged
+
+
+def test_device_resident_entry_points_refuse_near_the_cap():
+    import ctypes
+
+    P = HBTParams(qnpts=11, needed_number_of_pairs=10.0)
     h = HBT_correlation(P)
-    for b in batches:
-        h.calculate_HBT_correlation_function(b)
-    with pytest.raises(capi.HBTError) as e:
-        h.accumulators()
-    assert e.value.code == -4
+    x = np.zeros((64, 8))
+    rc = h._L.hbt_accumulate_same_dev(h._h, ctypes.c_void_p(1), 64, 0.0)
+    assert rc == -4  # HBT_ERR_CAP: only the host-buffer calls replay the cap in order
 
 
 SEEDED = {
