@@ -79,7 +79,16 @@ HBT_correlation::HBT_correlation(ParameterReader &paraRdr, std::string path,
     p.HBTrap_max = Krap_max_;
     p.needed_number_of_pairs = paraRdr_.getVal("needed_number_of_pairs");
 
-    const int ndev = device_count_from_env();
+    int ndev = device_count_from_env();
+    if (ndev > 1 && p.needed_number_of_pairs < 1e14) {
+        // the pair cap is cumulative over the batches IN ORDER (src/HBT_correlation.cpp:402-406):
+        // groups spread over several GPUs could not reproduce it, so a run whose cap can
+        // engage stays on one device
+        messager << "needed_number_of_pairs = " << p.needed_number_of_pairs
+                 << " can be reached: the ordered pair cap needs the batches in sequence, using 1 GPU";
+        messager.flush("warning");
+        ndev = 1;
+    }
     for (int d = 0; d < ndev; d++) {
         hbt_ctx *c = nullptr;
         const int rc = hbt_create(&p, d, &c);
