@@ -169,8 +169,9 @@ class Oracle:
 
 
 def run_reference(params: HBTParams, batches: List[Batch], same_only: bool = False,
-                  workdir: Optional[str] = None, quiet: bool = True) -> Accumulators:
-    """Push in-memory batches through the unmodified reference (oracle/_ref/ref_driver mem)."""
+                  workdir: Optional[str] = None, quiet: bool = True, only=None) -> Accumulators:
+    """Push in-memory batches through the unmodified reference (oracle/_ref/ref_driver mem).
+    ``only``: indices of the batches to process (the others only advance the RNG stream)."""
     assert have_reference(), "oracle/_ref/ref_driver missing: run `make -C oracle ref` where /root/reference exists"
     with tempfile.TemporaryDirectory(dir=workdir) as td:
         fin, fpar, fout = (os.path.join(td, n) for n in ("batches.bin", "parameters.dat", "out.bin"))
@@ -178,6 +179,8 @@ def run_reference(params: HBTParams, batches: List[Batch], same_only: bool = Fal
         with open(fpar, "w") as f:
             f.write(params.parameters_dat())
         cmd = [REF_DRIVER, "mem", fpar, fin, fout] + (["same_only"] if same_only else [])
+        if only is not None:
+            cmd.append("only=" + ",".join(str(int(i)) for i in only))
         r = subprocess.run(cmd, stdout=subprocess.DEVNULL if quiet else None, stderr=subprocess.PIPE)
         if r.returncode != 0:
             raise RuntimeError(f"ref_driver failed ({r.returncode}): {r.stderr.decode()[-400:]}")

@@ -8,7 +8,10 @@
 // `#define private public`; nothing of the reference is copied into this file.
 //
 // Modes
-//   ref_driver mem   <params.dat> <batches.bin> <out.bin> [same_only]
+//   ref_driver mem   <params.dat> <batches.bin> <out.bin> [same_only | only=i,j,k]
+//       (only=...: process just those batches; the draws of the others are replayed from the
+//        shared Random object in the reference's order, so a process that owns a subset of the
+//        groups sees exactly the stream positions of the single-process run)
 //       batches.bin (format HBTIN001, see tests/hbtio.py) is loaded into a
 //       particleSamples object in memory (particle_list / particle_list_mixed_event,
 //       src/particleSamples.h:82,90) and every batch is pushed through
@@ -28,6 +31,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -231,7 +235,23 @@ int main(int argc, char **argv) {
         if (!realpath(o.c_str(), abs_out)) die("output path");
     }
     bool same_only = false;
-    if (mode == "mem" && argc >= 6 && std::string(argv[5]) == "same_only") same_only = true;
+    std::vector<int> only;
+    bool use_only = false;
+    for (int ia = 5; mode == "mem" && ia < argc; ia++) {
+        const std::string arg(argv[ia]);
+        if (arg == "same_only") same_only = true;
+        if (arg.rfind("only=", 0) == 0) {
+            use_only = true;
+            const std::string lst = arg.substr(5);
+            size_t pos = 0;
+            while (pos < lst.size()) {
+                size_t c = lst.find(',', pos);
+                if (c == std::string::npos) c = lst.size();
+                if (c > pos) only.push_back(atoi(lst.substr(pos, c - pos).c_str()));
+                pos = c + 1;
+            }
+        }
+    }
     if (mode == "files") {
         if (argc < 6) die("files mode needs particles_out");
         FILE *t = fopen(argv[5], "wb");
@@ -276,7 +296,24 @@ int main(int argc, char **argv) {
         double mass = paraRdr.getVal("particle_mass", 0.13957);
         int monval = paraRdr.getVal("particle_monval");
         evlist_t *own_mixed = plist->particle_list_mixed_event;
+        int ibatch = -1;
         for (auto &b : batches) {
+            ibatch++;
+            if (use_only && std::find(only.begin(), only.end(), ibatch) == only.end()) {
+                // replay this batch's draws (src/HBT_correlation.cpp:200-215 and :495), no pair work
+                const int nev = b.same.size();
+                const int mixed_nev = b.mixed.empty() ? nev : static_cast<int>(b.mixed.size());
+                const int nmix = mixed_nev / 2 + 1;
+                for (int iev = 0; iev < nev && mixed_nev > 0 && !same_only; iev++) {
+                    for (int c = 0; c < nmix; c++) {
+                        int id = ran->rand_int_uniform() % mixed_nev;
+                        while (iev == id && mixed_nev != 1) id = ran->rand_int_uniform() % mixed_nev;
+                    }
+                    for (int c = 0; c < nmix; c++) ran->rand_uniform();
+                }
+                psi.push_back(0.0);
+                continue;
+            }
             fill(plist->particle_list, b.same, mass, monval);
             if (b.mixed.empty()) {
                 // same aliasing as src/particleSamples.cpp:528-530
