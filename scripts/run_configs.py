@@ -167,7 +167,7 @@ def main():
             tgen += time.perf_counter() - tg
             h.calculate_HBT_correlation_function(b)
         h.synchronize()
-        wall = time.perf_counter() - t0 - tgen
+        wall = time.perf_counter() - t0  # includes the host-side generation, which overlaps the GPU work
         tm = h.timers()
         res = {"pairs_same": h.pairs_same, "pairs_mixed": h.pairs_mixed, "wall_s": wall, "same_ms": tm["same_ms"],
                "mixed_ms": tm["mixed_ms"], "deferred": h.deferred_pairs()}
@@ -181,7 +181,7 @@ def main():
         ref, rwall, rcpu, nproc = collect_reference(c5_handle)
         o = report("C5", f"{a.c5_groups} groups of 100 ev x 1500 pi+ (oversampling 100), 41^3, 4 K_T bins, same+mixed; "
                    "parity on group 0 at full size (2.27e10 pairs) vs the reference", res, ref, acc0, rwall, rcpu, nproc,
-                   res0["pairs_same"] + res0["pairs_mixed"], note=f"host-side synthetic generation ({tgen:.1f} s) excluded from wall_s")
+                   res0["pairs_same"] + res0["pairs_mixed"], note=f"wall_s includes {tgen:.1f} s of host-side synthetic generation (overlapped with the GPU work)")
         rows.append(o)
 
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
