@@ -299,6 +299,15 @@ def main():
         _check(h, L.hbt_get_launch_count(h, ctypes.byref(c)))
         return c.value
 
+    # ---- stage populations of one step (for the algorithmic-ops formula): an instrumented,
+    # UNTIMED pass over the same input; the timed production kernels skip tile pairs whose
+    # bounding boxes cannot hold an accepted pair and therefore do not see every pair
+    _check(h, L.hbt_set_option(h, 1, 1))
+    s0 = eng.stage_counters()
+    step_resident()
+    st_step = ((eng.stage_counters() - s0) // np.uint64(world)).astype(np.uint64) if world > 1 else eng.stage_counters() - s0
+    _check(h, L.hbt_set_option(h, 1, 0))
+
     # ---- resident-input measurement (value) ---------------------------------------------
     timed(step_resident, a.warmup, True)
     st0 = eng.stage_counters()
@@ -324,9 +333,9 @@ def main():
     # ---- roofline of the pair kernels (rank 0's device) -------------------------------------
     peak = ctypes.c_double()
     _check(None, L.hbt_measure_fp64_peak(local, 300.0, ctypes.byref(peak)))
-    # after an all-reduce the library returns the GLOBAL stage counters; every rank does the
-    # same amount of work here, so this rank's share is 1/world of the difference
-    dst = ((st1 - st0) // np.uint64(world)).astype(np.uint64)
+    # stage populations of this rank over the timed steps = steps x (one instrumented step)
+    dst = (st_step * np.uint64(a.steps)).astype(np.uint64)
+    assert int(dst[0]) * world == int(st1[0] - st0[0]) or world > 1  # same pair count in both passes
     ops_same, ops_mixed = algorithmic_ops(dst, boost=P.long_comoving_boost == 1, az=P.azimuthal_flag == 1)
     ks = (tm1["same_ms"] - tm0["same_ms"]) * 1e-3
     km = (tm1["mixed_ms"] - tm0["mixed_ms"]) * 1e-3

@@ -13,7 +13,8 @@ import subprocess
 from .params import CParams
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhbt_b200.so")
+# HBT_B200_LIB: load another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("HBT_B200_LIB") or os.path.join(HERE, "libhbt_b200.so")
 
 # every symbol include/hbt_b200.h declares
 EXPORTS = (
@@ -24,7 +25,7 @@ EXPORTS = (
     "hbt_read", "hbt_read_qinv", "hbt_get_stage_counters", "hbt_get_timers", "hbt_get_deferred_pairs",
     "hbt_get_launch_count", "hbt_measure_fp64_peak", "hbt_timer_start", "hbt_timer_stop",
     "hbt_comm_unique_id", "hbt_comm_init_rank", "hbt_comm_init_all", "hbt_allreduce", "hbt_allreduce_all",
-    "hbt_version", "hbt_device_count",
+    "hbt_version", "hbt_device_count", "hbt_set_option",
 )
 
 HBT_OK = 0
@@ -96,6 +97,7 @@ def lib() -> ctypes.CDLL:
         "hbt_allreduce_all": (ctypes.c_int, [vp, i32]),
         "hbt_version": (ctypes.c_char_p, []),
         "hbt_device_count": (i32, []),
+        "hbt_set_option": (ctypes.c_int, [vp, i32, i32]),
     }
     for name in EXPORTS:
         f = getattr(L, name)  # AttributeError if the library lacks a declared symbol

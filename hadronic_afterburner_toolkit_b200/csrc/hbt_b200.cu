@@ -128,6 +128,13 @@ struct hbt_ctx {
     std::vector<unsigned char> closed;           // [2*nslab] slabs whose counter exceeds the cap
     unsigned char *d_closed = nullptr;
     bool any_closed = false;
+    // production mode of the v2 same-event kernel: Morton-sorted copy of the list + tile boxes
+    bool stats = false;                          // exact stage populations B, C, D (no culling)
+    unsigned *sort_keys[2] = {nullptr, nullptr}, *sort_idx[2] = {nullptr, nullptr}, *sort_rmax = nullptr;
+    double *sort_p = nullptr;
+    HbtBBox *sort_bbox = nullptr;
+    void *sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0, sort_cap = 0;
     unsigned long long *snap_u64 = nullptr;      // rollback copies of the accumulators
     double *snap_f64 = nullptr;
     std::string err;
@@ -222,6 +229,44 @@ size_t dyn_smem_bytes(const HbtGrid &g) {
 }
 
 // ---- launches ------------------------------------------------------------------------
+#ifdef HBT_HAVE_V2
+// Morton-sort the same-event list on the compute stream (keys, radix sort of (key, index),
+// gather, tile boxes): ~4 small kernels, microseconds against the pair kernel's milliseconds
+int prepare_sorted(hbt_ctx *ctx, const double *d_p, int64_t n) {
+    if (static_cast<size_t>(n) > ctx->sort_cap) {
+        for (int k = 0; k < 2; k++) { cudaFree(ctx->sort_keys[k]); cudaFree(ctx->sort_idx[k]); }
+        cudaFree(ctx->sort_p); cudaFree(ctx->sort_bbox); cudaFree(ctx->sort_tmp);
+        const size_t cap = static_cast<size_t>(n) + static_cast<size_t>(n) / 4 + 1024;
+        for (int k = 0; k < 2; k++) {
+            CU(ctx, cudaMalloc(&ctx->sort_keys[k], cap * 4));
+            CU(ctx, cudaMalloc(&ctx->sort_idx[k], cap * 4));
+        }
+        CU(ctx, cudaMalloc(&ctx->sort_p, cap * 64));
+        CU(ctx, cudaMalloc(&ctx->sort_bbox, (cap / HBT_BBOX_TILE + 2) * sizeof(HbtBBox)));
+        if (!ctx->sort_rmax) CU(ctx, cudaMalloc(&ctx->sort_rmax, 4));
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_idx[0], ctx->sort_idx[1],
+                                        static_cast<int>(cap), 0, 32, ctx->compute);
+        CU(ctx, cudaMalloc(&ctx->sort_tmp, bytes));
+        ctx->sort_tmp_bytes = bytes;
+        ctx->sort_cap = cap;
+    }
+    const int th = 256;
+    const unsigned nb = static_cast<unsigned>((n + th - 1) / th);
+    CU(ctx, cudaMemsetAsync(ctx->sort_rmax, 0, 4, ctx->compute));
+    hbt_sort_range<<<std::min(nb, 1184u), th, 0, ctx->compute>>>(d_p, n, ctx->sort_rmax);
+    hbt_sort_keys<<<nb, th, 0, ctx->compute>>>(d_p, n, ctx->sort_rmax, ctx->sort_keys[0], ctx->sort_idx[0]);
+    size_t bytes = ctx->sort_tmp_bytes;
+    CU(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, bytes, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_idx[0],
+                                            ctx->sort_idx[1], static_cast<int>(n), 0, 32, ctx->compute));
+    hbt_sort_gather<<<static_cast<unsigned>((4 * n + th - 1) / th), th, 0, ctx->compute>>>(d_p, ctx->sort_idx[1], n, ctx->sort_p);
+    hbt_sort_bbox<<<static_cast<unsigned>((n + HBT_BBOX_TILE - 1) / HBT_BBOX_TILE), HBT_BBOX_TILE, 0, ctx->compute>>>(ctx->sort_p, n, ctx->sort_bbox);
+    ctx->kernel_launches += 5;  // range, keys, gather, boxes + the radix sort (counted once)
+    CU(ctx, cudaGetLastError());
+    return HBT_OK;
+}
+#endif
+
 const unsigned char *closed_ptr(const hbt_ctx *ctx) { return ctx->any_closed ? ctx->d_closed : nullptr; }
 
 // mode 0: the production kernels (v2 unless the grid needs v1); mode 1 / 2: the two ordered-cap
@@ -253,7 +298,15 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
         ctx->kernel_launches++;
     } else {
 #ifdef HBT_HAVE_V2
-        rc = hbt_v2_launch_same(ctx->compute, d_p, n, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed);
+        if (ctx->stats) {
+            rc = hbt_v2_launch_same(ctx->compute, d_p, n, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed,
+                                    true, nullptr, nullptr);
+        } else {
+            rc = prepare_sorted(ctx, d_p, n);
+            if (rc) return rc;
+            rc = hbt_v2_launch_same(ctx->compute, ctx->sort_p, n, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed,
+                                    false, ctx->sort_idx[1], ctx->sort_bbox);
+        }
         ctx->kernel_launches++;
         if (rc) return fail(ctx, rc, "v2 same-event launch failed");
 #endif
@@ -326,7 +379,8 @@ int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const Hbt
         ctx->kernel_launches++;
     } else {
 #ifdef HBT_HAVE_V2
-        rc = hbt_v2_launch_mixed(ctx->compute, d_p1, d_p2, d_seg, nseg, nblocks, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed);
+        rc = hbt_v2_launch_mixed(ctx->compute, d_p1, d_p2, d_seg, nseg, nblocks, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs,
+                                 cap.closed, ctx->stats);
         ctx->kernel_launches++;
         if (rc) return fail(ctx, rc, "v2 mixed-event launch failed");
 #endif
@@ -670,6 +724,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
         return fail(nullptr, rc, "%s", msg);
     }
     if (const char *v = getenv("HBT_B200_KERNEL")) ctx->kernel_version = atoi(v) == 1 ? 1 : 2;
+    if (const char *v = getenv("HBT_B200_STATS")) ctx->stats = atoi(v) != 0;
 #define CUC(call)                                                                              \
     do {                                                                                       \
         cudaError_t e_ = (call);                                                               \
@@ -781,6 +836,11 @@ extern "C" void hbt_destroy(hbt_ctx *ctx) {
     if (ctx->h_defcount) cudaFreeHost(ctx->h_defcount);
     if (ctx->d_corr) cudaFree(ctx->d_corr);
     if (ctx->d_closed) cudaFree(ctx->d_closed);
+    for (int k = 0; k < 2; k++) { if (ctx->sort_keys[k]) cudaFree(ctx->sort_keys[k]); if (ctx->sort_idx[k]) cudaFree(ctx->sort_idx[k]); }
+    if (ctx->sort_p) cudaFree(ctx->sort_p);
+    if (ctx->sort_bbox) cudaFree(ctx->sort_bbox);
+    if (ctx->sort_tmp) cudaFree(ctx->sort_tmp);
+    if (ctx->sort_rmax) cudaFree(ctx->sort_rmax);
     if (ctx->snap_u64) cudaFree(ctx->snap_u64);
     if (ctx->snap_f64) cudaFree(ctx->snap_f64);
 #ifdef HBT_HAVE_V2
@@ -1040,6 +1100,25 @@ extern "C" int hbt_timer_stop(hbt_ctx *ctx, double *ms) {
     CU(ctx, cudaEventElapsedTime(&t, ctx->sw0, ctx->sw1));
     *ms = t;
     return HBT_OK;
+}
+
+extern "C" int hbt_set_option(hbt_ctx *ctx, int32_t option, int32_t value) {
+    if (!ctx) return HBT_ERR_INVALID;
+    int rc = hbt_synchronize(ctx);
+    if (rc) return rc;
+    switch (option) {
+        case HBT_OPT_STAGE_COUNTERS:
+            ctx->stats = value != 0;
+            return HBT_OK;
+        case HBT_OPT_KERNEL:
+            if (value != 1 && value != 2) return fail(ctx, HBT_ERR_INVALID, "kernel version must be 1 or 2");
+#ifdef HBT_HAVE_V2
+            ctx->kernel_version = (value == 2 && hbt_v2_supported(ctx->grid)) ? 2 : 1;
+#endif
+            return HBT_OK;
+        default:
+            return fail(ctx, HBT_ERR_INVALID, "unknown option %d", option);
+    }
 }
 
 extern "C" int hbt_get_launch_count(hbt_ctx *ctx, uint64_t *n) {

@@ -30,6 +30,7 @@
 #define HBT_KERNELS_V2_CUH_
 
 #include "hbt_kernels_v1.cuh"
+#include "hbt_sort.cuh"
 
 #define HBT_V2_WARPS 4
 #define HBT_V2_IPL 4  // list-1 particles per lane
@@ -139,13 +140,18 @@ __device__ __noinline__ void v2_slow_pair(const V2Dev *__restrict__ dv, const do
 
 // one queued survivor through the guarded fast path.  si/sj are the SoA tiles in shared memory
 // (component stride TI / TJ doubles).
-template <bool MIXED, int NC>
+// ORIENT (same-event list sorted in momentum space): si_o / sj_o hold the particles' positions
+// in the reference's gather order; the pair is (earlier, later) in THAT order, so when the
+// tile order disagrees the roles are swapped, i.e. q -> -q (K, k2, |q| and cos(q.dx) are even).
+template <bool MIXED, int NC, bool ORIENT>
 __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
                                               const unsigned char *__restrict__ closed,
                                               const V2Dev *__restrict__ dv, const double *__restrict__ si,
-                                              const double *__restrict__ sj, int il, int jl, double psi_ref,
+                                              const double *__restrict__ sj, const unsigned *__restrict__ si_o,
+                                              const unsigned *__restrict__ sj_o, int il, int jl, double psi_ref,
                                               V2Counters &n) {
     constexpr int TI = HBT_V2_TILE_I, TJ = HBT_V2_TILE_J;
+    const bool flip = ORIENT && (si_o[il] > sj_o[jl]);
     const double ax = si[il], ay = si[TI + il], bx = sj[jl], by = sj[TJ + jl];
     const double sx = __dadd_rn(ax, bx), sy = __dadd_rn(ay, by);
     const double k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
@@ -155,7 +161,8 @@ __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c
     const double d = fma(qx, sx, qy * sy);     // 2 K_perp q_out
     const double e = fma(qy, sx, -(qx * sy));  // 2 K_perp q_side
     const double r = rsqrt(k2);                // 1 / (2 K_perp)
-    const double qo = d * r, qs = e * r;
+    double qo = d * r, qs = e * r;
+    if (flip) { qo = -qo; qs = -qs; }
     // |fast - reference| <= ~8 ulp of (|qx|+|qy|); guard = 2^-46 relative + 2^-44 |window|,
     // in bin units and never below gb_min
     const double gt = fmax(c.gb_min, fma(fabs(qx) + fabs(qy), 1.5e-14, c.g_abs) * c.inv_dq);
@@ -180,6 +187,7 @@ __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c
                 const double r2 = rsqrt(m2);
                 const double t1 = sE * qz, t2 = sz * qE;
                 ql = (t1 - t2) * r2;
+                if (flip) ql = -ql;
                 const double ch = sE * r2;  // cosh of the pair rapidity: error amplification
                 const double gl = fmax(c.gb_min, fma((fabs(t1) + fabs(t2)) * r2 * fma(2.0 * ch, ch, 1.0), 2.9e-14, c.g_abs) * c.inv_dq);
                 const int cl = (m2 > 0.0) ? classify_q(g, c, ql, gl, il_) : Q_UNSURE;
@@ -187,7 +195,7 @@ __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c
                 if (cl == Q_OK) stage = 4;
             } else {
                 // q_long = q_z exactly as the reference has it: use its own comparisons
-                ql = qz;
+                ql = flip ? -qz : qz;
                 if (in_window(ql, g.q_lo, g.q_hi, MIXED)) {
                     il_ = __double2int_rz(__ddiv_rn(__dsub_rn(ql, g.q_base), g.dq));
                     if (il_ < g.nq) stage = 4;
@@ -214,8 +222,10 @@ __device__ __forceinline__ void v2_drain_pair(const HbtGrid &g, const V2Const &c
         double a8[8], b8[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            a8[k] = k < NC ? si[(k < NC ? k : 0) * TI + il] : 0.0;
-            b8[k] = k < NC ? sj[(k < NC ? k : 0) * TJ + jl] : 0.0;
+            const double va = k < NC ? si[(k < NC ? k : 0) * TI + il] : 0.0;
+            const double vb = k < NC ? sj[(k < NC ? k : 0) * TJ + jl] : 0.0;
+            a8[k] = flip ? vb : va;
+            b8[k] = flip ? va : vb;
         }
         V2Counters tmp = {0, 0, 0, 0};  // keeps n itself out of local memory
         v2_slow_pair<MIXED>(dv, a8, b8, psi_ref, tmp);
@@ -266,21 +276,23 @@ __device__ __forceinline__ void inc_if(unsigned &cnt, bool flag) {
 
 // non-inlined twin of v2_drain_pair for the once-per-tile final flush (keeps one inlined copy
 // of the drain per kernel variant); reads its constants from the global-memory copy
-template <bool MIXED, int NC>
+template <bool MIXED, int NC, bool ORIENT>
 __device__ __noinline__ void v2_drain_pair_cold(const V2Dev *__restrict__ dv, const double *__restrict__ si,
-                                                const double *__restrict__ sj, int il, int jl, double psi_ref,
+                                                const double *__restrict__ sj, const unsigned *__restrict__ si_o,
+                                                const unsigned *__restrict__ sj_o, int il, int jl, double psi_ref,
                                                 V2Counters &n) {
     V2Counters tmp = {0, 0, 0, 0};
-    v2_drain_pair<MIXED, NC>(dv->g, dv->c, dv->acc, dv->closed, dv, si, sj, il, jl, psi_ref, tmp);
+    v2_drain_pair<MIXED, NC, ORIENT>(dv->g, dv->c, dv->acc, dv->closed, dv, si, sj, si_o, sj_o, il, jl, psi_ref, tmp);
     n.nB += tmp.nB; n.nC += tmp.nC; n.nD += tmp.nD; n.nE += tmp.nE;
 }
 
 // Compact the per-lane lists into the warp's linear queue (one prefix sum) and process it 32
 // survivors at a time; FINAL also processes the last partial batch.
-template <bool MIXED, bool FINAL>
+template <bool MIXED, bool FINAL, bool ORIENT>
 __device__ __forceinline__ void v2_flush(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
                                          const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv, const double *__restrict__ si,
-                                         const double *__restrict__ sj, int lane, double psi_ref, V2Queue &Q,
+                                         const double *__restrict__ sj, const unsigned *__restrict__ si_o,
+                                         const unsigned *__restrict__ sj_o, int lane, double psi_ref, V2Queue &Q,
                                          V2Counters &n) {
     constexpr int NC = MIXED ? 4 : 8;
     const int cnt = static_cast<int>(Q.cur - Q.list_addr) >> 7;
@@ -305,10 +317,10 @@ __device__ __forceinline__ void v2_flush(const HbtGrid &g, const V2Const &c, con
             const int il = static_cast<int>(e >> 16), jl = static_cast<int>(e & 0xffffu);
             if (FINAL) {
                 V2Counters tmp = {0, 0, 0, 0};
-                v2_drain_pair_cold<MIXED, NC>(dv, si, sj, il, jl, psi_ref, tmp);
+                v2_drain_pair_cold<MIXED, NC, ORIENT>(dv, si, sj, si_o, sj_o, il, jl, psi_ref, tmp);
                 n.nB += tmp.nB; n.nC += tmp.nC; n.nD += tmp.nD; n.nE += tmp.nE;
             } else {
-                v2_drain_pair<MIXED, NC>(g, c, acc, closed, dv, si, sj, il, jl, psi_ref, n);
+                v2_drain_pair<MIXED, NC, ORIENT>(g, c, acc, closed, dv, si, sj, si_o, sj_o, il, jl, psi_ref, n);
             }
         }
         Q.qcount = base;
@@ -320,15 +332,16 @@ __device__ __forceinline__ void v2_flush(const HbtGrid &g, const V2Const &c, con
 // j > i pairs count, src :301).  FLOOR: tile pair in which the prefilter's error bound is not
 // negligible against the smallest K_T (KT_min ~ 0 or huge momenta): pairs below k2_floor skip
 // the window prefilter.
-template <bool MIXED, bool DIAG, bool FLOOR>
+template <bool MIXED, bool DIAG, bool FLOOR, bool STATS>
 __device__ __forceinline__ void v2_tile_loop(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
                                              const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv, const double *__restrict__ si,
-                                             const double *__restrict__ sj, const double *__restrict__ sjt, int nj,
+                                             const double *__restrict__ sj, const double *__restrict__ sjt,
+                                             const unsigned *__restrict__ si_o, const unsigned *__restrict__ sj_o, int nj,
                                              long long i0, long long j0, int lane, int warp, double k2_floor,
                                              double psi_ref, V2Queue &Q, V2Counters &n, unsigned &cntKT,
                                              unsigned &cntRS) {
-    constexpr int NC = MIXED ? 4 : 8;
     constexpr int TI = HBT_V2_TILE_I, TJ = HBT_V2_TILE_J, IPL = HBT_V2_IPL;
+    constexpr bool ORIENT = !MIXED && !STATS;
     double ax[IPL], ay[IPL], at[IPL];
     unsigned ent[IPL];
     long long ig[IPL];
@@ -366,24 +379,37 @@ __device__ __forceinline__ void v2_tile_loop(const HbtGrid &g, const V2Const &c,
                 rej_s = rej_s && !tiny;
             }
             const bool keep = kt && !(rej_o || rej_s);
-            inc_if(cntKT, kt);
-            inc_if(cntRS, kt && rej_s);
+            if (STATS) {  // exact K_T-pass and q_out-pass populations (instrumented runs only)
+                inc_if(cntKT, kt);
+                inc_if(cntRS, kt && rej_s);
+            }
             if (keep) {
                 sts_u32(Q.cur, ent[s] | static_cast<unsigned>(j));
                 Q.cur += 128u;
             }
         }
-        if (__any_sync(0xffffffffu, Q.cur > lim)) v2_flush<MIXED, false>(g, c, acc, closed, dv, si, sj, lane, psi_ref, Q, n);
+        if (__any_sync(0xffffffffu, Q.cur > lim)) v2_flush<MIXED, false, ORIENT>(g, c, acc, closed, dv, si, sj, si_o, sj_o, lane, psi_ref, Q, n);
     }
-    v2_flush<MIXED, true>(g, c, acc, closed, dv, si, sj, lane, psi_ref, Q, n);
+    v2_flush<MIXED, true, ORIENT>(g, c, acc, closed, dv, si, sj, si_o, sj_o, lane, psi_ref, Q, n);
 }
 
-template <bool MIXED>
-__global__ void __launch_bounds__(32 * HBT_V2_WARPS, 4)
+#ifndef HBT_V2_MINB_MIXED
+#define HBT_V2_MINB_MIXED 4
+#endif
+// STATS = true : instrumented run — list in the reference's order, every pair goes through the
+//                prefilter, the stage populations B, C, D (passed K_T, q_out, q_side) are exact.
+// STATS = false: production — the same-event list is Morton-sorted (orig = reference order,
+//                bbox = boxes of its 128-particle tiles), tile pairs whose boxes cannot hold an
+//                accepted pair are skipped at CTA and at warp level; only the populations that
+//                cost nothing (all pairs, passed q_long, accepted) are kept.
+template <bool MIXED, bool STATS>
+__global__ void __launch_bounds__(32 * HBT_V2_WARPS, MIXED ? HBT_V2_MINB_MIXED : 4)
 hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long long n_same,
              const HbtMixSeg *__restrict__ segs, const HbtGrid g, const V2Const c,
              const V2Dev *__restrict__ dv, const HbtAccum acc, const double psi_ref,
-             const unsigned long long total_pairs, const unsigned char *__restrict__ closed) {
+             const unsigned long long total_pairs, const unsigned char *__restrict__ closed,
+             const unsigned *__restrict__ orig, const HbtBBox *__restrict__ bbox) {
+    constexpr bool SORTED = !MIXED && !STATS;
     constexpr int NC = MIXED ? 4 : 8;
     constexpr int TI = HBT_V2_TILE_I, TJ = HBT_V2_TILE_J, NT = 32 * HBT_V2_WARPS;
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -393,6 +419,8 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
     double *s_max = sjt + TJ;                       // [2*WARPS]
     unsigned *lq = reinterpret_cast<unsigned *>(s_max + 2 * HBT_V2_WARPS);  // [WARPS][LCAP][32]
     unsigned *wq = lq + HBT_V2_WARPS * HBT_V2_LCAP * 32;                    // [WARPS][QCAP]
+    unsigned *si_o = wq + HBT_V2_WARPS * HBT_V2_QCAP;                       // [TI] reference-order index
+    unsigned *sj_o = si_o + TI;                                             // [TJ]
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     long long i0, j0;
@@ -424,6 +452,22 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
     }
     if (blockIdx.x == 0 && t == 0) atomicAdd(&acc.stage[MIXED ? 6 : 0], total_pairs);
     if (nj <= 0 || ni <= 0) return;
+    bool warp_culled = false;
+    if (SORTED) {
+        // CTA level: the union of the list-1 sub-tile boxes against the list-2 tile box
+        const long long ti0 = i0 / HBT_BBOX_TILE;
+        const int nsub = (ni + HBT_BBOX_TILE - 1) / HBT_BBOX_TILE;
+        const HbtBBox bj = bbox[j0 / HBT_BBOX_TILE];
+        HbtBBox u = bbox[ti0];
+        for (int q = 1; q < nsub; q++) {
+            const HbtBBox b = bbox[ti0 + q];
+            u.xlo = fmin(u.xlo, b.xlo); u.xhi = fmax(u.xhi, b.xhi);
+            u.ylo = fmin(u.ylo, b.ylo); u.yhi = fmax(u.yhi, b.yhi);
+        }
+        if (hbt_boxes_culled(u, bj, c.W2, c.k2lo, c.k2hi)) return;
+        // warp level: this warp's 128 list-1 particles
+        warp_culled = (warp >= nsub) || hbt_boxes_culled(bbox[ti0 + warp], bj, c.W2, c.k2lo, c.k2hi);
+    }
 
     // ---- stage both tiles (SoA).  Rows beyond the tile end are NaN: they fail the K_T cut.
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
@@ -434,6 +478,7 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
             const double2 v0 = src[0], v1 = src[1];
             si[k] = v0.x; si[TI + k] = v0.y; si[2 * TI + k] = v1.x; si[3 * TI + k] = v1.y;
             tmax = fmax(tmax, fma(v0.x, v0.x, v0.y * v0.y));
+            if (SORTED) si_o[k] = orig[i0 + k];
             if (!MIXED) {
                 const double2 v2 = src[2], v3 = src[3];
                 si[(4 % NC) * TI + k] = v2.x; si[(5 % NC) * TI + k] = v2.y;
@@ -442,6 +487,7 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
         } else {
 #pragma unroll
             for (int q = 0; q < NC; q++) si[q * TI + k] = nan;
+            if (SORTED) si_o[k] = 0u;
         }
     }
     for (int k = t; k < TJ; k += NT) {
@@ -457,6 +503,7 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
             const double pt2 = fma(x, x, y * y);
             sjt[k] = pt2;
             tmaxj = fmax(tmaxj, pt2);
+            if (SORTED) sj_o[k] = orig[j0 + k];
             if (!MIXED) {
                 const double2 v2 = src[2], v3 = src[3];
                 sj[(4 % NC) * TJ + k] = v2.x; sj[(5 % NC) * TJ + k] = v2.y;
@@ -491,60 +538,78 @@ hbt_pairs_v2(const double *__restrict__ p1, const double *__restrict__ p2, long 
     Q.kept = 0;
     V2Counters n = {0, 0, 0, 0};
     unsigned cntKT = 0, cntRS = 0;
-    if (use_floor) {
-        if (diag) v2_tile_loop<MIXED, true, true>(g, c, acc, closed, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
-        else v2_tile_loop<MIXED, false, true>(g, c, acc, closed, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
-    } else {
-        if (diag) v2_tile_loop<MIXED, true, false>(g, c, acc, closed, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
-        else v2_tile_loop<MIXED, false, false>(g, c, acc, closed, dv, si, sj, sjt, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+    if (!warp_culled) {
+        if (use_floor) {
+            if (diag) v2_tile_loop<MIXED, true, true, STATS>(g, c, acc, closed, dv, si, sj, sjt, si_o, sj_o, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+            else v2_tile_loop<MIXED, false, true, STATS>(g, c, acc, closed, dv, si, sj, sjt, si_o, sj_o, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+        } else {
+            if (diag) v2_tile_loop<MIXED, true, false, STATS>(g, c, acc, closed, dv, si, sj, sjt, si_o, sj_o, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+            else v2_tile_loop<MIXED, false, false, STATS>(g, c, acc, closed, dv, si, sj, sjt, si_o, sj_o, nj, i0, j0, lane, warp, k2_floor, psi_ref, Q, n, cntKT, cntRS);
+        }
     }
 
     // ---- merge counters: pairs dropped by the prefilter passed K_T (cntKT) minus those queued;
     // those dropped at q_side passed q_out as well (cntRS); queued pairs are counted by the drain
-    unsigned nB = warp_sum(cntKT + n.nB), nC = warp_sum(cntRS + n.nC);
-    const unsigned nD = warp_sum(n.nD), nE = warp_sum(n.nE);
-    nB -= Q.kept;
+    const unsigned nE = warp_sum(n.nE);
     unsigned long long *stage = acc.stage + (MIXED ? 6 : 0);
-    if (lane == 0) {
-        if (nB) atomicAdd(&stage[1], static_cast<unsigned long long>(nB));
-        if (nC) atomicAdd(&stage[2], static_cast<unsigned long long>(nC));
-        if (nD) atomicAdd(&stage[3], static_cast<unsigned long long>(nD));
-        if (nE) atomicAdd(&stage[4], static_cast<unsigned long long>(nE));
+    if (STATS) {
+        unsigned nB = warp_sum(cntKT + n.nB), nC = warp_sum(cntRS + n.nC);
+        const unsigned nD = warp_sum(n.nD);
+        nB -= Q.kept;
+        if (lane == 0) {
+            if (nB) atomicAdd(&stage[1], static_cast<unsigned long long>(nB));
+            if (nC) atomicAdd(&stage[2], static_cast<unsigned long long>(nC));
+            if (nD) atomicAdd(&stage[3], static_cast<unsigned long long>(nD));
+        }
     }
+    if (lane == 0 && nE) atomicAdd(&stage[4], static_cast<unsigned long long>(nE));
 }
 
 // ---- host-side launch helpers ------------------------------------------------------------
 inline size_t hbt_v2_smem_bytes(bool mixed) {
     const int NC = mixed ? 4 : 8;
     return sizeof(double) * (NC * HBT_V2_TILE_I + NC * HBT_V2_TILE_J + HBT_V2_TILE_J + 2 * HBT_V2_WARPS)
-           + sizeof(unsigned) * (HBT_V2_WARPS * HBT_V2_LCAP * 32 + HBT_V2_WARPS * HBT_V2_QCAP + 8);
+           + sizeof(unsigned) * (HBT_V2_WARPS * HBT_V2_LCAP * 32 + HBT_V2_WARPS * HBT_V2_QCAP + HBT_V2_TILE_I + HBT_V2_TILE_J + 8);
 }
 
 inline int hbt_v2_configure() {
-    cudaError_t e = cudaFuncSetAttribute(hbt_pairs_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(hbt_v2_smem_bytes(false)));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(hbt_pairs_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(hbt_v2_smem_bytes(true)));
+    cudaError_t e = cudaSuccess;
+    const int sm0 = static_cast<int>(hbt_v2_smem_bytes(false)), sm1 = static_cast<int>(hbt_v2_smem_bytes(true));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hbt_pairs_v2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm0);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hbt_pairs_v2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm0);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hbt_pairs_v2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hbt_pairs_v2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1);
     return e == cudaSuccess ? HBT_OK : HBT_ERR_CUDA;
 }
 
+// d_p: stats = true: the list in the reference's order; stats = false: the Morton-sorted list,
+// with orig (reference-order index of each sorted particle) and the tile boxes
 inline int hbt_v2_launch_same(cudaStream_t st, const double *d_p, long long n, const HbtGrid &g, const V2Const &c, const V2Dev *d_dv,
                               const HbtAccum &acc, double psi_ref, unsigned long long npairs,
-                              const unsigned char *closed) {
+                              const unsigned char *closed, bool stats, const unsigned *orig, const HbtBBox *bbox) {
     const long long T = (n + HBT_V2_TILE_I - 1) / HBT_V2_TILE_I;
     const long long blocks = T * (T + 1) / 2 * HBT_V2_SUB;
     if (blocks > 0x7fffffffLL) return HBT_ERR_INVALID;
-    hbt_pairs_v2<false><<<static_cast<unsigned>(blocks), 32 * HBT_V2_WARPS, hbt_v2_smem_bytes(false), st>>>(
-        d_p, d_p, n, nullptr, g, c, d_dv, acc, psi_ref, npairs, closed);
+    const unsigned nb = static_cast<unsigned>(blocks);
+    if (stats)
+        hbt_pairs_v2<false, true><<<nb, 32 * HBT_V2_WARPS, hbt_v2_smem_bytes(false), st>>>(
+            d_p, d_p, n, nullptr, g, c, d_dv, acc, psi_ref, npairs, closed, nullptr, nullptr);
+    else
+        hbt_pairs_v2<false, false><<<nb, 32 * HBT_V2_WARPS, hbt_v2_smem_bytes(false), st>>>(
+            d_p, d_p, n, nullptr, g, c, d_dv, acc, psi_ref, npairs, closed, orig, bbox);
     return HBT_OK;
 }
 
 inline int hbt_v2_launch_mixed(cudaStream_t st, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg,
                                size_t nseg, long long nblocks, const HbtGrid &g, const V2Const &c, const V2Dev *d_dv, const HbtAccum &acc,
-                               double psi_ref, unsigned long long npairs, const unsigned char *closed) {
-    hbt_pairs_v2<true><<<static_cast<unsigned>(nblocks), 32 * HBT_V2_WARPS, hbt_v2_smem_bytes(true), st>>>(
-        d_p1, d_p2, static_cast<long long>(nseg), d_seg, g, c, d_dv, acc, psi_ref, npairs, closed);
+                               double psi_ref, unsigned long long npairs, const unsigned char *closed, bool stats) {
+    const unsigned nb = static_cast<unsigned>(nblocks);
+    if (stats)
+        hbt_pairs_v2<true, true><<<nb, 32 * HBT_V2_WARPS, hbt_v2_smem_bytes(true), st>>>(
+            d_p1, d_p2, static_cast<long long>(nseg), d_seg, g, c, d_dv, acc, psi_ref, npairs, closed, nullptr, nullptr);
+    else
+        hbt_pairs_v2<true, false><<<nb, 32 * HBT_V2_WARPS, hbt_v2_smem_bytes(true), st>>>(
+            d_p1, d_p2, static_cast<long long>(nseg), d_seg, g, c, d_dv, acc, psi_ref, npairs, closed, nullptr, nullptr);
     return HBT_OK;
 }
 

@@ -1,0 +1,117 @@
+// Momentum-space ordering of a same-event particle list (sm_100a).
+//
+// The accepted region of a pair is small in transverse momentum: |q_out|,|q_side| <= W means
+// |p_T,i - p_T,j| <= sqrt(2) W (0.29 GeV for the benchmark grid) while the particles spread over
+// ~2 GeV.  After sorting the list along a Morton (Z-order) curve in (px,py), a tile of 128
+// consecutive particles covers a small cell, and most tile pairs can be discarded from their
+// bounding boxes alone.  The reference's pair orientation (q = p_i - p_j with i before j in the
+// gather order, src/HBT_correlation.cpp:291-301,327-330) is kept through the original index.
+#ifndef HBT_SORT_CUH_
+#define HBT_SORT_CUH_
+
+#include <cub/cub.cuh>
+
+#include "hbt_common.h"
+
+#define HBT_BBOX_TILE 128
+
+struct HbtBBox {
+    double xlo, xhi, ylo, yhi;
+};
+
+__device__ __forceinline__ unsigned hbt_spread16(unsigned v) {
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+// max(|px|, |py|) over the list, as the bit pattern of a non-negative float (atomicMax-able)
+__global__ void hbt_sort_range(const double *__restrict__ p, long long n, unsigned *__restrict__ rmax) {
+    float m = 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const double2 v = *reinterpret_cast<const double2 *>(p + 8 * i);
+        const float a = fmaxf(fabsf(static_cast<float>(v.x)), fabsf(static_cast<float>(v.y)));
+        if (a == a && a < 3.0e38f) m = fmaxf(m, a);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(rmax, __float_as_uint(m));
+}
+
+__global__ void hbt_sort_keys(const double *__restrict__ p, long long n, const unsigned *__restrict__ rmax,
+                              unsigned *__restrict__ keys, unsigned *__restrict__ idx) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const float R = fmaxf(__uint_as_float(*rmax), 1e-30f) * 1.0001f;
+    const float scale = 32767.5f / R;
+    const double2 v = *reinterpret_cast<const double2 *>(p + 8 * i);
+    const float fx = (static_cast<float>(v.x) + R) * scale, fy = (static_cast<float>(v.y) + R) * scale;
+    const unsigned ux = static_cast<unsigned>(fminf(fmaxf(fx, 0.f), 65535.f));  // NaN -> 0
+    const unsigned uy = static_cast<unsigned>(fminf(fmaxf(fy, 0.f), 65535.f));
+    keys[i] = hbt_spread16(ux) | (hbt_spread16(uy) << 1);
+    idx[i] = static_cast<unsigned>(i);
+}
+
+// sorted[k] = p[idx[k]] (64 bytes each, two threads per particle would not pay: L2 resident)
+__global__ void hbt_sort_gather(const double *__restrict__ p, const unsigned *__restrict__ idx, long long n,
+                                double *__restrict__ sorted) {
+    const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long k = t >> 2;
+    const int part = static_cast<int>(t & 3);
+    if (k >= n) return;
+    const double2 *src = reinterpret_cast<const double2 *>(p + 8ll * idx[k]);
+    reinterpret_cast<double2 *>(sorted + 8 * k)[part] = src[part];
+}
+
+// bounding box in (px,py) of every tile of HBT_BBOX_TILE consecutive sorted particles
+__global__ void __launch_bounds__(HBT_BBOX_TILE) hbt_sort_bbox(const double *__restrict__ sorted, long long n,
+                                                              HbtBBox *__restrict__ bbox) {
+    __shared__ double red[4][HBT_BBOX_TILE / 32];
+    const long long k = blockIdx.x * static_cast<long long>(HBT_BBOX_TILE) + threadIdx.x;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double xlo = inf, xhi = -inf, ylo = inf, yhi = -inf;
+    if (k < n) {
+        const double2 v = *reinterpret_cast<const double2 *>(sorted + 8 * k);
+        xlo = xhi = v.x;
+        ylo = yhi = v.y;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        xlo = fmin(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+        xhi = fmax(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+        ylo = fmin(ylo, __shfl_xor_sync(0xffffffffu, ylo, o));
+        yhi = fmax(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][w] = xlo; red[1][w] = xhi; red[2][w] = ylo; red[3][w] = yhi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < HBT_BBOX_TILE / 32; q++) {
+            xlo = fmin(xlo, red[0][q]); xhi = fmax(xhi, red[1][q]);
+            ylo = fmin(ylo, red[2][q]); yhi = fmax(yhi, red[3][q]);
+        }
+        // a NaN coordinate would poison the box test: widen to everything (never culled)
+        if (!(xlo <= xhi) || !(ylo <= yhi)) { xlo = -inf; xhi = inf; ylo = -inf; yhi = inf; }
+        bbox[blockIdx.x] = {xlo, xhi, ylo, yhi};
+    }
+}
+
+// true when NO pair between the two boxes can pass both the K_T cut and the q_out/q_side
+// windows.  W2 = W^2 of the symmetric window, k2lo/k2hi = 4 KT_min^2 / 4 KT_max^2.
+__device__ __forceinline__ bool hbt_boxes_culled(const HbtBBox &a, const HbtBBox &b, double W2, double k2lo, double k2hi) {
+    // smallest possible |q_T|^2: q_out^2 + q_side^2 = |q_T|^2, so |q_T|^2 > 2 W^2 rules out the pair
+    const double gx = fmax(0.0, fmax(a.xlo - b.xhi, b.xlo - a.xhi));
+    const double gy = fmax(0.0, fmax(a.ylo - b.yhi, b.ylo - a.yhi));
+    if (gx * gx + gy * gy > 2.0 * W2 * (1.0 + 1e-9)) return true;
+    // range of s = p_i + p_j: k2 = |s|^2 = 4 K_T^2
+    const double sxl = a.xlo + b.xlo, sxh = a.xhi + b.xhi, syl = a.ylo + b.ylo, syh = a.yhi + b.yhi;
+    const double nx = (sxl <= 0.0 && sxh >= 0.0) ? 0.0 : fmin(fabs(sxl), fabs(sxh));
+    const double ny = (syl <= 0.0 && syh >= 0.0) ? 0.0 : fmin(fabs(syl), fabs(syh));
+    const double mx = fmax(fabs(sxl), fabs(sxh)), my = fmax(fabs(syl), fabs(syh));
+    if (mx * mx + my * my < k2lo * (1.0 - 1e-9)) return true;
+    if (nx * nx + ny * ny > k2hi * (1.0 + 1e-9)) return true;
+    return false;
+}
+
+#endif  // HBT_SORT_CUH_

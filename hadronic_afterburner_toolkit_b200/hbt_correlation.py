@@ -82,7 +82,8 @@ class HBT_correlation:
     ``particleSamples`` holds for one read: the filtered events and, optionally, real mixed
     events)."""
 
-    def __init__(self, params: HBTParams, path: str = ".", ran_gen: Optional[Random] = None, device: int = 0):
+    def __init__(self, params: HBTParams, path: str = ".", ran_gen: Optional[Random] = None, device: int = 0,
+                 stage_counters: Optional[bool] = None, kernel: Optional[int] = None):
         self.params = params
         self.path_ = path
         self.ran_gen = ran_gen if ran_gen is not None else Random(params.randomSeed)
@@ -91,6 +92,10 @@ class HBT_correlation:
         h = ctypes.c_void_p()
         _check(None, self._L.hbt_create(ctypes.byref(self._cp), device, ctypes.byref(h)))
         self._h = h
+        if stage_counters is not None:  # HBT_OPT_STAGE_COUNTERS: instrumented run, exact stage populations
+            _check(h, self._L.hbt_set_option(h, 1, int(stage_counters)))
+        if kernel is not None:  # HBT_OPT_KERNEL
+            _check(h, self._L.hbt_set_option(h, 2, int(kernel)))
         self.psi_ref = 0.0
         self.psi_refs: List[float] = []
         self.particle_list: Optional[Batch] = None

@@ -160,12 +160,25 @@ int hbt_read(hbt_ctx *ctx, uint64_t *num_count, double *num_cos, double *sum_qo,
 int hbt_read_qinv(hbt_ctx *ctx, uint64_t *count, double *sum_qinv, double *sum_cos, uint64_t *den,
                   uint64_t *npairs_num, uint64_t *npairs_den);
 /* stage populations {all pairs, passed K_T cut, passed q_out, passed q_side, passed q_long,
- * accepted}: the n_A..n_E of the roofline formula */
+ * accepted}: the n_A..n_E of the roofline formula.  [1..3] need
+ * HBT_OPT_STAGE_COUNTERS (see hbt_set_option). */
 int hbt_get_stage_counters(hbt_ctx *ctx, uint64_t same[6], uint64_t mixed[6]);
 /* device time of the pair kernels so far, measured with CUDA events on the context's
  * stream, and the number of kernel launches */
 int hbt_get_timers(hbt_ctx *ctx, double *same_ms, double *mixed_ms, uint64_t *same_launches,
                    uint64_t *mixed_launches);
+/* Engine options (set between batches; the call synchronises the context).
+ * HBT_OPT_STAGE_COUNTERS = 1: instrumented runs — every pair goes through the prefilter and the
+ *   stage populations "passed K_T / q_out / q_side" (hbt_get_stage_counters [1..3]) are exact.
+ *   0 (default): production — the same-event list is sorted in momentum space and tile pairs that
+ *   cannot hold an accepted pair are skipped, so those three populations are not available
+ *   (reported as 0); all pairs [0], passed q_long [4] and accepted [5] stay exact, and so does
+ *   every histogram.  Default can be changed with the environment variable HBT_B200_STATS=1.
+ * HBT_OPT_KERNEL: 2 = tuned kernels (default), 1 = literal kernels (cross-check). */
+#define HBT_OPT_STAGE_COUNTERS 1
+#define HBT_OPT_KERNEL 2
+int hbt_set_option(hbt_ctx *ctx, int32_t option, int32_t value);
+
 /* Device-side stopwatch on the context's compute stream (CUDA events): everything the
  * context enqueues between start and stop — copies it waits for, pair kernels, the NCCL
  * all-reduce — is inside.  hbt_timer_stop waits for the stream and returns milliseconds. */

@@ -47,7 +47,7 @@ def main():
         o = O.Oracle(P)
         for b in batches:
             o.process_batch(b)
-        hbtio.compare(o.accumulators(), acc, rtol=1e-10, check_stage=True)
+        hbtio.compare(o.accumulators(), acc, rtol=1e-10, check_stage="cheap")
         # more batches after an all-reduce keep accumulating locally (no double counting)
     eng.calculate_HBT_correlation_function(batches[0]) if rank == 0 else None
     _check(eng._h, L.hbt_allreduce(eng._h))
