@@ -19,10 +19,10 @@
 #include "hbt_common.h"
 #include "hbt_kernels_v1.cuh"
 #ifdef HBT_HAVE_V2
-#include "hbt_kernels_v2.cuh"
+#include "hbt_kernels_v3.cuh"
 #else
-#define HBT_V2_TILE_I 128
-#define HBT_V2_TILE_J 128
+#define HBT_V3_SUB 128
+#define HBT_V3_TJ_MIXED 128
 #endif
 
 namespace {
@@ -130,6 +130,14 @@ struct hbt_ctx {
     bool any_closed = false;
     // production mode of the v2 same-event kernel: Morton-sorted copy of the list + tile boxes
     bool stats = false;                          // exact stage populations B, C, D (no culling)
+    int n_sm = 148;
+    int occ_same = 12, occ_same_stats = 12, occ_mixed = 12, occ_mixed_stats = 12;  // resident warps per SM
+    unsigned *d_work = nullptr;                  // [0] unit pop counter, [1] number of units (culled list)
+    unsigned *d_units = nullptr;                 // surviving units of the sorted same-event list
+    size_t units_cap = 0;
+    std::vector<int> row_item0;                  // same-event unit prefix per row (instrumented runs)
+    int *d_rows = nullptr;
+    size_t d_rows_cap = 0;
     unsigned *sort_keys[2] = {nullptr, nullptr}, *sort_idx[2] = {nullptr, nullptr}, *sort_rmax = nullptr;
     double *sort_p = nullptr;
     HbtBBox *sort_bbox = nullptr;
@@ -230,6 +238,11 @@ size_t dyn_smem_bytes(const HbtGrid &g) {
 
 // ---- launches ------------------------------------------------------------------------
 #ifdef HBT_HAVE_V2
+int ensure_work(hbt_ctx *ctx) {
+    if (!ctx->d_work) CU(ctx, cudaMalloc(&ctx->d_work, 8));
+    return HBT_OK;
+}
+
 // Morton-sort the same-event list on the compute stream (keys, radix sort of (key, index),
 // gather, tile boxes): ~4 small kernels, microseconds against the pair kernel's milliseconds
 int prepare_sorted(hbt_ctx *ctx, const double *d_p, int64_t n) {
@@ -298,14 +311,45 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
         ctx->kernel_launches++;
     } else {
 #ifdef HBT_HAVE_V2
-        if (ctx->stats) {
-            rc = hbt_v2_launch_same(ctx->compute, d_p, n, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed,
-                                    true, nullptr, nullptr);
-        } else {
+        rc = ensure_work(ctx);
+        if (rc) return rc;
+        CU(ctx, cudaMemsetAsync(ctx->d_work, 0, 8, ctx->compute));
+        const unsigned grid = static_cast<unsigned>(ctx->n_sm * (ctx->stats ? ctx->occ_same_stats : ctx->occ_same));
+        const long long all_units = hbt_v3_same_units(n, ctx->row_item0);
+        if (all_units > 0x7fffffffLL) return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld work units", all_units);
+        if (!ctx->stats && n <= HBT_V3_MAX_SORTED) {
+            // production: Morton-sorted copy + tile boxes, units that can hold an accepted pair
             rc = prepare_sorted(ctx, d_p, n);
             if (rc) return rc;
-            rc = hbt_v2_launch_same(ctx->compute, ctx->sort_p, n, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed,
-                                    false, ctx->sort_idx[1], ctx->sort_bbox);
+            if (static_cast<size_t>(all_units) > ctx->units_cap) {
+                cudaFree(ctx->d_units);
+                ctx->units_cap = static_cast<size_t>(all_units) + static_cast<size_t>(all_units) / 4;
+                CU(ctx, cudaMalloc(&ctx->d_units, ctx->units_cap * 4));
+            }
+            const long long n_rows = (n + HBT_V3_SUB - 1) / HBT_V3_SUB, ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
+            hbt_cull_units<<<dim3(static_cast<unsigned>((ntj + 127) / 128), static_cast<unsigned>(n_rows)), 128, 0, ctx->compute>>>(
+                ctx->sort_bbox, n, ctx->v2c.W2, ctx->v2c.k2lo, ctx->v2c.k2hi, ctx->d_units, ctx->d_work);
+            ctx->kernel_launches++;
+            hbt_pairs_v3<false, false><<<grid, 32, 0, ctx->compute>>>(
+                ctx->sort_p, ctx->sort_p, n, nullptr, nullptr, 0, ctx->d_units, ctx->d_work, 0, ctx->grid, ctx->v2c, ctx->d_dv,
+                ctx->acc, psi_ref, npairs, cap.closed, ctx->sort_idx[1]);
+        } else {
+            // instrumented (or a list too long for the unit encoding): every unit, reference order
+            const size_t rb = ctx->row_item0.size() * sizeof(int);
+            if (rb > ctx->d_rows_cap) {
+                cudaFree(ctx->d_rows);
+                CU(ctx, cudaMalloc(&ctx->d_rows, rb * 2));
+                ctx->d_rows_cap = rb * 2;
+            }
+            // (pageable source: the copy is staged before the call returns, the vector can be reused)
+            CU(ctx, cudaMemcpyAsync(ctx->d_rows, ctx->row_item0.data(), rb, cudaMemcpyHostToDevice, ctx->compute));
+            const int n_rows = static_cast<int>(ctx->row_item0.size()) - 1;
+            if (ctx->stats)
+                hbt_pairs_v3<false, true><<<grid, 32, 0, ctx->compute>>>(
+                    d_p, d_p, n, nullptr, ctx->d_rows, n_rows, nullptr, ctx->d_work, static_cast<unsigned>(all_units), ctx->grid,
+                    ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
+            else
+                return fail(ctx, HBT_ERR_INVALID, "more than %lld particles in one batch: set HBT_OPT_STAGE_COUNTERS", HBT_V3_MAX_SORTED);
         }
         ctx->kernel_launches++;
         if (rc) return fail(ctx, rc, "v2 same-event launch failed");
@@ -379,8 +423,19 @@ int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const Hbt
         ctx->kernel_launches++;
     } else {
 #ifdef HBT_HAVE_V2
-        rc = hbt_v2_launch_mixed(ctx->compute, d_p1, d_p2, d_seg, nseg, nblocks, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs,
-                                 cap.closed, ctx->stats);
+        rc = ensure_work(ctx);
+        if (rc) return rc;
+        CU(ctx, cudaMemsetAsync(ctx->d_work, 0, 8, ctx->compute));
+        const unsigned grid = static_cast<unsigned>(std::min<long long>(
+            nblocks, static_cast<long long>(ctx->n_sm) * (ctx->stats ? ctx->occ_mixed_stats : ctx->occ_mixed)));
+        if (ctx->stats)
+            hbt_pairs_v3<true, true><<<grid, 32, 0, ctx->compute>>>(
+                d_p1, d_p2, static_cast<long long>(nseg), d_seg, nullptr, 0, nullptr, ctx->d_work, static_cast<unsigned>(nblocks), ctx->grid,
+                ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
+        else
+            hbt_pairs_v3<true, false><<<grid, 32, 0, ctx->compute>>>(
+                d_p1, d_p2, static_cast<long long>(nseg), d_seg, nullptr, 0, nullptr, ctx->d_work, static_cast<unsigned>(nblocks), ctx->grid,
+                ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
         ctx->kernel_launches++;
         if (rc) return fail(ctx, rc, "v2 mixed-event launch failed");
 #endif
@@ -393,8 +448,8 @@ int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const Hbt
     return drain_timers(ctx, false);
 }
 
-int tile_i(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V2_TILE_I; }
-int tile_j(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V2_TILE_J; }
+int tile_i(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V3_SUB; }
+int tile_j(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V3_TJ_MIXED; }
 
 // host literal evaluation of the pairs the device deferred; leaves the stream idle
 // position filter of the ordered cap for host-evaluated pairs
@@ -742,6 +797,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
         hbt_destroy(ctx);
         return HBT_ERR_NO_DEVICE;
     }
+    ctx->n_sm = prop.multiProcessorCount;
     CUC(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
     const HbtGrid &g = ctx->grid;
@@ -786,12 +842,13 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     }
 #ifdef HBT_HAVE_V2
     ctx->v2c = hbt_v2_consts(g);
+    // persistent kernels: one grid-full of resident warps
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same, hbt_pairs_v3<false, false>, 32, 0));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same_stats, hbt_pairs_v3<false, true>, 32, 0));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed, hbt_pairs_v3<true, false>, 32, 0));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed_stats, hbt_pairs_v3<true, true>, 32, 0));
     if (!hbt_v2_supported(g)) ctx->kernel_version = 1;  // q_inv mode, one-sided q windows: literal kernels
-    if (hbt_v2_configure() != HBT_OK) {
-        fail(nullptr, HBT_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
-        hbt_destroy(ctx);
-        return HBT_ERR_CUDA;
-    }
+
     {
         V2Dev dv;
         dv.g = ctx->grid;
@@ -841,6 +898,9 @@ extern "C" void hbt_destroy(hbt_ctx *ctx) {
     if (ctx->sort_bbox) cudaFree(ctx->sort_bbox);
     if (ctx->sort_tmp) cudaFree(ctx->sort_tmp);
     if (ctx->sort_rmax) cudaFree(ctx->sort_rmax);
+    if (ctx->d_rows) cudaFree(ctx->d_rows);
+    if (ctx->d_work) cudaFree(ctx->d_work);
+    if (ctx->d_units) cudaFree(ctx->d_units);
     if (ctx->snap_u64) cudaFree(ctx->snap_u64);
     if (ctx->snap_f64) cudaFree(ctx->snap_f64);
 #ifdef HBT_HAVE_V2

@@ -1,0 +1,470 @@
+// v3 pair kernels (sm_100a): the v2 pipeline (prefilter -> per-lane survivor lists -> guarded
+// fast-path drain, see hbt_kernels_v2.cuh) on a different work decomposition.
+//
+// One CTA = one warp, persistent: warps pop work UNITS = (128 list-1 particles) x (TJ list-2
+// particles) from a global counter until the list is empty.  Why: after the same-event list is
+// sorted along a Morton curve, ~80 % of the units can be discarded from their bounding boxes
+// (hbt_cull_units builds the list of the others on the device); with several warps per CTA
+// sharing a list-2 tile the discarded warps sat idle while the CTA kept its shared memory (ncu:
+// 9.9 active warps/SM), and with a static split of the rows the dense-core rows made a long tail
+// (6.4 active warps/SM).  Dynamic units of equal size keep every resident warp busy.  No
+// __syncthreads anywhere; the survivor queue is flushed once per unit.
+#ifndef HBT_KERNELS_V3_CUH_
+#define HBT_KERNELS_V3_CUH_
+
+#include <type_traits>
+#include <vector>
+
+#include "hbt_kernels_v2.cuh"
+
+#define HBT_V3_SUB 128  // list-1 particles per warp
+#define HBT_V3_IPL 4
+#define HBT_V3_TJ_SAME 64    // list-2 tile, same-event (finer culling)
+#define HBT_V3_TJ_MIXED 128  // list-2 tile, mixed-event (no culling: fewer partial drains)
+#define HBT_V3_WARPS_PER_SM 12
+#define HBT_V3_MAX_SORTED (1ll << 21)  // unit encoding (row << 18 | tile) of the culled list
+
+// Units of the sorted same-event list that can hold an accepted pair: row a = particles
+// [128a, 128a+128), tile t = particles [64t, 64t+64), t >= 2a (upper triangle incl. the two
+// diagonal tiles).  work[1] counts them; work[0] is the pop counter of the pair kernel.
+__global__ void hbt_cull_units(const HbtBBox *__restrict__ bbox, long long n, double W2, double k2lo, double k2hi,
+                               unsigned *__restrict__ units, unsigned *__restrict__ work) {
+    constexpr int RB = HBT_V3_SUB / HBT_BBOX_TILE, TB = HBT_V3_TJ_SAME / HBT_BBOX_TILE;
+    const long long nb = (n + HBT_BBOX_TILE - 1) / HBT_BBOX_TILE;
+    const int a = blockIdx.y;
+    const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
+    bool alive = false;
+    if (t < ntj && t >= static_cast<long long>(a) * (HBT_V3_SUB / HBT_V3_TJ_SAME)) {
+        HbtBBox ra = bbox[static_cast<long long>(a) * RB], tb = bbox[t * TB];
+        for (int q = 1; q < RB; q++) {
+            if (static_cast<long long>(a) * RB + q >= nb) break;
+            const HbtBBox b = bbox[static_cast<long long>(a) * RB + q];
+            ra.xlo = fmin(ra.xlo, b.xlo); ra.xhi = fmax(ra.xhi, b.xhi); ra.ylo = fmin(ra.ylo, b.ylo); ra.yhi = fmax(ra.yhi, b.yhi);
+        }
+        for (int q = 1; q < TB; q++) {
+            if (t * TB + q >= nb) break;
+            const HbtBBox b = bbox[t * TB + q];
+            tb.xlo = fmin(tb.xlo, b.xlo); tb.xhi = fmax(tb.xhi, b.xhi); tb.ylo = fmin(tb.ylo, b.ylo); tb.yhi = fmax(tb.yhi, b.yhi);
+        }
+        alive = !hbt_boxes_culled(ra, tb, W2, k2lo, k2hi);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&work[1], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (alive) units[base + __popc(m & ((1u << lane) - 1u))] = (static_cast<unsigned>(a) << 18) | static_cast<unsigned>(t);
+    }
+}
+
+// ---- guarded fast path for one queued survivor ---------------------------------------------
+// In units of bins, u = (q - q_base)/delta_q, the reference's window is [eps, nq - eps] with
+// eps = 1e-8/delta_q (src :363-364) and its bin edges are the integers.  The fast path decides
+// only when u is farther than gb from every integer, gb >= 2 eps + the bound on
+// |fast - reference|: that single test covers the bin edges, both window edges and their
+// '>' / '>=' distinction.  Anything closer (a ~1e-5 fraction of the survivors) takes the literal
+// chain (v2_slow_pair).  Returns the stage the pair reached: 1 = passed K_T only ... 4 = passed
+// q_long (accepted), or -1 = undecided.
+struct V3Bins {
+    int io, is, il;
+    double qo, qs, ql, qx, qy, qz, qE;
+};
+
+template <bool MIXED, bool ORIENT, int TI, int TJ>
+__device__ __forceinline__ int v3_fast_bins(const HbtGrid &g, const V2Const &c, unsigned sia, unsigned sja, bool flip,
+                                            double &k2, V3Bins &o) {
+    const double ax = lds_f64(sia), ay = lds_f64(sia + 8 * TI), bx = lds_f64(sja), by = lds_f64(sja + 8 * TJ);
+    const double sx = __dadd_rn(ax, bx), sy = __dadd_rn(ay, by);
+    k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));  // (the K_T cut was decided exactly by the prefilter)
+    const double qx = ax - bx, qy = ay - by;
+    const double d = fma(qx, sx, qy * sy);     // 2 K_perp q_out
+    const double e = fma(qy, sx, -(qx * sy));  // 2 K_perp q_side
+    const double r = rsqrt(k2);                // 1 / (2 K_perp)
+    double qo = d * r, qs = e * r;
+    if (ORIENT && flip) { qo = -qo; qs = -qs; }
+    o.qx = qx; o.qy = qy; o.qo = qo; o.qs = qs;
+    // |fast - reference| <= ~8 ulp of (|qx|+|qy|): guard = 2^-46 relative + 2^-44 |window| + 2 eps
+    const double gb = fma(fabs(qx) + fabs(qy), c.gq, c.g0);
+    const double one_m = 1.0 - gb;
+    const unsigned nq = static_cast<unsigned>(g.nq);
+    {
+        const double u = fma(qo, c.inv_dq, c.ub);
+        const int i = __double2int_rd(u);
+        if (static_cast<unsigned>(i) >= nq) return (u > -gb && u < c.nq_d + gb) ? -1 : 1;  // outside (NaN too)
+        const double fr = u - static_cast<double>(i);
+        if (fr < gb || fr > one_m) return -1;
+        o.io = i;
+    }
+    {
+        const double u = fma(qs, c.inv_dq, c.ub);
+        const int i = __double2int_rd(u);
+        if (static_cast<unsigned>(i) >= nq) return (u > -gb && u < c.nq_d + gb) ? -1 : 2;
+        const double fr = u - static_cast<double>(i);
+        if (fr < gb || fr > one_m) return -1;
+        o.is = i;
+    }
+    const double az = lds_f64(sia + 16 * TI), aE = lds_f64(sia + 24 * TI), bz = lds_f64(sja + 16 * TJ), bE = lds_f64(sja + 24 * TJ);
+    const double qz = az - bz, qE = aE - bE;
+    o.qz = qz; o.qE = qE;
+    if (g.boost) {
+        // q_long = gamma (q_z - beta q_E) = (K_E q_z - K_z q_E) / Mt, src :383-390
+        const double sz = az + bz, sE = aE + bE;
+        const double m2 = (sE - sz) * (sE + sz);  // 4 Mt^2 without cancellation
+        if (!(m2 > 0.0)) return -1;
+        const double r2 = rsqrt(m2);
+        const double t1 = sE * qz, t2 = sz * qE;
+        double ql = (t1 - t2) * r2;
+        if (ORIENT && flip) ql = -ql;
+        o.ql = ql;
+        const double ch = sE * r2;  // cosh of the pair rapidity amplifies the rounding of Mt
+        const double gbl = fma((fabs(t1) + fabs(t2)) * r2 * fma(2.0 * ch, ch, 1.0), c.gl, c.g0);
+        const double u = fma(ql, c.inv_dq, c.ub);
+        const int i = __double2int_rd(u);
+        if (static_cast<unsigned>(i) >= nq) return (u > -gbl && u < c.nq_d + gbl) ? -1 : 3;
+        const double fr = u - static_cast<double>(i);
+        if (fr < gbl || fr > 1.0 - gbl) return -1;
+        o.il = i;
+    } else {
+        // q_long = q_z exactly as the reference has it: its own comparisons and index expression
+        const double ql = (ORIENT && flip) ? -qz : qz;
+        o.ql = ql;
+        if (!in_window(ql, g.q_lo, g.q_hi, MIXED)) return 3;
+        const int i = __double2int_rz(__ddiv_rn(__dsub_rn(ql, g.q_base), g.dq));
+        if (i >= g.nq) return 3;
+        o.il = i;
+    }
+    return 4;
+}
+
+// exact K_T bin of k2 = 4 K_perp_sq: float estimate, fixed up with the exact thresholds of
+// int((sqrt(K_perp_sq) - KT_min)/dKT) in k2 space (V2Const::kt4, found by bisection on the host)
+__device__ __forceinline__ int v3_kt_bin(const HbtGrid &g, const V2Const &c, double k2) {
+    const float kp = 0.5f * sqrtf(static_cast<float>(k2));
+    int iK = static_cast<int>((kp - c.kt_min_f) * c.inv_dkt_f);
+    iK = max(0, min(iK, g.nKT - 1));
+    while (iK > 0 && k2 < c.kt4[iK]) iK--;
+    while (iK < g.nKT - 1 && k2 >= c.kt4[iK + 1]) iK++;
+    return iK;
+}
+
+template <bool MIXED, int NC, bool ORIENT, bool STATS, int TI, int TJ>
+__device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
+                                              const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv,
+                                              unsigned si_addr, unsigned sj_addr, unsigned sio_addr, unsigned sjo_addr,
+                                              unsigned entry, double psi_ref, V2Counters &n) {
+    const unsigned il = entry >> 16, jl = entry & 0xffffu;
+    const unsigned sia = si_addr + 8 * il, sja = sj_addr + 8 * jl;
+    const bool flip = ORIENT && (lds_u32(sio_addr + 4 * il) > lds_u32(sjo_addr + 4 * jl));
+    V3Bins b;
+    double k2;
+    int stage = v3_fast_bins<MIXED, ORIENT, TI, TJ>(g, c, sia, sja, flip, k2, b);
+    int slab = 0;
+    if (stage == 4) {
+        slab = v3_kt_bin(g, c, k2);
+        if (g.az) {
+            const double Kx = 0.5 * (lds_f64(sia) + lds_f64(sja)), Ky = 0.5 * (lds_f64(sia + 8 * TI) + lds_f64(sja + 8 * TJ));
+            double dphi = __dsub_rn(atan2(Ky, Kx), psi_ref);
+            while (dphi < 0.) dphi = __dadd_rn(dphi, g.two_pi);
+            while (dphi > g.two_pi) dphi = __dsub_rn(dphi, g.two_pi);
+            const double u = __ddiv_rn(dphi, g.dKphi);
+            const int iphi = __double2int_rz(u);
+            if (fabs(u - rint(u)) < 1e-9) stage = -1;  // the literal path hands it to the host
+            else if (iphi < 0 || iphi >= g.nKphi) stage = 5;  // counted through q_long, then dropped
+            else slab = slab * g.nKphi + iphi;
+        }
+    }
+    if (stage < 0) {  // undecided: literal chain (roles swapped back into the reference's order)
+        double a8[8], b8[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double va = k < NC ? lds_f64(sia + 8 * TI * (k < NC ? k : 0)) : 0.0;
+            const double vb = k < NC ? lds_f64(sja + 8 * TJ * (k < NC ? k : 0)) : 0.0;
+            a8[k] = flip ? vb : va;
+            b8[k] = flip ? va : vb;
+        }
+        V2Counters tmp = {0, 0, 0, 0};  // keeps n itself out of local memory
+        v2_slow_pair<MIXED>(dv, a8, b8, psi_ref, tmp);
+        n.nB += tmp.nB; n.nC += tmp.nC; n.nD += tmp.nD; n.nE += tmp.nE;
+        return;
+    }
+    if (STATS) {
+        n.nB++;
+        if (stage >= 2) n.nC++;
+        if (stage >= 3) n.nD++;
+    }
+    if (stage < 4) return;
+    n.nE++;
+    if (stage != 4) return;
+    if (closed && closed[slab + (MIXED ? g.nslab : 0)]) return;  // needed_number_of_pairs reached earlier
+    const long long bin = ((static_cast<long long>(slab) * g.nq + b.io) * g.nq + b.is) * g.nq + b.il;
+    if (MIXED) {
+        atomicAdd(&acc.den_count[bin], 1ull);
+    } else {
+        const double xd = lds_f64(sia + 8 * TI * (4 % NC)) - lds_f64(sja + 8 * TJ * (4 % NC));
+        const double yd = lds_f64(sia + 8 * TI * (5 % NC)) - lds_f64(sja + 8 * TJ * (5 % NC));
+        const double zd = lds_f64(sia + 8 * TI * (6 % NC)) - lds_f64(sja + 8 * TJ * (6 % NC));
+        const double td = lds_f64(sia + 8 * TI * (7 % NC)) - lds_f64(sja + 8 * TJ * (7 % NC));
+        const double cv = pair_cos(g, b.qx, b.qy, b.qz, b.qE, xd, yd, zd, td);
+        atomicAdd(&acc.num_count[bin], 1ull);
+        atomicAdd(&acc.sum_qo[bin], b.qo);
+        atomicAdd(&acc.sum_qs[bin], b.qs);
+        atomicAdd(&acc.sum_ql[bin], b.ql);
+        atomicAdd(&acc.num_cos[bin], cv);
+    }
+}
+
+template <bool MIXED, bool STATS>
+__global__ void __launch_bounds__(32, HBT_V3_WARPS_PER_SM)
+hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long long n_same,
+             const HbtMixSeg *__restrict__ segs, const int *__restrict__ row_item0, int n_rows,
+             const unsigned *__restrict__ units, unsigned *__restrict__ work, unsigned n_units,
+             const HbtGrid g, const V2Const c, const V2Dev *__restrict__ dv, const HbtAccum acc,
+             const double psi_ref, const unsigned long long total_pairs,
+             const unsigned char *__restrict__ closed, const unsigned *__restrict__ orig) {
+    constexpr int NC = MIXED ? 4 : 8;
+    constexpr int SUB = HBT_V3_SUB, TJ = MIXED ? HBT_V3_TJ_MIXED : HBT_V3_TJ_SAME, IPL = HBT_V3_IPL;
+    constexpr bool SORTED = !MIXED && !STATS;
+    __shared__ double si[NC * SUB];
+    __shared__ double sj[NC * TJ];
+    __shared__ double sjt[TJ];
+    __shared__ unsigned si_o[SUB];
+    __shared__ unsigned sj_o[TJ];
+    __shared__ unsigned lq[HBT_V2_LCAP * 32];
+    __shared__ unsigned wq[HBT_V2_QCAP];
+
+    const int lane = threadIdx.x;
+    const unsigned si_addr = static_cast<unsigned>(__cvta_generic_to_shared(si));
+    const unsigned sj_addr = static_cast<unsigned>(__cvta_generic_to_shared(sj));
+    const unsigned sio_addr = static_cast<unsigned>(__cvta_generic_to_shared(si_o));
+    const unsigned sjo_addr = static_cast<unsigned>(__cvta_generic_to_shared(sj_o));
+    if (blockIdx.x == 0 && lane == 0) atomicAdd(&acc.stage[MIXED ? 6 : 0], total_pairs);
+    const unsigned total_units = SORTED ? work[1] : n_units;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    const double k2lo = c.k2lo, k2hi = c.k2hi, W2 = c.W2;
+
+    V2Queue Q;
+    Q.lane_list = lq + lane;
+    Q.list_addr = static_cast<unsigned>(__cvta_generic_to_shared(Q.lane_list));
+    Q.cur = Q.list_addr;
+    Q.wq = wq;
+    Q.qcount = 0;
+    Q.kept = 0;
+    V2Counters n = {0, 0, 0, 0};
+    unsigned cntKT = 0, cntRS = 0;
+    const unsigned lim = Q.list_addr + 128u * (HBT_V2_LCAP - IPL);
+
+  for (;;) {  // ---- pop the next unit --------------------------------------------------------
+    unsigned u = 0;
+    if (lane == 0) u = atomicAdd(&work[0], 1u);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= total_units) break;
+    long long i0, jbase, jcount;  // list-2 particles [jbase, jbase + jcount) belong to this row/segment
+    int ni, jt;
+    double rc = 1.0, rs = 0.0;
+    if (MIXED) {
+        const HbtMixSeg sg = segs[find_segment(segs, static_cast<int>(n_same), u)];
+        const int local = static_cast<int>(u - sg.block0);
+        const int ti = local / sg.tiles_j;
+        jt = local - ti * sg.tiles_j;
+        i0 = sg.i0 + static_cast<long long>(ti) * SUB;
+        ni = min(SUB, sg.ni - ti * SUB);
+        jbase = sg.j0;
+        jcount = sg.nj;
+        rc = sg.c; rs = sg.s;
+    } else {
+        int a;
+        if (SORTED) {
+            const unsigned e = units[u];
+            a = static_cast<int>(e >> 18);
+            jt = static_cast<int>(e & 0x3ffffu);
+        } else {  // every unit of the upper triangle: row a owns units [row_item0[a], row_item0[a+1])
+            int lo = 0, hi = n_rows - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (row_item0[mid] <= static_cast<int>(u)) lo = mid; else hi = mid - 1;
+            }
+            a = lo;
+            jt = a * (SUB / TJ) + (static_cast<int>(u) - row_item0[a]);
+        }
+        i0 = static_cast<long long>(a) * SUB;
+        ni = static_cast<int>(min(static_cast<long long>(SUB), n_same - i0));
+        jbase = 0;
+        jcount = n_same;
+    }
+    __syncwarp();  // the previous unit's drain has finished reading the tiles
+
+    // ---- list-1 sub-tile: shared memory (SoA, NaN padding) + this lane's 4 particles -------
+    double ax[IPL], ay[IPL], at[IPL];
+    unsigned ent[IPL];
+    long long ig[IPL];
+    double S1 = 0.0;
+#pragma unroll
+    for (int s = 0; s < IPL; s++) {
+        const int il = s * 32 + lane;
+        ent[s] = static_cast<unsigned>(il) << 16;
+        ig[s] = i0 + il;
+        if (il < ni) {
+            const double2 *src = reinterpret_cast<const double2 *>(p1 + 8 * (i0 + il));
+            const double2 v0 = src[0], v1 = src[1];
+            si[il] = v0.x; si[SUB + il] = v0.y; si[2 * SUB + il] = v1.x; si[3 * SUB + il] = v1.y;
+            if (!MIXED) {
+                const double2 v2 = src[2], v3 = src[3];
+                si[(4 % NC) * SUB + il] = v2.x; si[(5 % NC) * SUB + il] = v2.y;
+                si[(6 % NC) * SUB + il] = v3.x; si[(7 % NC) * SUB + il] = v3.y;
+            }
+            if (SORTED) si_o[il] = orig[i0 + il];
+            ax[s] = v0.x; ay[s] = v0.y;
+            at[s] = fma(v0.x, v0.x, v0.y * v0.y);
+            S1 = fmax(S1, at[s]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NC; q++) si[q * SUB + il] = nan;
+            if (SORTED) si_o[il] = 0u;
+            ax[s] = nan; ay[s] = nan; at[s] = nan;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) S1 = fmax(S1, __shfl_xor_sync(0xffffffffu, S1, o));
+
+    {
+        const long long jl0 = static_cast<long long>(jt) * TJ;
+        const int nj = static_cast<int>(min(static_cast<long long>(TJ), jcount - jl0));
+        // ---- stage the list-2 tile (the queue is empty here: entries index this unit) --------
+        double S2 = 0.0;
+        for (int k = lane; k < nj; k += 32) {
+            const double2 *src = reinterpret_cast<const double2 *>(p2 + 8 * (jbase + jl0 + k));
+            const double2 v0 = src[0], v1 = src[1];
+            double x = v0.x, y = v0.y;
+            if (MIXED) {  // rotation of the partner event, src/HBT_correlation.cpp:522-523
+                x = __dsub_rn(__dmul_rn(v0.x, rc), __dmul_rn(v0.y, rs));
+                y = __dadd_rn(__dmul_rn(v0.x, rs), __dmul_rn(v0.y, rc));
+            }
+            sj[k] = x; sj[TJ + k] = y; sj[2 * TJ + k] = v1.x; sj[3 * TJ + k] = v1.y;
+            const double pt2 = fma(x, x, y * y);
+            sjt[k] = pt2;
+            S2 = fmax(S2, pt2);
+            if (SORTED) sj_o[k] = orig[jl0 + k];
+            if (!MIXED) {
+                const double2 v2 = src[2], v3 = src[3];
+                sj[(4 % NC) * TJ + k] = v2.x; sj[(5 % NC) * TJ + k] = v2.y;
+                sj[(6 % NC) * TJ + k] = v3.x; sj[(7 % NC) * TJ + k] = v3.y;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) S2 = fmax(S2, __shfl_xor_sync(0xffffffffu, S2, o));
+        __syncwarp();
+        // prefilter error bound against the smallest K_T (see hbt_kernels_v2.cuh)
+        const double S = S1 + S2;
+        const double k2_floor = (5.6e-17 * S) * S / W2;
+        const bool use_floor = !(k2_floor <= k2lo);
+        const bool diag = !MIXED && (jl0 < i0 + SUB);  // tile reaches back to the diagonal: j > i only
+
+        // the pair loop, specialised on (unit touches the diagonal, error floor active)
+        auto tile_loop = [&](auto diag_c, auto floor_c) {
+            constexpr bool DIAG = decltype(diag_c)::value, FLOOR = decltype(floor_c)::value;
+            for (int j = 0; j <= nj; j++) {  // one extra trip: the per-unit final flush shares the call site
+                if (j < nj) {
+                    const double bx = sj[j], by = sj[TJ + j], bt = sjt[j];
+#pragma unroll
+                    for (int s = 0; s < IPL; s++) {
+                        const double sx = __dadd_rn(ax[s], bx), sy = __dadd_rn(ay[s], by);
+                        const double k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+                        bool kt = (k2 >= k2lo) && (k2 <= k2hi);  // exact K_T cut (NaN padding rows fail)
+                        if (DIAG) kt = kt && (jl0 + j > ig[s]);
+                        const double d = at[s] - bt;
+                        const double x = fma(bx, ay[s], -(ax[s] * by));
+                        const double d2 = d * d, x2 = x * x, w = W2 * k2;
+                        const int hw = __double2hiint(w);
+                        const int dd = __double2hiint(d2) - hw;               // d^2   vs W^2 k2
+                        const int dx = __double2hiint(x2) + 0x00200000 - hw;  // 4 x^2 vs W^2 k2
+                        bool rej_o = dd > 1;                 // q_out certainly outside the window
+                        bool rej_s = (dd < -1) && (dx > 1);  // q_out certainly inside, q_side certainly outside
+                        if (FLOOR) {
+                            const bool tiny = k2 < k2_floor;
+                            rej_o = rej_o && !tiny;
+                            rej_s = rej_s && !tiny;
+                        }
+                        const bool keep = kt && !(rej_o || rej_s);
+                        if (STATS) {  // exact K_T-pass and q_out-pass populations (instrumented runs only)
+                            inc_if(cntKT, kt);
+                            inc_if(cntRS, kt && rej_s);
+                        }
+                        if (keep) {
+                            sts_u32(Q.cur, ent[s] | static_cast<unsigned>(j));
+                            Q.cur += 128u;
+                        }
+                    }
+                }
+                const bool final = (j == nj);
+                if (final || __any_sync(0xffffffffu, Q.cur > lim)) {
+                    // compact the per-lane lists into the linear queue and drain it 32 at a time
+                    const int cnt = static_cast<int>(Q.cur - Q.list_addr) >> 7;
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    unsigned *dst = Q.wq + Q.qcount + (incl - cnt);
+                    for (int m = 0; m < cnt; m++) dst[m] = Q.lane_list[32 * m];
+                    Q.cur = Q.list_addr;
+                    Q.qcount += total;
+                    Q.kept += static_cast<unsigned>(total);
+                    __syncwarp();
+                    while (Q.qcount >= 32 || (final && Q.qcount > 0)) {
+                        const int take = min(32, Q.qcount);
+                        const int base = Q.qcount - take;
+                        if (lane < take)
+                            v3_drain_pair<MIXED, NC, SORTED, STATS, SUB, TJ>(g, c, acc, closed, dv, si_addr, sj_addr, sio_addr,
+                                                                             sjo_addr, Q.wq[base + lane], psi_ref, n);
+                        Q.qcount = base;
+                        __syncwarp();
+                    }
+                }
+            }
+        };
+        if (use_floor) {
+            if (diag) tile_loop(std::true_type{}, std::true_type{}); else tile_loop(std::false_type{}, std::true_type{});
+        } else {
+            if (diag) tile_loop(std::true_type{}, std::false_type{}); else tile_loop(std::false_type{}, std::false_type{});
+        }
+    }
+  }  // persistent loop
+
+    // ---- counters ------------------------------------------------------------------------
+    const unsigned nE = warp_sum(n.nE);
+    unsigned long long *stage = acc.stage + (MIXED ? 6 : 0);
+    if (STATS) {
+        unsigned nB = warp_sum(cntKT + n.nB), nC = warp_sum(cntRS + n.nC);
+        const unsigned nD = warp_sum(n.nD);
+        nB -= Q.kept;
+        if (lane == 0) {
+            if (nB) atomicAdd(&stage[1], static_cast<unsigned long long>(nB));
+            if (nC) atomicAdd(&stage[2], static_cast<unsigned long long>(nC));
+            if (nD) atomicAdd(&stage[3], static_cast<unsigned long long>(nD));
+        }
+    }
+    if (lane == 0 && nE) atomicAdd(&stage[4], static_cast<unsigned long long>(nE));
+}
+
+// ---- host side -----------------------------------------------------------------------------
+// instrumented same-event runs visit every unit of the upper triangle: row a (128 particles)
+// owns the tiles from the one holding particle 128a to the end.  Fills the prefix
+// row_item0[0..n_rows] and returns the number of units.
+inline long long hbt_v3_same_units(long long n, std::vector<int> &row_item0) {
+    const long long n_rows = (n + HBT_V3_SUB - 1) / HBT_V3_SUB;
+    const long long ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
+    row_item0.resize(n_rows + 1);
+    long long items = 0;
+    for (long long a = 0; a < n_rows; a++) {
+        row_item0[a] = static_cast<int>(items);
+        items += ntj - a * (HBT_V3_SUB / HBT_V3_TJ_SAME);
+    }
+    row_item0[n_rows] = static_cast<int>(items);
+    return items;
+}
+
+#endif  // HBT_KERNELS_V3_CUH_

@@ -13,7 +13,7 @@
 
 #include "hbt_common.h"
 
-#define HBT_BBOX_TILE 128
+#define HBT_BBOX_TILE 32
 
 struct HbtBBox {
     double xlo, xhi, ylo, yhi;
@@ -65,10 +65,9 @@ __global__ void hbt_sort_gather(const double *__restrict__ p, const unsigned *__
     reinterpret_cast<double2 *>(sorted + 8 * k)[part] = src[part];
 }
 
-// bounding box in (px,py) of every tile of HBT_BBOX_TILE consecutive sorted particles
+// bounding box in (px,py) of every tile of HBT_BBOX_TILE (= one warp) consecutive sorted particles
 __global__ void __launch_bounds__(HBT_BBOX_TILE) hbt_sort_bbox(const double *__restrict__ sorted, long long n,
                                                               HbtBBox *__restrict__ bbox) {
-    __shared__ double red[4][HBT_BBOX_TILE / 32];
     const long long k = blockIdx.x * static_cast<long long>(HBT_BBOX_TILE) + threadIdx.x;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     double xlo = inf, xhi = -inf, ylo = inf, yhi = -inf;
@@ -83,14 +82,7 @@ __global__ void __launch_bounds__(HBT_BBOX_TILE) hbt_sort_bbox(const double *__r
         ylo = fmin(ylo, __shfl_xor_sync(0xffffffffu, ylo, o));
         yhi = fmax(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
     }
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) { red[0][w] = xlo; red[1][w] = xhi; red[2][w] = ylo; red[3][w] = yhi; }
-    __syncthreads();
     if (threadIdx.x == 0) {
-        for (int q = 1; q < HBT_BBOX_TILE / 32; q++) {
-            xlo = fmin(xlo, red[0][q]); xhi = fmax(xhi, red[1][q]);
-            ylo = fmin(ylo, red[2][q]); yhi = fmax(yhi, red[3][q]);
-        }
         // a NaN coordinate would poison the box test: widen to everything (never culled)
         if (!(xlo <= xhi) || !(ylo <= yhi)) { xlo = -inf; xhi = inf; ylo = -inf; yhi = inf; }
         bbox[blockIdx.x] = {xlo, xhi, ylo, yhi};
