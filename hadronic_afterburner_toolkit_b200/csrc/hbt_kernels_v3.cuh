@@ -9,6 +9,15 @@
 // 9.9 active warps/SM), and with a static split of the rows the dense-core rows made a long tail
 // (6.4 active warps/SM).  Dynamic units of equal size keep every resident warp busy.  No
 // __syncthreads anywhere; the survivor queue is flushed once per unit.
+//
+// Production prefilter in packed FP32 (Blackwell FFMA2/FADD2/FMUL2, two list-1 particles per
+// instruction): k2, d = pT_i^2 - pT_j^2 and x = p_j x p_i are evaluated in float from float
+// copies of (px, py, pT^2); d^2 and 4x^2 are compared with W^2 k2 as integer bit patterns with a
+// margin of T ulps that bounds every rounding on the way (inputs, sums, products) from the
+// largest pT^2 of the two tiles; the K_T cut is tested with its own margin.  Only pairs that
+// CERTAINLY fail are dropped; the drain repeats the K_T cut exactly in FP64, so FP64 still
+// decides every cut and every bin edge.  Instrumented runs keep the FP64 prefilter, whose K_T
+// test is exact and which counts the stage populations.
 #ifndef HBT_KERNELS_V3_CUH_
 #define HBT_KERNELS_V3_CUH_
 
@@ -21,7 +30,9 @@
 #define HBT_V3_IPL 4
 #define HBT_V3_TJ_SAME 64    // list-2 tile, same-event (finer culling)
 #define HBT_V3_TJ_MIXED 128  // list-2 tile, mixed-event (no culling: fewer partial drains)
-#define HBT_V3_WARPS_PER_SM 12
+#ifndef HBT_V3_WARPS_PER_SM
+#define HBT_V3_WARPS_PER_SM 14
+#endif
 #define HBT_V3_MAX_SORTED (1ll << 21)  // unit encoding (row << 18 | tile) of the culled list
 
 // Units of the sorted same-event list that can hold an accepted pair: row a = particles
@@ -65,8 +76,8 @@ __global__ void hbt_cull_units(const HbtBBox *__restrict__ bbox, long long n, do
 // only when u is farther than gb from every integer, gb >= 2 eps + the bound on
 // |fast - reference|: that single test covers the bin edges, both window edges and their
 // '>' / '>=' distinction.  Anything closer (a ~1e-5 fraction of the survivors) takes the literal
-// chain (v2_slow_pair).  Returns the stage the pair reached: 1 = passed K_T only ... 4 = passed
-// q_long (accepted), or -1 = undecided.
+// chain (v2_slow_pair).  Returns the stage the pair reached: 0 = failed the K_T cut, 1 = passed
+// K_T only ... 4 = passed q_long (accepted), or -1 = undecided.
 struct V3Bins {
     int io, is, il;
     double qo, qs, ql, qx, qy, qz, qE;
@@ -77,7 +88,8 @@ __device__ __forceinline__ int v3_fast_bins(const HbtGrid &g, const V2Const &c, 
                                             double &k2, V3Bins &o) {
     const double ax = lds_f64(sia), ay = lds_f64(sia + 8 * TI), bx = lds_f64(sja), by = lds_f64(sja + 8 * TJ);
     const double sx = __dadd_rn(ax, bx), sy = __dadd_rn(ay, by);
-    k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));  // (the K_T cut was decided exactly by the prefilter)
+    k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+    if (!(k2 >= c.k2lo && k2 <= c.k2hi)) return 0;  // exact K_T cut (the float prefilter only pre-screens it)
     const double qx = ax - bx, qy = ay - by;
     const double d = fma(qx, sx, qy * sy);     // 2 K_perp q_out
     const double e = fma(qy, sx, -(qx * sy));  // 2 K_perp q_side
@@ -190,7 +202,7 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
         return;
     }
     if (STATS) {
-        n.nB++;
+        if (stage >= 1) n.nB++;
         if (stage >= 2) n.nC++;
         if (stage >= 3) n.nD++;
     }
@@ -229,6 +241,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
     __shared__ double si[NC * SUB];
     __shared__ double sj[NC * TJ];
     __shared__ double sjt[TJ];
+    __shared__ float sjf[3 * TJ];  // float px, py, pT^2 of the list-2 tile (production prefilter)
     __shared__ unsigned si_o[SUB];
     __shared__ unsigned sj_o[TJ];
     __shared__ unsigned lq[HBT_V2_LCAP * 32];
@@ -327,6 +340,16 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) S1 = fmax(S1, __shfl_xor_sync(0xffffffffu, S1, o));
+    float2 axf[IPL / 2], naxf[IPL / 2], ayf[IPL / 2], atf[IPL / 2];
+    if (!STATS) {
+#pragma unroll
+        for (int h = 0; h < IPL / 2; h++) {
+            axf[h] = make_float2(static_cast<float>(ax[2 * h]), static_cast<float>(ax[2 * h + 1]));
+            naxf[h] = make_float2(-axf[h].x, -axf[h].y);
+            ayf[h] = make_float2(static_cast<float>(ay[2 * h]), static_cast<float>(ay[2 * h + 1]));
+            atf[h] = make_float2(static_cast<float>(at[2 * h]), static_cast<float>(at[2 * h + 1]));
+        }
+    }
 
     {
         const long long jl0 = static_cast<long long>(jt) * TJ;
@@ -345,6 +368,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
             const double pt2 = fma(x, x, y * y);
             sjt[k] = pt2;
             S2 = fmax(S2, pt2);
+            if (!STATS) { sjf[k] = static_cast<float>(x); sjf[TJ + k] = static_cast<float>(y); sjf[2 * TJ + k] = static_cast<float>(pt2); }
             if (SORTED) sj_o[k] = orig[jl0 + k];
             if (!MIXED) {
                 const double2 v2 = src[2], v3 = src[3];
@@ -357,15 +381,67 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
         __syncwarp();
         // prefilter error bound against the smallest K_T (see hbt_kernels_v2.cuh)
         const double S = S1 + S2;
-        const double k2_floor = (5.6e-17 * S) * S / W2;
-        const bool use_floor = !(k2_floor <= k2lo);
+        double k2_floor = (5.6e-17 * S) * S / W2;
+        bool use_floor = !(k2_floor <= k2lo);
+        // ---- float prefilter margins (u = 2^-24; S bounds every squared momentum component):
+        //   |k2_f - k2| <= 64 u S,  |d_f - d| <= 8 u S,  |x_f - x| <= 16 u S  (inputs + every op)
+        //   at a window edge (d^2 = W^2 k2): relative error of d2_f / w_f
+        //        rho <= 64 u S / (W sqrt(k2)) + 64 u S / k2 + 4u ;   T = 2 rho / u  ulps
+        float klo_f = 0.f, khi_f = 0.f, kfloor_f = 0.f, W2f = 0.f;
+        int T = 0;
+        if (!STATS) {
+            const double u = 5.9604644775390625e-8, Ek = 64.0 * u * S;
+            const double Wd = sqrt(W2);
+            double k2e = k2lo - Ek > 0.0 ? k2lo - Ek : 0.0;
+            double rho = k2e > 0.0 ? 64.0 * u * S / (Wd * sqrt(k2e)) + 64.0 * u * S / k2e + 4.0 * u : 1.0;
+            use_floor = !(rho <= 0.03);
+            if (use_floor) {  // below this k2 the float window test is not trusted at all
+                const double a1 = 64.0 * u * S / (0.015 * Wd), a2 = 64.0 * u * S / 0.015;
+                k2_floor = fmax(a1 * a1, a2) + Ek;
+                rho = 0.03 + 4.0 * u;
+            }
+            T = static_cast<int>(2.0 * rho * 16777216.0) + 8;
+            klo_f = __double2float_rd(fmax(k2lo - Ek, 0.0));
+            khi_f = __double2float_ru(k2hi + Ek);
+            kfloor_f = __double2float_ru(k2_floor);
+            W2f = static_cast<float>(W2);
+        }
         const bool diag = !MIXED && (jl0 < i0 + SUB);  // tile reaches back to the diagonal: j > i only
 
         // the pair loop, specialised on (unit touches the diagonal, error floor active)
         auto tile_loop = [&](auto diag_c, auto floor_c) {
             constexpr bool DIAG = decltype(diag_c)::value, FLOOR = decltype(floor_c)::value;
             for (int j = 0; j <= nj; j++) {  // one extra trip: the per-unit final flush shares the call site
-                if (j < nj) {
+                if (!STATS && j < nj) {
+                    const float bxs = sjf[j], bys = sjf[TJ + j], bts = sjf[2 * TJ + j];
+                    const float2 bx2 = make_float2(bxs, bxs), by2 = make_float2(bys, bys), nbt2 = make_float2(-bts, -bts);
+                    const float2 W2f2 = make_float2(W2f, W2f);
+#pragma unroll
+                    for (int h = 0; h < IPL / 2; h++) {
+                        const float2 sx = __fadd2_rn(axf[h], bx2), sy = __fadd2_rn(ayf[h], by2);
+                        const float2 k2 = __ffma2_rn(sy, sy, __fmul2_rn(sx, sx));
+                        const float2 d = __fadd2_rn(atf[h], nbt2);
+                        const float2 x = __ffma2_rn(bx2, ayf[h], __fmul2_rn(naxf[h], by2));
+                        const float2 d2 = __fmul2_rn(d, d), x2 = __fmul2_rn(x, x), w = __fmul2_rn(k2, W2f2);
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int s = 2 * h + e;
+                            const float k2e = e ? k2.y : k2.x;
+                            bool kt = (k2e >= klo_f) && (k2e <= khi_f);  // K_T cut with margin (NaN rows fail)
+                            if (DIAG) kt = kt && (jl0 + j > ig[s]);
+                            const int hw = __float_as_int(e ? w.y : w.x);
+                            const int dd = __float_as_int(e ? d2.y : d2.x) - hw;               // d^2   vs W^2 k2
+                            const int dx = __float_as_int(e ? x2.y : x2.x) + 0x01000000 - hw;  // 4 x^2 vs W^2 k2
+                            bool rej = (dd > T) || (dx > T);  // q_out or q_side certainly outside the window
+                            if (FLOOR) rej = rej && !(k2e < kfloor_f);
+                            if (kt && !rej) {
+                                sts_u32(Q.cur, ent[s] | static_cast<unsigned>(j));
+                                Q.cur += 128u;
+                            }
+                        }
+                    }
+                }
+                if (STATS && j < nj) {
                     const double bx = sj[j], by = sj[TJ + j], bt = sjt[j];
 #pragma unroll
                     for (int s = 0; s < IPL; s++) {
