@@ -21,7 +21,7 @@
 #ifdef HBT_HAVE_V2
 #include "hbt_kernels_v3.cuh"
 #else
-#define HBT_V3_SUB 128
+#define HBT_V3_SUB_MIXED 128
 #define HBT_V3_TJ_MIXED 128
 #endif
 
@@ -326,7 +326,7 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
                 ctx->units_cap = static_cast<size_t>(all_units) + static_cast<size_t>(all_units) / 4;
                 CU(ctx, cudaMalloc(&ctx->d_units, ctx->units_cap * 4));
             }
-            const long long n_rows = (n + HBT_V3_SUB - 1) / HBT_V3_SUB, ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
+            const long long n_rows = (n + HBT_V3_SUB_SAME - 1) / HBT_V3_SUB_SAME, ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
             hbt_cull_units<<<dim3(static_cast<unsigned>((ntj + 127) / 128), static_cast<unsigned>(n_rows)), 128, 0, ctx->compute>>>(
                 ctx->sort_bbox, n, ctx->v2c.W2, ctx->v2c.k2lo, ctx->v2c.k2hi, ctx->d_units, ctx->d_work);
             ctx->kernel_launches++;
@@ -448,7 +448,7 @@ int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const Hbt
     return drain_timers(ctx, false);
 }
 
-int tile_i(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V3_SUB; }
+int tile_i(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V3_SUB_MIXED; }
 int tile_j(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V3_TJ_MIXED; }
 
 // host literal evaluation of the pairs the device deferred; leaves the stream idle

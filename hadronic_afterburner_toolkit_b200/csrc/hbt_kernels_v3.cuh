@@ -26,27 +26,29 @@
 
 #include "hbt_kernels_v2.cuh"
 
-#define HBT_V3_SUB 128  // list-1 particles per warp
-#define HBT_V3_IPL 4
+#ifndef HBT_V3_SUB_SAME
+#define HBT_V3_SUB_SAME 64   // list-1 particles per warp, same-event (2 per lane: more resident warps, finer culling)
+#endif
+#define HBT_V3_SUB_MIXED 128  // list-1 particles per warp, mixed-event (4 per lane)
 #define HBT_V3_TJ_SAME 64    // list-2 tile, same-event (finer culling)
 #define HBT_V3_TJ_MIXED 128  // list-2 tile, mixed-event (no culling: fewer partial drains)
 #ifndef HBT_V3_WARPS_PER_SM
 #define HBT_V3_WARPS_PER_SM 14
 #endif
-#define HBT_V3_MAX_SORTED (1ll << 21)  // unit encoding (row << 18 | tile) of the culled list
+#define HBT_V3_MAX_SORTED (1ll << 21)  // unit encoding (row << 16 | tile) of the culled list
 
 // Units of the sorted same-event list that can hold an accepted pair: row a = particles
-// [128a, 128a+128), tile t = particles [64t, 64t+64), t >= 2a (upper triangle incl. the two
+// [64a, 64a+64), tile t = particles [64t, 64t+64), t >= a (upper triangle incl. the
 // diagonal tiles).  work[1] counts them; work[0] is the pop counter of the pair kernel.
 __global__ void hbt_cull_units(const HbtBBox *__restrict__ bbox, long long n, double W2, double k2lo, double k2hi,
                                unsigned *__restrict__ units, unsigned *__restrict__ work) {
-    constexpr int RB = HBT_V3_SUB / HBT_BBOX_TILE, TB = HBT_V3_TJ_SAME / HBT_BBOX_TILE;
+    constexpr int RB = HBT_V3_SUB_SAME / HBT_BBOX_TILE, TB = HBT_V3_TJ_SAME / HBT_BBOX_TILE;
     const long long nb = (n + HBT_BBOX_TILE - 1) / HBT_BBOX_TILE;
     const int a = blockIdx.y;
     const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
     bool alive = false;
-    if (t < ntj && t >= static_cast<long long>(a) * (HBT_V3_SUB / HBT_V3_TJ_SAME)) {
+    if (t < ntj && t >= static_cast<long long>(a) * HBT_V3_SUB_SAME / HBT_V3_TJ_SAME) {
         HbtBBox ra = bbox[static_cast<long long>(a) * RB], tb = bbox[t * TB];
         for (int q = 1; q < RB; q++) {
             if (static_cast<long long>(a) * RB + q >= nb) break;
@@ -66,7 +68,7 @@ __global__ void hbt_cull_units(const HbtBBox *__restrict__ bbox, long long n, do
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(&work[1], __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (alive) units[base + __popc(m & ((1u << lane) - 1u))] = (static_cast<unsigned>(a) << 18) | static_cast<unsigned>(t);
+        if (alive) units[base + __popc(m & ((1u << lane) - 1u))] = (static_cast<unsigned>(a) << 16) | static_cast<unsigned>(t);
     }
 }
 
@@ -236,7 +238,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
              const double psi_ref, const unsigned long long total_pairs,
              const unsigned char *__restrict__ closed, const unsigned *__restrict__ orig) {
     constexpr int NC = MIXED ? 4 : 8;
-    constexpr int SUB = HBT_V3_SUB, TJ = MIXED ? HBT_V3_TJ_MIXED : HBT_V3_TJ_SAME, IPL = HBT_V3_IPL;
+    constexpr int SUB = MIXED ? HBT_V3_SUB_MIXED : HBT_V3_SUB_SAME, TJ = MIXED ? HBT_V3_TJ_MIXED : HBT_V3_TJ_SAME, IPL = SUB / 32;
     constexpr bool SORTED = !MIXED && !STATS;
     __shared__ double si[NC * SUB];
     __shared__ double sj[NC * TJ];
@@ -290,8 +292,8 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
         int a;
         if (SORTED) {
             const unsigned e = units[u];
-            a = static_cast<int>(e >> 18);
-            jt = static_cast<int>(e & 0x3ffffu);
+            a = static_cast<int>(e >> 16);
+            jt = static_cast<int>(e & 0xffffu);
         } else {  // every unit of the upper triangle: row a owns units [row_item0[a], row_item0[a+1])
             int lo = 0, hi = n_rows - 1;
             while (lo < hi) {
@@ -299,7 +301,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
                 if (row_item0[mid] <= static_cast<int>(u)) lo = mid; else hi = mid - 1;
             }
             a = lo;
-            jt = a * (SUB / TJ) + (static_cast<int>(u) - row_item0[a]);
+            jt = a * SUB / TJ + (static_cast<int>(u) - row_item0[a]);
         }
         i0 = static_cast<long long>(a) * SUB;
         ni = static_cast<int>(min(static_cast<long long>(SUB), n_same - i0));
@@ -528,16 +530,16 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
 
 // ---- host side -----------------------------------------------------------------------------
 // instrumented same-event runs visit every unit of the upper triangle: row a (128 particles)
-// owns the tiles from the one holding particle 128a to the end.  Fills the prefix
+// owns the tiles from the one holding its first particle to the end.  Fills the prefix
 // row_item0[0..n_rows] and returns the number of units.
 inline long long hbt_v3_same_units(long long n, std::vector<int> &row_item0) {
-    const long long n_rows = (n + HBT_V3_SUB - 1) / HBT_V3_SUB;
+    const long long n_rows = (n + HBT_V3_SUB_SAME - 1) / HBT_V3_SUB_SAME;
     const long long ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
     row_item0.resize(n_rows + 1);
     long long items = 0;
     for (long long a = 0; a < n_rows; a++) {
         row_item0[a] = static_cast<int>(items);
-        items += ntj - a * (HBT_V3_SUB / HBT_V3_TJ_SAME);
+        items += ntj - a * HBT_V3_SUB_SAME / HBT_V3_TJ_SAME;
     }
     row_item0[n_rows] = static_cast<int>(items);
     return items;
