@@ -30,7 +30,9 @@
 #define HBT_V3_SUB_SAME 64   // list-1 particles per warp, same-event (2 per lane: more resident warps, finer culling)
 #endif
 #define HBT_V3_SUB_MIXED 128  // list-1 particles per warp, mixed-event (4 per lane)
+#ifndef HBT_V3_TJ_SAME
 #define HBT_V3_TJ_SAME 64    // list-2 tile, same-event (finer culling)
+#endif
 #define HBT_V3_TJ_MIXED 128  // list-2 tile, mixed-event (no culling: fewer partial drains)
 #ifndef HBT_V3_WARPS_PER_SM
 #define HBT_V3_WARPS_PER_SM 14

@@ -100,6 +100,40 @@ def test_full_size_group_production_equals_literal_kernels():
     assert np.array_equal(tot, parts)
 
 
+@pytest.mark.parametrize("scale,ktmin", [(30.0, 0.15), (3000.0, 0.15), (1.0, 0.0), (1e-3, 0.0)])
+def test_prefilter_margins_with_outliers(scale, ktmin):
+    """The float prefilter's margins are derived from the largest pT^2 of the two tiles.  Momentum
+    outliers (a few particles scaled up by 30x / 3000x), a K_T range that starts at 0 and a sample
+    of tiny momenta must all still give the reference's integers (the prefilter may only get less
+    selective, never drop an accepted pair)."""
+    P = HBTParams(qnpts=21, KT_min=ktmin, KT_max=0.55 if ktmin else 1.0, n_KT=5)
+    batches = synth.make_batches(20260009, 1, 5, multiplicity=600)
+    rng = np.random.default_rng(3)
+    for b in batches:
+        for ev in b.same:
+            if scale >= 1.0:
+                k = rng.choice(len(ev), size=6, replace=False)
+                ev[k, 0:3] *= scale
+            else:
+                ev[:, 0:3] *= scale  # everything tiny: K_T << dKT, q << delta_q
+            ev[:, 3] = np.sqrt(0.138 ** 2 + (ev[:, 0:3] ** 2).sum(axis=1))
+    ref = run_oracle(P, batches)
+    for stats in (False, True):
+        _, acc = run_product(P, batches, stats=stats)
+        hbtio.compare(ref, acc, rtol=RTOL, check_stage=True if stats else "cheap", q_scale=0.25)
+
+
+def test_options_and_literal_kernels_agree():
+    P = HBTParams(qnpts=21)
+    batches = synth.make_batches(20260010, 2, 4, multiplicity=500)
+    ref = run_oracle(P, batches)
+    h = HBT_correlation(P, kernel=1)  # HBT_OPT_KERNEL = literal v1 kernels
+    for b in batches:
+        h.calculate_HBT_correlation_function(b)
+    hbtio.compare(ref, h.accumulators(), rtol=RTOL, check_stage=True)
+    assert h._L.hbt_set_option(h._h, 99, 0) == -1  # unknown option
+
+
 def test_device_resident_entry_points_refuse_near_the_cap():
     import ctypes
 
