@@ -44,7 +44,7 @@ SEED = 20260005
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--groups-per-gpu", type=int, default=2)
@@ -145,7 +145,7 @@ def reference_arm(a, rank, world):
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -153,9 +153,18 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except FileNotFoundError:
             self.p = None
+        self.t0 = self.t1 = None
+
+    def window_start(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def window_end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
 
     def stop(self):
         if self.p is None:
@@ -166,20 +175,19 @@ class ClockSampler:
         rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
         sm, mx, power, reasons = [], 0.0, [], set()
+        import datetime
         for r in rows:
             try:
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f")
+                if self.t0 and self.t1 and not (self.t0 <= ts <= self.t1):
+                    continue  # only samples taken DURING the timed region
                 sm.append(float(r[1])); mx = max(mx, float(r[2])); power.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if val.strip().lower().startswith("active"):
                     reasons.add(name)
-        # "under load" = samples in the upper half of the observed power range
-        if power:
-            thr = 0.5 * (min(power) + max(power))
-            load = [s for s, w in zip(sm, power) if w >= thr] or sm
-        else:
-            load = sm
+        load = sm  # every kept sample lies inside the timed region
         return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx or None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
@@ -309,11 +317,15 @@ def main():
     _check(h, L.hbt_set_option(h, 1, 0))
 
     # ---- resident-input measurement (value) ---------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None  # nvidia-smi needs a moment to start: launch it before the warm-up
     timed(step_resident, a.warmup, True)
     st0 = eng.stage_counters()
     tm0, l0 = eng.timers(), launches()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.window_start()
     t_value = timed(step_resident, a.steps, True)
+    if sampler:
+        sampler.window_end()
     clocks = sampler.stop() if sampler else None
     st1 = eng.stage_counters()
     tm1, l1 = eng.timers(), launches()
@@ -340,13 +352,24 @@ def main():
     ks = (tm1["same_ms"] - tm0["same_ms"]) * 1e-3
     km = (tm1["mixed_ms"] - tm0["mixed_ms"]) * 1e-3
     ach = (ops_same + ops_mixed) / (ks + km) / 1e12
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = {"unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one C5-shape group)",
+                   "same": tj["same"]["dram_bytes_per_launch"], "mixed": tj["mixed"]["dram_bytes_per_launch"],
+                   "algorithmic_bytes_per_launch": tj["same"]["algorithmic_bytes_per_launch"], "source": tj["source"]}
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
         "bound": "fp64", "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
-        "traffic": None,
+        "traffic": traffic,
         "peak_source": "measured on this device: DFMA dependent-chain microbenchmark (hbt_measure_fp64_peak); "
                        "FP64 is not in MEASURED_PEAKS.json",
-        "definition": "algorithmic FP64 ops (SURVEY.md 8d: 7nA+10nB+5nC+17nD+20nE same, ...+3nE mixed, from device stage "
-                      "counters) / CUDA-event time of the pair kernels on the launching stream",
+        "definition": "algorithmic FP64 ops (SURVEY.md 8d: 7nA+10nB+5nC+17nD+20nE same, ...+3nE mixed; stage populations from an "
+                      "instrumented, untimed pass over the same input) / CUDA-event time of the production pair kernels "
+                      "(incl. the same-event sort + cull kernels) on the launching stream",
+        "note": "the bound is the FP64 pipe (SURVEY.md 8d), not HBM or tensor cores; the production prefilter runs in packed "
+                "FP32, so the FP64 pipe itself is ~13-25 % busy (ncu) while the algorithmic-ops fraction is what is reported",
         "kernels": {
             "same": {"ms_per_launch": 1e3 * ks / max(1, tm1["same_launches"] - tm0["same_launches"]),
                      "pairs_per_s": float(dst[0]) / ks, "tflops": ops_same / ks / 1e12, "frac": ops_same / ks / 1e12 / peak.value,
