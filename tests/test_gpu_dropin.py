@@ -67,7 +67,7 @@ def test_same_files_as_reference_binary(name, tmp_path):
     synth.write_iss_gz(gz, batches)
     text = P.parameters_dat(event_buffer_size=nev * mult)  # groups of exactly nev events
     want, _ = run_binary(REF_EXE, str(tmp_path / "ref"), text, gz)
-    got, out = run_binary(OUR_EXE, str(tmp_path / "ours"), text, gz)
+    got, out = run_binary(OUR_EXE, str(tmp_path / "ours"), text, gz, env={"HBT_B200_DEVICES": "1"})
     assert "HBT pair loops run on 1 GPU(s)" in out
     same_text(want, got)
     assert len(want) == (P.n_KT - 1) * (P.n_Kphi if P.azimuthal_flag else 1) * (2 if P.invariant_radius_flag else 1)
