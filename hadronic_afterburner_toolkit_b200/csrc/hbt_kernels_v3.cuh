@@ -35,7 +35,7 @@
 #endif
 #define HBT_V3_TJ_MIXED 128  // list-2 tile, mixed-event (no culling: fewer partial drains)
 #ifndef HBT_V3_WARPS_PER_SM
-#define HBT_V3_WARPS_PER_SM 14
+#define HBT_V3_WARPS_PER_SM 18
 #endif
 #define HBT_V3_MAX_SORTED (1ll << 21)  // unit encoding (row << 16 | tile) of the culled list
 
