@@ -314,10 +314,11 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
         rc = ensure_work(ctx);
         if (rc) return rc;
         CU(ctx, cudaMemsetAsync(ctx->d_work, 0, 8, ctx->compute));
-        const unsigned grid = static_cast<unsigned>(ctx->n_sm * (ctx->stats ? ctx->occ_same_stats : ctx->occ_same));
+        const bool sorted = !ctx->stats && n <= HBT_V3_MAX_SORTED;  // longer lists: every unit, no sort
+        const unsigned grid = static_cast<unsigned>(ctx->n_sm * (sorted ? ctx->occ_same : ctx->occ_same_stats));
         const long long all_units = hbt_v3_same_units(n, ctx->row_item0);
         if (all_units > 0x7fffffffLL) return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld work units", all_units);
-        if (!ctx->stats && n <= HBT_V3_MAX_SORTED) {
+        if (sorted) {
             // production: Morton-sorted copy + tile boxes, units that can hold an accepted pair
             rc = prepare_sorted(ctx, d_p, n);
             if (rc) return rc;
@@ -344,12 +345,9 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
             // (pageable source: the copy is staged before the call returns, the vector can be reused)
             CU(ctx, cudaMemcpyAsync(ctx->d_rows, ctx->row_item0.data(), rb, cudaMemcpyHostToDevice, ctx->compute));
             const int n_rows = static_cast<int>(ctx->row_item0.size()) - 1;
-            if (ctx->stats)
-                hbt_pairs_v3<false, true><<<grid, 32, 0, ctx->compute>>>(
-                    d_p, d_p, n, nullptr, ctx->d_rows, n_rows, nullptr, ctx->d_work, static_cast<unsigned>(all_units), ctx->grid,
-                    ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
-            else
-                return fail(ctx, HBT_ERR_INVALID, "more than %lld particles in one batch: set HBT_OPT_STAGE_COUNTERS", HBT_V3_MAX_SORTED);
+            hbt_pairs_v3<false, true><<<grid, 32, 0, ctx->compute>>>(
+                d_p, d_p, n, nullptr, ctx->d_rows, n_rows, nullptr, ctx->d_work, static_cast<unsigned>(all_units), ctx->grid,
+                ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
         }
         ctx->kernel_launches++;
         if (rc) return fail(ctx, rc, "v2 same-event launch failed");

@@ -1,31 +1,7 @@
-// v2 pair kernels (sm_100a): prefilter + warp-level compaction + guarded fast path.
-//
-// Why: the literal chain (v1) spends ~150 FP64-pipe instructions per pair and runs 2/3 of
-// its lanes idle (ncu: 10.5 of 32 threads active per instruction), because 93 % of the
-// pairs leave the chain early at different stages.  v2 splits the work in two:
-//
-//  1. PREFILTER, every pair, no divergence, 13 FP64-pipe instructions.  Uses only
-//     (px, py, pT^2) of the two particles:
-//        s = p_i + p_j           k2 = rn(rn(sx^2) + rn(sy^2))  ( = 4 K_perp_sq, bit-exact: the
-//                                      reference's 0.5 factors are exact power-of-two scalings)
-//        d = pT_i^2 - pT_j^2     ( = q.s = 2 K_perp q_out )
-//        x = pxj*pyi - pxi*pyj   ( 2x = q x s = 2 K_perp q_side )
-//     K_T cut: exact compare of k2.  q_out / q_side windows: d^2 and 4x^2 against W^2 k2 with a
-//     relative band of ~3e-6 (integer compare of the high words); a pair is dropped only when
-//     it CERTAINLY fails; anything inside a band goes on.  ~92 % of the pairs end here.
-//  2. DRAIN.  Each lane appends its survivors (i,j) to a private shared-memory list (one
-//     predicated store, no cross-lane traffic in the hot loop).  When a list is about to
-//     fill, the warp compacts all lists into a linear queue (one prefix sum) and processes it
-//     32 pairs at a time with all lanes busy: K_T bin by exact thresholds in k2 space (no
-//     sqrt/divide), q_out/q_side/q_long from FMA arithmetic and rsqrt (a few ulp from the
-//     reference's values), each compared against the window and bin edges with a guard band
-//     that bounds the distance to the reference's own rounding.  Inside the guard
-//     (probability ~1e-12 per pair) the pair is re-evaluated with the literal chain of
-//     hbt_pair.cuh, so every bin decision equals the reference's.  Accepted pairs add
-//     cos(q.dx/hbarc) and the q sums with global atomics (histograms are L2 resident).
-//
-// The accumulated q_out/q_side/q_long are the fast-path values: within ~1e-15 relative of the
-// reference's, far inside the 1e-10 tolerance of the sums.
+// Pieces shared by the tuned pair kernels (hbt_kernels_v3.cuh): constants of the fast path,
+// the literal slow path for pairs the fast path cannot decide, the per-warp survivor queue and
+// small PTX helpers.  (The v2 kernels themselves — 4-warp CTAs, one tile pair per CTA — were
+// replaced by the persistent single-warp kernels of v3; see DESIGN.md §5 for the history.)
 #ifndef HBT_KERNELS_V2_CUH_
 #define HBT_KERNELS_V2_CUH_
 

@@ -37,7 +37,7 @@
 #ifndef HBT_V3_WARPS_PER_SM
 #define HBT_V3_WARPS_PER_SM 18
 #endif
-#define HBT_V3_MAX_SORTED (1ll << 21)  // unit encoding (row << 16 | tile) of the culled list
+#define HBT_V3_MAX_SORTED ((1ll << 22) - 64)  // unit encoding (row << 16 | tile) of the culled list, gridDim.y
 
 // Units of the sorted same-event list that can hold an accepted pair: row a = particles
 // [64a, 64a+64), tile t = particles [64t, 64t+64), t >= a (upper triangle incl. the

@@ -100,6 +100,23 @@ def test_full_size_group_production_equals_literal_kernels():
     assert np.array_equal(tot, parts)
 
 
+def test_batch_larger_than_the_sorted_unit_encoding():
+    """A batch with more particles than the culled-unit encoding can address (HBT_V3_MAX_SORTED,
+    ~4.19e6) runs the every-unit kernel instead of sort + cull; same integers as the literal
+    kernels.  21 500 events x 200 particles = 4.3e6 particles, 4.3e8 pairs."""
+    batch = synth.make_batches(20260011, 1, 21500, multiplicity=200)[0]
+    assert sum(len(e) for e in batch.same) > (1 << 22)
+    res = []
+    for kernel in (1, 2):
+        h = HBT_correlation(C3, kernel=kernel)
+        h.set_particle_list(batch)
+        h.combine_and_bin_particle_pairs(list(range(len(batch.same))))
+        res.append(h.accumulators())
+        h.close()
+    hbtio.compare(res[0], res[1], rtol=RTOL, check_stage="cheap")
+    assert int(res[1].stage[0]) == 21500 * (200 * 199 // 2)
+
+
 @pytest.mark.parametrize("scale,ktmin", [(30.0, 0.15), (3000.0, 0.15), (1.0, 0.0), (1e-3, 0.0)])
 def test_prefilter_margins_with_outliers(scale, ktmin):
     """The float prefilter's margins are derived from the largest pT^2 of the two tiles.  Momentum
