@@ -314,10 +314,11 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
         rc = ensure_work(ctx);
         if (rc) return rc;
         CU(ctx, cudaMemsetAsync(ctx->d_work, 0, 8, ctx->compute));
-        const bool sorted = !ctx->stats && n <= HBT_V3_MAX_SORTED;  // longer lists: every unit, no sort
+        const bool sorted = !ctx->stats;
         const unsigned grid = static_cast<unsigned>(ctx->n_sm * (sorted ? ctx->occ_same : ctx->occ_same_stats));
         const long long all_units = hbt_v3_same_units(n, ctx->row_item0);
-        if (all_units > 0x7fffffffLL) return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld work units", all_units);
+        if (all_units > 0x7fffffffLL || n > HBT_V3_MAX_SORTED)  // 8.8e12 pairs in one same-event list
+            return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld work units", all_units);
         if (sorted) {
             // production: Morton-sorted copy + tile boxes, units that can hold an accepted pair
             rc = prepare_sorted(ctx, d_p, n);
@@ -335,7 +336,7 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
                 ctx->sort_p, ctx->sort_p, n, nullptr, nullptr, 0, ctx->d_units, ctx->d_work, 0, ctx->grid, ctx->v2c, ctx->d_dv,
                 ctx->acc, psi_ref, npairs, cap.closed, ctx->sort_idx[1]);
         } else {
-            // instrumented (or a list too long for the unit encoding): every unit, reference order
+            // instrumented: every unit, reference order
             const size_t rb = ctx->row_item0.size() * sizeof(int);
             if (rb > ctx->d_rows_cap) {
                 cudaFree(ctx->d_rows);

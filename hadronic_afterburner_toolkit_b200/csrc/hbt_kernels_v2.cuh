@@ -123,6 +123,12 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
     return v;
 }
 
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ unsigned lds_u32(unsigned addr) {
     unsigned v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -131,6 +137,14 @@ __device__ __forceinline__ unsigned lds_u32(unsigned addr) {
 
 __device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// hides a value's origin from the compiler so that it stays in a register instead of being
+// rematerialised inside the hot loop
+__device__ __forceinline__ unsigned opaque_u32(unsigned v) {
+    unsigned r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
 }
 
 // cnt += 1 when flag: one predicated add

@@ -12,9 +12,9 @@
 //
 // Production prefilter in packed FP32 (Blackwell FFMA2/FADD2/FMUL2, two list-1 particles per
 // instruction): k2, d = pT_i^2 - pT_j^2 and x = p_j x p_i are evaluated in float from float
-// copies of (px, py, pT^2); d^2 and 4x^2 are compared with W^2 k2 as integer bit patterns with a
-// margin of T ulps that bounds every rounding on the way (inputs, sums, products) from the
-// largest pT^2 of the two tiles; the K_T cut is tested with its own margin.  Only pairs that
+// copies of (px, py, pT^2); max(d^2/4, x^2) is compared with (W^2/4)(1 + margin) k2, the margin
+// bounding every rounding on the way (inputs, sums, products) from the largest pT^2 of the two
+// tiles; the K_T cut is tested with its own margin.  Only pairs that
 // CERTAINLY fail are dropped; the drain repeats the K_T cut exactly in FP64, so FP64 still
 // decides every cut and every bin edge.  Instrumented runs keep the FP64 prefilter, whose K_T
 // test is exact and which counts the stage populations.
@@ -245,7 +245,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
     __shared__ double si[NC * SUB];
     __shared__ double sj[NC * TJ];
     __shared__ double sjt[TJ];
-    __shared__ float sjf[3 * TJ];  // float px, py, pT^2 of the list-2 tile (production prefilter)
+    __shared__ float sjf[3 * TJ];  // float px, py, -pT^2/2 of the list-2 tile (production prefilter)
     __shared__ unsigned si_o[SUB];
     __shared__ unsigned sj_o[TJ];
     __shared__ unsigned lq[HBT_V2_LCAP * 32];
@@ -256,6 +256,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
     const unsigned sj_addr = static_cast<unsigned>(__cvta_generic_to_shared(sj));
     const unsigned sio_addr = static_cast<unsigned>(__cvta_generic_to_shared(si_o));
     const unsigned sjo_addr = static_cast<unsigned>(__cvta_generic_to_shared(sj_o));
+    const unsigned sjf_addr = opaque_u32(static_cast<unsigned>(__cvta_generic_to_shared(sjf)));  // kept in a register: no per-trip S2UR/ULEA
     if (blockIdx.x == 0 && lane == 0) atomicAdd(&acc.stage[MIXED ? 6 : 0], total_pairs);
     const unsigned total_units = SORTED ? work[1] : n_units;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
@@ -270,7 +271,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
     Q.kept = 0;
     V2Counters n = {0, 0, 0, 0};
     unsigned cntKT = 0, cntRS = 0;
-    const unsigned lim = Q.list_addr + 128u * (HBT_V2_LCAP - IPL);
+    const unsigned lim = opaque_u32(Q.list_addr + 128u * (HBT_V2_LCAP - IPL));
 
   for (;;) {  // ---- pop the next unit --------------------------------------------------------
     unsigned u = 0;
@@ -351,7 +352,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
             axf[h] = make_float2(static_cast<float>(ax[2 * h]), static_cast<float>(ax[2 * h + 1]));
             naxf[h] = make_float2(-axf[h].x, -axf[h].y);
             ayf[h] = make_float2(static_cast<float>(ay[2 * h]), static_cast<float>(ay[2 * h + 1]));
-            atf[h] = make_float2(static_cast<float>(at[2 * h]), static_cast<float>(at[2 * h + 1]));
+            atf[h] = make_float2(static_cast<float>(0.5 * at[2 * h]), static_cast<float>(0.5 * at[2 * h + 1]));
         }
     }
 
@@ -372,7 +373,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
             const double pt2 = fma(x, x, y * y);
             sjt[k] = pt2;
             S2 = fmax(S2, pt2);
-            if (!STATS) { sjf[k] = static_cast<float>(x); sjf[TJ + k] = static_cast<float>(y); sjf[2 * TJ + k] = static_cast<float>(pt2); }
+            if (!STATS) { sjf[k] = static_cast<float>(x); sjf[TJ + k] = static_cast<float>(y); sjf[2 * TJ + k] = static_cast<float>(-0.5 * pt2); }
             if (SORTED) sj_o[k] = orig[jl0 + k];
             if (!MIXED) {
                 const double2 v2 = src[2], v3 = src[3];
@@ -390,9 +391,8 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
         // ---- float prefilter margins (u = 2^-24; S bounds every squared momentum component):
         //   |k2_f - k2| <= 64 u S,  |d_f - d| <= 8 u S,  |x_f - x| <= 16 u S  (inputs + every op)
         //   at a window edge (d^2 = W^2 k2): relative error of d2_f / w_f
-        //        rho <= 64 u S / (W sqrt(k2)) + 64 u S / k2 + 4u ;   T = 2 rho / u  ulps
-        float klo_f = 0.f, khi_f = 0.f, kfloor_f = 0.f, W2f = 0.f;
-        int T = 0;
+        //        rho <= 64 u S / (W sqrt(k2)) + 64 u S / k2 + 4u ;   the test allows 4 rho
+        float klo_f = 0.f, khi_f = 0.f, kfloor_f = 0.f, Wqf = 0.f;
         if (!STATS) {
             const double u = 5.9604644775390625e-8, Ek = 64.0 * u * S;
             const double Wd = sqrt(W2);
@@ -404,81 +404,91 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
                 k2_floor = fmax(a1 * a1, a2) + Ek;
                 rho = 0.03 + 4.0 * u;
             }
-            T = static_cast<int>(2.0 * rho * 16777216.0) + 8;
+            // the float test compares max(d_f^2, x_f^2) with fl(k2_f * Wqf): Wqf = (W^2/4)(1 + 4 rho) rounded
+            // up leaves more than the 2 rho the bound asks for (and the roundings of the three products)
+            Wqf = __double2float_ru(0.25 * W2 * (1.0 + 4.0 * rho + 16.0 * u));
             klo_f = __double2float_rd(fmax(k2lo - Ek, 0.0));
             khi_f = __double2float_ru(k2hi + Ek);
             kfloor_f = __double2float_ru(k2_floor);
-            W2f = static_cast<float>(W2);
         }
         const bool diag = !MIXED && (jl0 < i0 + SUB);  // tile reaches back to the diagonal: j > i only
 
         // the pair loop, specialised on (unit touches the diagonal, error floor active)
         auto tile_loop = [&](auto diag_c, auto floor_c) {
             constexpr bool DIAG = decltype(diag_c)::value, FLOOR = decltype(floor_c)::value;
-            for (int j = 0; j <= nj; j++) {  // one extra trip: the per-unit final flush shares the call site
-                if (!STATS && j < nj) {
-                    const float bxs = sjf[j], bys = sjf[TJ + j], bts = sjf[2 * TJ + j];
-                    const float2 bx2 = make_float2(bxs, bxs), by2 = make_float2(bys, bys), nbt2 = make_float2(-bts, -bts);
-                    const float2 W2f2 = make_float2(W2f, W2f);
+            int jthr[IPL];  // DIAG: pair (i, j) is taken when j > i, i.e. local j > jthr
 #pragma unroll
-                    for (int h = 0; h < IPL / 2; h++) {
-                        const float2 sx = __fadd2_rn(axf[h], bx2), sy = __fadd2_rn(ayf[h], by2);
-                        const float2 k2 = __ffma2_rn(sy, sy, __fmul2_rn(sx, sx));
-                        const float2 d = __fadd2_rn(atf[h], nbt2);
-                        const float2 x = __ffma2_rn(bx2, ayf[h], __fmul2_rn(naxf[h], by2));
-                        const float2 d2 = __fmul2_rn(d, d), x2 = __fmul2_rn(x, x), w = __fmul2_rn(k2, W2f2);
+            for (int s = 0; s < IPL; s++) jthr[s] = DIAG ? static_cast<int>(ig[s] - jl0) : 0;
+            const unsigned lane16 = static_cast<unsigned>(lane) << 16;
+            int j = 0;
+            for (;;) {
+                const bool final = (j >= nj);  // one extra trip: the per-unit final flush shares the call site
+                if (!final) {
+                    if (!STATS) {
+                        const unsigned ja = sjf_addr + 4u * static_cast<unsigned>(j);
+                        const float bxs = lds_f32(ja), bys = lds_f32(ja + 4 * TJ), nbh = lds_f32(ja + 8 * TJ);
+                        const float2 bx2 = make_float2(bxs, bxs), by2 = make_float2(bys, bys), nbt2 = make_float2(nbh, nbh);
+                        const float2 Wq2 = make_float2(Wqf, Wqf);
+                        const unsigned ej = lane16 + static_cast<unsigned>(j);
 #pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            const int s = 2 * h + e;
-                            const float k2e = e ? k2.y : k2.x;
-                            bool kt = (k2e >= klo_f) && (k2e <= khi_f);  // K_T cut with margin (NaN rows fail)
-                            if (DIAG) kt = kt && (jl0 + j > ig[s]);
-                            const int hw = __float_as_int(e ? w.y : w.x);
-                            const int dd = __float_as_int(e ? d2.y : d2.x) - hw;               // d^2   vs W^2 k2
-                            const int dx = __float_as_int(e ? x2.y : x2.x) + 0x01000000 - hw;  // 4 x^2 vs W^2 k2
-                            bool rej = (dd > T) || (dx > T);  // q_out or q_side certainly outside the window
-                            if (FLOOR) rej = rej && !(k2e < kfloor_f);
-                            if (kt && !rej) {
+                        for (int h = 0; h < IPL / 2; h++) {
+                            const float2 sx = __fadd2_rn(axf[h], bx2), sy = __fadd2_rn(ayf[h], by2);
+                            const float2 k2 = __ffma2_rn(sy, sy, __fmul2_rn(sx, sx));
+                            const float2 d = __fadd2_rn(atf[h], nbt2);  // (pT_i^2 - pT_j^2) / 2 = K_perp q_out
+                            const float2 x = __ffma2_rn(bx2, ayf[h], __fmul2_rn(naxf[h], by2));  // K_perp q_side
+                            const float2 d2 = __fmul2_rn(d, d), x2 = __fmul2_rn(x, x), w = __fmul2_rn(k2, Wq2);
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                const int s = 2 * h + e;
+                                const float k2e = e ? k2.y : k2.x;
+                                // K_T cut with margin (NaN rows fail), then max(d^2, x^2) against
+                                // (W^2/4)(1 + margin) k2: dropped only when certainly outside the window
+                                bool keep = (k2e >= klo_f) && (k2e <= khi_f);
+                                if (DIAG) keep = keep && (j > jthr[s]);
+                                const float m = fmaxf(e ? d2.y : d2.x, e ? x2.y : x2.x);
+                                bool in = m <= (e ? w.y : w.x);
+                                if (FLOOR) in = in || (k2e < kfloor_f);
+                                if (keep && in) {
+                                    sts_u32(Q.cur, ej + (static_cast<unsigned>(s) << 21));
+                                    Q.cur += 128u;
+                                }
+                            }
+                        }
+                    } else {
+                        const double bx = sj[j], by = sj[TJ + j], bt = sjt[j];
+#pragma unroll
+                        for (int s = 0; s < IPL; s++) {
+                            const double sx = __dadd_rn(ax[s], bx), sy = __dadd_rn(ay[s], by);
+                            const double k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+                            bool kt = (k2 >= k2lo) && (k2 <= k2hi);  // exact K_T cut (NaN padding rows fail)
+                            if (DIAG) kt = kt && (j > jthr[s]);
+                            const double d = at[s] - bt;
+                            const double x = fma(bx, ay[s], -(ax[s] * by));
+                            const double d2 = d * d, x2 = x * x, w = W2 * k2;
+                            const int hw = __double2hiint(w);
+                            const int dd = __double2hiint(d2) - hw;               // d^2   vs W^2 k2
+                            const int dx = __double2hiint(x2) + 0x00200000 - hw;  // 4 x^2 vs W^2 k2
+                            bool rej_o = dd > 1;                 // q_out certainly outside the window
+                            bool rej_s = (dd < -1) && (dx > 1);  // q_out certainly inside, q_side certainly outside
+                            if (FLOOR) {
+                                const bool tiny = k2 < k2_floor;
+                                rej_o = rej_o && !tiny;
+                                rej_s = rej_s && !tiny;
+                            }
+                            const bool keep = kt && !(rej_o || rej_s);
+                            // exact K_T-pass and q_out-pass populations (instrumented runs only)
+                            inc_if(cntKT, kt);
+                            inc_if(cntRS, kt && rej_s);
+                            if (keep) {
                                 sts_u32(Q.cur, ent[s] | static_cast<unsigned>(j));
                                 Q.cur += 128u;
                             }
                         }
                     }
+                    j++;
+                    if (!__any_sync(0xffffffffu, Q.cur > lim)) continue;
                 }
-                if (STATS && j < nj) {
-                    const double bx = sj[j], by = sj[TJ + j], bt = sjt[j];
-#pragma unroll
-                    for (int s = 0; s < IPL; s++) {
-                        const double sx = __dadd_rn(ax[s], bx), sy = __dadd_rn(ay[s], by);
-                        const double k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
-                        bool kt = (k2 >= k2lo) && (k2 <= k2hi);  // exact K_T cut (NaN padding rows fail)
-                        if (DIAG) kt = kt && (jl0 + j > ig[s]);
-                        const double d = at[s] - bt;
-                        const double x = fma(bx, ay[s], -(ax[s] * by));
-                        const double d2 = d * d, x2 = x * x, w = W2 * k2;
-                        const int hw = __double2hiint(w);
-                        const int dd = __double2hiint(d2) - hw;               // d^2   vs W^2 k2
-                        const int dx = __double2hiint(x2) + 0x00200000 - hw;  // 4 x^2 vs W^2 k2
-                        bool rej_o = dd > 1;                 // q_out certainly outside the window
-                        bool rej_s = (dd < -1) && (dx > 1);  // q_out certainly inside, q_side certainly outside
-                        if (FLOOR) {
-                            const bool tiny = k2 < k2_floor;
-                            rej_o = rej_o && !tiny;
-                            rej_s = rej_s && !tiny;
-                        }
-                        const bool keep = kt && !(rej_o || rej_s);
-                        if (STATS) {  // exact K_T-pass and q_out-pass populations (instrumented runs only)
-                            inc_if(cntKT, kt);
-                            inc_if(cntRS, kt && rej_s);
-                        }
-                        if (keep) {
-                            sts_u32(Q.cur, ent[s] | static_cast<unsigned>(j));
-                            Q.cur += 128u;
-                        }
-                    }
-                }
-                const bool final = (j == nj);
-                if (final || __any_sync(0xffffffffu, Q.cur > lim)) {
+                {
                     // compact the per-lane lists into the linear queue and drain it 32 at a time
                     const int cnt = static_cast<int>(Q.cur - Q.list_addr) >> 7;
                     int incl = cnt;
@@ -504,6 +514,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
                         __syncwarp();
                     }
                 }
+                if (final) break;
             }
         };
         if (use_floor) {

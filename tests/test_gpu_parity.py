@@ -100,21 +100,19 @@ def test_full_size_group_production_equals_literal_kernels():
     assert np.array_equal(tot, parts)
 
 
-def test_batch_larger_than_the_sorted_unit_encoding():
-    """A batch with more particles than the culled-unit encoding can address (HBT_V3_MAX_SORTED,
-    ~4.19e6) runs the every-unit kernel instead of sort + cull; same integers as the literal
-    kernels.  21 500 events x 200 particles = 4.3e6 particles, 4.3e8 pairs."""
+def test_batch_beyond_the_unit_encoding_is_refused():
+    """The same-event loop pairs every particle of the batch with every other one; a batch of more
+    than ~4.19e6 particles (8.8e12 pairs, 2^31 work units) does not fit the unit encoding and is
+    refused with HBT_ERR_INVALID before any kernel runs — never truncated."""
+    from hadronic_afterburner_toolkit_b200.capi import HBTError
     batch = synth.make_batches(20260011, 1, 21500, multiplicity=200)[0]
     assert sum(len(e) for e in batch.same) > (1 << 22)
-    res = []
-    for kernel in (1, 2):
-        h = HBT_correlation(C3, kernel=kernel)
-        h.set_particle_list(batch)
+    h = HBT_correlation(C3)
+    h.set_particle_list(batch)
+    with pytest.raises(HBTError, match="batch too large"):
         h.combine_and_bin_particle_pairs(list(range(len(batch.same))))
-        res.append(h.accumulators())
-        h.close()
-    hbtio.compare(res[0], res[1], rtol=RTOL, check_stage="cheap")
-    assert int(res[1].stage[0]) == 21500 * (200 * 199 // 2)
+    assert int(h.accumulators().num_count.sum()) == 0
+    h.close()
 
 
 @pytest.mark.parametrize("scale,ktmin", [(30.0, 0.15), (3000.0, 0.15), (1.0, 0.0), (1e-3, 0.0)])
