@@ -58,7 +58,10 @@ __host__ inline V2Const hbt_v2_consts(const HbtGrid &g) {
 // v2 handles the 3-D histograms with a window that is symmetric about zero; everything else
 // (q_inv mode, one-sided windows) runs on the literal v1 kernels
 __host__ inline bool hbt_v2_supported(const HbtGrid &g) {
-    return !g.qinv && hbt_v2_consts(g).symmetric && g.dq > 1e-6;
+    // K_T bins at least 1e-4 of KT_max wide: the float estimate of the K_T bin is then within one
+    // bin (relative error of the estimate ~4e-7); bin index in 32 bits
+    const double kt_max = g.KT_min + g.dKT * g.nKT;
+    return !g.qinv && hbt_v2_consts(g).symmetric && g.dq > 1e-6 && g.dKT > 1e-4 * kt_max && g.nbins < (1ll << 31);
 }
 
 // global-memory copy of everything the non-inlined device functions need (passing the

@@ -74,6 +74,25 @@ __global__ void hbt_cull_units(const HbtBBox *__restrict__ bbox, long long n, do
     }
 }
 
+// Shared memory of one warp, as byte offsets from one base address that the kernel keeps in a
+// register (every array is then an immediate offset of an LDS/STS; cvta of separate __shared__
+// arrays is recomputed at each use: S2UR + ULEA).
+template <bool MIXED, bool STATS>
+struct V3Smem {
+    static constexpr int NC = MIXED ? 4 : 8;  // doubles kept per particle (mixed-event pairs need no x^mu)
+    static constexpr int SUB = MIXED ? HBT_V3_SUB_MIXED : HBT_V3_SUB_SAME, TJ = MIXED ? HBT_V3_TJ_MIXED : HBT_V3_TJ_SAME;
+    static constexpr bool SORTED = !MIXED && !STATS;
+    static constexpr int SI = 0;                                 // double [NC][SUB]  list-1 sub-tile, SoA
+    static constexpr int SJ = SI + 8 * NC * SUB;                 // double [NC][TJ]   list-2 tile, SoA
+    static constexpr int SJT = SJ + 8 * NC * TJ;                 // double [TJ]       pT^2 of the list-2 tile (FP64 prefilter)
+    static constexpr int SJF = SJT + (STATS ? 8 * TJ : 0);       // float  [3][TJ]    px, py, -pT^2/2 (float prefilter)
+    static constexpr int SIO = SJF + (STATS ? 0 : 4 * 3 * TJ);   // u32    [SUB]      gather-order index (sorted lists)
+    static constexpr int SJO = SIO + (SORTED ? 4 * SUB : 0);     // u32    [TJ]
+    static constexpr int LQ = SJO + (SORTED ? 4 * TJ : 0);       // u32    [LCAP][32] per-lane survivor lists
+    static constexpr int WQ = LQ + 4 * HBT_V2_LCAP * 32;         // u32    [QCAP]     linear warp queue
+    static constexpr int BYTES = WQ + 4 * HBT_V2_QCAP;
+};
+
 // ---- guarded fast path for one queued survivor ---------------------------------------------
 // In units of bins, u = (q - q_base)/delta_q, the reference's window is [eps, nq - eps] with
 // eps = 1e-8/delta_q (src :363-364) and its bin edges are the integers.  The fast path decides
@@ -82,6 +101,57 @@ __global__ void hbt_cull_units(const HbtBBox *__restrict__ bbox, long long n, do
 // '>' / '>=' distinction.  Anything closer (a ~1e-5 fraction of the survivors) takes the literal
 // chain (v2_slow_pair).  Returns the stage the pair reached: 0 = failed the K_T cut, 1 = passed
 // K_T only ... 4 = passed q_long (accepted), or -1 = undecided.
+// 1/sqrt(x) for normal x > 0: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22) and one cubic
+// Newton step, e = 1 - x r0^2, r = r0 (1 + e/2 + 3e^2/8): |rel err| < 2^-51, inside the guard.
+// 6 instructions against ~20 of rsqrt() with its special-case handling.
+__device__ __forceinline__ double v3_rsqrt(double x) {
+    double r0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    const double e = fma(-(x * r0), r0, 1.0);
+    return fma(r0 * e, fma(e, 0.375, 0.5), r0);
+}
+
+// cos(x) with a 3-term Cody-Waite reduction by pi/2 and one degree-7 polynomial in r^2 whose
+// coefficients (fdlibm's) come from a constant table indexed by the quadrant parity:
+// cos r = P0(r^2), sin r = r P1(r^2).  |err| <= 3e-16 for |x| < 1e5 (checked on the host
+// against glibc on 2e7 arguments); larger arguments take the library routine.  Feeds a sum
+// with a 1e-10 tolerance.  ~35 instructions, no slow-path code in the hot loop.
+__constant__ double v3_cos_tab[2][8] = {
+    {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+     -1.38888888888741095749e-03, 4.16666666666666019037e-02, -0.5, 1.0},
+    {0.0, 1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+     -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01, 1.0}};
+
+// 2/pi and pi/2 in three pieces, as constant-bank operands (an FP64 immediate costs two UMOVs)
+__constant__ double v3_cos_red[4] = {6.36619772367581382433e-01, 1.57079632673412561417e+00, 6.07710050650619224932e-11,
+                                     2.02226624879595063154e-21};
+
+__device__ __forceinline__ double v3_cos(double x) {
+    if (!(fabs(x) < 1.0e5)) return cos(x);
+    const double nd = rint(x * v3_cos_red[0]);
+    double r = fma(-nd, v3_cos_red[1], x);
+    r = fma(-nd, v3_cos_red[2], r);
+    r = fma(-nd, v3_cos_red[3], r);
+    const int nq = __double2int_rn(nd);
+    const double z = r * r;
+    const double *t = v3_cos_tab[nq & 1];
+    double p = t[0];
+#pragma unroll
+    for (int k = 1; k < 8; k++) p = fma(p, z, t[k]);
+    const double v = p * ((nq & 1) ? r : 1.0);
+    return ((nq + 1) & 2) ? -v : v;
+}
+
+// reductions into the (global-memory) histograms: the accumulator pointers arrive as generic
+// pointers, for which atomicAdd compiles an address-space test and a shared-memory CAS loop
+// next to the RED
+__device__ __forceinline__ void red_add_f64(double *p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_inc_u64(unsigned long long *p) {
+    asm volatile("red.global.add.u64 [%0], 1;" ::"l"(__cvta_generic_to_global(p)) : "memory");
+}
+
 struct V3Bins {
     int io, is, il;
     double qo, qs, ql, qx, qy, qz, qE;
@@ -97,7 +167,7 @@ __device__ __forceinline__ int v3_fast_bins(const HbtGrid &g, const V2Const &c, 
     const double qx = ax - bx, qy = ay - by;
     const double d = fma(qx, sx, qy * sy);     // 2 K_perp q_out
     const double e = fma(qy, sx, -(qx * sy));  // 2 K_perp q_side
-    const double r = rsqrt(k2);                // 1 / (2 K_perp)
+    const double r = v3_rsqrt(k2);             // 1 / (2 K_perp); k2 >= k2lo > 0 or the NaN falls to the literal chain
     double qo = d * r, qs = e * r;
     if (ORIENT && flip) { qo = -qo; qs = -qs; }
     o.qx = qx; o.qy = qy; o.qo = qo; o.qs = qs;
@@ -110,7 +180,7 @@ __device__ __forceinline__ int v3_fast_bins(const HbtGrid &g, const V2Const &c, 
         const int i = __double2int_rd(u);
         if (static_cast<unsigned>(i) >= nq) return (u > -gb && u < c.nq_d + gb) ? -1 : 1;  // outside (NaN too)
         const double fr = u - static_cast<double>(i);
-        if (fr < gb || fr > one_m) return -1;
+        if (!(fr >= gb && fr <= one_m)) return -1;  // (a NaN lands here too)
         o.io = i;
     }
     {
@@ -118,7 +188,7 @@ __device__ __forceinline__ int v3_fast_bins(const HbtGrid &g, const V2Const &c, 
         const int i = __double2int_rd(u);
         if (static_cast<unsigned>(i) >= nq) return (u > -gb && u < c.nq_d + gb) ? -1 : 2;
         const double fr = u - static_cast<double>(i);
-        if (fr < gb || fr > one_m) return -1;
+        if (!(fr >= gb && fr <= one_m)) return -1;
         o.is = i;
     }
     const double az = lds_f64(sia + 16 * TI), aE = lds_f64(sia + 24 * TI), bz = lds_f64(sja + 16 * TJ), bE = lds_f64(sja + 24 * TJ);
@@ -129,7 +199,7 @@ __device__ __forceinline__ int v3_fast_bins(const HbtGrid &g, const V2Const &c, 
         const double sz = az + bz, sE = aE + bE;
         const double m2 = (sE - sz) * (sE + sz);  // 4 Mt^2 without cancellation
         if (!(m2 > 0.0)) return -1;
-        const double r2 = rsqrt(m2);
+        const double r2 = v3_rsqrt(m2);
         const double t1 = sE * qz, t2 = sz * qE;
         double ql = (t1 - t2) * r2;
         if (ORIENT && flip) ql = -ql;
@@ -140,7 +210,7 @@ __device__ __forceinline__ int v3_fast_bins(const HbtGrid &g, const V2Const &c, 
         const int i = __double2int_rd(u);
         if (static_cast<unsigned>(i) >= nq) return (u > -gbl && u < c.nq_d + gbl) ? -1 : 3;
         const double fr = u - static_cast<double>(i);
-        if (fr < gbl || fr > 1.0 - gbl) return -1;
+        if (!(fr >= gbl && fr <= 1.0 - gbl)) return -1;
         o.il = i;
     } else {
         // q_long = q_z exactly as the reference has it: its own comparisons and index expression
@@ -154,25 +224,30 @@ __device__ __forceinline__ int v3_fast_bins(const HbtGrid &g, const V2Const &c, 
     return 4;
 }
 
-// exact K_T bin of k2 = 4 K_perp_sq: float estimate, fixed up with the exact thresholds of
-// int((sqrt(K_perp_sq) - KT_min)/dKT) in k2 space (V2Const::kt4, found by bisection on the host)
+// exact K_T bin of k2 = 4 K_perp_sq: float estimate (within one bin: hbt_v2_supported refuses
+// grids whose K_T bins are too narrow for that), corrected by one step either way against the
+// exact thresholds of int((sqrt(K_perp_sq) - KT_min)/dKT) in k2 space (V2Const::kt4, found by
+// bisection on the host)
 __device__ __forceinline__ int v3_kt_bin(const HbtGrid &g, const V2Const &c, double k2) {
-    const float kp = 0.5f * sqrtf(static_cast<float>(k2));
+    const float k2f = static_cast<float>(k2);
+    const float kp = 0.5f * k2f * rsqrtf(k2f);
     int iK = static_cast<int>((kp - c.kt_min_f) * c.inv_dkt_f);
     iK = max(0, min(iK, g.nKT - 1));
-    while (iK > 0 && k2 < c.kt4[iK]) iK--;
-    while (iK < g.nKT - 1 && k2 >= c.kt4[iK + 1]) iK++;
+    if (iK > 0 && k2 < c.kt4[iK]) iK--;
+    else if (iK < g.nKT - 1 && k2 >= c.kt4[iK + 1]) iK++;
     return iK;
 }
 
-template <bool MIXED, int NC, bool ORIENT, bool STATS, int TI, int TJ>
+template <bool MIXED, bool STATS>
 __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
                                               const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv,
-                                              unsigned si_addr, unsigned sj_addr, unsigned sio_addr, unsigned sjo_addr,
-                                              unsigned entry, double psi_ref, V2Counters &n) {
-    const unsigned il = entry >> 16, jl = entry & 0xffffu;
-    const unsigned sia = si_addr + 8 * il, sja = sj_addr + 8 * jl;
-    const bool flip = ORIENT && (lds_u32(sio_addr + 4 * il) > lds_u32(sjo_addr + 4 * jl));
+                                              unsigned sbase, unsigned entry, double psi_ref, V2Counters &n) {
+    using L = V3Smem<MIXED, STATS>;
+    constexpr int NC = L::NC, TI = L::SUB, TJ = L::TJ;
+    constexpr bool ORIENT = L::SORTED;
+    const unsigned il4 = (entry >> 14) & ~3u, jl4 = (entry & 0xffffu) << 2;  // 4 x list-1 / list-2 slot
+    const unsigned sia = sbase + L::SI + 2 * il4, sja = sbase + L::SJ + 2 * jl4;
+    const bool flip = ORIENT && (lds_u32(sbase + L::SIO + il4) > lds_u32(sbase + L::SJO + jl4));
     V3Bins b;
     double k2;
     int stage = v3_fast_bins<MIXED, ORIENT, TI, TJ>(g, c, sia, sja, flip, k2, b);
@@ -214,20 +289,20 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
     n.nE++;
     if (stage != 4) return;
     if (closed && closed[slab + (MIXED ? g.nslab : 0)]) return;  // needed_number_of_pairs reached earlier
-    const long long bin = ((static_cast<long long>(slab) * g.nq + b.io) * g.nq + b.is) * g.nq + b.il;
+    const unsigned bin = ((static_cast<unsigned>(slab) * g.nq + b.io) * g.nq + b.is) * g.nq + b.il;  // < 2^31 (hbt_create)
     if (MIXED) {
-        atomicAdd(&acc.den_count[bin], 1ull);
+        red_inc_u64(&acc.den_count[bin]);
     } else {
         const double xd = lds_f64(sia + 8 * TI * (4 % NC)) - lds_f64(sja + 8 * TJ * (4 % NC));
         const double yd = lds_f64(sia + 8 * TI * (5 % NC)) - lds_f64(sja + 8 * TJ * (5 % NC));
         const double zd = lds_f64(sia + 8 * TI * (6 % NC)) - lds_f64(sja + 8 * TJ * (6 % NC));
         const double td = lds_f64(sia + 8 * TI * (7 % NC)) - lds_f64(sja + 8 * TJ * (7 % NC));
-        const double cv = pair_cos(g, b.qx, b.qy, b.qz, b.qE, xd, yd, zd, td);
-        atomicAdd(&acc.num_count[bin], 1ull);
-        atomicAdd(&acc.sum_qo[bin], b.qo);
-        atomicAdd(&acc.sum_qs[bin], b.qs);
-        atomicAdd(&acc.sum_ql[bin], b.ql);
-        atomicAdd(&acc.num_cos[bin], cv);
+        const double cv = v3_cos(g.hbarc_inv * (b.qE * td - b.qx * xd - b.qy * yd - b.qz * zd));  // src :431-433
+        red_inc_u64(&acc.num_count[bin]);
+        red_add_f64(&acc.sum_qo[bin], b.qo);
+        red_add_f64(&acc.sum_qs[bin], b.qs);
+        red_add_f64(&acc.sum_ql[bin], b.ql);
+        red_add_f64(&acc.num_cos[bin], cv);
     }
 }
 
@@ -239,24 +314,23 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
              const HbtGrid g, const V2Const c, const V2Dev *__restrict__ dv, const HbtAccum acc,
              const double psi_ref, const unsigned long long total_pairs,
              const unsigned char *__restrict__ closed, const unsigned *__restrict__ orig) {
-    constexpr int NC = MIXED ? 4 : 8;
-    constexpr int SUB = MIXED ? HBT_V3_SUB_MIXED : HBT_V3_SUB_SAME, TJ = MIXED ? HBT_V3_TJ_MIXED : HBT_V3_TJ_SAME, IPL = SUB / 32;
-    constexpr bool SORTED = !MIXED && !STATS;
-    __shared__ double si[NC * SUB];
-    __shared__ double sj[NC * TJ];
-    __shared__ double sjt[TJ];
-    __shared__ float sjf[3 * TJ];  // float px, py, -pT^2/2 of the list-2 tile (production prefilter)
-    __shared__ unsigned si_o[SUB];
-    __shared__ unsigned sj_o[TJ];
-    __shared__ unsigned lq[HBT_V2_LCAP * 32];
-    __shared__ unsigned wq[HBT_V2_QCAP];
+    using L = V3Smem<MIXED, STATS>;
+    constexpr int NC = L::NC, SUB = L::SUB, TJ = L::TJ, IPL = SUB / 32;
+    constexpr bool SORTED = L::SORTED;
+    __shared__ __align__(16) unsigned char smem[L::BYTES];
+    double *const si = reinterpret_cast<double *>(smem + L::SI);
+    double *const sj = reinterpret_cast<double *>(smem + L::SJ);
+    double *const sjt = reinterpret_cast<double *>(smem + L::SJT);
+    float *const sjf = reinterpret_cast<float *>(smem + L::SJF);
+    unsigned *const si_o = reinterpret_cast<unsigned *>(smem + L::SIO);
+    unsigned *const sj_o = reinterpret_cast<unsigned *>(smem + L::SJO);
+    unsigned *const lq = reinterpret_cast<unsigned *>(smem + L::LQ);
+    unsigned *const wq = reinterpret_cast<unsigned *>(smem + L::WQ);
 
     const int lane = threadIdx.x;
-    const unsigned si_addr = static_cast<unsigned>(__cvta_generic_to_shared(si));
-    const unsigned sj_addr = static_cast<unsigned>(__cvta_generic_to_shared(sj));
-    const unsigned sio_addr = static_cast<unsigned>(__cvta_generic_to_shared(si_o));
-    const unsigned sjo_addr = static_cast<unsigned>(__cvta_generic_to_shared(sj_o));
-    const unsigned sjf_addr = opaque_u32(static_cast<unsigned>(__cvta_generic_to_shared(sjf)));  // kept in a register: no per-trip S2UR/ULEA
+    // kept in a register: no per-use S2UR/ULEA
+    const unsigned sbase = opaque_u32(static_cast<unsigned>(__cvta_generic_to_shared(smem)));
+    const unsigned sjf_addr = sbase + L::SJF;
     if (blockIdx.x == 0 && lane == 0) atomicAdd(&acc.stage[MIXED ? 6 : 0], total_pairs);
     const unsigned total_units = SORTED ? work[1] : n_units;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
@@ -264,7 +338,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
 
     V2Queue Q;
     Q.lane_list = lq + lane;
-    Q.list_addr = static_cast<unsigned>(__cvta_generic_to_shared(Q.lane_list));
+    Q.list_addr = sbase + L::LQ + 4u * static_cast<unsigned>(lane);
     Q.cur = Q.list_addr;
     Q.wq = wq;
     Q.qcount = 0;
@@ -371,7 +445,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
             }
             sj[k] = x; sj[TJ + k] = y; sj[2 * TJ + k] = v1.x; sj[3 * TJ + k] = v1.y;
             const double pt2 = fma(x, x, y * y);
-            sjt[k] = pt2;
+            if (STATS) sjt[k] = pt2;  // (no such array in production: the offset is shared with sjf)
             S2 = fmax(S2, pt2);
             if (!STATS) { sjf[k] = static_cast<float>(x); sjf[TJ + k] = static_cast<float>(y); sjf[2 * TJ + k] = static_cast<float>(-0.5 * pt2); }
             if (SORTED) sj_o[k] = orig[jl0 + k];
@@ -508,8 +582,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
                         const int take = min(32, Q.qcount);
                         const int base = Q.qcount - take;
                         if (lane < take)
-                            v3_drain_pair<MIXED, NC, SORTED, STATS, SUB, TJ>(g, c, acc, closed, dv, si_addr, sj_addr, sio_addr,
-                                                                             sjo_addr, Q.wq[base + lane], psi_ref, n);
+                            v3_drain_pair<MIXED, STATS>(g, c, acc, closed, dv, sbase, Q.wq[base + lane], psi_ref, n);
                         Q.qcount = base;
                         __syncwarp();
                     }
