@@ -224,6 +224,62 @@ __device__ __forceinline__ int v3_fast_bins(const HbtGrid &g, const V2Const &c, 
     return 4;
 }
 
+// Production form of the fast path: the three components are evaluated side by side and decided
+// together, so that the q_out/q_side chain (rsqrt of k2) and the q_long chain (rsqrt of 4 Mt^2)
+// overlap instead of waiting for each other's early exits (86 % of the queued pairs pass all
+// three; the drain is latency-bound at 4-5 warps per scheduler).  Returns 4 (every component
+// safely inside a bin), 0 (the K_T cut or some component certainly outside the window) or -1.
+__device__ __forceinline__ void v3_classify(const V2Const &c, unsigned nq, double q, double gb, int &i, bool &ok, bool &out) {
+    const double u = fma(q, c.inv_dq, c.ub);
+    i = __double2int_rd(u);
+    const double fr = u - static_cast<double>(i);
+    ok = (static_cast<unsigned>(i) < nq) && (fr >= gb) && (fr <= 1.0 - gb);
+    out = !(u > -gb && u < c.nq_d + gb);  // certainly outside the window (a NaN too: the literal chain rejects it)
+}
+
+template <bool MIXED, bool ORIENT, int TI, int TJ>
+__device__ __forceinline__ int v3_fast_bins_all(const HbtGrid &g, const V2Const &c, unsigned sia, unsigned sja, bool flip,
+                                                double &k2, V3Bins &o) {
+    const double ax = lds_f64(sia), ay = lds_f64(sia + 8 * TI), bx = lds_f64(sja), by = lds_f64(sja + 8 * TJ);
+    const double az = lds_f64(sia + 16 * TI), aE = lds_f64(sia + 24 * TI), bz = lds_f64(sja + 16 * TJ), bE = lds_f64(sja + 24 * TJ);
+    const double sx = __dadd_rn(ax, bx), sy = __dadd_rn(ay, by);
+    k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+    const bool kt = (k2 >= c.k2lo) && (k2 <= c.k2hi);  // exact K_T cut (the float prefilter only pre-screens it)
+    const double qx = ax - bx, qy = ay - by, qz = az - bz, qE = aE - bE;
+    const double d = fma(qx, sx, qy * sy);     // 2 K_perp q_out
+    const double e = fma(qy, sx, -(qx * sy));  // 2 K_perp q_side
+    const double r = v3_rsqrt(k2);             // 1 / (2 K_perp)
+    double qo = d * r, qs = e * r, ql;
+    const double gb = fma(fabs(qx) + fabs(qy), c.gq, c.g0);
+    const unsigned nq = static_cast<unsigned>(g.nq);
+    bool ok_o, out_o, ok_s, out_s, ok_l, out_l;
+    if (g.boost) {
+        // q_long = gamma (q_z - beta q_E) = (K_E q_z - K_z q_E) / Mt, src :383-390
+        const double sz = az + bz, sE = aE + bE;
+        const double m2 = (sE - sz) * (sE + sz);  // 4 Mt^2 without cancellation
+        const double r2 = v3_rsqrt(m2);
+        const double t1 = sE * qz, t2 = sz * qE;
+        ql = (t1 - t2) * r2;
+        const double ch = sE * r2;  // cosh of the pair rapidity amplifies the rounding of Mt
+        const double gbl = fma((fabs(t1) + fabs(t2)) * r2 * fma(2.0 * ch, ch, 1.0), c.gl, c.g0);
+        if (ORIENT && flip) ql = -ql;
+        v3_classify(c, nq, ql, gbl, o.il, ok_l, out_l);
+        if (!(m2 > 0.0)) { ok_l = false; out_l = false; }  // undecided
+    } else {
+        // q_long = q_z exactly as the reference has it: its own comparisons and index expression
+        ql = (ORIENT && flip) ? -qz : qz;
+        o.il = __double2int_rz(__ddiv_rn(__dsub_rn(ql, g.q_base), g.dq));
+        ok_l = in_window(ql, g.q_lo, g.q_hi, MIXED) && (o.il < g.nq);
+        out_l = !ok_l;
+    }
+    if (ORIENT && flip) { qo = -qo; qs = -qs; }
+    v3_classify(c, nq, qo, gb, o.io, ok_o, out_o);
+    v3_classify(c, nq, qs, gb, o.is, ok_s, out_s);
+    o.qx = qx; o.qy = qy; o.qz = qz; o.qE = qE; o.qo = qo; o.qs = qs; o.ql = ql;
+    if (!kt || out_o || out_s || out_l) return 0;
+    return (ok_o && ok_s && ok_l) ? 4 : -1;
+}
+
 // exact K_T bin of k2 = 4 K_perp_sq: float estimate (within one bin: hbt_v2_supported refuses
 // grids whose K_T bins are too narrow for that), corrected by one step either way against the
 // exact thresholds of int((sqrt(K_perp_sq) - KT_min)/dKT) in k2 space (V2Const::kt4, found by
@@ -250,7 +306,8 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
     const bool flip = ORIENT && (lds_u32(sbase + L::SIO + il4) > lds_u32(sbase + L::SJO + jl4));
     V3Bins b;
     double k2;
-    int stage = v3_fast_bins<MIXED, ORIENT, TI, TJ>(g, c, sia, sja, flip, k2, b);
+    int stage = STATS ? v3_fast_bins<MIXED, ORIENT, TI, TJ>(g, c, sia, sja, flip, k2, b)
+                      : v3_fast_bins_all<MIXED, ORIENT, TI, TJ>(g, c, sia, sja, flip, k2, b);
     int slab = 0;
     if (stage == 4) {
         slab = v3_kt_bin(g, c, k2);
@@ -572,8 +629,8 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
                         if (lane >= o) incl += v;
                     }
                     const int total = __shfl_sync(0xffffffffu, incl, 31);
-                    unsigned *dst = Q.wq + Q.qcount + (incl - cnt);
-                    for (int m = 0; m < cnt; m++) dst[m] = Q.lane_list[32 * m];
+                    const unsigned dst = sbase + L::WQ + 4u * static_cast<unsigned>(Q.qcount + (incl - cnt));
+                    for (int m = 0; m < cnt; m++) sts_u32(dst + 4u * m, lds_u32(Q.list_addr + 128u * m));
                     Q.cur = Q.list_addr;
                     Q.qcount += total;
                     Q.kept += static_cast<unsigned>(total);
@@ -582,7 +639,8 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
                         const int take = min(32, Q.qcount);
                         const int base = Q.qcount - take;
                         if (lane < take)
-                            v3_drain_pair<MIXED, STATS>(g, c, acc, closed, dv, sbase, Q.wq[base + lane], psi_ref, n);
+                            v3_drain_pair<MIXED, STATS>(g, c, acc, closed, dv, sbase,
+                                                        lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(base + lane)), psi_ref, n);
                         Q.qcount = base;
                         __syncwarp();
                     }
