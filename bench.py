@@ -261,8 +261,8 @@ def main():
     def step_resident():
         for g in range(G):
             ids, cs = plans[g]
-            _check(h, L.hbt_accumulate_same_dev(h, dev[g].data_ptr(), n, 0.0))
-            _check(h, L.hbt_accumulate_mixed_dev(h, dev[g].data_ptr(), offs[g].ctypes.data, nev, None, None, 0,
+            # one fused launch per group (both loops); separate kernels with HBT_B200_FUSE=0 or stage counters on
+            _check(h, L.hbt_accumulate_batch_dev(h, dev[g].data_ptr(), offs[g].ctypes.data, nev,
                                                  ids.ctypes.data, cs.ctypes.data, nmix, 0.0))
         if world > 1:
             _check(h, L.hbt_allreduce(h))
@@ -352,6 +352,7 @@ def main():
     ks = (tm1["same_ms"] - tm0["same_ms"]) * 1e-3
     km = (tm1["mixed_ms"] - tm0["mixed_ms"]) * 1e-3
     ach = (ops_same + ops_mixed) / (ks + km) / 1e12
+    fused = os.environ.get("HBT_B200_FUSE", "1") != "0" and os.environ.get("HBT_B200_KERNEL", "2") != "1"
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -370,14 +371,19 @@ def main():
                       "(incl. the same-event sort + cull kernels) on the launching stream",
         "note": "the bound is the FP64 pipe (SURVEY.md 8d), not HBM or tensor cores; the production prefilter runs in packed "
                 "FP32, so the FP64 pipe itself is ~13-25 % busy (ncu) while the algorithmic-ops fraction is what is reported",
-        "kernels": {
+        "kernels": ({
+            # one launch per group works through the same-event and the mixed-event units interleaved
+            "hbt_pairs_v3_fused": {"ms_per_launch": 1e3 * (ks + km) / max(1, tm1["same_launches"] - tm0["same_launches"]),
+                                   "pairs_per_s": float(dst[0] + dst[6]) / (ks + km), "tflops": ach, "frac": ach / peak.value,
+                                   "ops_per_pair_same": ops_same / float(dst[0]), "ops_per_pair_mixed": ops_mixed / float(dst[6])},
+        } if fused else {
             "same": {"ms_per_launch": 1e3 * ks / max(1, tm1["same_launches"] - tm0["same_launches"]),
                      "pairs_per_s": float(dst[0]) / ks, "tflops": ops_same / ks / 1e12, "frac": ops_same / ks / 1e12 / peak.value,
                      "ops_per_pair": ops_same / float(dst[0])},
             "mixed": {"ms_per_launch": 1e3 * km / max(1, tm1["mixed_launches"] - tm0["mixed_launches"]),
                       "pairs_per_s": float(dst[6]) / km, "tflops": ops_mixed / km / 1e12, "frac": ops_mixed / km / 1e12 / peak.value,
                       "ops_per_pair": ops_mixed / float(dst[6])},
-        },
+        }),
         "stage_fractions_same": [float(x) / float(dst[0]) for x in dst[:6]],
         "kernel_share_of_step": (ks + km) / (t_value if world == 1 else max(t_value, 1e-12)),
     }

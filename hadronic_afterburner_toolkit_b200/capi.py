@@ -21,7 +21,8 @@ EXPORTS = (
     "hbt_create", "hbt_destroy", "hbt_last_error", "hbt_num_bins", "hbt_num_slabs", "hbt_reset",
     "hbt_gather_rapidity", "hbt_psi_ref", "hbt_rng_create", "hbt_rng_destroy", "hbt_rng_int_uniform",
     "hbt_rng_uniform", "hbt_rng_mixed_plan", "hbt_accumulate_same", "hbt_accumulate_mixed",
-    "hbt_accumulate_batch", "hbt_accumulate_same_dev", "hbt_accumulate_mixed_dev", "hbt_synchronize",
+    "hbt_accumulate_batch", "hbt_accumulate_same_dev", "hbt_accumulate_mixed_dev", "hbt_accumulate_batch_dev",
+    "hbt_synchronize",
     "hbt_read", "hbt_read_qinv", "hbt_get_stage_counters", "hbt_get_timers", "hbt_get_deferred_pairs",
     "hbt_get_launch_count", "hbt_measure_fp64_peak", "hbt_timer_start", "hbt_timer_stop",
     "hbt_comm_unique_id", "hbt_comm_init_rank", "hbt_comm_init_all", "hbt_allreduce", "hbt_allreduce_all",
@@ -80,6 +81,7 @@ def lib() -> ctypes.CDLL:
         "hbt_accumulate_batch": (ctypes.c_int, [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, dbl, i32, i32]),
         "hbt_accumulate_same_dev": (ctypes.c_int, [vp, vp, i64, dbl]),
         "hbt_accumulate_mixed_dev": (ctypes.c_int, [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, dbl]),
+        "hbt_accumulate_batch_dev": (ctypes.c_int, [vp, vp, vp, i32, vp, vp, i32, dbl]),
         "hbt_synchronize": (ctypes.c_int, [vp]),
         "hbt_read": (ctypes.c_int, [vp] * 9),
         "hbt_read_qinv": (ctypes.c_int, [vp] * 7),

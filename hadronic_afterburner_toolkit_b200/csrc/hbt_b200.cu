@@ -44,7 +44,8 @@ struct Slot {
 
 struct TimerRec {
     cudaEvent_t start, stop;
-    int kind;  // 0 same, 1 mixed
+    int kind;           // 0 same, 1 mixed, 2 fused (one kernel working through both unit lists)
+    double frac_same;   // fused: share of the launch's pairs that are same-event pairs
 };
 
 // ---- NCCL, loaded lazily so that the library itself has no link-time dependency ----------
@@ -104,6 +105,7 @@ struct hbt_ctx {
     bool reduced = false;                    // red_* hold the sum over ranks of the current state
     size_t n_u64 = 0, n_f64 = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
+    bool fuse = true;  // whole batches run the fused same+mixed kernel (HBT_B200_FUSE=0 / HBT_OPT_FUSE: separate kernels)
     Slot slots[kSlots];
     int next_slot = 0;
     std::vector<TimerRec> timers;
@@ -131,7 +133,7 @@ struct hbt_ctx {
     // production mode of the v2 same-event kernel: Morton-sorted copy of the list + tile boxes
     bool stats = false;                          // exact stage populations B, C, D (no culling)
     int n_sm = 148;
-    int occ_same = 12, occ_same_stats = 12, occ_mixed = 12, occ_mixed_stats = 12;  // resident warps per SM
+    int occ_same = 12, occ_same_stats = 12, occ_mixed = 12, occ_mixed_stats = 12, occ_fused = 12;  // resident warps per SM
     unsigned *d_work = nullptr;                  // [0] unit pop counter, [1] number of units (culled list)
     unsigned *d_units = nullptr;                 // surviving units of the sorted same-event list
     size_t units_cap = 0;
@@ -223,7 +225,12 @@ int drain_timers(hbt_ctx *ctx, bool all) {
         CU(ctx, cudaEventSynchronize(r.stop));
         float ms = 0.f;
         CU(ctx, cudaEventElapsedTime(&ms, r.start, r.stop));
-        (r.kind == 0 ? ctx->same_ms : ctx->mixed_ms) += ms;
+        if (r.kind == 2) {
+            ctx->same_ms += ms * r.frac_same;
+            ctx->mixed_ms += ms * (1.0 - r.frac_same);
+        } else {
+            (r.kind == 0 ? ctx->same_ms : ctx->mixed_ms) += ms;
+        }
         ctx->event_pool.emplace_back(r.start, r.stop);
         ctx->timers.erase(ctx->timers.begin());
     }
@@ -356,7 +363,7 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
     }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaEventRecord(e1, ctx->compute));
-    ctx->timers.push_back({e0, e1, 0});
+    ctx->timers.push_back({e0, e1, 0, 0.0});
     ctx->same_launches++;
     ctx->pending_num += npairs;
     return drain_timers(ctx, false);
@@ -441,11 +448,55 @@ int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const Hbt
     }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaEventRecord(e1, ctx->compute));
-    ctx->timers.push_back({e0, e1, 1});
+    ctx->timers.push_back({e0, e1, 1, 0.0});
     ctx->mixed_launches++;
     ctx->pending_den += npairs;
     return drain_timers(ctx, false);
 }
+
+#ifdef HBT_HAVE_V2
+// production launch of a whole batch: sort + cull of the same-event list, then one kernel that
+// works through the same-event and the mixed-event units interleaved (hbt_pairs_v3_fused)
+int launch_fused(hbt_ctx *ctx, const double *d_p, int64_t n, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg,
+                 size_t nseg, long long nblocks, unsigned long long npairs_mixed, double psi_ref) {
+    ctx->reduced = false;
+    cudaEvent_t e0, e1;
+    int rc = get_event_pair(ctx, &e0, &e1);
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(e0, ctx->compute));
+    const unsigned long long npairs_same = static_cast<unsigned long long>(n) * (n - 1) / 2;
+    rc = ensure_work(ctx);
+    if (rc) return rc;
+    CU(ctx, cudaMemsetAsync(ctx->d_work, 0, 8, ctx->compute));
+    const long long all_units = hbt_v3_same_units(n, ctx->row_item0);
+    if (all_units > 0x7fffffffLL || n > HBT_V3_MAX_SORTED || nblocks + all_units > 0x7fffffffLL)
+        return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld work units", all_units + nblocks);
+    rc = prepare_sorted(ctx, d_p, n);
+    if (rc) return rc;
+    if (static_cast<size_t>(all_units) > ctx->units_cap) {
+        cudaFree(ctx->d_units);
+        ctx->units_cap = static_cast<size_t>(all_units) + static_cast<size_t>(all_units) / 4;
+        CU(ctx, cudaMalloc(&ctx->d_units, ctx->units_cap * 4));
+    }
+    const long long n_rows = (n + HBT_V3_SUB_SAME - 1) / HBT_V3_SUB_SAME, ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
+    hbt_cull_units<<<dim3(static_cast<unsigned>((ntj + 127) / 128), static_cast<unsigned>(n_rows)), 128, 0, ctx->compute>>>(
+        ctx->sort_bbox, n, ctx->v2c.W2, ctx->v2c.k2lo, ctx->v2c.k2hi, ctx->d_units, ctx->d_work);
+    const unsigned grid = static_cast<unsigned>(ctx->n_sm * ctx->occ_fused);
+    hbt_pairs_v3_fused<<<grid, 32, 0, ctx->compute>>>(ctx->sort_p, n, ctx->d_units, ctx->sort_idx[1], d_p1, d_p2,
+                                                      static_cast<long long>(nseg), d_seg, static_cast<unsigned>(nblocks), ctx->d_work,
+                                                      ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs_same, npairs_mixed,
+                                                      closed_ptr(ctx));
+    ctx->kernel_launches += 2;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaEventRecord(e1, ctx->compute));
+    ctx->timers.push_back({e0, e1, 2, static_cast<double>(npairs_same) / static_cast<double>(npairs_same + npairs_mixed)});
+    ctx->same_launches++;
+    ctx->mixed_launches++;
+    ctx->pending_num += npairs_same;
+    ctx->pending_den += npairs_mixed;
+    return drain_timers(ctx, false);
+}
+#endif
 
 int tile_i(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V3_SUB_MIXED; }
 int tile_j(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V3_TJ_MIXED; }
@@ -779,6 +830,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     }
     if (const char *v = getenv("HBT_B200_KERNEL")) ctx->kernel_version = atoi(v) == 1 ? 1 : 2;
     if (const char *v = getenv("HBT_B200_STATS")) ctx->stats = atoi(v) != 0;
+    if (const char *v = getenv("HBT_B200_FUSE")) ctx->fuse = atoi(v) != 0;
 #define CUC(call)                                                                              \
     do {                                                                                       \
         cudaError_t e_ = (call);                                                               \
@@ -845,6 +897,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same, hbt_pairs_v3<false, false>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same_stats, hbt_pairs_v3<false, true>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed, hbt_pairs_v3<true, false>, 32, 0));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_fused, hbt_pairs_v3_fused, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed_stats, hbt_pairs_v3<true, true>, 32, 0));
     if (!hbt_v2_supported(g)) ctx->kernel_version = 1;  // q_inv mode, one-sided q windows: literal kernels
 
@@ -989,6 +1042,48 @@ extern "C" int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const 
     return HBT_OK;
 }
 
+// One whole batch, device resident: same-event loop over d_p[0, off[nev]) and the mixed-event
+// loops of the events of the same list (list 2 = list 1), as hbt_accumulate_batch does for host
+// buffers.  Runs the fused kernel when both halves are there.
+extern "C" int hbt_accumulate_batch_dev(hbt_ctx *ctx, const double *d_p, const int64_t *off, int32_t nev,
+                                        const int32_t *partner_ids, const double *cos_sin, int32_t nmix, double psi_ref) {
+    if (!ctx || nev < 0 || nmix < 0) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_batch_dev: bad argument");
+    if (nev == 0) return HBT_OK;
+    if (!d_p || !off) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_batch_dev: null argument");
+    const int64_t n = off[nev];
+#ifdef HBT_HAVE_V2
+    const bool do_mixed = nmix > 0 && partner_ids && cos_sin;
+    if (do_mixed && ctx->fuse && !ctx->stats && ctx->kernel_version != 1 && n > 1) {
+        for (size_t k = 0; k < static_cast<size_t>(nev) * nmix; k++)
+            if (partner_ids[k] < 0 || partner_ids[k] >= nev) return fail(ctx, HBT_ERR_INVALID, "partner id %d out of range", partner_ids[k]);
+        CU(ctx, cudaSetDevice(ctx->device));
+        Slot *s;
+        int rc = acquire_slot(ctx, &s);
+        if (rc) return rc;
+        rc = ensure_slot(ctx, *s, 0, static_cast<size_t>(nev) * nmix);
+        if (rc) return rc;
+        unsigned long long npairs;
+        long long nblocks;
+        const size_t nseg = build_segments(off, nev, off, 0, partner_ids, cos_sin, nmix, tile_i(ctx), tile_j(ctx), s->h_seg, &npairs, &nblocks);
+        const unsigned long long sp = static_cast<unsigned long long>(n) * (n - 1) / 2;
+        if (cap_may_engage(ctx, false, sp) || cap_may_engage(ctx, true, npairs))
+            return fail(ctx, HBT_ERR_CAP, "needed_number_of_pairs may be reached: use the host-buffer entry points, which replay the cap in order");
+        if (nseg && nblocks) {
+            CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, ctx->compute));
+            rc = launch_fused(ctx, d_p, n, d_p, d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
+            if (rc) return rc;
+            CU(ctx, cudaEventRecord(s->done, ctx->compute));
+            s->in_flight = true;
+            return HBT_OK;
+        }
+    }
+#endif
+    int rc = hbt_accumulate_same_dev(ctx, d_p, n, psi_ref);
+    if (rc) return rc;
+    if (nmix > 0) rc = hbt_accumulate_mixed_dev(ctx, d_p, off, nev, nullptr, nullptr, 0, partner_ids, cos_sin, nmix, psi_ref);
+    return rc;
+}
+
 // ---- host-buffer entry points ------------------------------------------------------------
 extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_t *off1, int32_t nev1,
                                     const double *p2, const int64_t *off2, int32_t nev2,
@@ -1041,8 +1136,17 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
     in.ids = partner_ids;
     in.cs = cos_sin;
     in.psi_ref = psi_ref;
+    const unsigned long long sp_all = n1 > 1 ? static_cast<unsigned long long>(n1) * (n1 - 1) / 2 : 0;
+#ifdef HBT_HAVE_V2
+    if (do_same && do_mixed && ctx->fuse && !ctx->stats && ctx->kernel_version != 1 && n1 > 1 && nseg > 0 && nblocks > 0 &&
+        !cap_may_engage(ctx, false, sp_all) && !cap_may_engage(ctx, true, npairs)) {
+        rc = launch_fused(ctx, s->d_p, n1, s->d_p, s->d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
+        if (rc) return rc;
+        do_same = do_mixed = 0;
+    }
+#endif
     if (do_same) {
-        const unsigned long long sp = n1 > 1 ? static_cast<unsigned long long>(n1) * (n1 - 1) / 2 : 0;
+        const unsigned long long sp = sp_all;
         in.mixed = false;
         rc = cap_may_engage(ctx, false, sp) ? capped_phase(ctx, in, nullptr, 0, 0, sp) : launch_same(ctx, s->d_p, n1, psi_ref);
         if (rc) return rc;
@@ -1174,6 +1278,9 @@ extern "C" int hbt_set_option(hbt_ctx *ctx, int32_t option, int32_t value) {
 #ifdef HBT_HAVE_V2
             ctx->kernel_version = (value == 2 && hbt_v2_supported(ctx->grid)) ? 2 : 1;
 #endif
+            return HBT_OK;
+        case HBT_OPT_FUSE:
+            ctx->fuse = value != 0;
             return HBT_OK;
         default:
             return fail(ctx, HBT_ERR_INVALID, "unknown option %d", option);

@@ -112,12 +112,9 @@ __device__ __noinline__ void v2_slow_pair(const V2Dev *__restrict__ dv, const do
 
 // state of one warp's survivor bookkeeping
 struct V2Queue {
-    unsigned *lane_list;  // this lane's private list: entry m at lane_list[32*m]
-    unsigned list_addr;   // its 32-bit shared-memory address
+    unsigned list_addr;   // shared-memory address of this lane's private list: entry m at list_addr + 128 m
     unsigned cur;         // shared-memory address of the next free slot (advances by 128 bytes)
-    unsigned *wq;         // the warp's linear queue
-    int qcount;           // entries in wq (warp-uniform)
-    unsigned kept;        // survivors queued so far (warp-uniform)
+    int qcount;           // entries in the warp's linear queue (warp-uniform)
 };
 
 __device__ __forceinline__ double lds_f64(unsigned addr) {

@@ -363,52 +363,35 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
     }
 }
 
+// One work unit (a list-1 sub-tile against one list-2 tile): stage the tiles, prefilter every
+// pair, compact the survivors and drain them.  The warp's survivor queue is empty on entry and on
+// return.  smem/sbase: this warp's shared memory (layout V3Smem<MIXED, STATS>).
 template <bool MIXED, bool STATS>
-__global__ void __launch_bounds__(32, HBT_V3_WARPS_PER_SM)
-hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long long n_same,
-             const HbtMixSeg *__restrict__ segs, const int *__restrict__ row_item0, int n_rows,
-             const unsigned *__restrict__ units, unsigned *__restrict__ work, unsigned n_units,
-             const HbtGrid g, const V2Const c, const V2Dev *__restrict__ dv, const HbtAccum acc,
-             const double psi_ref, const unsigned long long total_pairs,
-             const unsigned char *__restrict__ closed, const unsigned *__restrict__ orig) {
+__device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned sbase, const int lane, const unsigned u,
+                                            const double *__restrict__ p1, const double *__restrict__ p2, const long long n_same,
+                                            const HbtMixSeg *__restrict__ segs, const int *__restrict__ row_item0, const int n_rows,
+                                            const unsigned *__restrict__ units, const HbtGrid &g, const V2Const &c,
+                                            const V2Dev *__restrict__ dv, const HbtAccum &acc, const double psi_ref,
+                                            const unsigned char *__restrict__ closed, const unsigned *__restrict__ orig,
+                                            V2Counters &n, unsigned &cntKT, unsigned &cntRS, unsigned &kept) {
     using L = V3Smem<MIXED, STATS>;
     constexpr int NC = L::NC, SUB = L::SUB, TJ = L::TJ, IPL = SUB / 32;
     constexpr bool SORTED = L::SORTED;
-    __shared__ __align__(16) unsigned char smem[L::BYTES];
     double *const si = reinterpret_cast<double *>(smem + L::SI);
     double *const sj = reinterpret_cast<double *>(smem + L::SJ);
     double *const sjt = reinterpret_cast<double *>(smem + L::SJT);
     float *const sjf = reinterpret_cast<float *>(smem + L::SJF);
     unsigned *const si_o = reinterpret_cast<unsigned *>(smem + L::SIO);
     unsigned *const sj_o = reinterpret_cast<unsigned *>(smem + L::SJO);
-    unsigned *const lq = reinterpret_cast<unsigned *>(smem + L::LQ);
-    unsigned *const wq = reinterpret_cast<unsigned *>(smem + L::WQ);
-
-    const int lane = threadIdx.x;
-    // kept in a register: no per-use S2UR/ULEA
-    const unsigned sbase = opaque_u32(static_cast<unsigned>(__cvta_generic_to_shared(smem)));
     const unsigned sjf_addr = sbase + L::SJF;
-    if (blockIdx.x == 0 && lane == 0) atomicAdd(&acc.stage[MIXED ? 6 : 0], total_pairs);
-    const unsigned total_units = SORTED ? work[1] : n_units;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     const double k2lo = c.k2lo, k2hi = c.k2hi, W2 = c.W2;
-
     V2Queue Q;
-    Q.lane_list = lq + lane;
     Q.list_addr = sbase + L::LQ + 4u * static_cast<unsigned>(lane);
     Q.cur = Q.list_addr;
-    Q.wq = wq;
     Q.qcount = 0;
-    Q.kept = 0;
-    V2Counters n = {0, 0, 0, 0};
-    unsigned cntKT = 0, cntRS = 0;
     const unsigned lim = opaque_u32(Q.list_addr + 128u * (HBT_V2_LCAP - IPL));
 
-  for (;;) {  // ---- pop the next unit --------------------------------------------------------
-    unsigned u = 0;
-    if (lane == 0) u = atomicAdd(&work[0], 1u);
-    u = __shfl_sync(0xffffffffu, u, 0);
-    if (u >= total_units) break;
     long long i0, jbase, jcount;  // list-2 particles [jbase, jbase + jcount) belong to this row/segment
     int ni, jt;
     double rc = 1.0, rs = 0.0;
@@ -633,7 +616,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
                     for (int m = 0; m < cnt; m++) sts_u32(dst + 4u * m, lds_u32(Q.list_addr + 128u * m));
                     Q.cur = Q.list_addr;
                     Q.qcount += total;
-                    Q.kept += static_cast<unsigned>(total);
+                    kept += static_cast<unsigned>(total);
                     __syncwarp();
                     while (Q.qcount >= 32 || (final && Q.qcount > 0)) {
                         const int take = min(32, Q.qcount);
@@ -654,7 +637,33 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
             if (diag) tile_loop(std::true_type{}, std::false_type{}); else tile_loop(std::false_type{}, std::false_type{});
         }
     }
-  }  // persistent loop
+}
+
+template <bool MIXED, bool STATS>
+__global__ void __launch_bounds__(32, HBT_V3_WARPS_PER_SM)
+hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long long n_same,
+             const HbtMixSeg *__restrict__ segs, const int *__restrict__ row_item0, int n_rows,
+             const unsigned *__restrict__ units, unsigned *__restrict__ work, unsigned n_units,
+             const HbtGrid g, const V2Const c, const V2Dev *__restrict__ dv, const HbtAccum acc,
+             const double psi_ref, const unsigned long long total_pairs,
+             const unsigned char *__restrict__ closed, const unsigned *__restrict__ orig) {
+    using L = V3Smem<MIXED, STATS>;
+    __shared__ __align__(16) unsigned char smem[L::BYTES];
+    const int lane = threadIdx.x;
+    // kept in a register: no per-use S2UR/ULEA
+    const unsigned sbase = opaque_u32(static_cast<unsigned>(__cvta_generic_to_shared(smem)));
+    if (blockIdx.x == 0 && lane == 0) atomicAdd(&acc.stage[MIXED ? 6 : 0], total_pairs);
+    const unsigned total_units = L::SORTED ? work[1] : n_units;
+    V2Counters n = {0, 0, 0, 0};
+    unsigned cntKT = 0, cntRS = 0, kept = 0;
+    for (;;) {  // ---- pop the next unit ------------------------------------------------------
+        unsigned u = 0;
+        if (lane == 0) u = atomicAdd(&work[0], 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= total_units) break;
+        v3_run_unit<MIXED, STATS>(smem, sbase, lane, u, p1, p2, n_same, segs, row_item0, n_rows, units, g, c, dv, acc, psi_ref,
+                                  closed, orig, n, cntKT, cntRS, kept);
+    }
 
     // ---- counters ------------------------------------------------------------------------
     const unsigned nE = warp_sum(n.nE);
@@ -662,7 +671,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
     if (STATS) {
         unsigned nB = warp_sum(cntKT + n.nB), nC = warp_sum(cntRS + n.nC);
         const unsigned nD = warp_sum(n.nD);
-        nB -= Q.kept;
+        nB -= kept;
         if (lane == 0) {
             if (nB) atomicAdd(&stage[1], static_cast<unsigned long long>(nB));
             if (nC) atomicAdd(&stage[2], static_cast<unsigned long long>(nC));
@@ -670,6 +679,54 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
         }
     }
     if (lane == 0 && nE) atomicAdd(&stage[4], static_cast<unsigned long long>(nE));
+}
+
+// ---- fused launch: the same-event and the mixed-event units of one batch in one kernel --------
+// The same-event kernel alone is bound by the spread-address REDs of its accepted pairs (5 per
+// pair: the LSU accepts about one RED lane per cycle per SM; ncu: memory pipes 74 % busy, issue
+// slots 50 %), the mixed-event kernel alone by instruction issue in its prefilter (1 RED per
+// accepted pair).  Interleaving the two unit lists lets every SM work on both kinds at any time,
+// so the RED traffic of the same-event pairs is spread over the whole launch and hides behind
+// the mixed-event prefilter.  Unit u of the S + M units is a same-event unit when
+// floor((u+1) S / (S+M)) > floor(u S / (S+M)) (S = units kept by hbt_cull_units, read from
+// work[1]; M = mixed-event units).  Production mode only (no stage counters).
+__global__ void __launch_bounds__(32, HBT_V3_WARPS_PER_SM)
+hbt_pairs_v3_fused(const double *__restrict__ ps, const long long n_same, const unsigned *__restrict__ units,
+                   const unsigned *__restrict__ orig, const double *__restrict__ p1, const double *__restrict__ p2,
+                   const long long n_seg, const HbtMixSeg *__restrict__ segs, const unsigned n_mixed_units,
+                   unsigned *__restrict__ work, const HbtGrid g, const V2Const c, const V2Dev *__restrict__ dv, const HbtAccum acc,
+                   const double psi_ref, const unsigned long long pairs_same, const unsigned long long pairs_mixed,
+                   const unsigned char *__restrict__ closed) {
+    using LS = V3Smem<false, false>;
+    using LM = V3Smem<true, false>;
+    __shared__ __align__(16) unsigned char smem[LS::BYTES > LM::BYTES ? LS::BYTES : LM::BYTES];
+    const int lane = threadIdx.x;
+    const unsigned sbase = opaque_u32(static_cast<unsigned>(__cvta_generic_to_shared(smem)));
+    if (blockIdx.x == 0 && lane == 0) {
+        atomicAdd(&acc.stage[0], pairs_same);
+        atomicAdd(&acc.stage[6], pairs_mixed);
+    }
+    const unsigned long long S = work[1], T = S + n_mixed_units;
+    V2Counters ns = {0, 0, 0, 0}, nm = {0, 0, 0, 0};
+    unsigned unused0 = 0, unused1 = 0, unused2 = 0;
+    for (;;) {
+        unsigned u = 0;
+        if (lane == 0) u = atomicAdd(&work[0], 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= T) break;
+        const unsigned long long s0 = u * S / T, s1 = (u + 1ull) * S / T;
+        if (s1 > s0)
+            v3_run_unit<false, false>(smem, sbase, lane, static_cast<unsigned>(s0), ps, ps, n_same, nullptr, nullptr, 0, units, g, c,
+                                      dv, acc, psi_ref, closed, orig, ns, unused0, unused1, unused2);
+        else
+            v3_run_unit<true, false>(smem, sbase, lane, static_cast<unsigned>(u - s0), p1, p2, n_seg, segs, nullptr, 0, nullptr, g,
+                                     c, dv, acc, psi_ref, closed, nullptr, nm, unused0, unused1, unused2);
+    }
+    const unsigned eS = warp_sum(ns.nE), eM = warp_sum(nm.nE);
+    if (lane == 0) {
+        if (eS) atomicAdd(&acc.stage[4], static_cast<unsigned long long>(eS));
+        if (eM) atomicAdd(&acc.stage[10], static_cast<unsigned long long>(eM));
+    }
 }
 
 // ---- host side -----------------------------------------------------------------------------

@@ -143,6 +143,12 @@ int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const int64_t *of
                              const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
                              double psi_ref);
 
+/* One whole batch with list 2 = list 1 (the events of d_p are each other's mixing partners):
+ * body of calculate_HBT_correlation_function (:177-218) on a device-resident list.  Both loops
+ * run in one fused kernel (HBT_OPT_FUSE). */
+int hbt_accumulate_batch_dev(hbt_ctx *ctx, const double *d_p, const int64_t *off, int32_t nev,
+                             const int32_t *partner_ids, const double *cos_sin, int32_t nmix, double psi_ref);
+
 /* ---- results ---------------------------------------------------------------------- */
 int hbt_synchronize(hbt_ctx *ctx);
 /* Copies the accumulators out (any pointer may be NULL).  Sizes: hbt_num_bins for the six
@@ -174,9 +180,14 @@ int hbt_get_timers(hbt_ctx *ctx, double *same_ms, double *mixed_ms, uint64_t *sa
  *   cannot hold an accepted pair are skipped, so those three populations are not available
  *   (reported as 0); all pairs [0], passed q_long [4] and accepted [5] stay exact, and so does
  *   every histogram.  Default can be changed with the environment variable HBT_B200_STATS=1.
- * HBT_OPT_KERNEL: 2 = tuned kernels (default), 1 = literal kernels (cross-check). */
+ * HBT_OPT_KERNEL: 2 = tuned kernels (default), 1 = literal kernels (cross-check).
+ * HBT_OPT_FUSE: 1 (default) = a whole batch (hbt_accumulate_batch with both halves) runs as one
+ *   kernel that works through the same-event and the mixed-event units interleaved; 0 = one
+ *   kernel per loop.  Environment: HBT_B200_FUSE.  hbt_get_timers splits the time of a fused
+ *   launch between same_ms and mixed_ms by the pairs of each kind. */
 #define HBT_OPT_STAGE_COUNTERS 1
 #define HBT_OPT_KERNEL 2
+#define HBT_OPT_FUSE 3
 int hbt_set_option(hbt_ctx *ctx, int32_t option, int32_t value);
 
 /* Device-side stopwatch on the context's compute stream (CUDA events): everything the

@@ -115,6 +115,46 @@ def test_batch_beyond_the_unit_encoding_is_refused():
     h.close()
 
 
+def test_fused_and_separate_kernels_agree_and_device_resident_batch():
+    """A whole batch runs as one kernel over the interleaved same-event and mixed-event units
+    (HBT_OPT_FUSE, default) or as one kernel per loop: same integers, same oracle.  The
+    device-resident whole-batch entry point (hbt_accumulate_batch_dev) takes the same path."""
+    import torch
+    from hadronic_afterburner_toolkit_b200.hbt_correlation import gather_rapidity
+
+    P = C3.with_(qnpts=21)
+    batches = synth.make_batches(20260012, 2, 5, multiplicity=700)
+    ref = run_oracle(P, batches)
+    res = []
+    for fuse in (True, False):
+        h = HBT_correlation(P, fuse=fuse)
+        for b in batches:
+            h.calculate_HBT_correlation_function(b)
+        res.append(h.accumulators())
+        t = h.timers()
+        assert t["same_launches"] == t["mixed_launches"] == len(batches)
+        h.close()
+    hbtio.compare(ref, res[0], rtol=RTOL, check_stage="cheap")
+    hbtio.compare(res[0], res[1], rtol=RTOL, check_stage="cheap")
+    # device-resident list, same plan as the oracle's draws (the class shares the RNG stream)
+    h = HBT_correlation(P)
+    keep = []
+    for b in batches:
+        nev = len(b.same)
+        cut = [gather_rapidity(P, ev) for ev in b.same]
+        flat = np.ascontiguousarray(np.concatenate(cut))
+        off = np.zeros(nev + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(ev) for ev in cut])
+        ids, cs = h.ran_gen.mixed_plan(nev, nev)
+        d = torch.from_numpy(flat).cuda()
+        keep.append((d, off, ids, cs))
+        rc = h._L.hbt_accumulate_batch_dev(h._h, d.data_ptr(), off.ctypes.data, nev, ids.ctypes.data, cs.ctypes.data,
+                                           ids.shape[1], 0.0)
+        assert rc == 0, h._L.hbt_last_error(h._h)
+    hbtio.compare(ref, h.accumulators(), rtol=RTOL, check_stage="cheap")
+    h.close()
+
+
 @pytest.mark.parametrize("scale,ktmin", [(30.0, 0.15), (3000.0, 0.15), (1.0, 0.0), (1e-3, 0.0)])
 def test_prefilter_margins_with_outliers(scale, ktmin):
     """The float prefilter's margins are derived from the largest pT^2 of the two tiles.  Momentum
