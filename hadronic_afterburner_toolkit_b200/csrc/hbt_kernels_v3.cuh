@@ -231,10 +231,14 @@ __device__ __forceinline__ int v3_fast_bins(const HbtGrid &g, const V2Const &c, 
 // safely inside a bin), 0 (the K_T cut or some component certainly outside the window) or -1.
 __device__ __forceinline__ void v3_classify(const V2Const &c, unsigned nq, double q, double gb, int &i, bool &ok, bool &out) {
     const double u = fma(q, c.inv_dq, c.ub);
-    i = __double2int_rd(u);
-    const double fr = u - static_cast<double>(i);
-    ok = (static_cast<unsigned>(i) < nq) && (fr >= gb) && (fr <= 1.0 - gb);
-    out = !(u > -gb && u < c.nq_d + gb);  // certainly outside the window (a NaN too: the literal chain rejects it)
+    // floor(u) and the distance to the nearest integer without F2I/I2F (XU pipe, long latency):
+    // u + 1.5*2^52 holds rint(u) in its low word for |u| < 2^31
+    const double magic = __hiloint2double(0x43380000, 0);
+    const double t = u + magic;
+    const double d = u - (t - magic);  // u - rint(u), in [-0.5, 0.5]
+    i = __double2loint(t) - (d < 0.0 ? 1 : 0);
+    ok = (static_cast<unsigned>(i) < nq) && (fabs(d) >= gb);  // inside the grid and farther than gb from every bin edge
+    out = !(u > -gb && u < c.nq_d + gb);  // certainly outside the window (NaN, huge |u| too: the literal chain rejects them)
 }
 
 template <bool MIXED, bool ORIENT, int TI, int TJ>
@@ -535,12 +539,17 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
             for (int s = 0; s < IPL; s++) jthr[s] = DIAG ? static_cast<int>(ig[s] - jl0) : 0;
             const unsigned lane16 = static_cast<unsigned>(lane) << 16;
             int j = 0;
+            // the float copy of list-2 particle j is loaded one trip ahead (LDS latency off the loop's
+            // critical path; the last trip reads one slot past the tile, still this warp's shared memory)
+            float pbx = 0.f, pby = 0.f, pnb = 0.f;
+            if (!STATS) { pbx = lds_f32(sjf_addr); pby = lds_f32(sjf_addr + 4 * TJ); pnb = lds_f32(sjf_addr + 8 * TJ); }
             for (;;) {
                 const bool final = (j >= nj);  // one extra trip: the per-unit final flush shares the call site
                 if (!final) {
                     if (!STATS) {
-                        const unsigned ja = sjf_addr + 4u * static_cast<unsigned>(j);
-                        const float bxs = lds_f32(ja), bys = lds_f32(ja + 4 * TJ), nbh = lds_f32(ja + 8 * TJ);
+                        const float bxs = pbx, bys = pby, nbh = pnb;
+                        const unsigned ja = sjf_addr + 4u * static_cast<unsigned>(j + 1);
+                        pbx = lds_f32(ja); pby = lds_f32(ja + 4 * TJ); pnb = lds_f32(ja + 8 * TJ);
                         const float2 bx2 = make_float2(bxs, bxs), by2 = make_float2(bys, bys), nbt2 = make_float2(nbh, nbh);
                         const float2 Wq2 = make_float2(Wqf, Wqf);
                         const unsigned ej = lane16 + static_cast<unsigned>(j);
