@@ -224,6 +224,8 @@ __device__ __forceinline__ int v3_fast_bins(const HbtGrid &g, const V2Const &c, 
     return 4;
 }
 
+__device__ __forceinline__ int v3_kt_bin(const HbtGrid &g, const V2Const &c, double k2);
+
 // Production form of the fast path: the three components are evaluated side by side and decided
 // together, so that the q_out/q_side chain (rsqrt of k2) and the q_long chain (rsqrt of 4 Mt^2)
 // overlap instead of waiting for each other's early exits (86 % of the queued pairs pass all
@@ -243,12 +245,13 @@ __device__ __forceinline__ void v3_classify(const V2Const &c, unsigned nq, doubl
 
 template <bool MIXED, bool ORIENT, int TI, int TJ>
 __device__ __forceinline__ int v3_fast_bins_all(const HbtGrid &g, const V2Const &c, unsigned sia, unsigned sja, bool flip,
-                                                double &k2, V3Bins &o) {
+                                                double &k2, int &iK, V3Bins &o) {
     const double ax = lds_f64(sia), ay = lds_f64(sia + 8 * TI), bx = lds_f64(sja), by = lds_f64(sja + 8 * TJ);
     const double az = lds_f64(sia + 16 * TI), aE = lds_f64(sia + 24 * TI), bz = lds_f64(sja + 16 * TJ), bE = lds_f64(sja + 24 * TJ);
     const double sx = __dadd_rn(ax, bx), sy = __dadd_rn(ay, by);
     k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
     const bool kt = (k2 >= c.k2lo) && (k2 <= c.k2hi);  // exact K_T cut (the float prefilter only pre-screens it)
+    iK = v3_kt_bin(g, c, k2);  // here, not after the decision: its indexed constant loads overlap the chains below
     const double qx = ax - bx, qy = ay - by, qz = az - bz, qE = aE - bE;
     const double d = fma(qx, sx, qy * sy);     // 2 K_perp q_out
     const double e = fma(qy, sx, -(qx * sy));  // 2 K_perp q_side
@@ -310,11 +313,11 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
     const bool flip = ORIENT && (lds_u32(sbase + L::SIO + il4) > lds_u32(sbase + L::SJO + jl4));
     V3Bins b;
     double k2;
-    int stage = STATS ? v3_fast_bins<MIXED, ORIENT, TI, TJ>(g, c, sia, sja, flip, k2, b)
-                      : v3_fast_bins_all<MIXED, ORIENT, TI, TJ>(g, c, sia, sja, flip, k2, b);
     int slab = 0;
+    int stage = STATS ? v3_fast_bins<MIXED, ORIENT, TI, TJ>(g, c, sia, sja, flip, k2, b)
+                      : v3_fast_bins_all<MIXED, ORIENT, TI, TJ>(g, c, sia, sja, flip, k2, slab, b);
     if (stage == 4) {
-        slab = v3_kt_bin(g, c, k2);
+        if (STATS) slab = v3_kt_bin(g, c, k2);
         if (g.az) {
             const double Kx = 0.5 * (lds_f64(sia) + lds_f64(sja)), Ky = 0.5 * (lds_f64(sia + 8 * TI) + lds_f64(sja + 8 * TJ));
             double dphi = __dsub_rn(atan2(Ky, Kx), psi_ref);
@@ -571,10 +574,11 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                                 const float m = fmaxf(e ? d2.y : d2.x, e ? x2.y : x2.x);
                                 bool in = m <= (e ? w.y : w.x);
                                 if (FLOOR) in = in || (k2e < kfloor_f);
-                                if (keep && in) {
-                                    sts_u32(Q.cur, ej + (static_cast<unsigned>(s) << 21));
-                                    Q.cur += 128u;
-                                }
+                                // the next slot's address goes to a NEW register: advancing the cursor in place
+                                // would wait for the STS to release its address operand (WAR, short scoreboard)
+                                const unsigned slot = Q.cur;
+                                Q.cur = slot + ((keep && in) ? 128u : 0u);
+                                if (keep && in) sts_u32(slot, ej + (static_cast<unsigned>(s) << 21));
                             }
                         }
                     } else {
@@ -665,11 +669,12 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
     const unsigned total_units = L::SORTED ? work[1] : n_units;
     V2Counters n = {0, 0, 0, 0};
     unsigned cntKT = 0, cntRS = 0, kept = 0;
-    for (;;) {  // ---- pop the next unit ------------------------------------------------------
-        unsigned u = 0;
-        if (lane == 0) u = atomicAdd(&work[0], 1u);
-        u = __shfl_sync(0xffffffffu, u, 0);
+    unsigned popped = 0;  // lane 0 pops one unit ahead: the atomic's round trip hides behind the current unit
+    if (lane == 0) popped = atomicAdd(&work[0], 1u);
+    for (;;) {
+        const unsigned u = __shfl_sync(0xffffffffu, popped, 0);
         if (u >= total_units) break;
+        if (lane == 0) popped = atomicAdd(&work[0], 1u);
         v3_run_unit<MIXED, STATS>(smem, sbase, lane, u, p1, p2, n_same, segs, row_item0, n_rows, units, g, c, dv, acc, psi_ref,
                                   closed, orig, n, cntKT, cntRS, kept);
     }
@@ -718,11 +723,12 @@ hbt_pairs_v3_fused(const double *__restrict__ ps, const long long n_same, const 
     const unsigned long long S = work[1], T = S + n_mixed_units;
     V2Counters ns = {0, 0, 0, 0}, nm = {0, 0, 0, 0};
     unsigned unused0 = 0, unused1 = 0, unused2 = 0;
+    unsigned popped = 0;  // lane 0 pops one unit ahead
+    if (lane == 0) popped = atomicAdd(&work[0], 1u);
     for (;;) {
-        unsigned u = 0;
-        if (lane == 0) u = atomicAdd(&work[0], 1u);
-        u = __shfl_sync(0xffffffffu, u, 0);
+        const unsigned u = __shfl_sync(0xffffffffu, popped, 0);
         if (u >= T) break;
+        if (lane == 0) popped = atomicAdd(&work[0], 1u);
         const unsigned long long s0 = u * S / T, s1 = (u + 1ull) * S / T;
         if (s1 > s0)
             v3_run_unit<false, false>(smem, sbase, lane, static_cast<unsigned>(s0), ps, ps, n_same, nullptr, nullptr, 0, units, g, c,
