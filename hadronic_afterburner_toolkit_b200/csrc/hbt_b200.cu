@@ -555,6 +555,18 @@ int resolve_deferred(hbt_ctx *ctx, const CapFilter *f = nullptr) {
     return HBT_OK;
 }
 
+// Cap channels: c < nslab is the 3-D histogram of slab c, which takes the first needed+1 pairs
+// (:402-406, :651-655); in q_inv mode c = nslab + iK is the q_inv histogram of K_T bin iK, which
+// takes the first 50*needed (:340-341, :600-602).  The two kinds are independent of each other.
+int n_channels(const hbt_ctx *ctx) { return ctx->grid.nslab + (ctx->grid.qinv ? ctx->grid.nKT : 0); }
+uint64_t channel_quota(const hbt_ctx *ctx, int c) {
+    return c < ctx->grid.nslab ? ctx->grid.needed + 1 : 50 * ctx->grid.needed;
+}
+size_t closed_index(const hbt_ctx *ctx, int c, bool mixed) {
+    const int ns = ctx->grid.nslab, nk = ctx->grid.nKT;
+    return c < ns ? static_cast<size_t>(c + (mixed ? ns : 0)) : static_cast<size_t>(2 * ns + (c - ns) + (mixed ? nk : 0));
+}
+
 // per-slab accepted-pair counters = sums of the bin counts; refreshes the host copies
 int refresh_counts(hbt_ctx *ctx) {
     const long long q3 = static_cast<long long>(ctx->grid.nq) * ctx->grid.nq * ctx->grid.nq;
@@ -562,11 +574,15 @@ int refresh_counts(hbt_ctx *ctx) {
     hbt_finish_stage<<<1, 32, 0, ctx->compute>>>(ctx->acc, ctx->grid.nslab);
     ctx->kernel_launches += 2;
     CU(ctx, cudaGetLastError());
-    const size_t ns = ctx->grid.nslab;
-    ctx->exact_num.resize(ns);
-    ctx->exact_den.resize(ns);
+    const size_t ns = ctx->grid.nslab, nch = static_cast<size_t>(n_channels(ctx));
+    ctx->exact_num.resize(nch);  // [0, ns): slabs; [ns, nch): q_inv K_T bins
+    ctx->exact_den.resize(nch);
     CU(ctx, cudaMemcpyAsync(ctx->exact_num.data(), ctx->acc.npairs_num, ns * 8, cudaMemcpyDeviceToHost, ctx->compute));
     CU(ctx, cudaMemcpyAsync(ctx->exact_den.data(), ctx->acc.npairs_den, ns * 8, cudaMemcpyDeviceToHost, ctx->compute));
+    if (nch > ns) {
+        CU(ctx, cudaMemcpyAsync(ctx->exact_num.data() + ns, ctx->acc.npairs_num_qinv, (nch - ns) * 8, cudaMemcpyDeviceToHost, ctx->compute));
+        CU(ctx, cudaMemcpyAsync(ctx->exact_den.data() + ns, ctx->acc.npairs_den_qinv, (nch - ns) * 8, cudaMemcpyDeviceToHost, ctx->compute));
+    }
     CU(ctx, cudaStreamSynchronize(ctx->compute));
     ctx->pending_num = ctx->pending_den = 0;
     return HBT_OK;
@@ -596,26 +612,26 @@ struct PhaseInput {
 };
 
 bool cap_may_engage(const hbt_ctx *ctx, bool mixed, unsigned long long pairs) {
-    const uint64_t lim = ctx->grid.needed + 1;
-    if (lim >= (1ull << 62)) return false;
+    if (ctx->grid.needed >= (1ull << 56)) return false;
     const std::vector<uint64_t> &ex = mixed ? ctx->exact_den : ctx->exact_num;
     const uint64_t pend = (mixed ? ctx->pending_den : ctx->pending_num) + pairs;
-    const int ns = ctx->grid.nslab;
-    for (int k = 0; k < ns; k++) {
-        if (ctx->closed[k + (mixed ? ns : 0)]) continue;
-        const uint64_t have = ex.empty() ? 0 : ex[k];
-        if (have + pend > lim) return true;
+    const int nch = n_channels(ctx);
+    for (int c = 0; c < nch; c++) {
+        if (ctx->closed[closed_index(ctx, c, mixed)]) continue;
+        const uint64_t have = ex.empty() ? 0 : ex[c];
+        if (have + pend > channel_quota(ctx, c)) return true;
     }
     return false;
 }
 
 int sync_closed(hbt_ctx *ctx, bool mixed) {
-    const uint64_t needed = ctx->grid.needed;
-    const int ns = ctx->grid.nslab;
+    const int nch = n_channels(ctx);
     const std::vector<uint64_t> &ex = mixed ? ctx->exact_den : ctx->exact_num;
     bool changed = false;
-    for (int k = 0; k < ns; k++)
-        if (ex[k] > needed && !ctx->closed[k + (mixed ? ns : 0)]) { ctx->closed[k + (mixed ? ns : 0)] = 1; changed = true; }
+    for (int c = 0; c < nch; c++) {
+        const size_t ci = closed_index(ctx, c, mixed);
+        if (ex[c] >= channel_quota(ctx, c) && !ctx->closed[ci]) { ctx->closed[ci] = 1; changed = true; }
+    }
     if (changed) {
         ctx->any_closed = true;
         CU(ctx, cudaMemcpyAsync(ctx->d_closed, ctx->closed.data(), ctx->closed.size(), cudaMemcpyHostToDevice, ctx->compute));
@@ -624,14 +640,24 @@ int sync_closed(hbt_ctx *ctx, bool mixed) {
     return HBT_OK;
 }
 
-// position of the m-th pair (m >= 1) of row `row` that the reference accepts into slab K
-int64_t resolve_row(const hbt_ctx *ctx, const PhaseInput &in, int K, int64_t row, uint64_t m) {
-    const double *a = in.h1 + 8 * row;
+// does the reference accept the pair (a, b) into cap channel K (a slab, or a q_inv K_T bin)?
+bool pair_hits_channel(const hbt_ctx *ctx, const double *a, const double *b, int mixed, double psi_ref, int K) {
+    const int ns = ctx->grid.nslab;
+    if (K >= ns) {
+        int iK = -1, iq = -1;
+        return hbt_host_pair_qinv(&ctx->grid, a, b, &iK, &iq) && iK == K - ns;
+    }
     HbtCorrection c;
     uint64_t st[6];
+    return hbt_host_pair_literal(&ctx->grid, a, b, mixed, psi_ref, &c, st) && c.slab == K;
+}
+
+// position of the m-th pair (m >= 1) of row `row` that the reference accepts into channel K
+int64_t resolve_row(const hbt_ctx *ctx, const PhaseInput &in, int K, int64_t row, uint64_t m) {
+    const double *a = in.h1 + 8 * row;
     if (!in.mixed) {
         for (int64_t j = row + 1; j < in.n1; j++)
-            if (hbt_host_pair_literal(&ctx->grid, a, in.h1 + 8 * j, 0, in.psi_ref, &c, st) && c.slab == K && --m == 0) return j;
+            if (pair_hits_channel(ctx, a, in.h1 + 8 * j, 0, in.psi_ref, K) && --m == 0) return j;
         return -1;
     }
     const int iev = static_cast<int>(std::upper_bound(in.off1, in.off1 + in.nev1 + 1, row) - in.off1) - 1;
@@ -646,7 +672,7 @@ int64_t resolve_row(const hbt_ctx *ctx, const PhaseInput &in, int K, int64_t row
             const double t1 = q[0] * cphi, t2 = q[1] * sphi, t3 = q[0] * sphi, t4 = q[1] * cphi;  // :522-523
             b[0] = t1 - t2;
             b[1] = t3 + t4;
-            if (hbt_host_pair_literal(&ctx->grid, a, b, 1, in.psi_ref, &c, st) && c.slab == K && --m == 0) return pos;
+            if (pair_hits_channel(ctx, a, b, 1, in.psi_ref, K) && --m == 0) return pos;
         }
     }
     return -1;
@@ -654,8 +680,7 @@ int64_t resolve_row(const hbt_ctx *ctx, const PhaseInput &in, int K, int64_t row
 
 int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, size_t nseg, long long nblocks,
                  unsigned long long npairs) {
-    const int ns = ctx->grid.nslab;
-    const uint64_t lim = ctx->grid.needed + 1;
+    const int ns = ctx->grid.nslab, nch = n_channels(ctx);
     // exact counters before the phase
     int rc = hbt_synchronize(ctx);
     if (rc) return rc;
@@ -677,10 +702,13 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
     rc = refresh_counts(ctx);
     if (rc) return rc;
     const std::vector<uint64_t> &after = in.mixed ? ctx->exact_den : ctx->exact_num;
-    std::vector<int32_t> xidx(ns, -1);
+    std::vector<int32_t> xidx(nch, -1);
     std::vector<int> crossing;
-    for (int k = 0; k < ns; k++)
-        if (!ctx->closed[k + (in.mixed ? ns : 0)] && after[k] > lim) { xidx[k] = static_cast<int32_t>(crossing.size()); crossing.push_back(k); }
+    for (int k = 0; k < nch; k++)
+        if (!ctx->closed[closed_index(ctx, k, in.mixed)] && after[k] > channel_quota(ctx, k)) {
+            xidx[k] = static_cast<int32_t>(crossing.size());
+            crossing.push_back(k);
+        }
     if (crossing.empty()) return sync_closed(ctx, in.mixed);
 
     // ---- roll back and replay in order ----------------------------------------------------
@@ -697,10 +725,10 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
     unsigned long long np1 = npairs;
     long long nb1 = 0;
     size_t nseg1 = 0;
-    CU(ctx, cudaMalloc(&d_xidx, ns * sizeof(int32_t)));
+    CU(ctx, cudaMalloc(&d_xidx, nch * sizeof(int32_t)));
     CU(ctx, cudaMalloc(&d_rowcnt, nx * nrows * sizeof(unsigned)));
-    CU(ctx, cudaMalloc(&d_cut, 2 * ns * sizeof(int64_t)));
-    CU(ctx, cudaMemcpyAsync(d_xidx, xidx.data(), ns * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->compute));
+    CU(ctx, cudaMalloc(&d_cut, 2 * nch * sizeof(int64_t)));
+    CU(ctx, cudaMemcpyAsync(d_xidx, xidx.data(), nch * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->compute));
     CU(ctx, cudaMemsetAsync(d_rowcnt, 0, nx * nrows * sizeof(unsigned), ctx->compute));
     if (in.mixed) {  // the literal kernels tile differently: rebuild the segments for them
         seg1.resize(static_cast<size_t>(in.nev1) * in.nmix);
@@ -714,8 +742,8 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
     cap.rowcnt = d_rowcnt;
     cap.nrows = nrows;
     cap.cut_row = d_cut;
-    cap.cut_pos = d_cut + ns;
-    // pass 1: per-row counts of the crossing slabs
+    cap.cut_pos = d_cut + nch;
+    // pass 1: per-row counts of the crossing channels
     rc = in.mixed ? launch_mixed(ctx, in.d1, in.d2, d_seg1, nseg1, nb1, np1, in.psi_ref, 1, &cap)
                   : launch_same(ctx, in.d1, in.n1, in.psi_ref, 1, &cap);
     if (rc) return rc;
@@ -734,21 +762,22 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
                 rowcnt[static_cast<size_t>(xidx[c.slab]) * nrows + d.row]++;
         }
     }
-    std::vector<int64_t> cut_row(ns, INT64_MAX), cut_pos(ns, INT64_MAX);
+    std::vector<int64_t> cut_row(nch, INT64_MAX), cut_pos(nch, INT64_MAX);
     for (size_t x = 0; x < nx; x++) {
         const int K = crossing[x];
-        uint64_t quota = lim - before[K];  // >= 1: the slab was open
+        uint64_t quota = channel_quota(ctx, K) - before[K];  // >= 1 for an open slab; 0 for q_inv with needed = 0
+        if (quota == 0) { cut_row[K] = -1; cut_pos[K] = -1; continue; }
         int64_t row = 0;
         const unsigned *rc_x = rowcnt.data() + x * nrows;
         while (row < nrows && rc_x[row] < quota) { quota -= rc_x[row]; row++; }
-        if (row >= nrows) return fail(ctx, HBT_ERR_STATE, "ordered cap: quota not reached in the replay (slab %d)", K);
+        if (row >= nrows) return fail(ctx, HBT_ERR_STATE, "ordered cap: quota not reached in the replay (channel %d)", K);
         const int64_t pos = resolve_row(ctx, in, K, row, quota);
-        if (pos < 0) return fail(ctx, HBT_ERR_STATE, "ordered cap: host and device disagree on row %lld of slab %d", static_cast<long long>(row), K);
+        if (pos < 0) return fail(ctx, HBT_ERR_STATE, "ordered cap: host and device disagree on row %lld of channel %d", static_cast<long long>(row), K);
         cut_row[K] = row;
         cut_pos[K] = pos;
     }
-    CU(ctx, cudaMemcpyAsync(d_cut, cut_row.data(), ns * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->compute));
-    CU(ctx, cudaMemcpyAsync(d_cut + ns, cut_pos.data(), ns * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->compute));
+    CU(ctx, cudaMemcpyAsync(d_cut, cut_row.data(), nch * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->compute));
+    CU(ctx, cudaMemcpyAsync(d_cut + nch, cut_pos.data(), nch * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->compute));
     // pass 2: accumulate up to the cuts
     rc = in.mixed ? launch_mixed(ctx, in.d1, in.d2, d_seg1, nseg1, nb1, np1, in.psi_ref, 2, &cap)
                   : launch_same(ctx, in.d1, in.n1, in.psi_ref, 2, &cap);
@@ -793,7 +822,7 @@ int check_cap(hbt_ctx *ctx, const uint64_t *num, const uint64_t *den, const uint
                         static_cast<unsigned long long>(ctx->grid.needed), k);
     if (ctx->grid.qinv)
         for (int k = 0; k < ctx->grid.nKT; k++)
-            if ((qn && qn[k] > 50 * ctx->grid.needed) || (qd && qd[k] > 50 * ctx->grid.needed))
+            if (ctx->grid.needed < (1ull << 56) && ((qn && qn[k] > 50 * ctx->grid.needed) || (qd && qd[k] > 50 * ctx->grid.needed)))
                 return fail(ctx, HBT_ERR_CAP, "50*needed_number_of_pairs was exceeded in the q_inv histogram, K_T bin %d", k);
     return HBT_OK;
 }
@@ -884,9 +913,10 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     CUC(cudaMallocHost(&ctx->h_deferred, sizeof(HbtDeferred) * kDeferredCapacity));
     CUC(cudaMallocHost(&ctx->h_defcount, 8));
     CUC(cudaMalloc(&ctx->d_corr, sizeof(HbtCorrection) * kDeferredCapacity));
-    ctx->closed.assign(2 * ns, 0);
-    CUC(cudaMalloc(&ctx->d_closed, 2 * ns));
-    CUC(cudaMemset(ctx->d_closed, 0, 2 * ns));
+    const size_t nclosed = 2 * static_cast<size_t>(ns) + 2 * static_cast<size_t>(g.nKT);  // slabs (same, mixed), q_inv K_T bins (same, mixed)
+    ctx->closed.assign(nclosed, 0);
+    CUC(cudaMalloc(&ctx->d_closed, nclosed));
+    CUC(cudaMemset(ctx->d_closed, 0, nclosed));
     for (Slot &s : ctx->slots) {
         CUC(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));

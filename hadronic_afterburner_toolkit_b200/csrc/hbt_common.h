@@ -66,11 +66,13 @@ struct HbtDeferred {
 // row (list-1 particle) for the crossing slabs, the host locates the last accepted pair, pass 2
 // accumulates only pairs at or before that position.
 struct HbtCap {
-    const unsigned char *closed;  // [2*nslab] or null
-    const int32_t *xidx;          // pass 1: slab -> index among the crossing slabs, or -1
+    // channels: c < nslab = the 3-D histogram of slab c (first needed+1 pairs); nslab + iK = the q_inv
+    // histogram of K_T bin iK (first 50*needed pairs, invariant_radius_flag=1)
+    const unsigned char *closed;  // [2*nslab + 2*nKT]: slabs (same, mixed), q_inv K_T bins (same, mixed); or null
+    const int32_t *xidx;          // pass 1: channel -> index among the crossing channels, or -1
     unsigned int *rowcnt;         // pass 1: [n_crossing][nrows]
     int64_t nrows;
-    const int64_t *cut_row;       // pass 2: [nslab] last accepted row ...
+    const int64_t *cut_row;       // pass 2: [n_channels] last accepted row ...
     const int64_t *cut_pos;       // ... and position inside that row
 };
 
@@ -109,6 +111,7 @@ int hbt_host_derive_grid(const hbt_params *p, HbtGrid *g, char *err, int errlen)
 // accepted into a 3-D bin, 0 otherwise.  stage[6] is incremented like the device does.
 int hbt_host_pair_literal(const HbtGrid *g, const double *a, const double *b, int mixed,
                           double psi_ref, HbtCorrection *c, uint64_t *stage);
+int hbt_host_pair_qinv(const HbtGrid *g, const double *a, const double *b, int *iK, int *iq);
 #ifdef __cplusplus
 }
 #endif

@@ -164,6 +164,22 @@ extern "C" int32_t hbt_rng_mixed_plan(hbt_rng *rng, int32_t nev, int32_t nev_mix
 }
 
 // ---- literal evaluation of a single pair (deferred pairs only) -------------------------
+// q_inv branch of one pair, literally (src/HBT_correlation.cpp:326-356 / :590-607): 1 when the pair
+// enters the q_inv histogram of K_T bin *iK (window and index tests; the 50*needed cap is the
+// caller's business), with its bin in *iq.
+extern "C" int hbt_host_pair_qinv(const HbtGrid *g, const double *a, const double *b, int *iK, int *iq) {
+    const double Kx = 0.5 * (a[0] + b[0]);
+    const double Ky = 0.5 * (a[1] + b[1]);
+    const double K2 = Kx * Kx + Ky * Ky;
+    if (!(K2 >= g->KT_min_sq && K2 <= g->KT_max_sq)) return 0;
+    *iK = static_cast<int>((std::sqrt(K2) - g->KT_min) / g->dKT);
+    const double qx = a[0] - b[0], qy = a[1] - b[1], qz = a[2] - b[2], qE = a[3] - b[3];
+    const double qinv = std::sqrt(-(qE * qE - qx * qx - qy * qy - qz * qz));
+    if (!(qinv > g->q_lo && qinv < g->q_hi)) return 0;
+    *iq = static_cast<int>((qinv - g->q_base) / g->dq);
+    return *iq < g->nq ? 1 : 0;
+}
+
 // The device hands a pair back when its K_phi bin decision sits within 1e-9 of an edge:
 // there glibc's atan2 (which the reference uses) and CUDA's atan2 may disagree.  The chain
 // below is src/HBT_correlation.cpp:311-458 (same event) / :574-687 (mixed event).

@@ -122,7 +122,7 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
         const int jstart = diag ? t + 1 : 0;  // same-event: j > i only (:301)
         for (int j = jstart; j < nj; j++) {
             const double bx = sj[0][j], by = sj[1][j], bz = sj[2][j], bE = sj[3][j];
-            if (g.qinv && MODE == 0) {
+            if (g.qinv) {
                 // q_inv branch (:339-356 / :595-607); needs the K_T bin, so the cut first
                 const double Kx = __dmul_rn(0.5, __dadd_rn(a[0], bx));
                 const double Ky = __dmul_rn(0.5, __dadd_rn(a[1], by));
@@ -136,7 +136,20 @@ hbt_pairs_v1(const double *__restrict__ p1, const double *__restrict__ p2, long 
                     const double qinv = __dsqrt_rn(-m2);
                     if (qinv > g.q_lo && qinv < g.q_hi) {
                         const int iq = __double2int_rz(__ddiv_rn(__dsub_rn(qinv, g.q_base), g.dq));
-                        if (iq < g.nq) {
+                        // the q_inv histogram of a K_T bin is its own cap channel (nslab + iK): first 50*needed pairs
+                        bool take = iq < g.nq && !(cap.closed && cap.closed[2 * g.nslab + iK + (MIXED ? g.nKT : 0)]);
+                        if (MODE == 1) {
+                            if (take) {
+                                const int x = cap.xidx[g.nslab + iK];
+                                if (x >= 0) atomicAdd(&cap.rowcnt[x * cap.nrows + (i0 + t)], 1u);
+                            }
+                            take = false;
+                        }
+                        if (MODE == 2 && take) {
+                            const long long row = i0 + t, cr = cap.cut_row[g.nslab + iK];
+                            if (row > cr || (row == cr && pos_base + j > cap.cut_pos[g.nslab + iK])) take = false;
+                        }
+                        if (take) {
                             atomicAdd(&s_qpairs[iK], 1u);
                             atomicAdd(&s_qcnt[iK * g.nq + iq], 1u);
                             if (!MIXED) {

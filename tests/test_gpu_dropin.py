@@ -56,6 +56,7 @@ CASES = {
     "c4_shape_az": (C4.with_(qnpts=9, n_KT=4, n_Kphi=4), 2, 4, 300),
     "qinv": (HBTParams(qnpts=21, invariant_radius_flag=1), 2, 4, 200),
     "cap_reached": (C3.with_(qnpts=15, needed_number_of_pairs=2500.0), 4, 4, 300),
+    "qinv_cap_reached": (HBTParams(qnpts=21, invariant_radius_flag=1, needed_number_of_pairs=300.0), 3, 4, 300),
 }
 
 

@@ -53,6 +53,10 @@ CAPPED = {
     "cap_zero": (HBTParams(qnpts=11, needed_number_of_pairs=0.0), 2, 3, 150),
     "cap_az1": (C4.with_(qnpts=11, n_KT=4, n_Kphi=4, needed_number_of_pairs=900.0), 3, 4, 400),
     "cap_first_batch_only": (HBTParams(qnpts=21, needed_number_of_pairs=50000.0), 3, 4, 500),
+    # q_inv mode: the 1-D histograms stop at 50 x needed per K_T bin, independently of the 3-D slabs
+    "cap_qinv_first_batch": (HBTParams(qnpts=21, invariant_radius_flag=1, needed_number_of_pairs=20.0), 3, 4, 400),
+    "cap_qinv_late": (HBTParams(qnpts=21, invariant_radius_flag=1, needed_number_of_pairs=700.0), 4, 4, 400),
+    "cap_qinv_zero": (HBTParams(qnpts=11, invariant_radius_flag=1, needed_number_of_pairs=0.0), 2, 3, 150),
 }
 
 
@@ -67,6 +71,10 @@ def test_ordered_cap_against_oracle(name):
     assert int(acc.npairs_num.max()) <= lim and int(acc.npairs_den.max()) <= lim
     if name != "cap_first_batch_only":
         assert int(acc.npairs_num.max()) == lim  # the cap really engaged
+    if P.invariant_radius_flag == 1:
+        qlim = 50 * int(P.needed_number_of_pairs)
+        assert int(acc.npairs_num_qinv.max()) <= qlim and int(acc.npairs_den_qinv.max()) <= qlim
+        assert int(acc.npairs_num_qinv.max()) == qlim and int(acc.npairs_den_qinv.max()) == qlim  # engaged in both loops
 
 
 def test_full_size_group_production_equals_literal_kernels():
