@@ -27,6 +27,7 @@ EXPORTS = (
     "hbt_get_launch_count", "hbt_measure_fp64_peak", "hbt_timer_start", "hbt_timer_stop",
     "hbt_comm_unique_id", "hbt_comm_init_rank", "hbt_comm_init_all", "hbt_allreduce", "hbt_allreduce_all",
     "hbt_version", "hbt_device_count", "hbt_set_option",
+    "hbt_reader_open", "hbt_reader_next", "hbt_reader_error", "hbt_reader_bytes", "hbt_reader_close",
 )
 
 HBT_OK = 0
@@ -100,6 +101,11 @@ def lib() -> ctypes.CDLL:
         "hbt_version": (ctypes.c_char_p, []),
         "hbt_device_count": (i32, []),
         "hbt_set_option": (ctypes.c_int, [vp, i32, i32]),
+        "hbt_reader_open": (ctypes.c_int, [ctypes.c_char_p, i32, i32, i64, dbl, vp, vp]),
+        "hbt_reader_next": (i32, [vp, vp, vp, vp]),
+        "hbt_reader_error": (ctypes.c_char_p, [vp]),
+        "hbt_reader_bytes": (ctypes.c_uint64, [vp]),
+        "hbt_reader_close": (None, [vp]),
     }
     for name in EXPORTS:
         f = getattr(L, name)  # AttributeError if the library lacks a declared symbol

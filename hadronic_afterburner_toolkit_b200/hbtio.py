@@ -204,3 +204,58 @@ def compare(ref: Accumulators, got: Accumulators, rtol: float = 1e-10, check_sta
         a, b = np.asarray(ref.stage)[idx], np.asarray(got.stage)[idx]
         assert np.array_equal(a, b), f"stage counters differ: ref={ref.stage} got={got.stage}"
     return report
+
+
+class FastReader:
+    """``hbt_reader_*`` of ``include/hbt_b200.h``: the gzipped particle samples of
+    ``read_in_mode=10`` (``src/particleSamples.cpp:1247-1286``) as batches of events of one
+    species, grouped by the reference's ``event_buffer_size`` rule.  Iterating yields
+    :class:`Batch` objects (copies); ``all_particles`` holds the all-species count of the last one."""
+
+    def __init__(self, path: str, particle_monval: int, event_buffer_size: int, rap_shift: float = 0.0,
+                 rapidity_cut=None, read_in_mode: int = 10):
+        import ctypes
+
+        from . import capi
+
+        self._ct = ctypes
+        self._L = capi.lib()
+        self._cut = rapidity_cut.to_c() if rapidity_cut is not None else None
+        h = ctypes.c_void_p()
+        rc = self._L.hbt_reader_open(str(path).encode(), read_in_mode, particle_monval, event_buffer_size, rap_shift,
+                                     ctypes.byref(self._cut) if self._cut is not None else None, ctypes.byref(h))
+        if rc != 0:
+            raise capi.HBTError(rc, f"hbt_reader_open({path}, mode {read_in_mode}, monval {particle_monval})")
+        self._h = h
+        self.all_particles = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> Batch:
+        ct = self._ct
+        p, off, allp = ct.POINTER(ct.c_double)(), ct.POINTER(ct.c_int64)(), ct.c_int64()
+        nev = self._L.hbt_reader_next(self._h, ct.byref(p), ct.byref(off), ct.byref(allp))
+        if nev < 0:
+            from . import capi
+            raise capi.HBTError(nev, self._L.hbt_reader_error(self._h).decode())
+        if nev == 0:
+            raise StopIteration
+        offs = np.ctypeslib.as_array(off, shape=(nev + 1,)).copy()
+        flat = np.ctypeslib.as_array(p, shape=(int(offs[-1]), 8)).copy() if offs[-1] else np.zeros((0, 8))
+        self.all_particles = allp.value
+        return Batch([flat[offs[i]:offs[i + 1]] for i in range(nev)])
+
+    def bytes_read(self) -> int:
+        return int(self._L.hbt_reader_bytes(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            self._L.hbt_reader_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

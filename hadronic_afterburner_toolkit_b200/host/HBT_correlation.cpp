@@ -14,6 +14,7 @@
 #include <sstream>
 
 #include "../../include/hbt_b200.h"
+#include "hbt_output.h"
 
 namespace {
 
@@ -32,7 +33,7 @@ int device_count_from_env() {
 
 HBT_correlation::HBT_correlation(ParameterReader &paraRdr, std::string path,
                                  std::shared_ptr<RandomUtil::Random> ran_gen)
-    : paraRdr_(paraRdr), path_(path), next_ctx_(0), reduced_(false) {
+    : paraRdr_(paraRdr), path_(path), next_ctx_(0), reduced_(false), fetched_(false) {
     ran_gen_ptr_ = ran_gen;
 
     // same keys, same order as src/HBT_correlation.cpp:22-46 (a missing key exits in getVal)
@@ -64,7 +65,7 @@ HBT_correlation::HBT_correlation(ParameterReader &paraRdr, std::string path,
     number_of_mixed_events_ = 0;
     number_of_oversample_events_ = 0;
 
-    hbt_params p;
+    hbt_params &p = params_;
     p.qnpts = qnpts;
     p.n_KT = n_KT;
     p.n_Kphi = n_Kphi;
@@ -120,6 +121,7 @@ hbt_ctx *HBT_correlation::pick_context() {
     hbt_ctx *c = ctx_[next_ctx_];
     next_ctx_ = (next_ctx_ + 1) % ctx_.size();
     reduced_ = false;
+    fetched_ = false;
     return c;
 }
 
@@ -273,29 +275,11 @@ void HBT_correlation::combine_and_bin_particle_pairs_mixed_events(int event_id1,
 void HBT_correlation::fetch_results() {
     if (ctx_.size() > 1 && !reduced_) check(ctx_[0], hbt_allreduce_all(ctx_.data(), static_cast<int>(ctx_.size())), "hbt_allreduce_all");
     reduced_ = true;
-    hbt_ctx *c = ctx_[0];
-    const size_t nb = hbt_num_bins(c), ns = hbt_num_slabs(c);
-    num_count_.resize(nb); den_count_.resize(nb); num_cos_.resize(nb);
-    sum_qo_.resize(nb); sum_qs_.resize(nb); sum_ql_.resize(nb);
-    npairs_num_.resize(ns); npairs_den_.resize(ns);
-    check(c,
-          hbt_read(c, reinterpret_cast<uint64_t *>(num_count_.data()), num_cos_.data(), sum_qo_.data(), sum_qs_.data(),
-                   sum_ql_.data(), reinterpret_cast<uint64_t *>(den_count_.data()),
-                   reinterpret_cast<uint64_t *>(npairs_num_.data()), reinterpret_cast<uint64_t *>(npairs_den_.data())),
-          "hbt_read");
-    if (invariant_radius_flag_ == 1) {
-        const size_t n1 = static_cast<size_t>(n_KT) * qnpts;
-        inv_count_.resize(n1); inv_den_.resize(n1); inv_sum_.resize(n1); inv_cos_.resize(n1);
-        npairs_num_inv_.resize(n_KT); npairs_den_inv_.resize(n_KT);
-        check(c,
-              hbt_read_qinv(c, reinterpret_cast<uint64_t *>(inv_count_.data()), inv_sum_.data(), inv_cos_.data(),
-                            reinterpret_cast<uint64_t *>(inv_den_.data()),
-                            reinterpret_cast<uint64_t *>(npairs_num_inv_.data()),
-                            reinterpret_cast<uint64_t *>(npairs_den_inv_.data())),
-              "hbt_read_qinv");
-    }
+    check(ctx_[0], hbt_fetch_results(ctx_[0], params_, res_), "hbt_read");
+    fetched_ = true;
 }
 
+// the writers themselves (format frozen by src/HBT_correlation.cpp:694-855) live in hbt_output.h
 void HBT_correlation::output_HBTcorrelation() {
     fetch_results();
     if (invariant_radius_flag_ == 1) output_correlation_function_inv();
@@ -306,96 +290,19 @@ void HBT_correlation::output_HBTcorrelation() {
     }
 }
 
-//! src/HBT_correlation.cpp:694-724
+HbtOutputWriter HBT_correlation::writer() { return HbtOutputWriter(params_, path_, paraRdr_.getVal("ecoOutput", 0) == 1); }
+
 void HBT_correlation::output_correlation_function_inv() {
-    if (inv_count_.empty()) fetch_results();
-    const bool eco = (paraRdr_.getVal("ecoOutput", 0) == 1);
-    for (int iK = 0; iK < n_KT - 1; iK++) {
-        const double npair_ratio =
-            (static_cast<double>(npairs_num_inv_[iK]) / static_cast<double>(npairs_den_inv_[iK]));
-        std::ostringstream filename;
-        filename << path_ << "/HBT_correlation_function_inv_KT_" << KT_array_[iK] << "_" << KT_array_[iK + 1] << ".dat";
-        std::ofstream output(filename.str().c_str());
-        for (int iq = 0; iq < qnpts; iq++) {
-            const size_t k = static_cast<size_t>(iK) * qnpts + iq;
-            const double count = static_cast<double>(inv_count_[k]);
-            const double q_inv_local = inv_sum_[k] / count;
-            const double correl_fun_num = inv_cos_[k];
-            const double correl_fun_denorm = static_cast<double>(inv_den_[k]) * npair_ratio;
-            output << std::scientific << std::setw(18) << std::setprecision(8);
-            if (eco) {
-                output << correl_fun_num << "    " << correl_fun_denorm << std::endl;
-            } else {
-                output << q_inv_local << "    " << correl_fun_num << "    " << correl_fun_denorm << std::endl;
-            }
-        }
-        output.close();
-    }
+    if (!fetched_) fetch_results();
+    writer().write_inv(res_);
 }
 
-//! one (K_T[, K_phi]) slab: rows in the order q_long outer, q_out middle, q_side inner and the
-//! column layout of src/HBT_correlation.cpp:735-777
-void HBT_correlation::write_3d_file(const std::string &filename, size_t slab, double npair_ratio) {
-    const bool eco = (paraRdr_.getVal("ecoOutput", 0) == 1);
-    std::ofstream output(filename.c_str());
-    const size_t q3 = static_cast<size_t>(qnpts) * qnpts * qnpts;
-    for (int iqlong = 0; iqlong < qnpts; iqlong++) {
-        for (int iqout = 0; iqout < qnpts; iqout++) {
-            for (int iqside = 0; iqside < qnpts; iqside++) {
-                const size_t bin = slab * q3 + (static_cast<size_t>(iqout) * qnpts + iqside) * qnpts + iqlong;
-                // the reference keeps the counts in doubles and truncates them to int here
-                const int npart_num = static_cast<int>(static_cast<double>(num_count_[bin]));
-                const int npart_denorm = static_cast<int>(static_cast<double>(den_count_[bin]));
-                double q_out_local, q_side_local, q_long_local, correl_fun_num, correl_fun_denorm;
-                if (npart_num < 2 || npart_denorm < 2) {
-                    q_out_local = q_out[iqout];
-                    q_side_local = q_side[iqside];
-                    q_long_local = q_long[iqlong];
-                    correl_fun_num = 0.0;
-                    correl_fun_denorm = npart_denorm;
-                } else {
-                    q_out_local = sum_qo_[bin] / npart_num;
-                    q_side_local = sum_qs_[bin] / npart_num;
-                    q_long_local = sum_ql_[bin] / npart_num;
-                    correl_fun_num = num_cos_[bin];
-                    correl_fun_denorm = npair_ratio * static_cast<double>(den_count_[bin]);
-                }
-                output << std::scientific << std::setw(18) << std::setprecision(8);
-                if (eco) {
-                    output << correl_fun_num << "    " << correl_fun_denorm << std::endl;
-                } else {
-                    output << q_out_local << "    " << q_side_local << "    " << q_long_local << "    "
-                           << correl_fun_num << "    " << correl_fun_denorm << std::endl;
-                }
-            }
-        }
-    }
-    output.close();
-}
-
-//! src/HBT_correlation.cpp:726-783
 void HBT_correlation::output_correlation_function() {
-    if (num_count_.empty()) fetch_results();
-    for (int iK = 0; iK < n_KT - 1; iK++) {
-        const double npair_ratio = (static_cast<double>(npairs_num_[iK]) / static_cast<double>(npairs_den_[iK]));
-        std::ostringstream filename;
-        filename << path_ << "/HBT_correlation_function_KT_" << KT_array_[iK] << "_" << KT_array_[iK + 1] << ".dat";
-        write_3d_file(filename.str(), iK, npair_ratio);
-    }
+    if (!fetched_) fetch_results();
+    writer().write_KT(res_);
 }
 
-//! src/HBT_correlation.cpp:785-855
 void HBT_correlation::output_correlation_function_Kphi_differential() {
-    if (num_count_.empty()) fetch_results();
-    for (int iK = 0; iK < n_KT - 1; iK++) {
-        for (int iKphi = 0; iKphi < n_Kphi; iKphi++) {
-            const size_t slab = static_cast<size_t>(iK) * n_Kphi + iKphi;
-            const double npair_ratio =
-                (static_cast<double>(npairs_num_[slab]) / static_cast<double>(npairs_den_[slab]));
-            std::ostringstream filename;
-            filename << path_ << "/HBT_correlation_function_KT_" << KT_array_[iK] << "_" << KT_array_[iK + 1]
-                     << "_Kphi_" << Kphi_array_[iKphi] << ".dat";
-            write_3d_file(filename.str(), slab, npair_ratio);
-        }
-    }
+    if (!fetched_) fetch_results();
+    writer().write_KT_Kphi(res_);
 }

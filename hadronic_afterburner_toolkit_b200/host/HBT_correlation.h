@@ -24,7 +24,7 @@
 #include "particleSamples.h"
 #include "pretty_ostream.h"
 
-struct hbt_ctx;
+#include "hbt_output.h"
 
 class HBT_correlation {
   private:
@@ -58,10 +58,9 @@ class HBT_correlation {
     bool reduced_;
 
     // host copies of the accumulators, filled by fetch_results()
-    std::vector<unsigned long long> num_count_, den_count_, npairs_num_, npairs_den_;
-    std::vector<double> num_cos_, sum_qo_, sum_qs_, sum_ql_;
-    std::vector<unsigned long long> inv_count_, inv_den_, npairs_num_inv_, npairs_den_inv_;
-    std::vector<double> inv_sum_, inv_cos_;
+    hbt_params params_;
+    HbtHostResults res_;
+    bool fetched_;
 
     // scratch of the gathers
     std::vector<double> gather1_, gather2_;
@@ -72,7 +71,7 @@ class HBT_correlation {
     long long gather_events(bool mixed_list, const std::vector<int> &events, std::vector<double> &out,
                             std::vector<long long> &offsets);
     void fetch_results();
-    void write_3d_file(const std::string &filename, size_t slab, double npair_ratio);
+    HbtOutputWriter writer();
 
   public:
     HBT_correlation(ParameterReader &paraRdr, std::string path, std::shared_ptr<RandomUtil::Random> ran_gen);

@@ -1,0 +1,178 @@
+// hbt_fast_analysis.e — the HBT analysis of the reference program
+// (Analysis::HBTAnalysis, /root/reference/src/Analysis.cpp:817-835) end to end on libhbt_b200.so,
+// for the input format the production configs use (read_in_mode = 10, results/particle_samples.gz):
+//
+//   reader thread   hbt_reader_*      inflate + parse + species filter, two batches ahead
+//   host            psi_2, rapidity cut, the reference's RNG draws (partner events, rotation angles)
+//   GPU             hbt_accumulate_batch: one fused pair kernel per batch, asynchronous
+//   host            hbt_read + the reference's output files (hbt_output.h)
+//
+// Same command line as the reference (run in a directory with parameters.dat and results/;
+// name=value arguments override the file), same results/HBT_correlation_function_*.dat.
+// It does not link any reference code.  Switches it cannot honour (other read_in_mode values,
+// real mixed events, resonance feed-down, species groups) are refused with a message: use the
+// drop-in binary (hadronic_afterburner_tools_b200.e) for those.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/hbt_b200.h"
+#include "hbt_output.h"
+
+namespace {
+
+// "name = value  # comment" lines, then name=value arguments (ParameterReader::readFromFile / readFromArguments)
+struct Params {
+    std::map<std::string, double> v;
+    static std::string trim(const std::string &s) {
+        const size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+        return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+    }
+    void set(const std::string &line) {
+        std::string l = line.substr(0, line.find('#'));
+        const size_t eq = l.find('=');
+        if (eq == std::string::npos) return;
+        std::string name = trim(l.substr(0, eq)), val = trim(l.substr(eq + 1));
+        if (name.empty() || val.empty()) return;
+        char *end = nullptr;
+        const double x = std::strtod(val.c_str(), &end);
+        if (end == val.c_str()) return;
+        v[name] = x;
+    }
+    double get(const std::string &name) const {
+        const auto it = v.find(name);
+        if (it == v.end()) {
+            std::cerr << "[error] parameter " << name << " not found" << std::endl;
+            std::exit(1);
+        }
+        return it->second;
+    }
+    double get(const std::string &name, double dflt) const {
+        const auto it = v.find(name);
+        return it == v.end() ? dflt : it->second;
+    }
+};
+
+void die(const std::string &msg) {
+    std::cerr << "[error] hbt_fast_analysis: " << msg << std::endl;
+    std::exit(1);
+}
+
+void check(hbt_ctx *c, int rc, const char *what) {
+    if (rc == HBT_OK) return;
+    die(std::string(what) + " failed: " + hbt_last_error(c));
+}
+
+double seconds_since(const std::chrono::steady_clock::time_point &t0) {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // namespace
+
+int main(int argc, char *argv[]) {
+    const auto t_start = std::chrono::steady_clock::now();
+    const std::string path = "results";
+    Params P;
+    {
+        std::ifstream f("parameters.dat");
+        if (!f) die("parameters.dat not found in the working directory");
+        std::string line;
+        while (std::getline(f, line)) P.set(line);
+    }
+    for (int i = 1; i < argc; i++) P.set(argv[i]);
+
+    if (P.get("analyze_HBT", 0) != 1) die("analyze_HBT is not 1: nothing to do (the other analyses are the reference program's)");
+    if (P.get("read_in_mode") != 10) die("only read_in_mode = 10 (gzipped iSS samples) is read here");
+    if (P.get("read_in_real_mixed_events", 0) == 1) die("read_in_real_mixed_events = 1 is not supported here");
+    if (P.get("resonance_feed_down_flag", 0) == 1) die("resonance_feed_down_flag = 1 is not supported here");
+    if (P.get("readRapidityShiftFromFile", 0) == 1) die("readRapidityShiftFromFile = 1 is not supported here");
+
+    hbt_params hp;
+    hp.qnpts = static_cast<int>(P.get("qnpts"));
+    hp.n_KT = static_cast<int>(P.get("n_KT"));
+    hp.n_Kphi = static_cast<int>(P.get("n_Kphi"));
+    hp.azimuthal_flag = static_cast<int>(P.get("azimuthal_flag"));
+    hp.invariant_radius_flag = static_cast<int>(P.get("invariant_radius_flag"));
+    hp.long_comoving_boost = P.get("long_comoving_boost") == 1 ? 1 : 0;
+    hp.q_min = P.get("q_min");
+    hp.q_max = P.get("q_max");
+    hp.KT_min = P.get("KT_min");
+    hp.KT_max = P.get("KT_max");
+    hp.HBTrap_min = P.get("HBTrap_min");
+    hp.HBTrap_max = P.get("HBTrap_max");
+    hp.needed_number_of_pairs = P.get("needed_number_of_pairs");
+
+    hbt_ctx *ctx = nullptr;
+    if (hbt_create(&hp, 0, &ctx) != HBT_OK) die(std::string("cannot create the GPU engine: ") + hbt_last_error(nullptr));
+    hbt_rng *rng = nullptr;
+    if (hbt_rng_create(static_cast<int32_t>(P.get("randomSeed")), &rng) != HBT_OK) die("cannot create the random number generator");
+    hbt_reader *rd = nullptr;
+    const std::string file = path + "/particle_samples.gz";
+    if (hbt_reader_open(file.c_str(), 10, static_cast<int>(P.get("particle_monval")), static_cast<int64_t>(P.get("event_buffer_size")),
+                        P.get("rapidity_shift", 0), nullptr, &rd) != HBT_OK)
+        die("cannot open " + file + " for particle_monval " + std::to_string(static_cast<int>(P.get("particle_monval"))));
+
+    std::vector<double> cut;
+    std::vector<int64_t> off;
+    std::vector<int32_t> ids;
+    std::vector<double> cs;
+    long long n_batches = 0, n_events = 0;
+    unsigned long long pairs_same = 0, pairs_mixed = 0;
+    double t_wait = 0.0;
+    for (;;) {
+        const double *p = nullptr;
+        const int64_t *o = nullptr;
+        const auto tw = std::chrono::steady_clock::now();
+        const int nev = hbt_reader_next(rd, &p, &o, nullptr);
+        t_wait += seconds_since(tw);
+        if (nev < 0) die(std::string("reader: ") + hbt_reader_error(rd));
+        if (nev == 0) break;
+        // Psi_2 over every particle of the species in the batch (src/HBT_correlation.cpp:233-249)
+        const double psi_ref = hp.azimuthal_flag == 1 ? hbt_psi_ref(p, o[nev], 2) : 0.0;
+        // the gather of each event with its rapidity cut (:255-281)
+        cut.resize(static_cast<size_t>(o[nev]) * 8 + 8);
+        off.assign(1, 0);
+        for (int e = 0; e < nev; e++) {
+            const int64_t kept = hbt_gather_rapidity(&hp, p + 8 * o[e], o[e + 1] - o[e], cut.data() + 8 * off.back());
+            off.push_back(off.back() + kept);
+        }
+        // the draws of the batch in the reference's order (:202-217, :493-497)
+        const int nmix = nev / 2 + 1;
+        ids.resize(static_cast<size_t>(nev) * nmix);
+        cs.resize(static_cast<size_t>(nev) * nmix * 2);
+        hbt_rng_mixed_plan(rng, nev, nev, ids.data(), cs.data(), nullptr);
+        check(ctx, hbt_accumulate_batch(ctx, cut.data(), off.data(), nev, nullptr, nullptr, 0, ids.data(), cs.data(), nmix, psi_ref, 1, 1),
+              "hbt_accumulate_batch");
+        const unsigned long long n1 = static_cast<unsigned long long>(off.back());
+        pairs_same += n1 > 1 ? n1 * (n1 - 1) / 2 : 0;
+        for (int e = 0; e < nev; e++)
+            for (int c = 0; c < nmix; c++) {
+                const int id = ids[static_cast<size_t>(e) * nmix + c];
+                pairs_mixed += static_cast<unsigned long long>(off[e + 1] - off[e]) * (off[id + 1] - off[id]);
+            }
+        n_batches++;
+        n_events += nev;
+    }
+    check(ctx, hbt_synchronize(ctx), "hbt_synchronize");
+    const double t_loop = seconds_since(t_start);
+    HbtHostResults res;
+    check(ctx, hbt_fetch_results(ctx, hp, res), "hbt_read");
+    HbtOutputWriter(hp, path, P.get("ecoOutput", 0) == 1).write_all(res);
+    double same_ms = 0, mixed_ms = 0;
+    hbt_get_timers(ctx, &same_ms, &mixed_ms, nullptr, nullptr);
+    std::printf("[info] hbt_fast_analysis: %lld batches, %lld events, %llu same + %llu mixed pairs; %.3f s in all "
+                "(%.3f s waiting for the reader, %.1f MB of text, pair kernels %.3f s), output %.3f s\n",
+                n_batches, n_events, pairs_same, pairs_mixed, t_loop, t_wait, hbt_reader_bytes(rd) / 1e6,
+                (same_ms + mixed_ms) * 1e-3, seconds_since(t_start) - t_loop);
+    hbt_reader_close(rd);
+    hbt_rng_destroy(rng);
+    hbt_destroy(ctx);
+    return 0;
+}

@@ -109,6 +109,25 @@ double hbt_rng_uniform(hbt_rng *rng);
 int32_t hbt_rng_mixed_plan(hbt_rng *rng, int32_t nev, int32_t nev_mixed, int32_t *partner_ids,
                            double *cos_sin, double *angles);
 
+/* ---- fast reader: gzipped particle samples -> batches ("oversample groups") --------- */
+/* Replaces, for read_in_mode = 10 (results/particle_samples.gz), the reference's reader and the
+ * steps between it and the pair loops: read_in_particle_samples_gzipped + gz_readline
+ * (src/particleSamples.cpp:1247-1286, :2209-2218), boostParticles (:441-470), filter_particles for
+ * a single species (:625-678, :1329-1346) and, when rapidity_cut is not NULL, the HBT gather's
+ * tanh(HBTrap_min) < pz/E < tanh(HBTrap_max) (src/HBT_correlation.cpp:255-281).  Same grouping rule
+ * (events are appended while the particle count of all species is below event_buffer_size), same
+ * doubles, same order.  A background thread inflates and parses up to two batches ahead. */
+typedef struct hbt_reader hbt_reader;
+int hbt_reader_open(const char *path, int32_t read_in_mode, int32_t particle_monval, int64_t event_buffer_size,
+                    double rap_shift, const hbt_params *rapidity_cut, hbt_reader **out);
+/* Next batch: returns its number of events (0 at the end of the file, < 0 on error); *particles
+ * (8 doubles each: px py pz E x y z t) and *offsets (nev+1, in particles) stay valid until the
+ * next call; *all_particles = particles of every species read for the batch. */
+int32_t hbt_reader_next(hbt_reader *reader, const double **particles, const int64_t **offsets, int64_t *all_particles);
+const char *hbt_reader_error(const hbt_reader *reader);
+uint64_t hbt_reader_bytes(const hbt_reader *reader); /* inflated bytes consumed so far */
+void hbt_reader_close(hbt_reader *reader);
+
 /* ---- the hot path: HOST buffers in (copies are part of the call) ------------------ */
 /* Same-event pair loop (src/HBT_correlation.cpp:291-460) over the merged, rapidity-cut
  * particle list `p` (n x 8, reference gather order).  psi_ref is only read when

@@ -14,6 +14,8 @@ from hadronic_afterburner_toolkit_b200.params import C3, C4, HBTParams
 
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "hadronic_afterburner_tools.e")
 OUR_EXE = os.path.join(ROOT, "hadronic_afterburner_toolkit_b200", "host", "build", "hadronic_afterburner_tools_b200.e")
+# the HBT analysis without any reference code: fast gz reader -> GPU -> the same output files
+FAST_EXE = os.path.join(ROOT, "hadronic_afterburner_toolkit_b200", "host", "build", "hbt_fast_analysis.e")
 PDG = os.path.join(ROOT, "oracle", "_ref", "EOS", "pdg.dat")
 
 pytestmark = [pytest.mark.gpu,
@@ -72,6 +74,21 @@ def test_same_files_as_reference_binary(name, tmp_path):
     assert "HBT pair loops run on 1 GPU(s)" in out
     same_text(want, got)
     assert len(want) == (P.n_KT - 1) * (P.n_Kphi if P.azimuthal_flag else 1) * (2 if P.invariant_radius_flag else 1)
+    # third arm: our own reader and driver (no reference code at all) on the same directory layout
+    fast, out = run_binary(FAST_EXE, str(tmp_path / "fast"), text, gz)
+    assert "hbt_fast_analysis: %d batches, %d events" % (ngrp, ngrp * nev) in out
+    same_text(want, fast)
+
+
+def test_fast_driver_refuses_what_it_cannot_read(tmp_path):
+    P = C3.with_(qnpts=15)
+    batches = synth.make_batches(44, 1, 2, multiplicity=50)
+    gz = str(tmp_path / "input.gz")
+    synth.write_iss_gz(gz, batches)
+    for key, value in (("read_in_mode", 2), ("read_in_real_mixed_events", 1), ("resonance_feed_down_flag", 1)):
+        text = P.parameters_dat(event_buffer_size=100, **{key: value})
+        with pytest.raises(AssertionError, match="hbt_fast_analysis"):
+            run_binary(FAST_EXE, str(tmp_path / key), text, gz)
 
 
 def test_groups_sharded_over_all_gpus_of_the_box(tmp_path):
