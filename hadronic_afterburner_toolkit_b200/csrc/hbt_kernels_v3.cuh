@@ -631,12 +631,15 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                     Q.qcount += total;
                     kept += static_cast<unsigned>(total);
                     __syncwarp();
+                    // drain from the top of the queue, 32 entries a round; the entry of the NEXT round is
+                    // loaded before this round's pair is evaluated (one LDS round trip off the chain)
+                    unsigned entry = lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(max(Q.qcount - 32, 0) + lane));
                     while (Q.qcount >= 32 || (final && Q.qcount > 0)) {
                         const int take = min(32, Q.qcount);
                         const int base = Q.qcount - take;
-                        if (lane < take)
-                            v3_drain_pair<MIXED, STATS>(g, c, acc, closed, dv, sbase,
-                                                        lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(base + lane)), psi_ref, n);
+                        const unsigned next_entry = lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(max(base - 32, 0) + lane));
+                        if (lane < take) v3_drain_pair<MIXED, STATS>(g, c, acc, closed, dv, sbase, entry, psi_ref, n);
+                        entry = next_entry;
                         Q.qcount = base;
                         __syncwarp();
                     }
