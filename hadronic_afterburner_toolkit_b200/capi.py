@@ -28,6 +28,7 @@ EXPORTS = (
     "hbt_comm_unique_id", "hbt_comm_init_rank", "hbt_comm_init_all", "hbt_allreduce", "hbt_allreduce_all",
     "hbt_version", "hbt_device_count", "hbt_set_option",
     "hbt_reader_open", "hbt_reader_next", "hbt_reader_error", "hbt_reader_bytes", "hbt_reader_close",
+    "hbt_bf_create", "hbt_bf_destroy", "hbt_bf_last_error", "hbt_bf_accumulate", "hbt_bf_read", "hbt_bf_get_timers",
 )
 
 HBT_OK = 0
@@ -106,6 +107,12 @@ def lib() -> ctypes.CDLL:
         "hbt_reader_error": (ctypes.c_char_p, [vp]),
         "hbt_reader_bytes": (ctypes.c_uint64, [vp]),
         "hbt_reader_close": (None, [vp]),
+        "hbt_bf_create": (ctypes.c_int, [i32, dbl, i32, vp]),
+        "hbt_bf_destroy": (None, [vp]),
+        "hbt_bf_last_error": (ctypes.c_char_p, [vp]),
+        "hbt_bf_accumulate": (ctypes.c_int, [vp, i32, vp, vp, i32, vp, vp, i32, vp, vp]),
+        "hbt_bf_read": (ctypes.c_int, [vp, vp]),
+        "hbt_bf_get_timers": (ctypes.c_int, [vp, vp, vp]),
     }
     for name in EXPORTS:
         f = getattr(L, name)  # AttributeError if the library lacks a declared symbol

@@ -1,0 +1,243 @@
+// Device path of the BalanceFunction pair loops, C ABI in include/hbt_b200.h.
+//
+//   BalanceFunction::combine_and_bin_particle_pairs         src/BalanceFunction.cpp:120-157
+//   BalanceFunction::combine_and_bin_mixed_particle_pairs   src/BalanceFunction.cpp:159-197
+//
+// The loops only histogram (Delta y, Delta phi) of particle pairs of ONE event (or one event and
+// its drawn partner); everything per pair is IEEE add / divide / floor / int cast on values the
+// host computed per particle, so evaluating the reference's expressions literally (__dsub_rn,
+// __ddiv_rn: no FMA contraction, no reciprocal) gives the reference's bin for every pair — no guard
+// bands needed.  One thread block = 128 list-a particles of one event against the partner
+// event's list b staged through shared memory; the [Bnpts][20] histogram is privatised per block
+// in shared memory (u32) and flushed with one u64 atomic per non-empty bin.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hbt_b200.h"
+
+namespace {
+
+constexpr int kTile = 128;
+
+struct BfGrid {
+    int nrap;         // Bnpts
+    double rap_min;   // Brap_min = -|Brap_max| - drap/2
+    double drap;
+    double phi_min;   // -pi/2
+    double dphi;      // 2 pi / 20
+};
+
+struct BfSeg {  // one event of list a: its particles, the partner event's particles, the rotation
+    long long a0, b0;
+    int na, nb;
+    int block0;  // first thread block of this event
+    int pad;
+    double rotation;
+};
+
+__global__ void __launch_bounds__(kTile) bf_pairs(const double2 *__restrict__ a, const double2 *__restrict__ b,
+                                                   const BfSeg *__restrict__ segs, int nseg, BfGrid g,
+                                                   unsigned long long *__restrict__ hist) {
+    extern __shared__ unsigned s_hist[];  // [nrap * 20]
+    __shared__ double2 sb[kTile];
+    const int t = threadIdx.x;
+    const int nbins = g.nrap * HBT_BF_NPHI;
+    for (int k = t; k < nbins; k += kTile) s_hist[k] = 0u;
+    int lo = 0, hi = nseg - 1;  // the event that owns this block
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (segs[mid].block0 <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+    }
+    const BfSeg sg = segs[lo];
+    const int ia = (static_cast<int>(blockIdx.x) - sg.block0) * kTile + t;
+    const bool live = ia < sg.na;
+    double2 pa = make_double2(0.0, 0.0);
+    if (live) pa = a[sg.a0 + ia];
+    for (int j0 = 0; j0 < sg.nb; j0 += kTile) {
+        __syncthreads();
+        if (j0 + t < sg.nb) sb[t] = b[sg.b0 + j0 + t];
+        __syncthreads();
+        if (!live) continue;
+        const int nj = min(kTile, sg.nb - j0);
+        for (int j = 0; j < nj; j++) {
+            const double2 pb = sb[j];
+            // :134-139 / :175-180 — (a.phi - b.phi) + rotation, then floor((. - Bphi_min)/dphi) % Bnphi
+            const double dphi_local = __dadd_rn(__dsub_rn(pa.x, pb.x), sg.rotation);
+            int phi_idx = static_cast<int>(floor(__ddiv_rn(__dsub_rn(dphi_local, g.phi_min), g.dphi))) % HBT_BF_NPHI;
+            if (phi_idx < 0) phi_idx += HBT_BF_NPHI;
+            // :141-151 / :182-192
+            const double dy = __dsub_rn(pa.y, pb.y);
+            if (fabs(dy) < 1e-10) continue;
+            if (dy < g.rap_min) continue;
+            const int y_idx = static_cast<int>(__ddiv_rn(__dsub_rn(dy, g.rap_min), g.drap));
+            if (y_idx >= 0 && y_idx < g.nrap) atomicAdd(&s_hist[y_idx * HBT_BF_NPHI + phi_idx], 1u);
+        }
+    }
+    __syncthreads();
+    for (int k = t; k < nbins; k += kTile)
+        if (s_hist[k]) atomicAdd(&hist[k], static_cast<unsigned long long>(s_hist[k]));
+}
+
+}  // namespace
+
+struct hbt_bf {
+    int device = 0;
+    BfGrid grid{};
+    cudaStream_t stream = nullptr;
+    unsigned long long *d_hist = nullptr;  // [8][nrap][20]
+    double2 *d_a = nullptr, *d_b = nullptr;
+    BfSeg *d_seg = nullptr;
+    size_t cap_a = 0, cap_b = 0, cap_seg = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double kernel_ms = 0.0;
+    uint64_t pairs = 0;
+    std::string err;
+};
+
+namespace {
+std::string g_bf_error;
+
+int bf_fail(hbt_bf *bf, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    (bf ? bf->err : g_bf_error) = buf;
+    return code;
+}
+
+#define BFCU(bf, call)                                                                              \
+    do {                                                                                            \
+        const cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) return bf_fail(bf, HBT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+int bf_reserve(hbt_bf *bf, T **p, size_t *cap, size_t n) {
+    if (n <= *cap) return HBT_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = n + n / 4 + 1024;
+    BFCU(bf, cudaMalloc(p, *cap * sizeof(T)));
+    return HBT_OK;
+}
+}  // namespace
+
+extern "C" const char *hbt_bf_last_error(const hbt_bf *bf) { return bf ? bf->err.c_str() : g_bf_error.c_str(); }
+
+extern "C" int hbt_bf_create(int32_t Bnpts, double Brap_max, int32_t device, hbt_bf **out) {
+    if (!out) return HBT_ERR_INVALID;
+    *out = nullptr;
+    if (Bnpts < 2 || Bnpts > 2048) return bf_fail(nullptr, HBT_ERR_INVALID, "Bnpts = %d out of range", Bnpts);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return bf_fail(nullptr, HBT_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return bf_fail(nullptr, HBT_ERR_INVALID, "device %d of %d", device, ndev);
+    hbt_bf *bf = new hbt_bf;
+    bf->device = device;
+    // the constructor's grid, evaluated the same way (src/BalanceFunction.cpp:27-36)
+    bf->grid.nrap = Bnpts;
+    bf->grid.drap = 2. * std::abs(Brap_max) / (Bnpts - 1);
+    bf->grid.rap_min = -std::abs(Brap_max) - 0.5 * bf->grid.drap;
+    bf->grid.dphi = 2. * M_PI / HBT_BF_NPHI;
+    bf->grid.phi_min = -M_PI / 2.;
+    *out = bf;
+    BFCU(bf, cudaSetDevice(device));
+    BFCU(bf, cudaStreamCreateWithFlags(&bf->stream, cudaStreamNonBlocking));
+    BFCU(bf, cudaEventCreate(&bf->e0));
+    BFCU(bf, cudaEventCreate(&bf->e1));
+    const size_t n = static_cast<size_t>(HBT_BF_NHIST) * Bnpts * HBT_BF_NPHI;
+    BFCU(bf, cudaMalloc(&bf->d_hist, n * 8));
+    BFCU(bf, cudaMemset(bf->d_hist, 0, n * 8));
+    return HBT_OK;
+}
+
+extern "C" void hbt_bf_destroy(hbt_bf *bf) {
+    if (!bf) return;
+    cudaSetDevice(bf->device);
+    if (bf->stream) cudaStreamSynchronize(bf->stream);
+    cudaFree(bf->d_hist);
+    cudaFree(bf->d_a);
+    cudaFree(bf->d_b);
+    cudaFree(bf->d_seg);
+    if (bf->e0) cudaEventDestroy(bf->e0);
+    if (bf->e1) cudaEventDestroy(bf->e1);
+    if (bf->stream) cudaStreamDestroy(bf->stream);
+    delete bf;
+}
+
+extern "C" int hbt_bf_accumulate(hbt_bf *bf, int32_t hist, const double *a, const int64_t *off_a, int32_t nev,
+                                 const double *b, const int64_t *off_b, int32_t nev_b, const int32_t *partner,
+                                 const double *rotation) {
+    if (!bf || hist < 0 || hist >= HBT_BF_NHIST || nev < 0 || nev_b < 0) return bf_fail(bf, HBT_ERR_INVALID, "hbt_bf_accumulate: bad argument");
+    if (nev == 0) return HBT_OK;
+    if (!off_a || !off_b || !partner || !rotation) return bf_fail(bf, HBT_ERR_INVALID, "hbt_bf_accumulate: null argument");
+    const int64_t na = off_a[nev], nb = off_b[nev_b];
+    if ((na > 0 && !a) || (nb > 0 && !b)) return bf_fail(bf, HBT_ERR_INVALID, "hbt_bf_accumulate: null particles");
+    std::vector<BfSeg> segs;
+    long long blocks = 0;
+    uint64_t pairs = 0;
+    for (int iev = 0; iev < nev; iev++) {
+        const int id = partner[iev];
+        if (id < 0 || id >= nev_b) return bf_fail(bf, HBT_ERR_INVALID, "partner event %d out of range", id);
+        BfSeg s;
+        s.a0 = off_a[iev];
+        s.na = static_cast<int>(off_a[iev + 1] - off_a[iev]);
+        s.b0 = off_b[id];
+        s.nb = static_cast<int>(off_b[id + 1] - off_b[id]);
+        s.rotation = rotation[iev];
+        s.pad = 0;
+        if (s.na <= 0 || s.nb <= 0) continue;
+        s.block0 = static_cast<int>(blocks);
+        blocks += (s.na + kTile - 1) / kTile;
+        pairs += static_cast<uint64_t>(s.na) * s.nb;
+        segs.push_back(s);
+    }
+    if (segs.empty()) return HBT_OK;
+    if (blocks > 0x7fffffffLL) return bf_fail(bf, HBT_ERR_INVALID, "batch too large: %lld blocks", blocks);
+    BFCU(bf, cudaSetDevice(bf->device));
+    BFCU(bf, cudaStreamSynchronize(bf->stream));  // the staging buffers below are reused (pageable sources)
+    int rc = bf_reserve(bf, &bf->d_a, &bf->cap_a, static_cast<size_t>(na));
+    if (rc) return rc;
+    rc = bf_reserve(bf, &bf->d_b, &bf->cap_b, static_cast<size_t>(nb));
+    if (rc) return rc;
+    rc = bf_reserve(bf, &bf->d_seg, &bf->cap_seg, segs.size());
+    if (rc) return rc;
+    BFCU(bf, cudaMemcpyAsync(bf->d_a, a, static_cast<size_t>(na) * 16, cudaMemcpyHostToDevice, bf->stream));
+    BFCU(bf, cudaMemcpyAsync(bf->d_b, b, static_cast<size_t>(nb) * 16, cudaMemcpyHostToDevice, bf->stream));
+    BFCU(bf, cudaMemcpyAsync(bf->d_seg, segs.data(), segs.size() * sizeof(BfSeg), cudaMemcpyHostToDevice, bf->stream));
+    const size_t nbins = static_cast<size_t>(bf->grid.nrap) * HBT_BF_NPHI;
+    BFCU(bf, cudaEventRecord(bf->e0, bf->stream));
+    bf_pairs<<<static_cast<unsigned>(blocks), kTile, nbins * sizeof(unsigned), bf->stream>>>(
+        bf->d_a, bf->d_b, bf->d_seg, static_cast<int>(segs.size()), bf->grid, bf->d_hist + static_cast<size_t>(hist) * nbins);
+    BFCU(bf, cudaGetLastError());
+    BFCU(bf, cudaEventRecord(bf->e1, bf->stream));
+    BFCU(bf, cudaStreamSynchronize(bf->stream));  // segs / a / b may be freed by the caller on return
+    float ms = 0.f;
+    BFCU(bf, cudaEventElapsedTime(&ms, bf->e0, bf->e1));
+    bf->kernel_ms += ms;
+    bf->pairs += pairs;
+    return HBT_OK;
+}
+
+extern "C" int hbt_bf_read(hbt_bf *bf, uint64_t *hist) {
+    if (!bf || !hist) return HBT_ERR_INVALID;
+    BFCU(bf, cudaSetDevice(bf->device));
+    BFCU(bf, cudaStreamSynchronize(bf->stream));
+    const size_t n = static_cast<size_t>(HBT_BF_NHIST) * bf->grid.nrap * HBT_BF_NPHI;
+    BFCU(bf, cudaMemcpy(hist, bf->d_hist, n * 8, cudaMemcpyDeviceToHost));
+    return HBT_OK;
+}
+
+extern "C" int hbt_bf_get_timers(hbt_bf *bf, double *kernel_ms, uint64_t *pairs) {
+    if (!bf) return HBT_ERR_INVALID;
+    if (kernel_ms) *kernel_ms = bf->kernel_ms;
+    if (pairs) *pairs = bf->pairs;
+    return HBT_OK;
+}

@@ -236,6 +236,33 @@ int hbt_allreduce_all(hbt_ctx **ctxs, int32_t n);
  * Measurement aid for bench.py; not part of the reference's interface. */
 int hbt_measure_fp64_peak(int32_t device, double ms, double *tflops);
 
+/* ---- next row: the pair loops of class BalanceFunction ------- */
+/* BalanceFunction::combine_and_bin_particle_pairs (src/BalanceFunction.cpp:120-157) and
+ * combine_and_bin_mixed_particle_pairs (:159-197): per event, every particle of list a against every
+ * particle of list b of the partner event, histogram [Bnpts][20] in (Delta y, Delta phi).  The host keeps
+ * what the reference computes once per particle with glibc (phi_p = atan2(py,px), rap_y / rap_eta =
+ * asinh(...), src/particleSamples.cpp:441-470), the pT cut (:127,129) and the RNG draws (:167-170); the
+ * device does the O(n_a n_b) loop with the reference's own IEEE operations (subtract, divide, floor,
+ * int cast), so every bin count is the reference's.  Grid constants as in the constructor (:27-36):
+ * Bnphi = 20, dphi = 2 pi/20, Bphi_min = -pi/2, drap = 2|Brap_max|/(Bnpts-1), Brap_min = -|Brap_max| - drap/2. */
+typedef struct hbt_bf hbt_bf;
+#define HBT_BF_NPHI 20
+#define HBT_BF_NHIST 8 /* C_ab, C_abarbbar, C_abbar, C_abarb, then the four mixed-event ones */
+int hbt_bf_create(int32_t Bnpts, double Brap_max, int32_t device, hbt_bf **out);
+void hbt_bf_destroy(hbt_bf *bf);
+const char *hbt_bf_last_error(const hbt_bf *bf);
+/* One call of either routine for all nev events of a batch.  a / b: (phi_p, rapidity) pairs of the
+ * particles that passed the pT cut, flat, with nev+1 / nev_b+1 offsets (in particles); partner[iev] =
+ * event of list b that event iev of list a is paired with (iev itself for the same-event routine, the
+ * drawn iev_mixed for the mixed one); rotation[iev] is added to Delta phi as the reference adds its
+ * global_random_rotation (pass 0.0 for the same-event routine: x + 0.0 is x).  hist in [0, 8). */
+int hbt_bf_accumulate(hbt_bf *bf, int32_t hist, const double *a, const int64_t *off_a, int32_t nev,
+                      const double *b, const int64_t *off_b, int32_t nev_b, const int32_t *partner,
+                      const double *rotation);
+/* counts [8][Bnpts][20] (the reference keeps them in doubles; they are integers) */
+int hbt_bf_read(hbt_bf *bf, uint64_t *hist);
+int hbt_bf_get_timers(hbt_bf *bf, double *kernel_ms, uint64_t *pairs);
+
 /* number of CUDA devices visible to the process (0 when there is none) */
 int32_t hbt_device_count(void);
 

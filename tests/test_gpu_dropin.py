@@ -91,6 +91,27 @@ def test_fast_driver_refuses_what_it_cannot_read(tmp_path):
             run_binary(FAST_EXE, str(tmp_path / key), text, gz)
 
 
+@pytest.mark.parametrize("alpha,beta,rap_type,buf", [(211, -211, 1, 1300), (9998, -9998, 0, 100000)])
+def test_balance_function_operator_same_files(alpha, beta, rap_type, buf, tmp_path):
+    """SURVEY.md 8f rank 3: Analysis::BalanceFunctionAnalysis with OUR BalanceFunction class inside the
+    reference binary (reference reader incl. the charged-hadron species groups, reference RNG) writes
+    the reference's three files, character for character (all histogram entries are integers)."""
+    gz = os.path.join(ROOT, "tests", "golden", "bf_input.gz")
+    text = HBTParams(randomSeed=77).parameters_dat(
+        analyze_HBT=0, analyze_balance_function=1, event_buffer_size=buf, particle_alpha=alpha, particle_beta=beta,
+        Bnpts=21, Brap_max=2.0, BpT_min=0.2, BpT_max=3.0, rap_type=rap_type)
+
+    def run(exe, wd):
+        run_binary(exe, wd, text, gz)
+        res = os.path.join(wd, "results")
+        return {fn: open(os.path.join(res, fn)).read() for fn in sorted(os.listdir(res)) if fn.endswith(".dat")}
+    want = run(REF_EXE, str(tmp_path / "ref"))
+    got = run(OUR_EXE, str(tmp_path / "ours"))
+    assert len(want) == 3 and sorted(want) == sorted(got)
+    for fn in want:
+        assert want[fn] == got[fn], fn
+
+
 def test_groups_sharded_over_all_gpus_of_the_box(tmp_path):
     from hadronic_afterburner_toolkit_b200 import capi
 
