@@ -329,3 +329,34 @@ def test_output_files_match_reference_text(name, tmp_path):
                     assert abs(float(a) - float(b)) <= 2e-8 * max(abs(float(a)), 1e-300), (lw, lg)
         checked += 1
     assert checked >= 1
+
+
+def _random_case(k):
+    """a seeded random parameters.dat: grid sizes, windows, K_T / K_phi binning, boost, rapidity cut,
+    pair cap, species mass and sample size all vary"""
+    r = np.random.default_rng(7000 + k)
+    qmax = float(r.choice([0.05, 0.1, 0.2, 0.3, 0.4]))
+    az = int(r.random() < 0.35)
+    ktmin = float(r.choice([0.0, 0.05, 0.15, 0.3]))
+    cap = float(r.choice([1e15, 1e15, 3000.0, 150.0]))
+    P = HBTParams(qnpts=int(r.integers(5, 34)), q_min=-qmax, q_max=qmax, n_KT=int(r.integers(2, 8)), KT_min=ktmin,
+                  KT_max=ktmin + float(r.choice([0.2, 0.4, 0.9])), n_Kphi=int(r.integers(1, 13)) if az else 8, azimuthal_flag=az,
+                  invariant_radius_flag=int(r.random() < 0.15), long_comoving_boost=int(r.random() < 0.8),
+                  HBTrap_min=-float(r.choice([0.2, 0.5, 1.0])), HBTrap_max=float(r.choice([0.2, 0.5, 1.0])),
+                  needed_number_of_pairs=cap, randomSeed=int(r.integers(1, 10 ** 6)))
+    mass = float(r.choice([0.138, KAON_MASS, 0.938]))
+    return P, int(r.integers(1, 4)), int(r.integers(1, 6)), int(r.integers(150, 700)), mass
+
+
+@pytest.mark.parametrize("k", range(16))
+def test_random_parameter_sets_against_oracle(k):
+    """16 seeded random parameter files (every switch of the class varies) through the production path
+    and, for the uncapped ones, the instrumented path: all integers equal, sums within 1e-10."""
+    P, ngrp, nev, mult, mass = _random_case(k)
+    batches = synth.make_batches(20261000 + k, ngrp, nev, mass=mass, multiplicity=mult)
+    ref = run_oracle(P, batches)
+    _, acc = run_product(P, batches)
+    hbtio.compare(ref, acc, rtol=RTOL, check_stage="cheap", q_scale=P.q_max)
+    if P.needed_number_of_pairs > 1e14:
+        _, acc = run_product(P, batches, stats=True)
+        hbtio.compare(ref, acc, rtol=RTOL, check_stage=True, q_scale=P.q_max)
