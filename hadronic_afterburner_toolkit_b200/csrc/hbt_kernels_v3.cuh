@@ -83,10 +83,13 @@ struct V3Smem {
     static constexpr int SUB = MIXED ? HBT_V3_SUB_MIXED : HBT_V3_SUB_SAME, TJ = MIXED ? HBT_V3_TJ_MIXED : HBT_V3_TJ_SAME;
     static constexpr bool SORTED = !MIXED && !STATS;
     static constexpr int SI = 0;                                 // double [NC][SUB]  list-1 sub-tile, SoA
-    static constexpr int SJ = SI + 8 * NC * SUB;                 // double [NC][TJ]   list-2 tile, SoA
+    // float [3][TJ] px, py, -pT^2/2 of the list-2 tile (float prefilter).  It sits BEFORE the FP64 tile: the
+    // prefilter loads particle j+1 while it works on j, and the slot past the last array is then sj[0],
+    // which nobody writes during the pair loop
+    static constexpr int SJF = SI + 8 * NC * SUB;
+    static constexpr int SJ = SJF + (STATS ? 0 : 4 * 3 * TJ);    // double [NC][TJ]   list-2 tile, SoA
     static constexpr int SJT = SJ + 8 * NC * TJ;                 // double [TJ]       pT^2 of the list-2 tile (FP64 prefilter)
-    static constexpr int SJF = SJT + (STATS ? 8 * TJ : 0);       // float  [3][TJ]    px, py, -pT^2/2 (float prefilter)
-    static constexpr int SIO = SJF + (STATS ? 0 : 4 * 3 * TJ);   // u32    [SUB]      gather-order index (sorted lists)
+    static constexpr int SIO = SJT + (STATS ? 8 * TJ : 0);       // u32    [SUB]      gather-order index (sorted lists)
     static constexpr int SJO = SIO + (SORTED ? 4 * SUB : 0);     // u32    [TJ]
     static constexpr int LQ = SJO + (SORTED ? 4 * TJ : 0);       // u32    [LCAP][32] per-lane survivor lists
     static constexpr int WQ = LQ + 4 * HBT_V2_LCAP * 32;         // u32    [QCAP]     linear warp queue
@@ -543,7 +546,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
             const unsigned lane16 = static_cast<unsigned>(lane) << 16;
             int j = 0;
             // the float copy of list-2 particle j is loaded one trip ahead (LDS latency off the loop's
-            // critical path; the last trip reads one slot past the tile, still this warp's shared memory)
+            // critical path; the last trip reads the first slot of the next array, see V3Smem)
             float pbx = 0.f, pby = 0.f, pnb = 0.f;
             if (!STATS) { pbx = lds_f32(sjf_addr); pby = lds_f32(sjf_addr + 4 * TJ); pnb = lds_f32(sjf_addr + 8 * TJ); }
             for (;;) {
@@ -633,15 +636,18 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                     __syncwarp();
                     // drain from the top of the queue, 32 entries a round; the entry of the NEXT round is
                     // loaded before this round's pair is evaluated (one LDS round trip off the chain)
-                    unsigned entry = lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(max(Q.qcount - 32, 0) + lane));
-                    while (Q.qcount >= 32 || (final && Q.qcount > 0)) {
-                        const int take = min(32, Q.qcount);
-                        const int base = Q.qcount - take;
-                        const unsigned next_entry = lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(max(base - 32, 0) + lane));
-                        if (lane < take) v3_drain_pair<MIXED, STATS>(g, c, acc, closed, dv, sbase, entry, psi_ref, n);
-                        entry = next_entry;
-                        Q.qcount = base;
-                        __syncwarp();
+                    // (every queue read is followed by a __syncwarp before the next flush writes the queue)
+                    if (Q.qcount >= 32 || (final && Q.qcount > 0)) {
+                        unsigned entry = lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(max(Q.qcount - 32, 0) + lane));
+                        do {
+                            const int take = min(32, Q.qcount);
+                            const int base = Q.qcount - take;
+                            const unsigned next_entry = lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(max(base - 32, 0) + lane));
+                            if (lane < take) v3_drain_pair<MIXED, STATS>(g, c, acc, closed, dv, sbase, entry, psi_ref, n);
+                            entry = next_entry;
+                            Q.qcount = base;
+                            __syncwarp();
+                        } while (Q.qcount >= 32 || (final && Q.qcount > 0));
                     }
                 }
                 if (final) break;
