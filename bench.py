@@ -349,28 +349,33 @@ def main():
     dst = (st_step * np.uint64(a.steps)).astype(np.uint64)
     assert int(dst[0]) * world == int(st1[0] - st0[0]) or world > 1  # same pair count in both passes
     ops_same, ops_mixed = algorithmic_ops(dst, boost=P.long_comoving_boost == 1, az=P.azimuthal_flag == 1)
+    fused = os.environ.get("HBT_B200_FUSE", "1") != "0" and os.environ.get("HBT_B200_KERNEL", "2") != "1"
     ks = (tm1["same_ms"] - tm0["same_ms"]) * 1e-3
     km = (tm1["mixed_ms"] - tm0["mixed_ms"]) * 1e-3
     ach = (ops_same + ops_mixed) / (ks + km) / 1e12
-    fused = os.environ.get("HBT_B200_FUSE", "1") != "0" and os.environ.get("HBT_B200_KERNEL", "2") != "1"
     traffic = None
+    traffic_detail = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = {"unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one C5-shape group)",
-                   "same": tj["same"]["dram_bytes_per_launch"], "mixed": tj["mixed"]["dram_bytes_per_launch"],
-                   "algorithmic_bytes_per_launch": tj["same"]["algorithmic_bytes_per_launch"], "source": tj["source"]}
+        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch (one C5-shape group)
+        traffic = tj["fused" if fused else "same"]["dram_bytes_per_launch"] + (0 if fused else tj["mixed"]["dram_bytes_per_launch"])
+        traffic_detail = {"unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one C5-shape group per launch)",
+                          "fused": tj["fused"]["dram_bytes_per_launch"], "same": tj["same"]["dram_bytes_per_launch"],
+                          "mixed": tj["mixed"]["dram_bytes_per_launch"],
+                          "algorithmic_bytes_per_launch": tj["fused"]["algorithmic_bytes_per_launch"], "source": tj["source"]}
     except (OSError, KeyError, ValueError):
         pass
     roofline = {
         "bound": "fp64", "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
-        "traffic": traffic,
+        "traffic": traffic, "traffic_detail": traffic_detail,
         "peak_source": "measured on this device: DFMA dependent-chain microbenchmark (hbt_measure_fp64_peak); "
                        "FP64 is not in MEASURED_PEAKS.json",
         "definition": "algorithmic FP64 ops (SURVEY.md 8d: 7nA+10nB+5nC+17nD+20nE same, ...+3nE mixed; stage populations from an "
                       "instrumented, untimed pass over the same input) / CUDA-event time of the production pair kernels "
                       "(incl. the same-event sort + cull kernels) on the launching stream",
         "note": "the bound is the FP64 pipe (SURVEY.md 8d), not HBM or tensor cores; the production prefilter runs in packed "
-                "FP32, so the FP64 pipe itself is ~13-25 % busy (ncu) while the algorithmic-ops fraction is what is reported",
+                "FP32, so the FP64 pipe itself is ~27 % busy (ncu, fused kernel; issue slots 66 %) while the algorithmic-ops fraction is "
+                "what is reported; same-event units are bounded by their 5 spread-address REDs per accepted pair (DESIGN.md 5)",
         "kernels": ({
             # one launch per group works through the same-event and the mixed-event units interleaved
             "hbt_pairs_v3_fused": {"ms_per_launch": 1e3 * (ks + km) / max(1, tm1["same_launches"] - tm0["same_launches"]),
