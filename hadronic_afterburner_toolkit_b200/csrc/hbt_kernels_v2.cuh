@@ -29,6 +29,7 @@ struct V2Const {
     double g0;                // guard, constant part, in bin units: gb_min + g_abs*inv_dq
     double gq;                // guard per unit of (|qx|+|qy|), in bin units: 2^-46 * inv_dq
     double gl;                // same for the q_long error bound (2^-45 * inv_dq)
+    double inv_dkphi;         // 1/dK_phi (float-estimate path of the K_phi bin only; never decides an edge)
     float kt_min_f, inv_dkt_f;  // float estimate of the K_T bin (fixed up with the exact thresholds)
     int symmetric;            // |q_lo| == |q_hi| up to 2^-24 relative
 };
@@ -49,6 +50,7 @@ __host__ inline V2Const hbt_v2_consts(const HbtGrid &g) {
     c.g0 = c.gb_min + c.g_abs * g.inv_dq;
     c.gq = 1.5e-14 * g.inv_dq;
     c.gl = 2.9e-14 * g.inv_dq;
+    c.inv_dkphi = g.dKphi > 0.0 ? 1.0 / g.dKphi : 0.0;
     c.kt_min_f = static_cast<float>(g.KT_min);
     c.inv_dkt_f = static_cast<float>(1.0 / g.dKT);
     c.symmetric = (g.q_lo < 0.0 && g.q_hi > 0.0 && fabs(a - b) <= 5.9e-8 * c.W2) ? 1 : 0;

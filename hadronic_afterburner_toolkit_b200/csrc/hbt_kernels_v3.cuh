@@ -323,14 +323,27 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
         if (STATS) slab = v3_kt_bin(g, c, k2);
         if (g.az) {
             const double Kx = 0.5 * (lds_f64(sia) + lds_f64(sja)), Ky = 0.5 * (lds_f64(sia + 8 * TI) + lds_f64(sja + 8 * TJ));
-            double dphi = __dsub_rn(atan2(Ky, Kx), psi_ref);
-            while (dphi < 0.) dphi = __dadd_rn(dphi, g.two_pi);
-            while (dphi > g.two_pi) dphi = __dsub_rn(dphi, g.two_pi);
-            const double u = __ddiv_rn(dphi, g.dKphi);
-            const int iphi = __double2int_rz(u);
-            if (fabs(u - rint(u)) < 1e-9) stage = -1;  // the literal path hands it to the host
-            else if (iphi < 0 || iphi >= g.nKphi) stage = 5;  // counted through q_long, then dropped
-            else slab = slab * g.nKphi + iphi;
+            // K_phi bin (:392-400).  First a float estimate: atan2f (<= 3 ulp) of the float-rounded K gives
+            // Delta phi / dK_phi within ~2e-6 n_Kphi/8 of the reference's value; farther than 1e-4 from every
+            // integer (bin edges, both ends of the range) the bin is decided.  Otherwise the double-precision
+            // expression, and within 1e-9 of an edge the host (glibc atan2).
+            double de = static_cast<double>(atan2f(static_cast<float>(Ky), static_cast<float>(Kx))) - psi_ref;
+            de = de < 0. ? de + g.two_pi : de;
+            de = de > g.two_pi ? de - g.two_pi : de;
+            const double ue = de * c.inv_dkphi;
+            const double fe = ue - floor(ue);
+            if (!STATS && fe > 1e-4 && fe < 1.0 - 1e-4 && ue > 0. && ue < static_cast<double>(g.nKphi) && g.nKphi <= 256) {
+                slab = slab * g.nKphi + static_cast<int>(ue);
+            } else {
+                double dphi = __dsub_rn(atan2(Ky, Kx), psi_ref);
+                while (dphi < 0.) dphi = __dadd_rn(dphi, g.two_pi);
+                while (dphi > g.two_pi) dphi = __dsub_rn(dphi, g.two_pi);
+                const double u = __ddiv_rn(dphi, g.dKphi);
+                const int iphi = __double2int_rz(u);
+                if (fabs(u - rint(u)) < 1e-9) stage = -1;  // the literal path hands it to the host
+                else if (iphi < 0 || iphi >= g.nKphi) stage = 5;  // counted through q_long, then dropped
+                else slab = slab * g.nKphi + iphi;
+            }
         }
     }
     if (stage < 0) {  // undecided: literal chain (roles swapped back into the reference's order)
