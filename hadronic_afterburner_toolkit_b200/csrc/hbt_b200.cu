@@ -29,7 +29,8 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
+constexpr int kLanes = 2;  // compute streams that take production batches in turn (HBT_B200_LANES / HBT_OPT_LANES)
 constexpr unsigned kDeferredCapacity = 1u << 16;
 constexpr int kTileV1 = 128;
 
@@ -40,6 +41,26 @@ struct Slot {
     size_t cap_seg = 0;
     cudaEvent_t uploaded = nullptr, done = nullptr;
     bool in_flight = false;
+};
+
+// One compute lane = a stream plus the scratch a production launch needs (unit pop counter, culled
+// unit list, Morton-sorted copy of the same-event list), so that consecutive batches can be in
+// flight together: the sort / cull helpers of batch k+1 and its first units run while the last
+// persistent warps of batch k are still draining.  Every accumulation is a RED into the
+// context's histograms, so the batches commute.  Lane 0's stream is ctx->compute, which also
+// carries everything ordered (cap replay, reductions, the all-reduce, the stopwatch).
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t tail = nullptr;                  // last submission (joins into ctx->compute)
+    bool busy = false;                           // something was enqueued since the last join
+    unsigned *d_work = nullptr;                  // [0] unit pop counter, [1] number of units (culled list)
+    unsigned *d_units = nullptr;                 // surviving units of the sorted same-event list
+    size_t units_cap = 0;
+    unsigned *sort_keys[2] = {nullptr, nullptr}, *sort_idx[2] = {nullptr, nullptr}, *sort_rmax = nullptr;
+    double *sort_p = nullptr;
+    HbtBBox *sort_bbox = nullptr;
+    void *sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0, sort_cap = 0;
 };
 
 struct TimerRec {
@@ -104,7 +125,11 @@ struct hbt_ctx {
     double *red_f64 = nullptr;
     bool reduced = false;                    // red_* hold the sum over ranks of the current state
     size_t n_u64 = 0, n_f64 = 0;
-    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaStream_t compute = nullptr, copy = nullptr;  // compute == lanes[0].stream
+    Lane lanes[kLanes];
+    int n_lanes = kLanes, next_lane = 0;
+    cudaEvent_t epoch = nullptr;    // time origin of the launch timers, renewed whenever the context is idle
+    double covered_ms = 0.;         // end (since epoch) of the latest-ending launch already counted
     bool fuse = true;  // whole batches run the fused same+mixed kernel (HBT_B200_FUSE=0 / HBT_OPT_FUSE: separate kernels)
     Slot slots[kSlots];
     int next_slot = 0;
@@ -134,17 +159,9 @@ struct hbt_ctx {
     bool stats = false;                          // exact stage populations B, C, D (no culling)
     int n_sm = 148;
     int occ_same = 12, occ_same_stats = 12, occ_mixed = 12, occ_mixed_stats = 12, occ_fused = 12;  // resident warps per SM
-    unsigned *d_work = nullptr;                  // [0] unit pop counter, [1] number of units (culled list)
-    unsigned *d_units = nullptr;                 // surviving units of the sorted same-event list
-    size_t units_cap = 0;
     std::vector<int> row_item0;                  // same-event unit prefix per row (instrumented runs)
     int *d_rows = nullptr;
     size_t d_rows_cap = 0;
-    unsigned *sort_keys[2] = {nullptr, nullptr}, *sort_idx[2] = {nullptr, nullptr}, *sort_rmax = nullptr;
-    double *sort_p = nullptr;
-    HbtBBox *sort_bbox = nullptr;
-    void *sort_tmp = nullptr;
-    size_t sort_tmp_bytes = 0, sort_cap = 0;
     unsigned long long *snap_u64 = nullptr;      // rollback copies of the accumulators
     double *snap_f64 = nullptr;
     std::string err;
@@ -217,14 +234,22 @@ int get_event_pair(hbt_ctx *ctx, cudaEvent_t *a, cudaEvent_t *b) {
 }
 
 // fold finished timer records into the totals (all of them when `all`, which requires the
-// stream to be idle or blocks until each stop event has fired)
+// streams to be idle or blocks until each stop event has fired).  Launches of different lanes
+// overlap in time, so a record contributes only the part of [start, stop] that lies after the
+// end of everything counted before it: same_ms + mixed_ms is the time during which at least one
+// pair launch was running.  Times are taken against an epoch event that hbt_synchronize renews
+// whenever the context is idle (float milliseconds: microsecond resolution over minutes).
 int drain_timers(hbt_ctx *ctx, bool all) {
     size_t keep = all ? 0 : 64;
     while (ctx->timers.size() > keep) {
         TimerRec r = ctx->timers.front();
         CU(ctx, cudaEventSynchronize(r.stop));
-        float ms = 0.f;
-        CU(ctx, cudaEventElapsedTime(&ms, r.start, r.stop));
+        float t0 = 0.f, t1 = 0.f;
+        CU(ctx, cudaEventElapsedTime(&t0, ctx->epoch, r.start));
+        CU(ctx, cudaEventElapsedTime(&t1, ctx->epoch, r.stop));
+        const double a = std::max<double>(t0, ctx->covered_ms), b = t1;
+        const double ms = b > a ? b - a : 0.0;
+        ctx->covered_ms = std::max<double>(ctx->covered_ms, b);
         if (r.kind == 2) {
             ctx->same_ms += ms * r.frac_same;
             ctx->mixed_ms += ms * (1.0 - r.frac_same);
@@ -237,6 +262,33 @@ int drain_timers(hbt_ctx *ctx, bool all) {
     return HBT_OK;
 }
 
+// every lane's work so far happens-before whatever is enqueued on ctx->compute next
+int join_lanes(hbt_ctx *ctx) {
+    for (int l = 1; l < kLanes; l++) {
+        Lane &L = ctx->lanes[l];
+        if (!L.busy) continue;
+        CU(ctx, cudaEventRecord(L.tail, L.stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->compute, L.tail, 0));
+        L.busy = false;
+    }
+    return HBT_OK;
+}
+
+// the lane that takes the next production batch
+Lane &next_lane(hbt_ctx *ctx) {
+    Lane &L = ctx->lanes[ctx->next_lane];
+    ctx->next_lane = (ctx->next_lane + 1) % std::max(1, ctx->n_lanes);
+    L.busy = true;
+    return L;
+}
+
+// production batches alternate between the lanes; instrumented runs, the literal kernels and
+// everything near the pair cap stay on lane 0 (= ctx->compute)
+Lane &pick_lane(hbt_ctx *ctx, bool ordered = false) {
+    if (ordered || ctx->n_lanes < 2 || ctx->stats || ctx->kernel_version == 1) return ctx->lanes[0];
+    return next_lane(ctx);
+}
+
 size_t dyn_smem_bytes(const HbtGrid &g) {
     const size_t nslab_pad = (g.nslab + 1) & ~1;
     const size_t nqi = g.qinv ? static_cast<size_t>(g.nKT) * g.nq : 0;
@@ -245,42 +297,56 @@ size_t dyn_smem_bytes(const HbtGrid &g) {
 
 // ---- launches ------------------------------------------------------------------------
 #ifdef HBT_HAVE_V2
-int ensure_work(hbt_ctx *ctx) {
-    if (!ctx->d_work) CU(ctx, cudaMalloc(&ctx->d_work, 8));
+int ensure_work(hbt_ctx *ctx, Lane &L) {
+    if (!L.d_work) CU(ctx, cudaMalloc(&L.d_work, 8));
     return HBT_OK;
 }
 
-// Morton-sort the same-event list on the compute stream (keys, radix sort of (key, index),
+int ensure_units(hbt_ctx *ctx, Lane &L, long long all_units) {
+    if (static_cast<size_t>(all_units) > L.units_cap) {
+        CU(ctx, cudaStreamSynchronize(L.stream));  // the previous launch of this lane may still read the list
+        cudaFree(L.d_units);
+        L.d_units = nullptr;
+        L.units_cap = static_cast<size_t>(all_units) + static_cast<size_t>(all_units) / 4;
+        CU(ctx, cudaMalloc(&L.d_units, L.units_cap * 4));
+    }
+    return HBT_OK;
+}
+
+// Morton-sort the same-event list on the lane's stream (keys, radix sort of (key, index),
 // gather, tile boxes): ~4 small kernels, microseconds against the pair kernel's milliseconds
-int prepare_sorted(hbt_ctx *ctx, const double *d_p, int64_t n) {
-    if (static_cast<size_t>(n) > ctx->sort_cap) {
-        for (int k = 0; k < 2; k++) { cudaFree(ctx->sort_keys[k]); cudaFree(ctx->sort_idx[k]); }
-        cudaFree(ctx->sort_p); cudaFree(ctx->sort_bbox); cudaFree(ctx->sort_tmp);
+int prepare_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n) {
+    if (static_cast<size_t>(n) > L.sort_cap) {
+        CU(ctx, cudaStreamSynchronize(L.stream));  // the previous launch of this lane may still read the buffers
+        for (int k = 0; k < 2; k++) { cudaFree(L.sort_keys[k]); cudaFree(L.sort_idx[k]); }
+        cudaFree(L.sort_p); cudaFree(L.sort_bbox); cudaFree(L.sort_tmp);
+        for (int k = 0; k < 2; k++) L.sort_keys[k] = L.sort_idx[k] = nullptr;
+        L.sort_p = nullptr; L.sort_bbox = nullptr; L.sort_tmp = nullptr; L.sort_cap = 0;
         const size_t cap = static_cast<size_t>(n) + static_cast<size_t>(n) / 4 + 1024;
         for (int k = 0; k < 2; k++) {
-            CU(ctx, cudaMalloc(&ctx->sort_keys[k], cap * 4));
-            CU(ctx, cudaMalloc(&ctx->sort_idx[k], cap * 4));
+            CU(ctx, cudaMalloc(&L.sort_keys[k], cap * 4));
+            CU(ctx, cudaMalloc(&L.sort_idx[k], cap * 4));
         }
-        CU(ctx, cudaMalloc(&ctx->sort_p, cap * 64));
-        CU(ctx, cudaMalloc(&ctx->sort_bbox, (cap / HBT_BBOX_TILE + 2) * sizeof(HbtBBox)));
-        if (!ctx->sort_rmax) CU(ctx, cudaMalloc(&ctx->sort_rmax, 4));
+        CU(ctx, cudaMalloc(&L.sort_p, cap * 64));
+        CU(ctx, cudaMalloc(&L.sort_bbox, (cap / HBT_BBOX_TILE + 2) * sizeof(HbtBBox)));
+        if (!L.sort_rmax) CU(ctx, cudaMalloc(&L.sort_rmax, 4));
         size_t bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, bytes, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_idx[0], ctx->sort_idx[1],
-                                        static_cast<int>(cap), 0, 32, ctx->compute);
-        CU(ctx, cudaMalloc(&ctx->sort_tmp, bytes));
-        ctx->sort_tmp_bytes = bytes;
-        ctx->sort_cap = cap;
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, L.sort_keys[0], L.sort_keys[1], L.sort_idx[0], L.sort_idx[1],
+                                        static_cast<int>(cap), 0, 32, L.stream);
+        CU(ctx, cudaMalloc(&L.sort_tmp, bytes));
+        L.sort_tmp_bytes = bytes;
+        L.sort_cap = cap;
     }
     const int th = 256;
     const unsigned nb = static_cast<unsigned>((n + th - 1) / th);
-    CU(ctx, cudaMemsetAsync(ctx->sort_rmax, 0, 4, ctx->compute));
-    hbt_sort_range<<<std::min(nb, 1184u), th, 0, ctx->compute>>>(d_p, n, ctx->sort_rmax);
-    hbt_sort_keys<<<nb, th, 0, ctx->compute>>>(d_p, n, ctx->sort_rmax, ctx->sort_keys[0], ctx->sort_idx[0]);
-    size_t bytes = ctx->sort_tmp_bytes;
-    CU(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, bytes, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_idx[0],
-                                            ctx->sort_idx[1], static_cast<int>(n), 0, 32, ctx->compute));
-    hbt_sort_gather<<<static_cast<unsigned>((4 * n + th - 1) / th), th, 0, ctx->compute>>>(d_p, ctx->sort_idx[1], n, ctx->sort_p);
-    hbt_sort_bbox<<<static_cast<unsigned>((n + HBT_BBOX_TILE - 1) / HBT_BBOX_TILE), HBT_BBOX_TILE, 0, ctx->compute>>>(ctx->sort_p, n, ctx->sort_bbox);
+    CU(ctx, cudaMemsetAsync(L.sort_rmax, 0, 4, L.stream));
+    hbt_sort_range<<<std::min(nb, 1184u), th, 0, L.stream>>>(d_p, n, L.sort_rmax);
+    hbt_sort_keys<<<nb, th, 0, L.stream>>>(d_p, n, L.sort_rmax, L.sort_keys[0], L.sort_idx[0]);
+    size_t bytes = L.sort_tmp_bytes;
+    CU(ctx, cub::DeviceRadixSort::SortPairs(L.sort_tmp, bytes, L.sort_keys[0], L.sort_keys[1], L.sort_idx[0],
+                                            L.sort_idx[1], static_cast<int>(n), 0, 32, L.stream));
+    hbt_sort_gather<<<static_cast<unsigned>((4 * n + th - 1) / th), th, 0, L.stream>>>(d_p, L.sort_idx[1], n, L.sort_p);
+    hbt_sort_bbox<<<static_cast<unsigned>((n + HBT_BBOX_TILE - 1) / HBT_BBOX_TILE), HBT_BBOX_TILE, 0, L.stream>>>(L.sort_p, n, L.sort_bbox);
     ctx->kernel_launches += 5;  // range, keys, gather, boxes + the radix sort (counted once)
     CU(ctx, cudaGetLastError());
     return HBT_OK;
@@ -291,13 +357,14 @@ const unsigned char *closed_ptr(const hbt_ctx *ctx) { return ctx->any_closed ? c
 
 // mode 0: the production kernels (v2 unless the grid needs v1); mode 1 / 2: the two ordered-cap
 // passes, always on the literal v1 kernels
-int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int mode = 0, const HbtCap *capin = nullptr) {
+// `L`: the lane the launch goes to (the ordered-cap passes and the literal kernels always get lane 0)
+int launch_same(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, double psi_ref, int mode = 0, const HbtCap *capin = nullptr) {
     if (n < 2) return HBT_OK;
     ctx->reduced = false;
     cudaEvent_t e0, e1;
     int rc = get_event_pair(ctx, &e0, &e1);
     if (rc) return rc;
-    CU(ctx, cudaEventRecord(e0, ctx->compute));
+    CU(ctx, cudaEventRecord(e0, L.stream));
     const unsigned long long npairs = static_cast<unsigned long long>(n) * (n - 1) / 2;
     HbtCap cap{};
     if (capin) cap = *capin;
@@ -309,18 +376,18 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
         const unsigned nb = static_cast<unsigned>(blocks);
         const size_t sm = dyn_smem_bytes(ctx->grid);
         if (mode != 1) {
-            hbt_add_stage_a<<<1, 1, 0, ctx->compute>>>(ctx->acc, 0, npairs);
+            hbt_add_stage_a<<<1, 1, 0, L.stream>>>(ctx->acc, 0, npairs);
             ctx->kernel_launches++;
         }
-        if (mode == 0) hbt_pairs_v1<kTileV1, false, 0><<<nb, kTileV1, sm, ctx->compute>>>(d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref, cap);
-        else if (mode == 1) hbt_pairs_v1<kTileV1, false, 1><<<nb, kTileV1, sm, ctx->compute>>>(d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref, cap);
-        else hbt_pairs_v1<kTileV1, false, 2><<<nb, kTileV1, sm, ctx->compute>>>(d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref, cap);
+        if (mode == 0) hbt_pairs_v1<kTileV1, false, 0><<<nb, kTileV1, sm, L.stream>>>(d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref, cap);
+        else if (mode == 1) hbt_pairs_v1<kTileV1, false, 1><<<nb, kTileV1, sm, L.stream>>>(d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref, cap);
+        else hbt_pairs_v1<kTileV1, false, 2><<<nb, kTileV1, sm, L.stream>>>(d_p, d_p, n, nullptr, ctx->grid, ctx->acc, psi_ref, cap);
         ctx->kernel_launches++;
     } else {
 #ifdef HBT_HAVE_V2
-        rc = ensure_work(ctx);
+        rc = ensure_work(ctx, L);
         if (rc) return rc;
-        CU(ctx, cudaMemsetAsync(ctx->d_work, 0, 8, ctx->compute));
+        CU(ctx, cudaMemsetAsync(L.d_work, 0, 8, L.stream));
         const bool sorted = !ctx->stats;
         const unsigned grid = static_cast<unsigned>(ctx->n_sm * (sorted ? ctx->occ_same : ctx->occ_same_stats));
         const long long all_units = hbt_v3_same_units(n, ctx->row_item0);
@@ -328,20 +395,17 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
             return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld work units", all_units);
         if (sorted) {
             // production: Morton-sorted copy + tile boxes, units that can hold an accepted pair
-            rc = prepare_sorted(ctx, d_p, n);
+            rc = prepare_sorted(ctx, L, d_p, n);
             if (rc) return rc;
-            if (static_cast<size_t>(all_units) > ctx->units_cap) {
-                cudaFree(ctx->d_units);
-                ctx->units_cap = static_cast<size_t>(all_units) + static_cast<size_t>(all_units) / 4;
-                CU(ctx, cudaMalloc(&ctx->d_units, ctx->units_cap * 4));
-            }
+            rc = ensure_units(ctx, L, all_units);
+            if (rc) return rc;
             const long long n_rows = (n + HBT_V3_SUB_SAME - 1) / HBT_V3_SUB_SAME, ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
-            hbt_cull_units<<<dim3(static_cast<unsigned>((ntj + 127) / 128), static_cast<unsigned>(n_rows)), 128, 0, ctx->compute>>>(
-                ctx->sort_bbox, n, ctx->v2c.W2, ctx->v2c.k2lo, ctx->v2c.k2hi, ctx->d_units, ctx->d_work);
+            hbt_cull_units<<<dim3(static_cast<unsigned>((ntj + 127) / 128), static_cast<unsigned>(n_rows)), 128, 0, L.stream>>>(
+                L.sort_bbox, n, ctx->v2c.W2, ctx->v2c.k2lo, ctx->v2c.k2hi, L.d_units, L.d_work);
             ctx->kernel_launches++;
-            hbt_pairs_v3<false, false><<<grid, 32, 0, ctx->compute>>>(
-                ctx->sort_p, ctx->sort_p, n, nullptr, nullptr, 0, ctx->d_units, ctx->d_work, 0, ctx->grid, ctx->v2c, ctx->d_dv,
-                ctx->acc, psi_ref, npairs, cap.closed, ctx->sort_idx[1]);
+            hbt_pairs_v3<false, false><<<grid, 32, 0, L.stream>>>(
+                L.sort_p, L.sort_p, n, nullptr, nullptr, 0, L.d_units, L.d_work, 0, ctx->grid, ctx->v2c, ctx->d_dv,
+                ctx->acc, psi_ref, npairs, cap.closed, L.sort_idx[1]);
         } else {
             // instrumented: every unit, reference order
             const size_t rb = ctx->row_item0.size() * sizeof(int);
@@ -351,10 +415,10 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
                 ctx->d_rows_cap = rb * 2;
             }
             // (pageable source: the copy is staged before the call returns, the vector can be reused)
-            CU(ctx, cudaMemcpyAsync(ctx->d_rows, ctx->row_item0.data(), rb, cudaMemcpyHostToDevice, ctx->compute));
+            CU(ctx, cudaMemcpyAsync(ctx->d_rows, ctx->row_item0.data(), rb, cudaMemcpyHostToDevice, L.stream));
             const int n_rows = static_cast<int>(ctx->row_item0.size()) - 1;
-            hbt_pairs_v3<false, true><<<grid, 32, 0, ctx->compute>>>(
-                d_p, d_p, n, nullptr, ctx->d_rows, n_rows, nullptr, ctx->d_work, static_cast<unsigned>(all_units), ctx->grid,
+            hbt_pairs_v3<false, true><<<grid, 32, 0, L.stream>>>(
+                d_p, d_p, n, nullptr, ctx->d_rows, n_rows, nullptr, L.d_work, static_cast<unsigned>(all_units), ctx->grid,
                 ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
         }
         ctx->kernel_launches++;
@@ -362,7 +426,7 @@ int launch_same(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref, int 
 #endif
     }
     CU(ctx, cudaGetLastError());
-    CU(ctx, cudaEventRecord(e1, ctx->compute));
+    CU(ctx, cudaEventRecord(e1, L.stream));
     ctx->timers.push_back({e0, e1, 0, 0.0});
     ctx->same_launches++;
     ctx->pending_num += npairs;
@@ -403,14 +467,14 @@ size_t build_segments(const int64_t *off1, int32_t nev1, const int64_t *off2, in
     return ns;
 }
 
-int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg, size_t nseg,
+int launch_mixed(hbt_ctx *ctx, Lane &L, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg, size_t nseg,
                  long long nblocks, unsigned long long npairs, double psi_ref, int mode = 0, const HbtCap *capin = nullptr) {
     if (nseg == 0 || nblocks == 0) return HBT_OK;
     ctx->reduced = false;
     cudaEvent_t e0, e1;
     int rc = get_event_pair(ctx, &e0, &e1);
     if (rc) return rc;
-    CU(ctx, cudaEventRecord(e0, ctx->compute));
+    CU(ctx, cudaEventRecord(e0, L.stream));
     if (nblocks > 0x7fffffffLL) return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld tiles", nblocks);
     HbtCap cap{};
     if (capin) cap = *capin;
@@ -420,34 +484,34 @@ int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const Hbt
         const size_t sm = dyn_smem_bytes(ctx->grid);
         const long long ns = static_cast<long long>(nseg);
         if (mode != 1) {
-            hbt_add_stage_a<<<1, 1, 0, ctx->compute>>>(ctx->acc, 6, npairs);
+            hbt_add_stage_a<<<1, 1, 0, L.stream>>>(ctx->acc, 6, npairs);
             ctx->kernel_launches++;
         }
-        if (mode == 0) hbt_pairs_v1<kTileV1, true, 0><<<nb, kTileV1, sm, ctx->compute>>>(d_p1, d_p2, ns, d_seg, ctx->grid, ctx->acc, psi_ref, cap);
-        else if (mode == 1) hbt_pairs_v1<kTileV1, true, 1><<<nb, kTileV1, sm, ctx->compute>>>(d_p1, d_p2, ns, d_seg, ctx->grid, ctx->acc, psi_ref, cap);
-        else hbt_pairs_v1<kTileV1, true, 2><<<nb, kTileV1, sm, ctx->compute>>>(d_p1, d_p2, ns, d_seg, ctx->grid, ctx->acc, psi_ref, cap);
+        if (mode == 0) hbt_pairs_v1<kTileV1, true, 0><<<nb, kTileV1, sm, L.stream>>>(d_p1, d_p2, ns, d_seg, ctx->grid, ctx->acc, psi_ref, cap);
+        else if (mode == 1) hbt_pairs_v1<kTileV1, true, 1><<<nb, kTileV1, sm, L.stream>>>(d_p1, d_p2, ns, d_seg, ctx->grid, ctx->acc, psi_ref, cap);
+        else hbt_pairs_v1<kTileV1, true, 2><<<nb, kTileV1, sm, L.stream>>>(d_p1, d_p2, ns, d_seg, ctx->grid, ctx->acc, psi_ref, cap);
         ctx->kernel_launches++;
     } else {
 #ifdef HBT_HAVE_V2
-        rc = ensure_work(ctx);
+        rc = ensure_work(ctx, L);
         if (rc) return rc;
-        CU(ctx, cudaMemsetAsync(ctx->d_work, 0, 8, ctx->compute));
+        CU(ctx, cudaMemsetAsync(L.d_work, 0, 8, L.stream));
         const unsigned grid = static_cast<unsigned>(std::min<long long>(
             nblocks, static_cast<long long>(ctx->n_sm) * (ctx->stats ? ctx->occ_mixed_stats : ctx->occ_mixed)));
         if (ctx->stats)
-            hbt_pairs_v3<true, true><<<grid, 32, 0, ctx->compute>>>(
-                d_p1, d_p2, static_cast<long long>(nseg), d_seg, nullptr, 0, nullptr, ctx->d_work, static_cast<unsigned>(nblocks), ctx->grid,
+            hbt_pairs_v3<true, true><<<grid, 32, 0, L.stream>>>(
+                d_p1, d_p2, static_cast<long long>(nseg), d_seg, nullptr, 0, nullptr, L.d_work, static_cast<unsigned>(nblocks), ctx->grid,
                 ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
         else
-            hbt_pairs_v3<true, false><<<grid, 32, 0, ctx->compute>>>(
-                d_p1, d_p2, static_cast<long long>(nseg), d_seg, nullptr, 0, nullptr, ctx->d_work, static_cast<unsigned>(nblocks), ctx->grid,
+            hbt_pairs_v3<true, false><<<grid, 32, 0, L.stream>>>(
+                d_p1, d_p2, static_cast<long long>(nseg), d_seg, nullptr, 0, nullptr, L.d_work, static_cast<unsigned>(nblocks), ctx->grid,
                 ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
         ctx->kernel_launches++;
         if (rc) return fail(ctx, rc, "v2 mixed-event launch failed");
 #endif
     }
     CU(ctx, cudaGetLastError());
-    CU(ctx, cudaEventRecord(e1, ctx->compute));
+    CU(ctx, cudaEventRecord(e1, L.stream));
     ctx->timers.push_back({e0, e1, 1, 0.0});
     ctx->mixed_launches++;
     ctx->pending_den += npairs;
@@ -457,38 +521,35 @@ int launch_mixed(hbt_ctx *ctx, const double *d_p1, const double *d_p2, const Hbt
 #ifdef HBT_HAVE_V2
 // production launch of a whole batch: sort + cull of the same-event list, then one kernel that
 // works through the same-event and the mixed-event units interleaved (hbt_pairs_v3_fused)
-int launch_fused(hbt_ctx *ctx, const double *d_p, int64_t n, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg,
+int launch_fused(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg,
                  size_t nseg, long long nblocks, unsigned long long npairs_mixed, double psi_ref) {
     ctx->reduced = false;
     cudaEvent_t e0, e1;
     int rc = get_event_pair(ctx, &e0, &e1);
     if (rc) return rc;
-    CU(ctx, cudaEventRecord(e0, ctx->compute));
+    CU(ctx, cudaEventRecord(e0, L.stream));
     const unsigned long long npairs_same = static_cast<unsigned long long>(n) * (n - 1) / 2;
-    rc = ensure_work(ctx);
+    rc = ensure_work(ctx, L);
     if (rc) return rc;
-    CU(ctx, cudaMemsetAsync(ctx->d_work, 0, 8, ctx->compute));
+    CU(ctx, cudaMemsetAsync(L.d_work, 0, 8, L.stream));
     const long long all_units = hbt_v3_same_units(n, ctx->row_item0);
     if (all_units > 0x7fffffffLL || n > HBT_V3_MAX_SORTED || nblocks + all_units > 0x7fffffffLL)
         return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld work units", all_units + nblocks);
-    rc = prepare_sorted(ctx, d_p, n);
+    rc = prepare_sorted(ctx, L, d_p, n);
     if (rc) return rc;
-    if (static_cast<size_t>(all_units) > ctx->units_cap) {
-        cudaFree(ctx->d_units);
-        ctx->units_cap = static_cast<size_t>(all_units) + static_cast<size_t>(all_units) / 4;
-        CU(ctx, cudaMalloc(&ctx->d_units, ctx->units_cap * 4));
-    }
+    rc = ensure_units(ctx, L, all_units);
+    if (rc) return rc;
     const long long n_rows = (n + HBT_V3_SUB_SAME - 1) / HBT_V3_SUB_SAME, ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
-    hbt_cull_units<<<dim3(static_cast<unsigned>((ntj + 127) / 128), static_cast<unsigned>(n_rows)), 128, 0, ctx->compute>>>(
-        ctx->sort_bbox, n, ctx->v2c.W2, ctx->v2c.k2lo, ctx->v2c.k2hi, ctx->d_units, ctx->d_work);
+    hbt_cull_units<<<dim3(static_cast<unsigned>((ntj + 127) / 128), static_cast<unsigned>(n_rows)), 128, 0, L.stream>>>(
+        L.sort_bbox, n, ctx->v2c.W2, ctx->v2c.k2lo, ctx->v2c.k2hi, L.d_units, L.d_work);
     const unsigned grid = static_cast<unsigned>(ctx->n_sm * ctx->occ_fused);
-    hbt_pairs_v3_fused<<<grid, 32, 0, ctx->compute>>>(ctx->sort_p, n, ctx->d_units, ctx->sort_idx[1], d_p1, d_p2,
-                                                      static_cast<long long>(nseg), d_seg, static_cast<unsigned>(nblocks), ctx->d_work,
+    hbt_pairs_v3_fused<<<grid, 32, 0, L.stream>>>(L.sort_p, n, L.d_units, L.sort_idx[1], d_p1, d_p2,
+                                                      static_cast<long long>(nseg), d_seg, static_cast<unsigned>(nblocks), L.d_work,
                                                       ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs_same, npairs_mixed,
                                                       closed_ptr(ctx));
     ctx->kernel_launches += 2;
     CU(ctx, cudaGetLastError());
-    CU(ctx, cudaEventRecord(e1, ctx->compute));
+    CU(ctx, cudaEventRecord(e1, L.stream));
     ctx->timers.push_back({e0, e1, 2, static_cast<double>(npairs_same) / static_cast<double>(npairs_same + npairs_mixed)});
     ctx->same_launches++;
     ctx->mixed_launches++;
@@ -692,8 +753,9 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
     CU(ctx, cudaMemcpyAsync(ctx->snap_f64, ctx->blob_f64, ctx->n_f64 * 8, cudaMemcpyDeviceToDevice, ctx->compute));
     const std::vector<uint64_t> before = in.mixed ? ctx->exact_den : ctx->exact_num;
     // optimistic pass
-    rc = in.mixed ? launch_mixed(ctx, in.d1, in.d2, d_seg, nseg, nblocks, npairs, in.psi_ref)
-                  : launch_same(ctx, in.d1, in.n1, in.psi_ref);
+    Lane &L0 = ctx->lanes[0];
+    rc = in.mixed ? launch_mixed(ctx, L0, in.d1, in.d2, d_seg, nseg, nblocks, npairs, in.psi_ref)
+                  : launch_same(ctx, L0, in.d1, in.n1, in.psi_ref);
     if (rc) return rc;
     CU(ctx, cudaStreamSynchronize(ctx->compute));
     // deferred pairs of this pass (K_phi edge cases) count too: fold them in before looking
@@ -744,8 +806,8 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
     cap.cut_row = d_cut;
     cap.cut_pos = d_cut + nch;
     // pass 1: per-row counts of the crossing channels
-    rc = in.mixed ? launch_mixed(ctx, in.d1, in.d2, d_seg1, nseg1, nb1, np1, in.psi_ref, 1, &cap)
-                  : launch_same(ctx, in.d1, in.n1, in.psi_ref, 1, &cap);
+    rc = in.mixed ? launch_mixed(ctx, L0, in.d1, in.d2, d_seg1, nseg1, nb1, np1, in.psi_ref, 1, &cap)
+                  : launch_same(ctx, L0, in.d1, in.n1, in.psi_ref, 1, &cap);
     if (rc) return rc;
     std::vector<unsigned> rowcnt(nx * nrows);
     CU(ctx, cudaMemcpyAsync(rowcnt.data(), d_rowcnt, rowcnt.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->compute));
@@ -779,8 +841,8 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
     CU(ctx, cudaMemcpyAsync(d_cut, cut_row.data(), nch * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->compute));
     CU(ctx, cudaMemcpyAsync(d_cut + nch, cut_pos.data(), nch * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->compute));
     // pass 2: accumulate up to the cuts
-    rc = in.mixed ? launch_mixed(ctx, in.d1, in.d2, d_seg1, nseg1, nb1, np1, in.psi_ref, 2, &cap)
-                  : launch_same(ctx, in.d1, in.n1, in.psi_ref, 2, &cap);
+    rc = in.mixed ? launch_mixed(ctx, L0, in.d1, in.d2, d_seg1, nseg1, nb1, np1, in.psi_ref, 2, &cap)
+                  : launch_same(ctx, L0, in.d1, in.n1, in.psi_ref, 2, &cap);
     if (rc) return rc;
     CU(ctx, cudaStreamSynchronize(ctx->compute));
     CapFilter f;
@@ -878,7 +940,14 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
         return HBT_ERR_NO_DEVICE;
     }
     ctx->n_sm = prop.multiProcessorCount;
-    CUC(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    for (Lane &L : ctx->lanes) {
+        CUC(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CUC(cudaEventCreateWithFlags(&L.tail, cudaEventDisableTiming));
+    }
+    ctx->compute = ctx->lanes[0].stream;
+    if (const char *v = getenv("HBT_B200_LANES")) ctx->n_lanes = std::min(kLanes, std::max(1, atoi(v)));
+    CUC(cudaEventCreate(&ctx->epoch));
+    CUC(cudaEventRecord(ctx->epoch, ctx->compute));
     CUC(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
     const HbtGrid &g = ctx->grid;
     const size_t nb = static_cast<size_t>(g.nbins), ns = g.nslab, nqi = static_cast<size_t>(g.nKT) * g.nq;
@@ -952,7 +1021,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
 extern "C" void hbt_destroy(hbt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->compute) cudaStreamSynchronize(ctx->compute);
+    for (Lane &L : ctx->lanes) if (L.stream) cudaStreamSynchronize(L.stream);
     if (ctx->copy) cudaStreamSynchronize(ctx->copy);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     for (Slot &s : ctx->slots) {
@@ -975,14 +1044,18 @@ extern "C" void hbt_destroy(hbt_ctx *ctx) {
     if (ctx->h_defcount) cudaFreeHost(ctx->h_defcount);
     if (ctx->d_corr) cudaFree(ctx->d_corr);
     if (ctx->d_closed) cudaFree(ctx->d_closed);
-    for (int k = 0; k < 2; k++) { if (ctx->sort_keys[k]) cudaFree(ctx->sort_keys[k]); if (ctx->sort_idx[k]) cudaFree(ctx->sort_idx[k]); }
-    if (ctx->sort_p) cudaFree(ctx->sort_p);
-    if (ctx->sort_bbox) cudaFree(ctx->sort_bbox);
-    if (ctx->sort_tmp) cudaFree(ctx->sort_tmp);
-    if (ctx->sort_rmax) cudaFree(ctx->sort_rmax);
+    for (Lane &L : ctx->lanes) {
+        for (int k = 0; k < 2; k++) { if (L.sort_keys[k]) cudaFree(L.sort_keys[k]); if (L.sort_idx[k]) cudaFree(L.sort_idx[k]); }
+        if (L.sort_p) cudaFree(L.sort_p);
+        if (L.sort_bbox) cudaFree(L.sort_bbox);
+        if (L.sort_tmp) cudaFree(L.sort_tmp);
+        if (L.sort_rmax) cudaFree(L.sort_rmax);
+        if (L.d_work) cudaFree(L.d_work);
+        if (L.d_units) cudaFree(L.d_units);
+        if (L.tail) cudaEventDestroy(L.tail);
+    }
+    if (ctx->epoch) cudaEventDestroy(ctx->epoch);
     if (ctx->d_rows) cudaFree(ctx->d_rows);
-    if (ctx->d_work) cudaFree(ctx->d_work);
-    if (ctx->d_units) cudaFree(ctx->d_units);
     if (ctx->snap_u64) cudaFree(ctx->snap_u64);
     if (ctx->snap_f64) cudaFree(ctx->snap_f64);
 #ifdef HBT_HAVE_V2
@@ -990,7 +1063,7 @@ extern "C" void hbt_destroy(hbt_ctx *ctx) {
 #endif
     if (ctx->sw0) cudaEventDestroy(ctx->sw0);
     if (ctx->sw1) cudaEventDestroy(ctx->sw1);
-    if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    for (Lane &L : ctx->lanes) if (L.stream) cudaStreamDestroy(L.stream);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
     delete ctx;
 }
@@ -1023,10 +1096,15 @@ extern "C" int hbt_synchronize(hbt_ctx *ctx) {
     if (!ctx) return HBT_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->copy));
-    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    for (Lane &L : ctx->lanes) {
+        CU(ctx, cudaStreamSynchronize(L.stream));
+        L.busy = false;
+    }
     for (Slot &s : ctx->slots) s.in_flight = false;
     int rc = drain_timers(ctx, true);
     if (rc) return rc;
+    CU(ctx, cudaEventRecord(ctx->epoch, ctx->compute));  // idle: new time origin for the launch timers
+    ctx->covered_ms = 0.;
     rc = resolve_deferred(ctx);
     if (rc) return rc;
     // accepted-pair counters per slab = sum of the slab's bin counts (every accepted pair
@@ -1040,7 +1118,7 @@ extern "C" int hbt_accumulate_same_dev(hbt_ctx *ctx, const double *d_p, int64_t 
     CU(ctx, cudaSetDevice(ctx->device));
     if (cap_may_engage(ctx, false, n > 1 ? static_cast<unsigned long long>(n) * (n - 1) / 2 : 0))
         return fail(ctx, HBT_ERR_CAP, "needed_number_of_pairs may be reached: use the host-buffer entry points, which replay the cap in order");
-    return launch_same(ctx, d_p, n, psi_ref);
+    return launch_same(ctx, pick_lane(ctx), d_p, n, psi_ref);
 }
 
 extern "C" int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const int64_t *off1, int32_t nev1,
@@ -1064,10 +1142,11 @@ extern "C" int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const 
     const size_t nseg = build_segments(off1, nev1, off2, 0, partner_ids, cos_sin, nmix, tile_i(ctx), tile_j(ctx), s->h_seg, &npairs, &nblocks);
     if (cap_may_engage(ctx, true, npairs))
         return fail(ctx, HBT_ERR_CAP, "needed_number_of_pairs may be reached: use the host-buffer entry points, which replay the cap in order");
-    if (nseg) CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, ctx->compute));
-    rc = launch_mixed(ctx, d_p1, d_p2, s->d_seg, nseg, nblocks, npairs, psi_ref);
+    Lane &L = pick_lane(ctx);
+    if (nseg) CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, L.stream));
+    rc = launch_mixed(ctx, L, d_p1, d_p2, s->d_seg, nseg, nblocks, npairs, psi_ref);
     if (rc) return rc;
-    CU(ctx, cudaEventRecord(s->done, ctx->compute));
+    CU(ctx, cudaEventRecord(s->done, L.stream));
     s->in_flight = true;
     return HBT_OK;
 }
@@ -1099,10 +1178,11 @@ extern "C" int hbt_accumulate_batch_dev(hbt_ctx *ctx, const double *d_p, const i
         if (cap_may_engage(ctx, false, sp) || cap_may_engage(ctx, true, npairs))
             return fail(ctx, HBT_ERR_CAP, "needed_number_of_pairs may be reached: use the host-buffer entry points, which replay the cap in order");
         if (nseg && nblocks) {
-            CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, ctx->compute));
-            rc = launch_fused(ctx, d_p, n, d_p, d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
+            Lane &L = pick_lane(ctx);
+            CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, L.stream));
+            rc = launch_fused(ctx, L, d_p, n, d_p, d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
             if (rc) return rc;
-            CU(ctx, cudaEventRecord(s->done, ctx->compute));
+            CU(ctx, cudaEventRecord(s->done, L.stream));
             s->in_flight = true;
             return HBT_OK;
         }
@@ -1152,7 +1232,10 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
         if (nseg) CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, ctx->copy));
     }
     CU(ctx, cudaEventRecord(s->uploaded, ctx->copy));
-    CU(ctx, cudaStreamWaitEvent(ctx->compute, s->uploaded, 0));
+    const unsigned long long sp_all = n1 > 1 ? static_cast<unsigned long long>(n1) * (n1 - 1) / 2 : 0;
+    const bool near_cap = (do_same && cap_may_engage(ctx, false, sp_all)) || (do_mixed && cap_may_engage(ctx, true, npairs));
+    Lane &L = pick_lane(ctx, near_cap);
+    CU(ctx, cudaStreamWaitEvent(L.stream, s->uploaded, 0));
     PhaseInput in;
     in.h1 = s->h_p;
     in.h2 = alias ? s->h_p : s->h_p + 8 * n1;
@@ -1166,11 +1249,10 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
     in.ids = partner_ids;
     in.cs = cos_sin;
     in.psi_ref = psi_ref;
-    const unsigned long long sp_all = n1 > 1 ? static_cast<unsigned long long>(n1) * (n1 - 1) / 2 : 0;
 #ifdef HBT_HAVE_V2
     if (do_same && do_mixed && ctx->fuse && !ctx->stats && ctx->kernel_version != 1 && n1 > 1 && nseg > 0 && nblocks > 0 &&
-        !cap_may_engage(ctx, false, sp_all) && !cap_may_engage(ctx, true, npairs)) {
-        rc = launch_fused(ctx, s->d_p, n1, s->d_p, s->d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
+        !near_cap) {
+        rc = launch_fused(ctx, L, s->d_p, n1, s->d_p, s->d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
         if (rc) return rc;
         do_same = do_mixed = 0;
     }
@@ -1178,16 +1260,16 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
     if (do_same) {
         const unsigned long long sp = sp_all;
         in.mixed = false;
-        rc = cap_may_engage(ctx, false, sp) ? capped_phase(ctx, in, nullptr, 0, 0, sp) : launch_same(ctx, s->d_p, n1, psi_ref);
+        rc = cap_may_engage(ctx, false, sp) ? capped_phase(ctx, in, nullptr, 0, 0, sp) : launch_same(ctx, L, s->d_p, n1, psi_ref);
         if (rc) return rc;
     }
     if (do_mixed) {
         in.mixed = true;
         rc = cap_may_engage(ctx, true, npairs) ? capped_phase(ctx, in, s->d_seg, nseg, nblocks, npairs)
-                                               : launch_mixed(ctx, s->d_p, s->d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
+                                               : launch_mixed(ctx, L, s->d_p, s->d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
         if (rc) return rc;
     }
-    CU(ctx, cudaEventRecord(s->done, ctx->compute));
+    CU(ctx, cudaEventRecord(s->done, L.stream));
     s->in_flight = true;
     return HBT_OK;
 }
@@ -1279,14 +1361,19 @@ extern "C" int hbt_timer_start(hbt_ctx *ctx) {
         CU(ctx, cudaEventCreate(&ctx->sw1));
     }
     CU(ctx, cudaStreamSynchronize(ctx->copy));
+    int rc = join_lanes(ctx);
+    if (rc) return rc;
     CU(ctx, cudaEventRecord(ctx->sw0, ctx->compute));
+    for (int l = 1; l < kLanes; l++) CU(ctx, cudaStreamWaitEvent(ctx->lanes[l].stream, ctx->sw0, 0));  // nothing starts before the stopwatch
     return HBT_OK;
 }
 
 extern "C" int hbt_timer_stop(hbt_ctx *ctx, double *ms) {
     if (!ctx || !ms || !ctx->sw0) return HBT_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaStreamSynchronize(ctx->copy));  // everything uploaded has been handed to compute
+    CU(ctx, cudaStreamSynchronize(ctx->copy));  // everything uploaded has been handed to a compute lane
+    int rc = join_lanes(ctx);
+    if (rc) return rc;
     CU(ctx, cudaEventRecord(ctx->sw1, ctx->compute));
     CU(ctx, cudaEventSynchronize(ctx->sw1));
     float t = 0.f;
@@ -1311,6 +1398,11 @@ extern "C" int hbt_set_option(hbt_ctx *ctx, int32_t option, int32_t value) {
             return HBT_OK;
         case HBT_OPT_FUSE:
             ctx->fuse = value != 0;
+            return HBT_OK;
+        case HBT_OPT_LANES:
+            if (value < 1 || value > kLanes) return fail(ctx, HBT_ERR_INVALID, "lanes must be in [1, %d]", kLanes);
+            ctx->n_lanes = value;
+            ctx->next_lane = 0;
             return HBT_OK;
         default:
             return fail(ctx, HBT_ERR_INVALID, "unknown option %d", option);

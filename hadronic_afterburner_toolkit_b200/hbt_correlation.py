@@ -83,7 +83,8 @@ class HBT_correlation:
     events)."""
 
     def __init__(self, params: HBTParams, path: str = ".", ran_gen: Optional[Random] = None, device: int = 0,
-                 stage_counters: Optional[bool] = None, kernel: Optional[int] = None, fuse: Optional[bool] = None):
+                 stage_counters: Optional[bool] = None, kernel: Optional[int] = None, fuse: Optional[bool] = None,
+                 lanes: Optional[int] = None):
         self.params = params
         self.path_ = path
         self.ran_gen = ran_gen if ran_gen is not None else Random(params.randomSeed)
@@ -98,6 +99,8 @@ class HBT_correlation:
             _check(h, self._L.hbt_set_option(h, 2, int(kernel)))
         if fuse is not None:  # HBT_OPT_FUSE: one kernel for both loops of a batch (default) or one per loop
             _check(h, self._L.hbt_set_option(h, 3, int(fuse)))
+        if lanes is not None:  # HBT_OPT_LANES: compute streams that take production batches in turn
+            _check(h, self._L.hbt_set_option(h, 4, int(lanes)))
         self.psi_ref = 0.0
         self.psi_refs: List[float] = []
         self.particle_list: Optional[Batch] = None

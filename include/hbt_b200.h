@@ -203,10 +203,17 @@ int hbt_get_timers(hbt_ctx *ctx, double *same_ms, double *mixed_ms, uint64_t *sa
  * HBT_OPT_FUSE: 1 (default) = a whole batch (hbt_accumulate_batch with both halves) runs as one
  *   kernel that works through the same-event and the mixed-event units interleaved; 0 = one
  *   kernel per loop.  Environment: HBT_B200_FUSE.  hbt_get_timers splits the time of a fused
- *   launch between same_ms and mixed_ms by the pairs of each kind. */
+ *   launch between same_ms and mixed_ms by the pairs of each kind.
+ * HBT_OPT_LANES: 2 (default) = consecutive production batches go to two compute streams in turn,
+ *   each with its own scratch, so the sort / cull helpers and the first units of batch k+1 run
+ *   under the tail of batch k (batches commute: every accumulation is an atomic add into the
+ *   context's histograms); 1 = one stream.  Instrumented runs, the literal kernels and batches
+ *   near the pair cap always use one stream.  Environment: HBT_B200_LANES.  hbt_get_timers counts
+ *   the time during which at least one pair launch was running (overlaps once). */
 #define HBT_OPT_STAGE_COUNTERS 1
 #define HBT_OPT_KERNEL 2
 #define HBT_OPT_FUSE 3
+#define HBT_OPT_LANES 4
 int hbt_set_option(hbt_ctx *ctx, int32_t option, int32_t value);
 
 /* Device-side stopwatch on the context's compute stream (CUDA events): everything the

@@ -2,6 +2,7 @@
 (1) the golden vectors produced by the unmodified reference and (2) the CPU oracle on the
 same seeded inputs.  Tolerances (north_star): every integer accumulator bit-exact; floating
 sums within 1e-10 relative (see hbtio.compare for the conditioning floor)."""
+import ctypes
 import gzip
 import os
 
@@ -160,6 +161,43 @@ def test_fused_and_separate_kernels_agree_and_device_resident_batch():
                                            ids.shape[1], 0.0)
         assert rc == 0, h._L.hbt_last_error(h._h)
     hbtio.compare(ref, h.accumulators(), rtol=RTOL, check_stage="cheap")
+    h.close()
+
+
+@pytest.mark.parametrize("same_only", [False, True])
+def test_batches_in_flight_on_two_lanes(same_only):
+    """Production batches alternate between two compute streams (HBT_OPT_LANES, default 2), each
+    with its own sort / cull scratch, so consecutive batches overlap on the device.  Batches
+    commute (atomic adds), so one lane and two lanes must give the oracle's integers; the batch
+    sizes grow and shrink so that a lane's scratch is reallocated while the other lane is busy,
+    and more batches than staging slots are submitted without a synchronize in between.  The
+    launch timers count overlapping launches once: their sum cannot exceed the stopwatch."""
+    P = C3.with_(qnpts=21)
+    batches = []
+    for g, (nev, mult) in enumerate([(3, 300), (4, 900), (2, 200), (5, 1200), (3, 500), (6, 1500), (2, 100), (4, 800), (3, 400)]):
+        batches += synth.make_batches(20260020 + g, 1, nev, multiplicity=mult)
+    ref = run_oracle(P, batches, do_mixed=not same_only)
+    res = []
+    for lanes in (2, 1):
+        h = HBT_correlation(P, lanes=lanes)
+        assert h._L.hbt_timer_start(h._h) == 0
+        for b in batches:
+            if same_only:
+                h.set_particle_list(b)
+                h.combine_and_bin_particle_pairs(list(range(len(b.same))))
+            else:
+                h.calculate_HBT_correlation_function(b)
+        ms = ctypes.c_double()
+        assert h._L.hbt_timer_stop(h._h, ctypes.byref(ms)) == 0
+        res.append(h.accumulators())
+        t = h.timers()
+        assert t["same_launches"] == len(batches)
+        assert 0.0 < t["same_ms"] + t["mixed_ms"] <= ms.value * 1.02 + 0.05
+        h.close()
+    hbtio.compare(ref, res[0], rtol=RTOL, check_stage="cheap")
+    hbtio.compare(ref, res[1], rtol=RTOL, check_stage="cheap")
+    h = HBT_correlation(P)
+    assert h._L.hbt_set_option(h._h, 4, 3) == -1  # at most two lanes
     h.close()
 
 
