@@ -1,7 +1,11 @@
-// Fast reader for the gzipped particle samples that feed the HBT path.
+// Fast reader for the particle samples that feed the HBT path.
 //
-// Replaces, for read_in_mode = 10 ("particle_samples.gz"), the chain
-//   particleSamples::read_in_particle_samples_gzipped   src/particleSamples.cpp:1247-1286
+// Replaces, for read_in_mode = 10 ("particle_samples.gz": gzipped iSS text), 2 ("particle_list.dat":
+// gzipped UrQMD text) and 21 ("particle_list.bin": UrQMD binary), the chain
+//   particleSamples::read_in_particle_samples_gzipped        src/particleSamples.cpp:1247-1286
+//   particleSamples::read_in_particle_samples_UrQMD_zipped   src/particleSamples.cpp:910-974
+//   particleSamples::read_in_particle_samples_UrQMD_binary   src/particleSamples.cpp:976-1059
+//   build_map_urqmd_to_pdg_id / get_pdg_id                   src/particleSamples.cpp:325-357,389-400
 //   gz_readline (one gzread per byte + a stringstream)   src/particleSamples.cpp:2209-2218
 //   boostParticles (rap_shift)                           src/particleSamples.cpp:441-470
 //   filter_particles / decide_to_pick_OSCAR              src/particleSamples.cpp:625-678,1329-1346
@@ -19,6 +23,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -38,10 +43,33 @@ struct Batch {
     int64_t all_particles = 0;   // particles of every species read for this batch
 };
 
+// UrQMD (particle id, 2 x isospin projection) -> Monte-Carlo number, for the species the reference
+// knows (src/particleSamples.cpp:325-357); anything else gets 0 and is dropped by the filter, but
+// still counts towards event_buffer_size.
+struct UrqmdSpecies {
+    int id, iso3, pdg;
+};
+const UrqmdSpecies kUrqmdSpecies[] = {
+    // mesons: pi, K, phi, eta, photon
+    {101, 2, 211},   {101, 0, 111},    {101, -2, -211}, {106, 1, 321},    {106, -1, 311},  {-106, 1, -311},
+    {-106, -1, -321}, {109, 0, 333},   {102, 0, 221},   {100, 0, 22},
+    // baryons: N, Sigma, Xi, Lambda, Omega and their antiparticles
+    {1, 1, 2212},    {1, -1, 2112},    {-1, -1, -2212}, {-1, 1, -2112},   {40, 2, 3222},   {-40, -2, -3222},
+    {40, 0, 3212},   {-40, 0, -3212},  {40, -2, 3112},  {-40, 2, -3112},  {49, 1, 3322},   {-49, -1, -3322},
+    {49, -1, 3312},  {-49, 1, -3312},  {27, 0, 3122},   {-27, 0, -3122},  {55, 0, 3334},   {-55, 0, -3334},
+};
+int urqmd_to_pdg(long long id, long long iso3) {
+    for (const UrqmdSpecies &s : kUrqmdSpecies)
+        if (s.id == id && s.iso3 == iso3) return s.pdg;
+    return 0;
+}
+
 }  // namespace
 
 struct hbt_reader {
     gzFile gz = nullptr;
+    FILE *bin = nullptr;  // read_in_mode 21
+    int32_t mode = 10;
     int32_t monval = 0;
     int64_t buffer_size = 0;
     double rap_shift = 0.0;
@@ -127,8 +155,116 @@ struct hbt_reader {
         return r.ptr;
     }
 
-    // one batch, src/particleSamples.cpp:1256-1284; returns false when nothing at all could be read
+    // boostParticles (:447-452, evaluated as written), the single-species filter (:672-676) and,
+    // optionally, the HBT gather's rapidity cut (src/HBT_correlation.cpp:261-266)
+    void keep(Batch &b, long long mv, double ch, double sh, double t, double x, double y, double z, double E, double px,
+              double py, double pz) const {
+        if (mv != monval) return;
+        const double E_s = E * ch + pz * sh;
+        const double pz_s = pz * ch + E * sh;
+        if (cut) {
+            const double ratio = pz_s / E_s;
+            if (!(ratio > cut_lo && ratio < cut_hi)) return;
+        }
+        const double rec[8] = {px, py, pz_s, E_s, x, y, z, t};
+        b.p.insert(b.p.end(), rec, rec + 8);
+    }
+
     std::unique_ptr<Batch> read_batch() {
+        return mode == 21 ? read_batch_urqmd_binary() : mode == 2 ? read_batch_urqmd_text() : read_batch_iss();
+    }
+
+    // read_in_mode 2, src/particleSamples.cpp:921-972: "<n>", one line that is skipped, then n lines
+    // "id iso3 charge <2 numbers> process mass t x y z E px py pz"
+    std::unique_ptr<Batch> read_batch_urqmd_text() {
+        std::unique_ptr<Batch> b(new Batch);
+        b->off.push_back(0);
+        const double ch = std::cosh(rap_shift), sh = std::sinh(rap_shift);
+        int64_t num_particles = 0;
+        while (num_particles < buffer_size) {
+            const char *lb, *le;
+            readline(&lb, &le);
+            if (hit_eof) break;  // gzeof() after the header read (:924)
+            long long n_particle = 0;
+            parse_int(lb, le, &n_particle);
+            if (!readline(&lb, &le) && hit_eof && n_particle > 0) {
+                error = "particle_list.dat ends inside an event";
+                return b;
+            }
+            for (long long ip = 0; ip < n_particle; ip++) {
+                if (!readline(&lb, &le) && hit_eof) {
+                    error = "particle_list.dat ends inside an event";
+                    return b;
+                }
+                long long id = 0, iso3 = 0, charge = 0, proc = 0;
+                double d1, d2, mass, t, x, y, z, E, px, py, pz;
+                const char *q = parse_int(lb, le, &id);
+                q = parse_int(q, le, &iso3);
+                q = parse_int(q, le, &charge);
+                q = parse_double(q, le, &d1);
+                q = parse_double(q, le, &d2);
+                q = parse_int(q, le, &proc);
+                q = parse_double(q, le, &mass);
+                q = parse_double(q, le, &t);
+                q = parse_double(q, le, &x);
+                q = parse_double(q, le, &y);
+                q = parse_double(q, le, &z);
+                q = parse_double(q, le, &E);
+                q = parse_double(q, le, &px);
+                q = parse_double(q, le, &py);
+                q = parse_double(q, le, &pz);
+                keep(*b, urqmd_to_pdg(id, iso3), ch, sh, t, x, y, z, E, px, py, pz);
+            }
+            num_particles += n_particle;
+            b->off.push_back(static_cast<int64_t>(b->p.size() / 8));
+        }
+        b->all_particles = num_particles;
+        return b;
+    }
+
+    // read_in_mode 21, src/particleSamples.cpp:985-1057: int n, 8 ints that are skipped, then per
+    // particle 6 ints (id, iso3, ...) and 9 floats (mass t x y z E px py pz), native byte order
+    std::unique_ptr<Batch> read_batch_urqmd_binary() {
+        std::unique_ptr<Batch> b(new Batch);
+        b->off.push_back(0);
+        const double ch = std::cosh(rap_shift), sh = std::sinh(rap_shift);
+        int64_t num_particles = 0;
+        std::vector<unsigned char> rec;
+        while (num_particles < buffer_size) {
+            int32_t head[9];
+            const size_t got = std::fread(head, 1, 4, bin);
+            bytes_inflated += got;
+            if (got < 4) break;  // inputfile.eof() after the read of n_particle (:986)
+            const int32_t n_particle = head[0];
+            if (std::fread(head + 1, 4, 8, bin) != 8 && n_particle > 0) {
+                error = "particle_list.bin ends inside an event";
+                return b;
+            }
+            bytes_inflated += 32;
+            if (n_particle > 0) {
+                rec.resize(static_cast<size_t>(n_particle) * 60);
+                if (std::fread(rec.data(), 60, static_cast<size_t>(n_particle), bin) != static_cast<size_t>(n_particle)) {
+                    error = "particle_list.bin ends inside an event";
+                    return b;
+                }
+                bytes_inflated += rec.size();
+            }
+            for (int32_t ip = 0; ip < n_particle; ip++) {
+                int32_t info[6];
+                float v[9];
+                std::memcpy(info, rec.data() + static_cast<size_t>(ip) * 60, 24);
+                std::memcpy(v, rec.data() + static_cast<size_t>(ip) * 60 + 24, 36);
+                keep(*b, urqmd_to_pdg(info[0], info[1]), ch, sh, v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+            }
+            num_particles += n_particle;
+            b->off.push_back(static_cast<int64_t>(b->p.size() / 8));
+        }
+        b->all_particles = num_particles;
+        return b;
+    }
+
+    // read_in_mode 10, src/particleSamples.cpp:1256-1284
+    std::unique_ptr<Batch> read_batch_iss() {
         std::unique_ptr<Batch> b(new Batch);
         b->off.push_back(0);
         const double ch = std::cosh(rap_shift), sh = std::sinh(rap_shift);
@@ -157,16 +293,7 @@ struct hbt_reader {
                 q = parse_double(q, le, &py);
                 q = parse_double(q, le, &pz);
                 (void)mass;
-                if (mv != monval) continue;  // decide_to_pick_OSCAR, single-species branch (:672-676)
-                // boostParticles (:447-452), evaluated as written
-                const double E_s = E * ch + pz * sh;
-                const double pz_s = pz * ch + E * sh;
-                if (cut) {  // the HBT gather's rapidity cut (src/HBT_correlation.cpp:261-266)
-                    const double ratio = pz_s / E_s;
-                    if (!(ratio > cut_lo && ratio < cut_hi)) continue;
-                }
-                const double rec[8] = {px, py, pz_s, E_s, x, y, z, t};
-                b->p.insert(b->p.end(), rec, rec + 8);
+                keep(*b, mv, ch, sh, t, x, y, z, E, px, py, pz);
             }
             num_particles += n_particle;
             b->off.push_back(static_cast<int64_t>(b->p.size() / 8));
@@ -182,7 +309,7 @@ struct hbt_reader {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return ready.size() < 2 || stop; });
             if (stop) return;
-            if (b->off.size() > 1) ready.push_back(std::move(b));
+            if (b->off.size() > 1 && error.empty()) ready.push_back(std::move(b));  // a batch cut short by an error is not delivered
             if (last) done = true;
             cv.notify_all();
             if (last) return;
@@ -194,15 +321,25 @@ extern "C" int hbt_reader_open(const char *path, int32_t read_in_mode, int32_t p
                                double rap_shift, const hbt_params *rapidity_cut, hbt_reader **out) {
     if (!path || !out) return HBT_ERR_INVALID;
     *out = nullptr;
-    if (read_in_mode != 10) return HBT_ERR_INVALID;  // the text format of read_in_particle_samples_gzipped only
+    if (read_in_mode != 10 && read_in_mode != 2 && read_in_mode != 21) return HBT_ERR_INVALID;
     // species groups (9999, 9998, ... : all charged, ...) need the particle table; single species only
     const int32_t a = particle_monval < 0 ? -particle_monval : particle_monval;
     if (a >= 9996 && a <= 99999 && (a <= 9999 || a == 99999)) return HBT_ERR_INVALID;
-    gzFile gz = gzopen(path, "rb");
-    if (!gz) return HBT_ERR_INVALID;
-    gzbuffer(gz, 1 << 20);
+    gzFile gz = nullptr;
+    FILE *bin = nullptr;
+    if (read_in_mode == 21) {
+        bin = std::fopen(path, "rb");
+        if (!bin) return HBT_ERR_INVALID;
+        std::setvbuf(bin, nullptr, _IOFBF, 1 << 20);
+    } else {
+        gz = gzopen(path, "rb");
+        if (!gz) return HBT_ERR_INVALID;
+        gzbuffer(gz, 1 << 20);
+    }
     hbt_reader *r = new hbt_reader;
     r->gz = gz;
+    r->bin = bin;
+    r->mode = read_in_mode;
     r->monval = particle_monval;
     r->buffer_size = event_buffer_size;
     r->rap_shift = rap_shift;
@@ -250,5 +387,6 @@ extern "C" void hbt_reader_close(hbt_reader *r) {
     r->cv.notify_all();
     if (r->worker.joinable()) r->worker.join();
     if (r->gz) gzclose(r->gz);
+    if (r->bin) std::fclose(r->bin);
     delete r;
 }

@@ -207,8 +207,9 @@ def compare(ref: Accumulators, got: Accumulators, rtol: float = 1e-10, check_sta
 
 
 class FastReader:
-    """``hbt_reader_*`` of ``include/hbt_b200.h``: the gzipped particle samples of
-    ``read_in_mode=10`` (``src/particleSamples.cpp:1247-1286``) as batches of events of one
+    """``hbt_reader_*`` of ``include/hbt_b200.h``: the particle samples of ``read_in_mode=10``
+    (gzipped iSS text, ``src/particleSamples.cpp:1247-1286``), ``2`` (gzipped UrQMD text, ``:910-974``)
+    or ``21`` (UrQMD binary, ``:976-1059``) as batches of events of one
     species, grouped by the reference's ``event_buffer_size`` rule.  Iterating yields
     :class:`Batch` objects (copies); ``all_particles`` holds the all-species count of the last one."""
 

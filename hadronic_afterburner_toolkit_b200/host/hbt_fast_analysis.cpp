@@ -1,6 +1,8 @@
 // hbt_fast_analysis.e — the HBT analysis of the reference program
 // (Analysis::HBTAnalysis, /root/reference/src/Analysis.cpp:817-835) end to end on libhbt_b200.so,
-// for the input format the production configs use (read_in_mode = 10, results/particle_samples.gz):
+// for the input formats hbt_reader_* reads (read_in_mode = 10: results/particle_samples.gz, the
+// production configs' format; 2: gzipped UrQMD text results/particle_list.dat; 21: UrQMD binary
+// results/particle_list.bin):
 //
 //   reader thread   hbt_reader_*      inflate + parse + species filter, two batches ahead
 //   host            psi_2, rapidity cut, the reference's RNG draws (partner events, rotation angles)
@@ -89,7 +91,11 @@ int main(int argc, char *argv[]) {
     for (int i = 1; i < argc; i++) P.set(argv[i]);
 
     if (P.get("analyze_HBT", 0) != 1) die("analyze_HBT is not 1: nothing to do (the other analyses are the reference program's)");
-    if (P.get("read_in_mode") != 10) die("only read_in_mode = 10 (gzipped iSS samples) is read here");
+    const int read_in_mode = static_cast<int>(P.get("read_in_mode"));
+    if (read_in_mode != 10 && read_in_mode != 2 && read_in_mode != 21)
+        die("only read_in_mode = 10 (gzipped iSS samples), 2 (gzipped UrQMD text) and 21 (UrQMD binary) are read here");
+    // (modes 2 and 21 do not force these off as mode 10 does, src/particleSamples.cpp:409-412)
+    if (read_in_mode != 10 && P.get("resonance_weak_feed_down_flag", 0) == 1) die("resonance_weak_feed_down_flag = 1 is not supported here");
     if (P.get("read_in_real_mixed_events", 0) == 1) die("read_in_real_mixed_events = 1 is not supported here");
     if (P.get("resonance_feed_down_flag", 0) == 1) die("resonance_feed_down_flag = 1 is not supported here");
     if (P.get("readRapidityShiftFromFile", 0) == 1) die("readRapidityShiftFromFile = 1 is not supported here");
@@ -114,8 +120,9 @@ int main(int argc, char *argv[]) {
     hbt_rng *rng = nullptr;
     if (hbt_rng_create(static_cast<int32_t>(P.get("randomSeed")), &rng) != HBT_OK) die("cannot create the random number generator");
     hbt_reader *rd = nullptr;
-    const std::string file = path + "/particle_samples.gz";
-    if (hbt_reader_open(file.c_str(), 10, static_cast<int>(P.get("particle_monval")), static_cast<int64_t>(P.get("event_buffer_size")),
+    // file names of src/particleSamples.cpp:133-149
+    const std::string file = path + (read_in_mode == 10 ? "/particle_samples.gz" : read_in_mode == 2 ? "/particle_list.dat" : "/particle_list.bin");
+    if (hbt_reader_open(file.c_str(), read_in_mode, static_cast<int>(P.get("particle_monval")), static_cast<int64_t>(P.get("event_buffer_size")),
                         P.get("rapidity_shift", 0), nullptr, &rd) != HBT_OK)
         die("cannot open " + file + " for particle_monval " + std::to_string(static_cast<int>(P.get("particle_monval"))));
 

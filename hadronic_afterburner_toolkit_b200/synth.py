@@ -71,3 +71,54 @@ def write_iss_gz(path: str, batches: List[Batch], monval: int = 211, mass: float
                 for p in ev:
                     f.write("%d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n"
                             % (monval, mass, p[7], p[4], p[5], p[6], p[3], p[0], p[1], p[2]))
+
+
+# UrQMD (particle id, 2 x isospin projection) of the species the writers below can emit
+URQMD_IDS = {211: (101, 2), -211: (101, -2), 111: (101, 0), 321: (106, 1), -321: (-106, -1), 2212: (1, 1), 2112: (1, -1),
+             3122: (27, 0), 0: (104, 0)}  # 0: an id the reference does not know (rho: dropped, but counted)
+_URQMD_CHARGE = {211: 1, -211: -1, 111: 0, 321: 1, -321: -1, 2212: 1, 2112: 0, 3122: 0, 0: 0}
+
+
+def urqmd_records(events, rng, other_fraction: float = 0.3, others=(321, -211, 2212, 0)):
+    """Per event a list of (pdg, mass, p[8]) records: the given particles as pi+ with particles of
+    other species (and of an id the reference's table does not hold) interleaved — they count
+    for event_buffer_size and are dropped by the species filter."""
+    out = []
+    for ev in events:
+        rows = []
+        for p in ev:
+            rows.append((211, PION_MASS, p))
+            if rng.random() < other_fraction:
+                rows.append((int(rng.choice(others)), 0.494, p * rng.uniform(0.5, 1.5)))
+        out.append(rows)
+    return out
+
+
+def write_urqmd_gz(path: str, records, trailing_newline: bool = True) -> None:
+    """read_in_mode=2 text (gzipped ``particle_list.dat``, ``src/particleSamples.cpp:910-974``):
+    per event the particle count, one line the reader skips, then per particle
+    ``id iso3 charge n1 n2 process mass t x y z E px py pz`` (%.17g: the text parse returns the
+    same doubles)."""
+    lines = []
+    for rows in records:
+        lines.append(f"{len(rows)} ")
+        lines.append("65 4 61 0 221 11 0 0 ")
+        for pdg, mass, p in rows:
+            uid, iso3 = URQMD_IDS[pdg]
+            lines.append("%d %d %d %d %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g"
+                         % (uid, iso3, _URQMD_CHARGE[pdg], 1, 6, 99, mass, p[7], p[4], p[5], p[6], p[3], p[0], p[1], p[2]))
+    with gzip.open(path, "wt", compresslevel=1) as f:
+        f.write("\n".join(lines) + ("\n" if trailing_newline else ""))
+
+
+def write_urqmd_bin(path: str, records) -> None:
+    """read_in_mode=21 binary (``particle_list.bin``, ``src/particleSamples.cpp:976-1059``): per
+    event int32 count + 8 int32 that are skipped, per particle 6 int32 (id, iso3, charge, ...)
+    and 9 float32 (mass t x y z E px py pz).  The values are rounded to float32 on the way."""
+    with open(path, "wb") as f:
+        for rows in records:
+            f.write(np.array([len(rows), 65, 4, 61, 0, 221, 11, 0, 0], dtype=np.int32).tobytes())
+            for pdg, mass, p in rows:
+                uid, iso3 = URQMD_IDS[pdg]
+                f.write(np.array([uid, iso3, _URQMD_CHARGE[pdg], 1, 6, 99], dtype=np.int32).tobytes())
+                f.write(np.array([mass, p[7], p[4], p[5], p[6], p[3], p[0], p[1], p[2]], dtype=np.float32).tobytes())

@@ -109,10 +109,13 @@ double hbt_rng_uniform(hbt_rng *rng);
 int32_t hbt_rng_mixed_plan(hbt_rng *rng, int32_t nev, int32_t nev_mixed, int32_t *partner_ids,
                            double *cos_sin, double *angles);
 
-/* ---- fast reader: gzipped particle samples -> batches ("oversample groups") --------- */
-/* Replaces, for read_in_mode = 10 (results/particle_samples.gz), the reference's reader and the
- * steps between it and the pair loops: read_in_particle_samples_gzipped + gz_readline
- * (src/particleSamples.cpp:1247-1286, :2209-2218), boostParticles (:441-470), filter_particles for
+/* ---- fast reader: particle samples -> batches ("oversample groups") ------------------ */
+/* Replaces, for read_in_mode = 10 (results/particle_samples.gz, gzipped iSS text), 2
+ * (results/particle_list.dat, gzipped UrQMD text) and 21 (results/particle_list.bin, UrQMD binary),
+ * the reference's reader and the steps between it and the pair loops:
+ * read_in_particle_samples_gzipped / _UrQMD_zipped / _UrQMD_binary + gz_readline
+ * (src/particleSamples.cpp:1247-1286, :910-974, :976-1059, :2209-2218), the UrQMD id map
+ * (:325-357, :389-400; unknown ids are dropped but counted), boostParticles (:441-470), filter_particles for
  * a single species (:625-678, :1329-1346) and, when rapidity_cut is not NULL, the HBT gather's
  * tanh(HBTrap_min) < pz/E < tanh(HBTrap_max) (src/HBT_correlation.cpp:255-281).  Same grouping rule
  * (events are appended while the particle count of all species is below event_buffer_size), same

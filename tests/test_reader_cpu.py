@@ -146,9 +146,74 @@ def test_errors(tmp_path):
     path = tmp_path / "p.gz"
     with gzip.open(path, "wt") as f:
         f.write("2\n211 0.138 1 0 0 0 1 0.1 0.1 0.1\n")  # the event announces 2 particles, holds 1
-    assert L.hbt_reader_open(str(path).encode(), 2, 211, 100, 0.0, None, ctypes.byref(h)) == -1  # only mode 10
+    assert L.hbt_reader_open(str(path).encode(), 1, 211, 100, 0.0, None, ctypes.byref(h)) == -1  # modes 10, 2, 21 only
     assert L.hbt_reader_open(str(path).encode(), 10, 9999, 100, 0.0, None, ctypes.byref(h)) == -1  # species groups need pdg.dat
     r = hbtio.FastReader(str(path), 211, 100)
+    with pytest.raises(capi.HBTError):
+        next(r)
+    r.close()
+
+
+# ---- UrQMD formats (read_in_mode 2 and 21) against the reference reader's own output ------------
+import json
+import os
+
+from conftest import GOLDEN
+
+READER_CASES = json.load(open(os.path.join(GOLDEN, "reader_cases.json")))
+
+
+@pytest.mark.parametrize("name", sorted(READER_CASES))
+def test_urqmd_modes_match_the_reference_reader(name):
+    """tests/golden/make_golden_readers.py pushed the committed particle_list.dat (gzipped UrQMD
+    text) / particle_list.bin (UrQMD binary) through the unmodified reference reader and dumped
+    the filtered particle lists per batch; hbt_reader must return the same batches, events and
+    doubles (id map, species filter, unknown ids and other species counted for event_buffer_size,
+    an empty event, float32 -> double, the rapidity shift)."""
+    c = READER_CASES[name]
+    want = hbtio.read_batches(os.path.join(GOLDEN, name + ".particles.bin"))
+    # when the file ends exactly on a batch boundary the reference's loop makes one more read that
+    # returns no event (src/Analysis.cpp:821: an analysis call on zero events, a no-op); hbt_reader
+    # reports the end of the file instead
+    want = [b for b in want if len(b.same) > 0]
+    got = collect(os.path.join(GOLDEN, c["input"]), c["particle_monval"], c["event_buffer_size"],
+                  rap_shift=c["rapidity_shift"], read_in_mode=c["read_in_mode"])
+    assert len(got) == len(want) > 0
+    for (evs, _), b in zip(got, want):
+        assert len(evs) == len(b.same)
+        for x, y in zip(evs, b.same):
+            assert x.shape == y.shape and np.array_equal(x, y)
+
+
+def test_urqmd_text_and_binary_agree_up_to_float32(tmp_path):
+    """The two writers of synth.py describe the same events; the binary format stores float32."""
+    rng = np.random.default_rng(5)
+    events = [ev for b in synth.make_batches(20260023, 1, 3, multiplicity=50) for ev in b.same]
+    rec = synth.urqmd_records(events, rng)
+    synth.write_urqmd_gz(str(tmp_path / "particle_list.dat"), rec, trailing_newline=False)
+    synth.write_urqmd_bin(str(tmp_path / "particle_list.bin"), rec)
+    a = collect(tmp_path / "particle_list.dat", 211, 10 ** 9, read_in_mode=2)
+    b = collect(tmp_path / "particle_list.bin", 211, 10 ** 9, read_in_mode=21)
+    assert len(a) == len(b) == 1 and a[0][1] == b[0][1] == sum(len(r) for r in rec)
+    for x, y, ev in zip(a[0][0], b[0][0], events):
+        assert np.array_equal(x, ev)  # %.17g text: the generator's doubles
+        assert np.array_equal(y, x.astype(np.float32).astype(np.float64))
+
+
+def test_urqmd_truncated_files_are_errors(tmp_path):
+    rng = np.random.default_rng(6)
+    events = [ev for b in synth.make_batches(20260024, 1, 2, multiplicity=20) for ev in b.same]
+    rec = synth.urqmd_records(events, rng)
+    synth.write_urqmd_bin(str(tmp_path / "full.bin"), rec)
+    data = open(tmp_path / "full.bin", "rb").read()
+    open(tmp_path / "cut.bin", "wb").write(data[:len(data) - 17])
+    r = hbtio.FastReader(str(tmp_path / "cut.bin"), 211, 10 ** 9, read_in_mode=21)
+    with pytest.raises(capi.HBTError):
+        next(r)
+    r.close()
+    with gzip.open(tmp_path / "cut.dat", "wt") as f:
+        f.write("3 \nskipped\n101 2 1 1 6 99 0.138 1 0 0 0 1 0.1 0.1 0.1\n")
+    r = hbtio.FastReader(str(tmp_path / "cut.dat"), 211, 10 ** 9, read_in_mode=2)
     with pytest.raises(capi.HBTError):
         next(r)
     r.close()
