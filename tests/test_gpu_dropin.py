@@ -103,7 +103,7 @@ def test_urqmd_input_formats_same_files(mode, input_name, tmp_path):
     got, _ = run_binary(OUR_EXE, str(tmp_path / "ours"), text, src, env={"HBT_B200_DEVICES": "1"}, input_name=input_name)
     same_text(want, got)
     fast, out = run_binary(FAST_EXE, str(tmp_path / "fast"), text, src, input_name=input_name)
-    assert "hbt_fast_analysis: 3 batches, 9 events" in out
+    assert "hbt_fast_analysis: 2 batches, 9 events" in out
     same_text(want, fast)
     assert any(float(l.split()[3]) != 0.0 for fn in want for l in want[fn])  # the files hold pairs
 
