@@ -992,6 +992,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     }
 #ifdef HBT_HAVE_V2
     ctx->v2c = hbt_v2_consts(g);
+    if (const char *v = getenv("HBT_B200_F32MIX")) ctx->v2c.f32_mixed = atoi(v) != 0;  // 0: every survivor through the FP64 path
     // persistent kernels: one grid-full of resident warps
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same, hbt_pairs_v3<false, false>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same_stats, hbt_pairs_v3<false, true>, 32, 0));
@@ -1113,18 +1114,37 @@ extern "C" int hbt_synchronize(hbt_ctx *ctx) {
 }
 
 // ---- device-resident entry points --------------------------------------------------------
-extern "C" int hbt_accumulate_same_dev(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref) {
+namespace {
+// the device-resident loops on a given lane (both loops of one batch go to the same lane)
+int same_dev_on(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, double psi_ref) {
     if (!ctx || (n > 0 && !d_p) || n < 0) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_same_dev: bad argument");
     CU(ctx, cudaSetDevice(ctx->device));
     if (cap_may_engage(ctx, false, n > 1 ? static_cast<unsigned long long>(n) * (n - 1) / 2 : 0))
         return fail(ctx, HBT_ERR_CAP, "needed_number_of_pairs may be reached: use the host-buffer entry points, which replay the cap in order");
-    return launch_same(ctx, pick_lane(ctx), d_p, n, psi_ref);
+    return launch_same(ctx, L, d_p, n, psi_ref);
+}
+int mixed_dev_on(hbt_ctx *ctx, Lane &L, const double *d_p1, const int64_t *off1, int32_t nev1, const double *d_p2,
+                 const int64_t *off2, int32_t nev2, const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
+                 double psi_ref);
+}  // namespace
+
+extern "C" int hbt_accumulate_same_dev(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref) {
+    if (!ctx) return HBT_ERR_INVALID;
+    return same_dev_on(ctx, pick_lane(ctx), d_p, n, psi_ref);
 }
 
 extern "C" int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const int64_t *off1, int32_t nev1,
                                         const double *d_p2, const int64_t *off2, int32_t nev2,
                                         const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
                                         double psi_ref) {
+    if (!ctx) return HBT_ERR_INVALID;
+    return mixed_dev_on(ctx, pick_lane(ctx), d_p1, off1, nev1, d_p2, off2, nev2, partner_ids, cos_sin, nmix, psi_ref);
+}
+
+namespace {
+int mixed_dev_on(hbt_ctx *ctx, Lane &L, const double *d_p1, const int64_t *off1, int32_t nev1, const double *d_p2,
+                 const int64_t *off2, int32_t nev2, const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
+                 double psi_ref) {
     if (!ctx || nev1 < 0 || nmix < 0) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_mixed_dev: bad argument");
     if (nev1 == 0 || nmix == 0) return HBT_OK;
     if (!d_p1 || !off1 || !partner_ids || !cos_sin) return fail(ctx, HBT_ERR_INVALID, "hbt_accumulate_mixed_dev: null argument");
@@ -1142,7 +1162,6 @@ extern "C" int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const 
     const size_t nseg = build_segments(off1, nev1, off2, 0, partner_ids, cos_sin, nmix, tile_i(ctx), tile_j(ctx), s->h_seg, &npairs, &nblocks);
     if (cap_may_engage(ctx, true, npairs))
         return fail(ctx, HBT_ERR_CAP, "needed_number_of_pairs may be reached: use the host-buffer entry points, which replay the cap in order");
-    Lane &L = pick_lane(ctx);
     if (nseg) CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, L.stream));
     rc = launch_mixed(ctx, L, d_p1, d_p2, s->d_seg, nseg, nblocks, npairs, psi_ref);
     if (rc) return rc;
@@ -1150,6 +1169,7 @@ extern "C" int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const 
     s->in_flight = true;
     return HBT_OK;
 }
+}  // namespace
 
 // One whole batch, device resident: same-event loop over d_p[0, off[nev]) and the mixed-event
 // loops of the events of the same list (list 2 = list 1), as hbt_accumulate_batch does for host
@@ -1188,9 +1208,10 @@ extern "C" int hbt_accumulate_batch_dev(hbt_ctx *ctx, const double *d_p, const i
         }
     }
 #endif
-    int rc = hbt_accumulate_same_dev(ctx, d_p, n, psi_ref);
+    Lane &L = pick_lane(ctx);
+    int rc = same_dev_on(ctx, L, d_p, n, psi_ref);
     if (rc) return rc;
-    if (nmix > 0) rc = hbt_accumulate_mixed_dev(ctx, d_p, off, nev, nullptr, nullptr, 0, partner_ids, cos_sin, nmix, psi_ref);
+    if (nmix > 0) rc = mixed_dev_on(ctx, L, d_p, off, nev, nullptr, nullptr, 0, partner_ids, cos_sin, nmix, psi_ref);
     return rc;
 }
 

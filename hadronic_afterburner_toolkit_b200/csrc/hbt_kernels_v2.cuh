@@ -32,6 +32,14 @@ struct V2Const {
     double inv_dkphi;         // 1/dK_phi (float-estimate path of the K_phi bin only; never decides an edge)
     float kt_min_f, inv_dkt_f;  // float estimate of the K_T bin (fixed up with the exact thresholds)
     int symmetric;            // |q_lo| == |q_hi| up to 2^-24 relative
+    // ---- FP32 decision of mixed-event survivors (v3_mixed_f32): a pair is decided in float only
+    // when every quantity is farther from every edge than a bound on the float evaluation error
+    float f_inv_dq, f_ub;     // u = q * f_inv_dq + f_ub, bin units
+    float f_gs;               // error bound (in units of 2^-24 GeV) -> bin units, with a safety factor 2
+    float f_g0;               // constant part of the float guard, bin units: g0 + 8 * 2^-24 * nq
+    float f_nkphi;            // n_Kphi as a float (conditioning test of the float K_phi estimate)
+    float ktf[HBT_MAX_KT + 1];  // K_T thresholds in k2 space as floats: [0] = k2lo, [k] = kt4[k], [nKT] = k2hi
+    int f32_mixed;            // 1: the float path is enabled (HBT_B200_F32MIX=0 disables it)
 };
 
 __host__ inline V2Const hbt_v2_consts(const HbtGrid &g) {
@@ -54,6 +62,18 @@ __host__ inline V2Const hbt_v2_consts(const HbtGrid &g) {
     c.kt_min_f = static_cast<float>(g.KT_min);
     c.inv_dkt_f = static_cast<float>(1.0 / g.dKT);
     c.symmetric = (g.q_lo < 0.0 && g.q_hi > 0.0 && fabs(a - b) <= 5.9e-8 * c.W2) ? 1 : 0;
+    const double u24 = 5.9604644775390625e-8;  // 2^-24, unit roundoff of binary32
+    c.f_inv_dq = static_cast<float>(g.inv_dq);
+    c.f_ub = static_cast<float>(c.ub);
+    c.f_gs = static_cast<float>(2.0 * u24 * g.inv_dq * 1.001);
+    c.f_g0 = static_cast<float>((c.g0 + 8.0 * u24 * (c.nq_d + 2.0)) * 1.001);
+    c.f_nkphi = static_cast<float>(g.nKphi);
+    for (int k = 0; k <= HBT_MAX_KT; k++) c.ktf[k] = 0.f;
+    const int nkt = g.nKT < HBT_MAX_KT ? g.nKT : HBT_MAX_KT;
+    c.ktf[0] = static_cast<float>(c.k2lo);
+    for (int k = 1; k < nkt; k++) c.ktf[k] = static_cast<float>(c.kt4[k]);
+    c.ktf[nkt] = static_cast<float>(c.k2hi);
+    c.f32_mixed = 1;
     return c;
 }
 

@@ -304,6 +304,107 @@ __device__ __forceinline__ int v3_kt_bin(const HbtGrid &g, const V2Const &c, dou
     return iK;
 }
 
+// ---- FP32 decision of a queued mixed-event survivor --------------------------------------------
+// A mixed-event pair contributes one count to one bin (src/HBT_correlation.cpp:682): only its K_T
+// bin and its three q bins are needed, not the values.  They are evaluated here in binary32 from
+// the rounded particle components, together with a bound on |float result - exact value| (u = 2^-24,
+// every input rounding and every operation accounted for; X = |ax|+|bx|, Y = |ay|+|by|, S = X+Y,
+// Z = |az|+|bz|, E = |aE|+|bE|, r ~ 1/sqrt(k2), r2 ~ 1/sqrt(m2), MUFU.RSQ within 2^-22):
+//     |k2_f - k2|       <= u (4 S^2 + 2 k2)
+//     |q_out,side_f - q| <= u (6 S^2 r + |q| (6 + 2 S^2 r^2))
+//     |q_long_f - q|    <= u (10 W Z + |q| (2 W^2 + 8)),   W = (E + Z) r2
+// In bin units (x 1/delta_q) twice that bound plus the guard of the FP64 path and the rounding of
+// the float grid constants is the guard band: the pair is decided only if every component is
+// farther than its band from every integer (bin edges and both window edges) and k2 is farther
+// than its band from the K_T cut and from both edges of its K_T bin.  Otherwise (~1e-3 of the
+// survivors) the FP64 path below decides, so every bin index still equals the reference's.
+// Returns 1 (accepted: slab and bin set), 0 (certainly outside the window) or -1 (undecided).
+__device__ __forceinline__ float v3_rsqrt_f32(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// floor(u) and the distance to the nearest integer for |u| < 2^22 (u + 1.5*2^23 holds rint(u) in
+// its mantissa); beyond that the band (which grows with |u|) exceeds any distance this returns
+__device__ __forceinline__ void v3_classify_f32(float u, float gb, unsigned nq, int &i, bool &ok, bool &out) {
+    const float magic = 12582912.f;
+    const float t = u + magic;
+    const float d = u - (t - magic);  // u - rint(u)
+    i = __float_as_int(t) - 0x4B400000 - (d < 0.f ? 1 : 0);
+    const bool far = fabsf(d) > gb;   // false for NaN / inf
+    const bool in_grid = static_cast<unsigned>(i) < nq;
+    ok = far && in_grid;
+    out = far && !in_grid;
+}
+
+template <int TI, int TJ>
+__device__ __forceinline__ int v3_mixed_f32(const HbtGrid &g, const V2Const &c, unsigned sia, unsigned sja, double psi_ref,
+                                            int &slab, unsigned &bin) {
+    const float ax = static_cast<float>(lds_f64(sia)), ay = static_cast<float>(lds_f64(sia + 8 * TI));
+    const float az = static_cast<float>(lds_f64(sia + 16 * TI)), aE = static_cast<float>(lds_f64(sia + 24 * TI));
+    const float bx = static_cast<float>(lds_f64(sja)), by = static_cast<float>(lds_f64(sja + 8 * TJ));
+    const float bz = static_cast<float>(lds_f64(sja + 16 * TJ)), bE = static_cast<float>(lds_f64(sja + 24 * TJ));
+    const float u8 = 4.76837158203125e-7f;  // 8 * 2^-24
+    // transverse plane: k2 = 4 K_perp^2, q_out = d r, q_side = e r
+    const float sx = ax + bx, sy = ay + by, qx = ax - bx, qy = ay - by;
+    const float S = (fabsf(ax) + fabsf(bx)) + (fabsf(ay) + fabsf(by));
+    const float S2 = S * S;
+    const float k2 = fmaf(sy, sy, sx * sx);
+    const float r = v3_rsqrt_f32(k2);
+    // K_T: float estimate of the bin, then k2 against the cut / the bin's own edges with the band
+    int iK = static_cast<int>((0.5f * k2 * r - c.kt_min_f) * c.inv_dkt_f);
+    iK = max(0, min(iK, g.nKT - 1));
+    const float ek = (S2 + k2) * u8;  // 2 x the bound, threshold rounding included
+    const bool kt_ok = (k2 - c.ktf[iK] > ek) && (c.ktf[iK + 1] - k2 > ek);
+    const float d = fmaf(qx, sx, qy * sy), e = fmaf(qy, sx, -(qx * sy));
+    const float qo = d * r, qs = e * r;
+    const float A = S2 * r, R = A * r;
+    const float c6 = fmaf(2.f, R, 6.f), A6 = 6.f * A;
+    const float gbo = fmaf(fmaf(fabsf(qo), c6, A6), c.f_gs, c.f_g0);
+    const float gbs = fmaf(fmaf(fabsf(qs), c6, A6), c.f_gs, c.f_g0);
+    // longitudinal: q_long = (K_E q_z - K_z q_E) / Mt in the LCMS (src :383-390), or q_z
+    const float qz = az - bz;
+    const float Z = fabsf(az) + fabsf(bz);
+    float ql, gbl;
+    if (g.boost) {
+        const float sz = az + bz, sE = aE + bE, qE = aE - bE;
+        const float m2 = (sE - sz) * (sE + sz);
+        const float r2 = v3_rsqrt_f32(m2);  // m2 <= 0: inf / NaN, the band test fails
+        const float t1 = sE * qz, t2 = sz * qE;
+        ql = (t1 - t2) * r2;
+        const float W = ((fabsf(aE) + fabsf(bE)) + Z) * r2;
+        gbl = fmaf(fmaf(fabsf(ql), fmaf(2.f * W, W, 8.f), 10.f * W * Z), c.f_gs, c.f_g0);
+    } else {
+        ql = qz;
+        gbl = fmaf(2.f * Z, c.f_gs, c.f_g0);
+    }
+    const unsigned nq = static_cast<unsigned>(g.nq);
+    int io, is, il;
+    bool ok_o, out_o, ok_s, out_s, ok_l, out_l;
+    v3_classify_f32(fmaf(qo, c.f_inv_dq, c.f_ub), gbo, nq, io, ok_o, out_o);
+    v3_classify_f32(fmaf(qs, c.f_inv_dq, c.f_ub), gbs, nq, is, ok_s, out_s);
+    v3_classify_f32(fmaf(ql, c.f_inv_dq, c.f_ub), gbl, nq, il, ok_l, out_l);
+    // decided means: K_T decided inside, and every component either safely inside a bin or safely outside
+    if (!(kt_ok && (ok_o || out_o) && (ok_s || out_s) && (ok_l || out_l))) return -1;
+    if (out_o || out_s || out_l) return 0;
+    slab = iK;
+    if (g.az) {
+        // K_phi bin (:392-400) from the float estimate, as in the FP64 path; the angle of the float K
+        // is within 2u S r of the exact one: ask for a well-conditioned K and 1e-4 from every edge
+        if (!(S * r * c.f_nkphi <= 256.f) || g.nKphi > 256) return -1;
+        double de = static_cast<double>(atan2f(sy, sx)) - psi_ref;
+        de = de < 0. ? de + g.two_pi : de;
+        de = de > g.two_pi ? de - g.two_pi : de;
+        const double ue = de * c.inv_dkphi;
+        const double fe = ue - floor(ue);
+        if (!(fe > 1e-4 && fe < 1.0 - 1e-4 && ue > 0. && ue < static_cast<double>(g.nKphi))) return -1;
+        slab = iK * g.nKphi + static_cast<int>(ue);
+    }
+    bin = ((static_cast<unsigned>(slab) * nq + io) * nq + is) * nq + il;
+    return 1;
+}
+
 template <bool MIXED, bool STATS>
 __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
                                               const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv,
@@ -313,6 +414,18 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
     constexpr bool ORIENT = L::SORTED;
     const unsigned il4 = (entry >> 14) & ~3u, jl4 = (entry & 0xffffu) << 2;  // 4 x list-1 / list-2 slot
     const unsigned sia = sbase + L::SI + 2 * il4, sja = sbase + L::SJ + 2 * jl4;
+    if (MIXED && !STATS && c.f32_mixed) {
+        int fslab;
+        unsigned fbin;
+        const int fs = v3_mixed_f32<TI, TJ>(g, c, sia, sja, psi_ref, fslab, fbin);
+        if (fs == 0) return;
+        if (fs > 0) {
+            n.nE++;
+            if (closed && closed[fslab + g.nslab]) return;  // needed_number_of_pairs reached earlier
+            red_inc_u64(&acc.den_count[fbin]);
+            return;
+        }
+    }
     const bool flip = ORIENT && (lds_u32(sbase + L::SIO + il4) > lds_u32(sbase + L::SJO + jl4));
     V3Bins b;
     double k2;

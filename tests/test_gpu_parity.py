@@ -201,6 +201,103 @@ def test_batches_in_flight_on_two_lanes(same_only):
     h.close()
 
 
+def _craft_edge_pairs(P, rng_plan, rng, n, which):
+    """Two events of n pi+ such that the mixed-event pair (event 0 particle i, event 1 particle i
+    rotated by the first partner angle of event 0) has q_out (which=0) or q_long (which=1) at a
+    log-uniform distance 1e-7 ... 2e-3 bin widths from a bin edge, on either side; the other two
+    components sit at a bin centre and K_T inside the cut."""
+    ids, cs = rng_plan.mixed_plan(2, 2)
+    assert ids[0, 0] == 1
+    c, s = cs[0, 0]
+    m = 0.138
+    dq = (P.q_max - P.q_min) / (P.qnpts - 1)
+    q_base = P.q_min - dq / 2
+    pt = rng.uniform(0.22, 0.5, n)
+    ph = rng.uniform(0, 2 * np.pi, n)
+    y = rng.uniform(-0.4, 0.4, n)
+    ax, ay = pt * np.cos(ph), pt * np.sin(ph)
+    mTa = np.sqrt(m * m + ax * ax + ay * ay)
+    az, aE = mTa * np.sinh(y), mTa * np.cosh(y)
+    if which == 2:
+        # K_T = |a_T + b'_T| / 2 at a relative distance 1e-9 ... 1e-4 from a K_T bin edge (or from the cut):
+        # b'_T = a_T + 0.03 a_T/|a_T| (collinear: q_side = 0, q_out = -0.03, both bin centres), same rapidity
+        dKT = (P.KT_max - P.KT_min) / (P.n_KT - 1)
+        kedge = P.KT_min + dKT * rng.integers(0, P.n_KT, n)
+        kt = kedge * (1.0 + rng.choice([-1.0, 1.0], n) * 10.0 ** rng.uniform(-9, -4, n))
+        pt = kt - 0.015
+        ax, ay = pt * np.cos(ph), pt * np.sin(ph)
+        mTa = np.sqrt(m * m + pt * pt)
+        az, aE = mTa * np.sinh(y), mTa * np.cosh(y)
+        bx, by = (pt + 0.03) * np.cos(ph), (pt + 0.03) * np.sin(ph)
+        mTb = np.sqrt(m * m + (pt + 0.03) ** 2)
+        bz, bE = mTb * np.sinh(y), mTb * np.cosh(y)
+        ux, uy = c * bx + s * by, -s * bx + c * by
+        pos = lambda k: rng.normal(0, 4, k)
+        ev0 = np.column_stack([ax, ay, az, aE, pos(n), pos(n), pos(n), np.abs(pos(n)) + 5])
+        ev1 = np.column_stack([ux, uy, bz, bE, pos(n), pos(n), pos(n), np.abs(pos(n)) + 5])
+        return hbtio.Batch([ev0, ev1]), kt
+    edge = rng.integers(P.qnpts // 2 - 6, P.qnpts // 2 + 7, n).astype(np.float64)
+    target = edge + rng.choice([-1.0, 1.0], n) * 10.0 ** rng.uniform(-7, np.log10(2e-3), n)
+
+    def forward(lam):  # b' (already rotated) as a function of the scan parameter; returns (b', u)
+        if which == 0:
+            bx, by = ax - lam * np.cos(ph), ay - lam * np.sin(ph)
+            mTb = np.sqrt(m * m + bx * bx + by * by)
+            bz, bE = mTb * np.sinh(y), mTb * np.cosh(y)
+            Kx, Ky = 0.5 * (ax + bx), 0.5 * (ay + by)
+            Kp = np.sqrt(Kx * Kx + Ky * Ky)
+            q = (ax - bx) * (Kx / Kp) + (ay - by) * (Ky / Kp)
+        else:
+            bx, by = ax.copy(), ay.copy()
+            bz, bE = mTa * np.sinh(y - lam), mTa * np.cosh(y - lam)
+            Kz, KE = 0.5 * (az + bz), 0.5 * (aE + bE)
+            Mt = np.sqrt(KE * KE - Kz * Kz)
+            q = (KE * (az - bz) - Kz * (aE - bE)) / Mt
+        return (bx, by, bz, bE), (q - q_base) / dq
+
+    lo, hi = np.full(n, -0.3), np.full(n, 0.3)  # u is increasing in lam on this range
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        _, u = forward(mid)
+        up = u < target
+        lo, hi = np.where(up, mid, lo), np.where(up, hi, mid)
+    (bx, by, bz, bE), u = forward(0.5 * (lo + hi))
+    assert np.max(np.abs(u - target)) < 1e-9
+    # undo the rotation the mixed-event loop applies to the partner (src :522-523)
+    ux, uy = c * bx + s * by, -s * bx + c * by
+    pos = lambda k: rng.normal(0, 4, k)
+    ev0 = np.column_stack([ax, ay, az, aE, pos(n), pos(n), pos(n), np.abs(pos(n)) + 5])
+    ev1 = np.column_stack([ux, uy, bz, bE, pos(n), pos(n), pos(n), np.abs(pos(n)) + 5])
+    return hbtio.Batch([ev0, ev1]), target
+
+
+@pytest.mark.parametrize("which", [0, 1, 2])
+def test_fp32_decision_bands_hold_next_to_bin_edges(which):
+    """Mixed-event survivors are binned in FP32 when every component is farther from every edge
+    than a bound on the float evaluation error (v3_mixed_f32), in FP64 otherwise.  Thousands of
+    pairs placed 1e-7 ... 2e-3 bin widths from an edge of q_out / q_long, on both sides — inside the
+    float band, just outside it, and well outside — must all land in the reference's bins; likewise
+    pairs whose K_T is 1e-9 ... 1e-4 (relative) from a K_T bin edge or from the K_T cut (which=2)."""
+    P = C3.with_(qnpts=41)
+    rng = np.random.default_rng(77 + which)
+    plan = Random(P.randomSeed)
+    batches, targets = [], []
+    for _ in range(3):
+        b, t = _craft_edge_pairs(P, plan, rng, 700, which)
+        batches.append(b)
+        targets.append(t)
+    ref = run_oracle(P, batches)
+    for env in ("1", "0"):  # with the float path and with every survivor through the FP64 path
+        os.environ["HBT_B200_F32MIX"] = env
+        try:
+            _, acc = run_product(P, batches)
+        finally:
+            del os.environ["HBT_B200_F32MIX"]
+        hbtio.compare(ref, acc, rtol=RTOL, check_stage="cheap")
+    # the crafted pairs are really there: the central q_side (and q_long / q_out) row holds them
+    assert int(ref.den_count.sum()) > 3 * 700
+
+
 @pytest.mark.parametrize("scale,ktmin", [(30.0, 0.15), (3000.0, 0.15), (1.0, 0.0), (1e-3, 0.0)])
 def test_prefilter_margins_with_outliers(scale, ktmin):
     """The float prefilter's margins are derived from the largest pT^2 of the two tiles.  Momentum
