@@ -61,6 +61,13 @@ struct Lane {
     HbtBBox *sort_bbox = nullptr;
     void *sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0, sort_cap = 0;
+    // per-event pT-sorted copy of the buffer the mixed-event loops read (production mode)
+    unsigned long long *mix_keys[2] = {nullptr, nullptr};
+    unsigned *mix_idx[2] = {nullptr, nullptr};
+    double *mix_p = nullptr;
+    long long *mix_off = nullptr;
+    void *mix_tmp = nullptr;
+    size_t mix_tmp_bytes = 0, mix_cap = 0, mix_off_cap = 0;
 };
 
 struct TimerRec {
@@ -130,6 +137,11 @@ struct hbt_ctx {
     int n_lanes = kLanes, next_lane = 0;
     cudaEvent_t epoch = nullptr;    // time origin of the launch timers, renewed whenever the context is idle
     double covered_ms = 0.;         // end (since epoch) of the latest-ending launch already counted
+    // mixed-event loops read a per-event pT-sorted copy: 0 never, 1 when the batch has enough mixed-event pairs to
+    // pay for the sort kernels (default), 2 always (HBT_B200_PTSORT / HBT_OPT_PTSORT)
+    int ptsort = 1;
+    unsigned long long ptsort_min_pairs = 500000000ull;
+    std::vector<long long> evoff;  // event boundaries of the buffer being sorted
     bool fuse = true;  // whole batches run the fused same+mixed kernel (HBT_B200_FUSE=0 / HBT_OPT_FUSE: separate kernels)
     Slot slots[kSlots];
     int next_slot = 0;
@@ -352,6 +364,69 @@ int prepare_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n) {
     return HBT_OK;
 }
 #endif
+
+#ifdef HBT_HAVE_V2
+// Per-event pT order of the buffer the mixed-event loops read (ctx->evoff: its event boundaries):
+// keys, one radix sort of (event, pT^2), gather.  pT is invariant under the partner rotation, so one
+// sort per batch serves every (event, partner) segment; v3_run_unit then skips the list-2 particles
+// whose pT is farther than the q_out window from the sub-tile's pT range.  Returns the sorted copy.
+int prepare_mixed_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, const double **out) {
+    *out = d_p;
+    const int nev = static_cast<int>(ctx->evoff.size()) - 1;
+    if (n < 2 || nev < 1) return HBT_OK;
+    if (static_cast<size_t>(n) > L.mix_cap) {
+        CU(ctx, cudaStreamSynchronize(L.stream));
+        for (int k = 0; k < 2; k++) { cudaFree(L.mix_keys[k]); cudaFree(L.mix_idx[k]); L.mix_keys[k] = nullptr; L.mix_idx[k] = nullptr; }
+        cudaFree(L.mix_p); cudaFree(L.mix_tmp);
+        L.mix_p = nullptr; L.mix_tmp = nullptr; L.mix_cap = 0;
+        const size_t cap = static_cast<size_t>(n) + static_cast<size_t>(n) / 4 + 1024;
+        for (int k = 0; k < 2; k++) {
+            CU(ctx, cudaMalloc(&L.mix_keys[k], cap * 8));
+            CU(ctx, cudaMalloc(&L.mix_idx[k], cap * 4));
+        }
+        CU(ctx, cudaMalloc(&L.mix_p, cap * 64));
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, L.mix_keys[0], L.mix_keys[1], L.mix_idx[0], L.mix_idx[1],
+                                        static_cast<int>(cap), 0, 64, L.stream);
+        CU(ctx, cudaMalloc(&L.mix_tmp, bytes));
+        L.mix_tmp_bytes = bytes;
+        L.mix_cap = cap;
+    }
+    if (ctx->evoff.size() > L.mix_off_cap) {
+        CU(ctx, cudaStreamSynchronize(L.stream));
+        cudaFree(L.mix_off);
+        L.mix_off = nullptr;
+        L.mix_off_cap = ctx->evoff.size() * 2;
+        CU(ctx, cudaMalloc(&L.mix_off, L.mix_off_cap * 8));
+    }
+    // (pageable source: the copy is staged before the call returns, the vector can be reused)
+    CU(ctx, cudaMemcpyAsync(L.mix_off, ctx->evoff.data(), ctx->evoff.size() * 8, cudaMemcpyHostToDevice, L.stream));
+    const int th = 256;
+    hbt_mix_keys<<<static_cast<unsigned>((n + th - 1) / th), th, 0, L.stream>>>(d_p, n, L.mix_off, nev, L.mix_keys[0], L.mix_idx[0]);
+    int ev_bits = 1;
+    while ((1ll << ev_bits) < nev) ev_bits++;
+    size_t bytes = L.mix_tmp_bytes;
+    CU(ctx, cub::DeviceRadixSort::SortPairs(L.mix_tmp, bytes, L.mix_keys[0], L.mix_keys[1], L.mix_idx[0], L.mix_idx[1],
+                                            static_cast<int>(n), 0, 32 + ev_bits, L.stream));
+    hbt_sort_gather<<<static_cast<unsigned>((4 * n + th - 1) / th), th, 0, L.stream>>>(d_p, L.mix_idx[1], n, L.mix_p);
+    ctx->kernel_launches += 3;  // keys, gather + the radix sort (counted once)
+    CU(ctx, cudaGetLastError());
+    *out = L.mix_p;
+    return HBT_OK;
+}
+#endif
+
+// event boundaries of a buffer that holds list 1 (off1) followed, unless it aliases list 1, by list 2
+void set_evoff(hbt_ctx *ctx, const int64_t *off1, int32_t nev1, const int64_t *off2, int32_t nev2, int64_t base2, bool alias) {
+    ctx->evoff.clear();
+    for (int e = 0; e <= nev1; e++) ctx->evoff.push_back(off1[e]);
+    if (!alias)
+        for (int e = 1; e <= nev2; e++) ctx->evoff.push_back(base2 + off2[e]);
+}
+
+bool production_mixed(const hbt_ctx *ctx, unsigned long long npairs) {
+    return (ctx->ptsort == 2 || (ctx->ptsort == 1 && npairs >= ctx->ptsort_min_pairs)) && !ctx->stats && ctx->kernel_version != 1;
+}
 
 const unsigned char *closed_ptr(const hbt_ctx *ctx) { return ctx->any_closed ? ctx->d_closed : nullptr; }
 
@@ -922,6 +997,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     if (const char *v = getenv("HBT_B200_KERNEL")) ctx->kernel_version = atoi(v) == 1 ? 1 : 2;
     if (const char *v = getenv("HBT_B200_STATS")) ctx->stats = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_FUSE")) ctx->fuse = atoi(v) != 0;
+    if (const char *v = getenv("HBT_B200_PTSORT")) ctx->ptsort = std::min(2, std::max(0, atoi(v)));
 #define CUC(call)                                                                              \
     do {                                                                                       \
         cudaError_t e_ = (call);                                                               \
@@ -1053,6 +1129,10 @@ extern "C" void hbt_destroy(hbt_ctx *ctx) {
         if (L.sort_rmax) cudaFree(L.sort_rmax);
         if (L.d_work) cudaFree(L.d_work);
         if (L.d_units) cudaFree(L.d_units);
+        for (int k = 0; k < 2; k++) { if (L.mix_keys[k]) cudaFree(L.mix_keys[k]); if (L.mix_idx[k]) cudaFree(L.mix_idx[k]); }
+        if (L.mix_p) cudaFree(L.mix_p);
+        if (L.mix_off) cudaFree(L.mix_off);
+        if (L.mix_tmp) cudaFree(L.mix_tmp);
         if (L.tail) cudaEventDestroy(L.tail);
     }
     if (ctx->epoch) cudaEventDestroy(ctx->epoch);
@@ -1163,6 +1243,14 @@ int mixed_dev_on(hbt_ctx *ctx, Lane &L, const double *d_p1, const int64_t *off1,
     if (cap_may_engage(ctx, true, npairs))
         return fail(ctx, HBT_ERR_CAP, "needed_number_of_pairs may be reached: use the host-buffer entry points, which replay the cap in order");
     if (nseg) CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, L.stream));
+#ifdef HBT_HAVE_V2
+    if (d_p2 == d_p1 && nseg && production_mixed(ctx, npairs)) {  // (two separate device lists are read as given)
+        set_evoff(ctx, off1, nev1, nullptr, 0, 0, true);
+        rc = prepare_mixed_sorted(ctx, L, d_p1, off1[nev1], &d_p1);
+        if (rc) return rc;
+        d_p2 = d_p1;
+    }
+#endif
     rc = launch_mixed(ctx, L, d_p1, d_p2, s->d_seg, nseg, nblocks, npairs, psi_ref);
     if (rc) return rc;
     CU(ctx, cudaEventRecord(s->done, L.stream));
@@ -1200,7 +1288,13 @@ extern "C" int hbt_accumulate_batch_dev(hbt_ctx *ctx, const double *d_p, const i
         if (nseg && nblocks) {
             Lane &L = pick_lane(ctx);
             CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, L.stream));
-            rc = launch_fused(ctx, L, d_p, n, d_p, d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
+            const double *d_mix = d_p;
+            if (production_mixed(ctx, npairs)) {
+                set_evoff(ctx, off, nev, nullptr, 0, 0, true);
+                rc = prepare_mixed_sorted(ctx, L, d_p, n, &d_mix);
+                if (rc) return rc;
+            }
+            rc = launch_fused(ctx, L, d_p, n, d_mix, d_mix, s->d_seg, nseg, nblocks, npairs, psi_ref);
             if (rc) return rc;
             CU(ctx, cudaEventRecord(s->done, L.stream));
             s->in_flight = true;
@@ -1273,7 +1367,13 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
 #ifdef HBT_HAVE_V2
     if (do_same && do_mixed && ctx->fuse && !ctx->stats && ctx->kernel_version != 1 && n1 > 1 && nseg > 0 && nblocks > 0 &&
         !near_cap) {
-        rc = launch_fused(ctx, L, s->d_p, n1, s->d_p, s->d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
+        const double *d_mix = s->d_p;
+        if (production_mixed(ctx, npairs)) {
+            set_evoff(ctx, off1, nev1, off2, nev2, n1, alias);
+            rc = prepare_mixed_sorted(ctx, L, s->d_p, n1 + n2, &d_mix);
+            if (rc) return rc;
+        }
+        rc = launch_fused(ctx, L, s->d_p, n1, d_mix, d_mix, s->d_seg, nseg, nblocks, npairs, psi_ref);
         if (rc) return rc;
         do_same = do_mixed = 0;
     }
@@ -1286,8 +1386,19 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
     }
     if (do_mixed) {
         in.mixed = true;
-        rc = cap_may_engage(ctx, true, npairs) ? capped_phase(ctx, in, s->d_seg, nseg, nblocks, npairs)
-                                               : launch_mixed(ctx, L, s->d_p, s->d_p, s->d_seg, nseg, nblocks, npairs, psi_ref);
+        if (cap_may_engage(ctx, true, npairs)) {
+            rc = capped_phase(ctx, in, s->d_seg, nseg, nblocks, npairs);
+        } else {
+            const double *d_mix = s->d_p;
+#ifdef HBT_HAVE_V2
+            if (nseg && production_mixed(ctx, npairs)) {
+                set_evoff(ctx, off1, nev1, off2, nev2, n1, alias);
+                rc = prepare_mixed_sorted(ctx, L, s->d_p, n1 + n2, &d_mix);
+                if (rc) return rc;
+            }
+#endif
+            rc = launch_mixed(ctx, L, d_mix, d_mix, s->d_seg, nseg, nblocks, npairs, psi_ref);
+        }
         if (rc) return rc;
     }
     CU(ctx, cudaEventRecord(s->done, L.stream));
@@ -1419,6 +1530,10 @@ extern "C" int hbt_set_option(hbt_ctx *ctx, int32_t option, int32_t value) {
             return HBT_OK;
         case HBT_OPT_FUSE:
             ctx->fuse = value != 0;
+            return HBT_OK;
+        case HBT_OPT_PTSORT:
+            if (value < 0 || value > 2) return fail(ctx, HBT_ERR_INVALID, "ptsort must be 0, 1 or 2");
+            ctx->ptsort = value;
             return HBT_OK;
         case HBT_OPT_LANES:
             if (value < 1 || value > kLanes) return fail(ctx, HBT_ERR_INVALID, "lanes must be in [1, %d]", kLanes);

@@ -567,7 +567,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
     double ax[IPL], ay[IPL], at[IPL];
     unsigned ent[IPL];
     long long ig[IPL];
-    double S1 = 0.0;
+    double S1 = 0.0, L1 = __longlong_as_double(0x7ff0000000000000ll);  // largest / smallest pT^2 of the sub-tile
 #pragma unroll
     for (int s = 0; s < IPL; s++) {
         const int il = s * 32 + lane;
@@ -586,6 +586,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
             ax[s] = v0.x; ay[s] = v0.y;
             at[s] = fma(v0.x, v0.x, v0.y * v0.y);
             S1 = fmax(S1, at[s]);
+            L1 = fmin(L1, at[s]);
         } else {
 #pragma unroll
             for (int q = 0; q < NC; q++) si[q * SUB + il] = nan;
@@ -595,6 +596,23 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) S1 = fmax(S1, __shfl_xor_sync(0xffffffffu, S1, o));
+    // Mixed-event units, production: |q_out| = |pT_i^2 - pT_j^2| / (2 K_perp) >= |pT_i - pT_j| because
+    // K_perp <= (pT_i + pT_j)/2, so a list-2 particle whose pT is farther than W from the whole pT range
+    // of this sub-tile cannot be accepted with any of its particles.  The host hands the mixed-event
+    // loops a copy in which every event is sorted by pT (rotation invariant), so those particles sit
+    // at the two ends of the tile: the pair loop runs over [j_first, j_last] only.  (Positions, not
+    // counts: nothing is assumed about the order, an unsorted list just skips less.)
+    constexpr bool PTRANGE = MIXED && !STATS;
+    double pt2_lo = 0.0, pt2_hi = 0.0;
+    if (PTRANGE) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) L1 = fmin(L1, __shfl_xor_sync(0xffffffffu, L1, o));
+        const double Wd = sqrt(W2) * (1.0 + 1e-9);
+        const double a = sqrt(L1) - Wd, b = sqrt(S1) + Wd;
+        pt2_lo = a > 0.0 ? a * a * (1.0 - 1e-9) : 0.0;
+        pt2_hi = b * b * (1.0 + 1e-9);
+        if (!(L1 <= S1)) { pt2_lo = 0.0; pt2_hi = __longlong_as_double(0x7ff0000000000000ll); }  // empty / NaN rows: no restriction
+    }
     float2 axf[IPL / 2], naxf[IPL / 2], ayf[IPL / 2], atf[IPL / 2];
     if (!STATS) {
 #pragma unroll
@@ -611,6 +629,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
         const int nj = static_cast<int>(min(static_cast<long long>(TJ), jcount - jl0));
         // ---- stage the list-2 tile (the queue is empty here: entries index this unit) --------
         double S2 = 0.0;
+        int j_first = TJ, j_last = -1;  // first position with pT^2 >= pt2_lo, last position with pT^2 <= pt2_hi
         for (int k = lane; k < nj; k += 32) {
             const double2 *src = reinterpret_cast<const double2 *>(p2 + 8 * (jbase + jl0 + k));
             const double2 v0 = src[0], v1 = src[1];
@@ -623,6 +642,10 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
             const double pt2 = fma(x, x, y * y);
             if (STATS) sjt[k] = pt2;  // (no such array in production: the offset is shared with sjf)
             S2 = fmax(S2, pt2);
+            if (PTRANGE) {
+                if (!(pt2 < pt2_lo)) j_first = min(j_first, k);  // (a NaN stays inside the range)
+                if (!(pt2 > pt2_hi)) j_last = k;                  // k increases along the loop
+            }
             if (!STATS) { sjf[k] = static_cast<float>(x); sjf[TJ + k] = static_cast<float>(y); sjf[2 * TJ + k] = static_cast<float>(-0.5 * pt2); }
             if (SORTED) sj_o[k] = orig[jl0 + k];
             if (!MIXED) {
@@ -633,6 +656,16 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) S2 = fmax(S2, __shfl_xor_sync(0xffffffffu, S2, o));
+        int j_begin = 0, j_end = nj;
+        if (PTRANGE) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                j_first = min(j_first, __shfl_xor_sync(0xffffffffu, j_first, o));
+                j_last = max(j_last, __shfl_xor_sync(0xffffffffu, j_last, o));
+            }
+            j_begin = min(j_first, nj);
+            j_end = max(j_last + 1, j_begin);
+        }
         __syncwarp();
         // prefilter error bound against the smallest K_T (see hbt_kernels_v2.cuh)
         const double S = S1 + S2;
@@ -670,13 +703,16 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
 #pragma unroll
             for (int s = 0; s < IPL; s++) jthr[s] = DIAG ? static_cast<int>(ig[s] - jl0) : 0;
             const unsigned lane16 = static_cast<unsigned>(lane) << 16;
-            int j = 0;
+            int j = j_begin;
             // the float copy of list-2 particle j is loaded one trip ahead (LDS latency off the loop's
             // critical path; the last trip reads the first slot of the next array, see V3Smem)
             float pbx = 0.f, pby = 0.f, pnb = 0.f;
-            if (!STATS) { pbx = lds_f32(sjf_addr); pby = lds_f32(sjf_addr + 4 * TJ); pnb = lds_f32(sjf_addr + 8 * TJ); }
+            if (!STATS) {
+                const unsigned ja0 = sjf_addr + 4u * static_cast<unsigned>(j_begin);
+                pbx = lds_f32(ja0); pby = lds_f32(ja0 + 4 * TJ); pnb = lds_f32(ja0 + 8 * TJ);
+            }
             for (;;) {
-                const bool final = (j >= nj);  // one extra trip: the per-unit final flush shares the call site
+                const bool final = (j >= j_end);  // one extra trip: the per-unit final flush shares the call site
                 if (!final) {
                     if (!STATS) {
                         const float bxs = pbx, bys = pby, nbh = pnb;

@@ -54,6 +54,25 @@ __global__ void hbt_sort_keys(const double *__restrict__ p, long long n, const u
     idx[i] = static_cast<unsigned>(i);
 }
 
+// ---- per-event pT order for the mixed-event loops ---------------------------------------------
+// key = (event index << 32) | bits of float(pT^2) (non-negative floats order like their bit
+// patterns; NaN sorts last): one radix sort orders every event of the buffer by pT, events stay
+// where they are.  evoff[0..nev] are the event boundaries (in particles) of the buffer.
+__global__ void hbt_mix_keys(const double *__restrict__ p, long long n, const long long *__restrict__ evoff, int nev,
+                             unsigned long long *__restrict__ keys, unsigned *__restrict__ idx) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = nev - 1;  // last event with evoff[e] <= i
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (evoff[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const double2 v = *reinterpret_cast<const double2 *>(p + 8 * i);
+    const float pt2 = static_cast<float>(v.x * v.x + v.y * v.y);
+    keys[i] = (static_cast<unsigned long long>(lo) << 32) | (__float_as_uint(pt2) & 0x7fffffffu);
+    idx[i] = static_cast<unsigned>(i);
+}
+
 // sorted[k] = p[idx[k]] (64 bytes each, two threads per particle would not pay: L2 resident)
 __global__ void hbt_sort_gather(const double *__restrict__ p, const unsigned *__restrict__ idx, long long n,
                                 double *__restrict__ sorted) {

@@ -84,7 +84,7 @@ class HBT_correlation:
 
     def __init__(self, params: HBTParams, path: str = ".", ran_gen: Optional[Random] = None, device: int = 0,
                  stage_counters: Optional[bool] = None, kernel: Optional[int] = None, fuse: Optional[bool] = None,
-                 lanes: Optional[int] = None):
+                 lanes: Optional[int] = None, ptsort: Optional[int] = None):
         self.params = params
         self.path_ = path
         self.ran_gen = ran_gen if ran_gen is not None else Random(params.randomSeed)
@@ -101,6 +101,8 @@ class HBT_correlation:
             _check(h, self._L.hbt_set_option(h, 3, int(fuse)))
         if lanes is not None:  # HBT_OPT_LANES: compute streams that take production batches in turn
             _check(h, self._L.hbt_set_option(h, 4, int(lanes)))
+        if ptsort is not None:  # HBT_OPT_PTSORT: per-event pT-sorted copy for the mixed-event loops (0 never, 1 auto, 2 always)
+            _check(h, self._L.hbt_set_option(h, 5, int(ptsort)))
         self.psi_ref = 0.0
         self.psi_refs: List[float] = []
         self.particle_list: Optional[Batch] = None

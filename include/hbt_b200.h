@@ -212,11 +212,18 @@ int hbt_get_timers(hbt_ctx *ctx, double *same_ms, double *mixed_ms, uint64_t *sa
  *   under the tail of batch k (batches commute: every accumulation is an atomic add into the
  *   context's histograms); 1 = one stream.  Instrumented runs, the literal kernels and batches
  *   near the pair cap always use one stream.  Environment: HBT_B200_LANES.  hbt_get_timers counts
- *   the time during which at least one pair launch was running (overlaps once). */
+ *   the time during which at least one pair launch was running (overlaps once).
+ * HBT_OPT_PTSORT: the production mixed-event loops can read a copy of the batch in which every event
+ *   is sorted by pT (one radix sort per batch; pT is invariant under the partner rotation).  Since
+ *   |q_out| >= |pT_i - pT_j|, a work unit then only visits the stretch of its list-2 tile whose pT
+ *   lies within the q_out window of its list-1 particles (~40 % fewer pairs to pre-screen on the
+ *   benchmark sample).  1 (default) = sort batches with at least 5e8 mixed-event pairs, 2 = always,
+ *   0 = never.  Results do not depend on it.  Environment: HBT_B200_PTSORT. */
 #define HBT_OPT_STAGE_COUNTERS 1
 #define HBT_OPT_KERNEL 2
 #define HBT_OPT_FUSE 3
 #define HBT_OPT_LANES 4
+#define HBT_OPT_PTSORT 5
 int hbt_set_option(hbt_ctx *ctx, int32_t option, int32_t value);
 
 /* Device-side stopwatch on the context's compute stream (CUDA events): everything the

@@ -201,6 +201,40 @@ def test_batches_in_flight_on_two_lanes(same_only):
     h.close()
 
 
+@pytest.mark.parametrize("case", ["c3", "c4_az", "ragged", "real_mixed", "outliers", "kt_from_0"])
+def test_mixed_loops_on_the_pt_sorted_copy(case):
+    """HBT_OPT_PTSORT: the production mixed-event loops read a copy in which every event is sorted by
+    pT and skip the list-2 particles whose pT is farther than the q_out window from the sub-tile's pT
+    range (|q_out| >= |pT_i - pT_j|).  Forced on (2: the default sorts only batches with >= 5e8
+    mixed-event pairs) and off (0), the accumulators are the oracle's."""
+    rng = np.random.default_rng(11)
+    if case == "real_mixed":
+        P, batches, ref, _ = load_golden("unit_iss_gz_realmixed")
+    else:
+        P = {"c3": C3.with_(qnpts=21), "c4_az": C4.with_(qnpts=11, n_KT=4, n_Kphi=4), "ragged": C3.with_(qnpts=21),
+             "outliers": HBTParams(qnpts=21), "kt_from_0": HBTParams(qnpts=21, KT_min=0.0, KT_max=1.0, n_KT=5)}[case]
+        batches = synth.make_batches(20260040, 2, 6, multiplicity=700)
+        if case == "ragged":  # events of very different sizes, an empty one, a single particle
+            for b in batches:
+                b.same[1] = b.same[1][:0]
+                b.same[2] = b.same[2][:1]
+                b.same[3] = b.same[3][:137]
+        if case == "outliers":
+            for b in batches:
+                for ev in b.same:
+                    k = rng.choice(len(ev), size=5, replace=False)
+                    ev[k, 0:3] *= 300.0
+                    ev[:, 3] = np.sqrt(0.138 ** 2 + (ev[:, 0:3] ** 2).sum(axis=1))
+        ref = run_oracle(P, batches)
+    for ptsort in (2, 0):
+        h = HBT_correlation(P, ptsort=ptsort)
+        for b in batches:
+            h.calculate_HBT_correlation_function(b)
+        hbtio.compare(ref, h.accumulators(), rtol=RTOL, check_stage="cheap")
+        assert h._L.hbt_set_option(h._h, 5, 3) == -1
+        h.close()
+
+
 def _craft_edge_pairs(P, rng_plan, rng, n, which):
     """Two events of n pi+ such that the mixed-event pair (event 0 particle i, event 1 particle i
     rotated by the first partner angle of event 0) has q_out (which=0) or q_long (which=1) at a
