@@ -140,7 +140,7 @@ def reference_arm(a, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------
@@ -202,8 +202,27 @@ def algorithmic_ops(stage, boost=True, az=False):
     return same, mixed
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    global _REAL_STDOUT
     a = parse()
+    # libraries print to stdout too (NCCL's version banner under NCCL_DEBUG=VERSION/WARN): everything but the
+    # JSON line goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -414,7 +433,7 @@ def main():
             "pairs_per_step": world * pairs_step_rank, "kernel": os.environ.get("HBT_B200_KERNEL", "default"),
             "deferred_pairs": eng.deferred_pairs(),
         }
-        print(json.dumps(out))
+        emit(out)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

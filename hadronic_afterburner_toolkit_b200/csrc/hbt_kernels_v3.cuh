@@ -114,6 +114,12 @@ __device__ __forceinline__ double v3_rsqrt(double x) {
     return fma(r0 * e, fma(e, 0.375, 0.5), r0);
 }
 
+__device__ __forceinline__ float v3_rsqrt_f32(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // cos(x) with a 3-term Cody-Waite reduction by pi/2 and one degree-7 polynomial in r^2 whose
 // coefficients (fdlibm's) come from a constant table indexed by the quadrant parity:
 // cos r = P0(r^2), sin r = r P1(r^2).  |err| <= 3e-16 for |x| < 1e5 (checked on the host
@@ -138,9 +144,12 @@ __device__ __forceinline__ double v3_cos(double x) {
     const int nq = __double2int_rn(nd);
     const double z = r * r;
     const double *t = v3_cos_tab[nq & 1];
-    double p = t[0];
-#pragma unroll
-    for (int k = 1; k < 8; k++) p = fma(p, z, t[k]);
+    // Estrin's scheme: three dependent FMAs after z instead of seven (the drain is bound by the
+    // latency of its dependent FP64 chains, not by their number)
+    const double z2 = z * z;
+    const double e01 = fma(t[0], z, t[1]), e23 = fma(t[2], z, t[3]), e45 = fma(t[4], z, t[5]), e67 = fma(t[6], z, t[7]);
+    const double z4 = z2 * z2;
+    const double p = fma(fma(e01, z2, e23), z4, fma(e45, z2, e67));
     const double v = p * ((nq & 1) ? r : 1.0);
     return ((nq + 1) & 2) ? -v : v;
 }
@@ -259,7 +268,11 @@ __device__ __forceinline__ int v3_fast_bins_all(const HbtGrid &g, const V2Const 
     const double d = fma(qx, sx, qy * sy);     // 2 K_perp q_out
     const double e = fma(qy, sx, -(qx * sy));  // 2 K_perp q_side
     const double r = v3_rsqrt(k2);             // 1 / (2 K_perp)
-    double qo = d * r, qs = e * r, ql;
+    // sorted lists: the pair may be stored the other way round than the reference takes it; q_out, q_side
+    // and q_long change sign with it (a sign folded into the factor: d * (-r) == -(d * r) exactly)
+    const double rs = (ORIENT && flip) ? -r : r;
+    const double qo = d * rs, qs = e * rs;
+    double ql;
     const double gb = fma(fabs(qx) + fabs(qy), c.gq, c.g0);
     const unsigned nq = static_cast<unsigned>(g.nq);
     bool ok_o, out_o, ok_s, out_s, ok_l, out_l;
@@ -269,10 +282,9 @@ __device__ __forceinline__ int v3_fast_bins_all(const HbtGrid &g, const V2Const 
         const double m2 = (sE - sz) * (sE + sz);  // 4 Mt^2 without cancellation
         const double r2 = v3_rsqrt(m2);
         const double t1 = sE * qz, t2 = sz * qE;
-        ql = (t1 - t2) * r2;
+        ql = (t1 - t2) * ((ORIENT && flip) ? -r2 : r2);
         const double ch = sE * r2;  // cosh of the pair rapidity amplifies the rounding of Mt
         const double gbl = fma((fabs(t1) + fabs(t2)) * r2 * fma(2.0 * ch, ch, 1.0), c.gl, c.g0);
-        if (ORIENT && flip) ql = -ql;
         v3_classify(c, nq, ql, gbl, o.il, ok_l, out_l);
         if (!(m2 > 0.0)) { ok_l = false; out_l = false; }  // undecided
     } else {
@@ -282,7 +294,6 @@ __device__ __forceinline__ int v3_fast_bins_all(const HbtGrid &g, const V2Const 
         ok_l = in_window(ql, g.q_lo, g.q_hi, MIXED) && (o.il < g.nq);
         out_l = !ok_l;
     }
-    if (ORIENT && flip) { qo = -qo; qs = -qs; }
     v3_classify(c, nq, qo, gb, o.io, ok_o, out_o);
     v3_classify(c, nq, qs, gb, o.is, ok_s, out_s);
     o.qx = qx; o.qy = qy; o.qz = qz; o.qE = qE; o.qo = qo; o.qs = qs; o.ql = ql;
@@ -296,7 +307,8 @@ __device__ __forceinline__ int v3_fast_bins_all(const HbtGrid &g, const V2Const 
 // bisection on the host)
 __device__ __forceinline__ int v3_kt_bin(const HbtGrid &g, const V2Const &c, double k2) {
     const float k2f = static_cast<float>(k2);
-    const float kp = 0.5f * k2f * rsqrtf(k2f);
+    // (one MUFU: rsqrtf() adds denormal scaling; an estimate only, k2 below 1e-30 lands in bin 0 either way)
+    const float kp = 0.5f * k2f * v3_rsqrt_f32(fmaxf(k2f, 1e-30f));
     int iK = static_cast<int>((kp - c.kt_min_f) * c.inv_dkt_f);
     iK = max(0, min(iK, g.nKT - 1));
     if (iK > 0 && k2 < c.kt4[iK]) iK--;
@@ -319,12 +331,6 @@ __device__ __forceinline__ int v3_kt_bin(const HbtGrid &g, const V2Const &c, dou
 // than its band from the K_T cut and from both edges of its K_T bin.  Otherwise (~1e-3 of the
 // survivors) the FP64 path below decides, so every bin index still equals the reference's.
 // Returns 1 (accepted: slab and bin set), 0 (certainly outside the window) or -1 (undecided).
-__device__ __forceinline__ float v3_rsqrt_f32(float x) {
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
 // floor(u) and the distance to the nearest integer for |u| < 2^22 (u + 1.5*2^23 holds rint(u) in
 // its mantissa); beyond that the band (which grows with |u|) exceeds any distance this returns
 __device__ __forceinline__ void v3_classify_f32(float u, float gb, unsigned nq, int &i, bool &ok, bool &out) {
