@@ -396,8 +396,9 @@ def main():
                       "instrumented, untimed pass over the same input) / CUDA-event time of the production pair kernels "
                       "(incl. the same-event sort + cull kernels) on the launching stream",
         "note": "the bound is the FP64 pipe (SURVEY.md 8d), not HBM or tensor cores; the production prefilter runs in packed "
-                "FP32, so the FP64 pipe itself is ~27 % busy (ncu, fused kernel; issue slots 66 %) while the algorithmic-ops fraction is "
-                "what is reported; same-event units are bounded by their 5 spread-address REDs per accepted pair (DESIGN.md 5)",
+                "FP32 and mixed-event survivors are binned in FP32 wherever a rigorous error band allows, so the FP64 pipe itself is "
+                "~19 % busy (ncu, fused kernel; issue slots 65 %) while the algorithmic-ops fraction is what is reported; same-event "
+                "units are bounded by their 5 spread-address REDs per accepted pair (DESIGN.md 5)",
         "kernels": ({
             # one launch per group works through the same-event and the mixed-event units interleaved
             "hbt_pairs_v3_fused": {"ms_per_launch": 1e3 * (ks + km) / max(1, tm1["same_launches"] - tm0["same_launches"]),

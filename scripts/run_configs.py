@@ -107,14 +107,16 @@ def main():
     ap.add_argument("--c4-events", type=int, default=500)
     ap.add_argument("--c4-qnpts", type=int, default=31)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.json"))
+    ap.add_argument("--no-reference", action="store_true",
+                    help="GPU timings only (C2-C4): no reference processes, no parity columns")
     a = ap.parse_args()
     want = a.configs.split(",")
     rows = []
     tmp = tempfile.TemporaryDirectory()
-    assert O.have_reference(), "oracle/_ref missing"
+    assert a.no_reference or O.have_reference(), "oracle/_ref missing"
 
     c5_handle = None
-    if "C5" in want:  # one full-size group on the reference, overlapping everything else
+    if "C5" in want and not a.no_reference:  # one full-size group on the reference, overlapping everything else
         b0 = synth.make_batches(20260005, 1, 100, PION_MASS)
         td = os.path.join(tmp.name, "c5ref"); os.makedirs(td)
         c5_handle = start_reference(C5, b0, td, nproc=1)
@@ -139,11 +141,15 @@ def main():
             continue
         batches = synth.make_batches(20260000 + int(name[1]), 100, 10, PION_MASS)
         td = os.path.join(tmp.name, name); os.makedirs(td)
-        hd = start_reference(P, batches, td, same_only=not mixed, nproc=CORES - (1 if c5_handle else 0))
+        desc = "1000 ev x 1500 pi+, oversampling 10, 41^3, 4 K_T bins, same" + ("+mixed" if mixed else " only")
+        # the GPU run first: the reference's processes would take the cores away from the submitting thread
         acc, res = run_gpu(P, batches, do_mixed=mixed)
+        if a.no_reference:
+            rows.append(report(name, desc, res))
+            continue
+        hd = start_reference(P, batches, td, same_only=not mixed, nproc=CORES - (1 if c5_handle else 0))
         ref, wall, cpu, nproc = collect_reference(hd)
-        rows.append(report(name, "1000 ev x 1500 pi+, oversampling 10, 41^3, 4 K_T bins, same" + ("+mixed" if mixed else " only"),
-                           res, ref, acc, wall, cpu, nproc, res["pairs_same"] + res["pairs_mixed"]))
+        rows.append(report(name, desc, res, ref, acc, wall, cpu, nproc, res["pairs_same"] + res["pairs_mixed"]))
 
     if "C4" in want:
         for sp, mass, mon in (("pi+", PION_MASS, 211), ("K+", KAON_MASS, 321)):
@@ -151,13 +157,16 @@ def main():
             ng = a.c4_events // 50
             batches = synth.make_batches(20260004 + mon, ng, 50, mass)
             td = os.path.join(tmp.name, "C4" + sp); os.makedirs(td)
-            hd = start_reference(P, batches, td, nproc=CORES - (1 if c5_handle else 0))
+            desc = f"{a.c4_events} ev x 1500 {sp}, oversampling 50, 8 K_T x 8 K_phi bins, {a.c4_qnpts}^3, same+mixed"
             acc, res = run_gpu(P, batches)
+            if a.no_reference:
+                rows.append(report("C4:" + sp, desc, res))
+                continue
+            hd = start_reference(P, batches, td, nproc=CORES - (1 if c5_handle else 0))
             ref, wall, cpu, nproc = collect_reference(hd)
-            rows.append(report("C4:" + sp, f"{a.c4_events} ev x 1500 {sp}, oversampling 50, 8 K_T x 8 K_phi bins, {a.c4_qnpts}^3, same+mixed",
-                               res, ref, acc, wall, cpu, nproc, res["pairs_same"] + res["pairs_mixed"]))
+            rows.append(report("C4:" + sp, desc, res, ref, acc, wall, cpu, nproc, res["pairs_same"] + res["pairs_mixed"]))
 
-    if "C5" in want:
+    if "C5" in want and not a.no_reference:
         # the full run: groups generated on the fly (1.9 GB would not be kept at once)
         h = HBT_correlation(C5)
         t0 = time.perf_counter(); tgen = 0.0
