@@ -816,7 +816,7 @@ int64_t resolve_row(const hbt_ctx *ctx, const PhaseInput &in, int K, int64_t row
 
 int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, size_t nseg, long long nblocks,
                  unsigned long long npairs) {
-    const int ns = ctx->grid.nslab, nch = n_channels(ctx);
+    const int nch = n_channels(ctx);
     // exact counters before the phase
     int rc = hbt_synchronize(ctx);
     if (rc) return rc;
@@ -954,8 +954,8 @@ int check_cap(hbt_ctx *ctx, const uint64_t *num, const uint64_t *den, const uint
     for (int k = 0; k < ctx->grid.nslab; k++)
         if ((num && num[k] > lim) || (den && den[k] > lim))
             return fail(ctx, HBT_ERR_CAP,
-                        "needed_number_of_pairs=%llu was exceeded in slab %d: the ordered pair cap is not "
-                        "implemented on the device path; raise needed_number_of_pairs",
+                        "needed_number_of_pairs=%llu was exceeded in slab %d (internal error: the ordered pair cap "
+                        "should have closed the slab at needed+1 pairs)",
                         static_cast<unsigned long long>(ctx->grid.needed), k);
     if (ctx->grid.qinv)
         for (int k = 0; k < ctx->grid.nKT; k++)
