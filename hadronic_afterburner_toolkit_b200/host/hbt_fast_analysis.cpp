@@ -11,9 +11,12 @@
 //
 // Same command line as the reference (run in a directory with parameters.dat and results/;
 // name=value arguments override the file), same results/HBT_correlation_function_*.dat.
+// read_in_real_mixed_events = 1 reads the partner events from the second file of the mode
+// (results/particle_samples_mixed_event.gz, particle_list_mixed_event.dat / .bin), one batch per
+// batch of the main file, as Analysis::HBTAnalysis does.
 // It does not link any reference code.  Switches it cannot honour (other read_in_mode values,
-// real mixed events, resonance feed-down, species groups) are refused with a message: use the
-// drop-in binary (hadronic_afterburner_tools_b200.e) for those.
+// resonance feed-down, species groups) are refused with a message: use the drop-in binary
+// (hadronic_afterburner_tools_b200.e) for those.
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -96,7 +99,7 @@ int main(int argc, char *argv[]) {
         die("only read_in_mode = 10 (gzipped iSS samples), 2 (gzipped UrQMD text) and 21 (UrQMD binary) are read here");
     // (modes 2 and 21 do not force these off as mode 10 does, src/particleSamples.cpp:409-412)
     if (read_in_mode != 10 && P.get("resonance_weak_feed_down_flag", 0) == 1) die("resonance_weak_feed_down_flag = 1 is not supported here");
-    if (P.get("read_in_real_mixed_events", 0) == 1) die("read_in_real_mixed_events = 1 is not supported here");
+    const bool real_mixed = P.get("read_in_real_mixed_events", 0) == 1;
     if (P.get("resonance_feed_down_flag", 0) == 1) die("resonance_feed_down_flag = 1 is not supported here");
     if (P.get("readRapidityShiftFromFile", 0) == 1) die("readRapidityShiftFromFile = 1 is not supported here");
 
@@ -125,9 +128,17 @@ int main(int argc, char *argv[]) {
     if (hbt_reader_open(file.c_str(), read_in_mode, static_cast<int>(P.get("particle_monval")), static_cast<int64_t>(P.get("event_buffer_size")),
                         P.get("rapidity_shift", 0), nullptr, &rd) != HBT_OK)
         die("cannot open " + file + " for particle_monval " + std::to_string(static_cast<int>(P.get("particle_monval"))));
+    hbt_reader *rd2 = nullptr;  // the mixed-event file (src/particleSamples.cpp:133-149, :527-535)
+    if (real_mixed) {
+        const std::string file2 = path + (read_in_mode == 10 ? "/particle_samples_mixed_event.gz"
+                                          : read_in_mode == 2 ? "/particle_list_mixed_event.dat" : "/particle_list_mixed_event.bin");
+        if (hbt_reader_open(file2.c_str(), read_in_mode, static_cast<int>(P.get("particle_monval")),
+                            static_cast<int64_t>(P.get("event_buffer_size")), P.get("rapidity_shift", 0), nullptr, &rd2) != HBT_OK)
+            die("cannot open " + file2);
+    }
 
-    std::vector<double> cut;
-    std::vector<int64_t> off;
+    std::vector<double> cut, cut2;
+    std::vector<int64_t> off, off2;
     std::vector<int32_t> ids;
     std::vector<double> cs;
     long long n_batches = 0, n_events = 0;
@@ -150,19 +161,39 @@ int main(int argc, char *argv[]) {
             const int64_t kept = hbt_gather_rapidity(&hp, p + 8 * o[e], o[e + 1] - o[e], cut.data() + 8 * off.back());
             off.push_back(off.back() + kept);
         }
-        // the draws of the batch in the reference's order (:202-217, :493-497)
-        const int nmix = nev / 2 + 1;
+        // the partner events: the batch itself, or the next batch of the mixed-event file (same gather)
+        int nev2 = nev;
+        const int64_t *o2 = off.data();
+        if (rd2) {
+            const double *p2 = nullptr;
+            const int64_t *r2 = nullptr;
+            nev2 = hbt_reader_next(rd2, &p2, &r2, nullptr);
+            if (nev2 < 0) die(std::string("reader (mixed events): ") + hbt_reader_error(rd2));
+            off2.assign(1, 0);
+            if (nev2 > 0) {
+                cut2.resize(static_cast<size_t>(r2[nev2]) * 8 + 8);
+                for (int e = 0; e < nev2; e++) {
+                    const int64_t kept = hbt_gather_rapidity(&hp, p2 + 8 * r2[e], r2[e + 1] - r2[e], cut2.data() + 8 * off2.back());
+                    off2.push_back(off2.back() + kept);
+                }
+            }
+            o2 = off2.data();
+        }
+        // the draws of the batch in the reference's order (:202-217, :493-497); a batch without partner events
+        // has no mixed-event loop (the reference would take "% 0" there)
+        const int nmix = nev2 > 0 ? nev2 / 2 + 1 : 0;
         ids.resize(static_cast<size_t>(nev) * nmix);
         cs.resize(static_cast<size_t>(nev) * nmix * 2);
-        hbt_rng_mixed_plan(rng, nev, nev, ids.data(), cs.data(), nullptr);
-        check(ctx, hbt_accumulate_batch(ctx, cut.data(), off.data(), nev, nullptr, nullptr, 0, ids.data(), cs.data(), nmix, psi_ref, 1, 1),
+        if (nmix) hbt_rng_mixed_plan(rng, nev, nev2, ids.data(), cs.data(), nullptr);
+        check(ctx, hbt_accumulate_batch(ctx, cut.data(), off.data(), nev, rd2 ? cut2.data() : nullptr, rd2 ? off2.data() : nullptr,
+                                        rd2 ? nev2 : 0, ids.data(), cs.data(), nmix, psi_ref, 1, nmix > 0 ? 1 : 0),
               "hbt_accumulate_batch");
         const unsigned long long n1 = static_cast<unsigned long long>(off.back());
         pairs_same += n1 > 1 ? n1 * (n1 - 1) / 2 : 0;
         for (int e = 0; e < nev; e++)
             for (int c = 0; c < nmix; c++) {
                 const int id = ids[static_cast<size_t>(e) * nmix + c];
-                pairs_mixed += static_cast<unsigned long long>(off[e + 1] - off[e]) * (off[id + 1] - off[id]);
+                pairs_mixed += static_cast<unsigned long long>(off[e + 1] - off[e]) * (o2[id + 1] - o2[id]);
             }
         n_batches++;
         n_events += nev;
@@ -179,6 +210,7 @@ int main(int argc, char *argv[]) {
                 n_batches, n_events, pairs_same, pairs_mixed, t_loop, t_wait, hbt_reader_bytes(rd) / 1e6,
                 (same_ms + mixed_ms) * 1e-3, seconds_since(t_start) - t_loop);
     hbt_reader_close(rd);
+    if (rd2) hbt_reader_close(rd2);
     hbt_rng_destroy(rng);
     hbt_destroy(ctx);
     return 0;

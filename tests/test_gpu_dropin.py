@@ -23,11 +23,13 @@ pytestmark = [pytest.mark.gpu,
                                  reason="compiled reference / drop-in binary not present")]
 
 
-def run_binary(exe, workdir, params_text, gz_src, env=None, input_name="particle_samples.gz"):
+def run_binary(exe, workdir, params_text, gz_src, env=None, input_name="particle_samples.gz", extra_files=None):
     os.makedirs(os.path.join(workdir, "EOS"))
     os.makedirs(os.path.join(workdir, "results"))
     shutil.copy(PDG, os.path.join(workdir, "EOS", "pdg.dat"))
     shutil.copy(gz_src, os.path.join(workdir, "results", input_name))
+    for name, src in (extra_files or {}).items():
+        shutil.copy(src, os.path.join(workdir, "results", name))
     with open(os.path.join(workdir, "parameters.dat"), "w") as f:
         f.write(params_text)
     e = dict(os.environ)
@@ -85,10 +87,31 @@ def test_fast_driver_refuses_what_it_cannot_read(tmp_path):
     batches = synth.make_batches(44, 1, 2, multiplicity=50)
     gz = str(tmp_path / "input.gz")
     synth.write_iss_gz(gz, batches)
-    for key, value in (("read_in_mode", 1), ("read_in_real_mixed_events", 1), ("resonance_feed_down_flag", 1)):
+    for key, value in (("read_in_mode", 1), ("resonance_feed_down_flag", 1), ("particle_monval", 9999),
+                       ("read_in_real_mixed_events", 1)):  # (the last: no mixed-event file in the directory)
         text = P.parameters_dat(event_buffer_size=100, **{key: value})
         with pytest.raises(AssertionError, match="hbt_fast_analysis"):
             run_binary(FAST_EXE, str(tmp_path / key), text, gz)
+
+
+def test_real_mixed_events_same_files(tmp_path):
+    """read_in_real_mixed_events = 1: the partner events come from results/particle_samples_mixed_event.gz, one
+    batch per batch of the main file (src/Analysis.cpp:824-825); batches of different event counts in the two
+    files, so the draws use nev_mixed != nev.  Reference binary, drop-in binary and fast driver: same files."""
+    P = C3.with_(qnpts=15)
+    main = synth.make_batches(51, 3, 4, multiplicity=300)
+    mixed = synth.make_batches(52, 3, 6, multiplicity=200)   # 6 events of 200 per 1200-particle batch
+    gz, gz2 = str(tmp_path / "input.gz"), str(tmp_path / "mixed.gz")
+    synth.write_iss_gz(gz, main)
+    synth.write_iss_gz(gz2, mixed)
+    text = P.parameters_dat(event_buffer_size=1200, read_in_real_mixed_events=1)
+    extra = {"particle_samples_mixed_event.gz": gz2}
+    want, _ = run_binary(REF_EXE, str(tmp_path / "ref"), text, gz, extra_files=extra)
+    got, _ = run_binary(OUR_EXE, str(tmp_path / "ours"), text, gz, env={"HBT_B200_DEVICES": "1"}, extra_files=extra)
+    same_text(want, got)
+    fast, out = run_binary(FAST_EXE, str(tmp_path / "fast"), text, gz, extra_files=extra)
+    assert "hbt_fast_analysis: 3 batches, 12 events" in out
+    same_text(want, fast)
 
 
 @pytest.mark.parametrize("mode,input_name", [(2, "particle_list.dat"), (21, "particle_list.bin")])
