@@ -191,8 +191,9 @@ int hbt_read_qinv(hbt_ctx *ctx, uint64_t *count, double *sum_qinv, double *sum_c
  * accepted}: the n_A..n_E of the roofline formula.  [1..3] need
  * HBT_OPT_STAGE_COUNTERS (see hbt_set_option). */
 int hbt_get_stage_counters(hbt_ctx *ctx, uint64_t same[6], uint64_t mixed[6]);
-/* device time of the pair kernels so far, measured with CUDA events on the context's
- * stream, and the number of kernel launches */
+/* device time of the pair kernels so far (CUDA events on the launching streams; launches of the two
+ * compute lanes that overlap are counted once: the time during which at least one pair launch was
+ * running, sort / cull helpers included), and the number of pair-kernel launches */
 int hbt_get_timers(hbt_ctx *ctx, double *same_ms, double *mixed_ms, uint64_t *same_launches,
                    uint64_t *mixed_launches);
 /* Engine options (set between batches; the call synchronises the context).
