@@ -327,7 +327,9 @@ int ensure_units(hbt_ctx *ctx, Lane &L, long long all_units) {
 
 // Morton-sort the same-event list on the lane's stream (keys, radix sort of (key, index),
 // gather, tile boxes): ~4 small kernels, microseconds against the pair kernel's milliseconds
-int prepare_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n) {
+// host_range: max(|px|, |py|) of the list when the caller has the particles on the host (saves the range
+// kernel and its memset), negative otherwise
+int prepare_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, float host_range = -1.f) {
     if (static_cast<size_t>(n) > L.sort_cap) {
         CU(ctx, cudaStreamSynchronize(L.stream));  // the previous launch of this lane may still read the buffers
         for (int k = 0; k < 2; k++) { cudaFree(L.sort_keys[k]); cudaFree(L.sort_idx[k]); }
@@ -351,15 +353,21 @@ int prepare_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n) {
     }
     const int th = 256;
     const unsigned nb = static_cast<unsigned>((n + th - 1) / th);
-    CU(ctx, cudaMemsetAsync(L.sort_rmax, 0, 4, L.stream));
-    hbt_sort_range<<<std::min(nb, 1184u), th, 0, L.stream>>>(d_p, n, L.sort_rmax);
-    hbt_sort_keys<<<nb, th, 0, L.stream>>>(d_p, n, L.sort_rmax, L.sort_keys[0], L.sort_idx[0]);
+    if (host_range >= 0.f) {
+        hbt_sort_keys<<<nb, th, 0, L.stream>>>(d_p, n, nullptr, host_range, L.sort_keys[0], L.sort_idx[0]);
+    } else {
+        CU(ctx, cudaMemsetAsync(L.sort_rmax, 0, 4, L.stream));
+        hbt_sort_range<<<std::min(nb, 1184u), th, 0, L.stream>>>(d_p, n, L.sort_rmax);
+        hbt_sort_keys<<<nb, th, 0, L.stream>>>(d_p, n, L.sort_rmax, 0.f, L.sort_keys[0], L.sort_idx[0]);
+        ctx->kernel_launches++;
+    }
+    // the top 24 bits of the Morton key (4096 x 4096 cells) order the tiles as well as all 32: one radix pass fewer
     size_t bytes = L.sort_tmp_bytes;
     CU(ctx, cub::DeviceRadixSort::SortPairs(L.sort_tmp, bytes, L.sort_keys[0], L.sort_keys[1], L.sort_idx[0],
-                                            L.sort_idx[1], static_cast<int>(n), 0, 32, L.stream));
+                                            L.sort_idx[1], static_cast<int>(n), 8, 32, L.stream));
     hbt_sort_gather<<<static_cast<unsigned>((4 * n + th - 1) / th), th, 0, L.stream>>>(d_p, L.sort_idx[1], n, L.sort_p);
     hbt_sort_bbox<<<static_cast<unsigned>((n + HBT_BBOX_TILE - 1) / HBT_BBOX_TILE), HBT_BBOX_TILE, 0, L.stream>>>(L.sort_p, n, L.sort_bbox);
-    ctx->kernel_launches += 5;  // range, keys, gather, boxes + the radix sort (counted once)
+    ctx->kernel_launches += 4;  // keys, gather, boxes + the radix sort (counted once); the range kernel above
     CU(ctx, cudaGetLastError());
     return HBT_OK;
 }
@@ -407,7 +415,7 @@ int prepare_mixed_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, co
     while ((1ll << ev_bits) < nev) ev_bits++;
     size_t bytes = L.mix_tmp_bytes;
     CU(ctx, cub::DeviceRadixSort::SortPairs(L.mix_tmp, bytes, L.mix_keys[0], L.mix_keys[1], L.mix_idx[0], L.mix_idx[1],
-                                            static_cast<int>(n), 0, 32 + ev_bits, L.stream));
+                                            static_cast<int>(n), 8, 32 + ev_bits, L.stream));  // (pT^2 to 2^-15: the order need not be exact)
     hbt_sort_gather<<<static_cast<unsigned>((4 * n + th - 1) / th), th, 0, L.stream>>>(d_p, L.mix_idx[1], n, L.mix_p);
     ctx->kernel_launches += 3;  // keys, gather + the radix sort (counted once)
     CU(ctx, cudaGetLastError());
@@ -433,7 +441,8 @@ const unsigned char *closed_ptr(const hbt_ctx *ctx) { return ctx->any_closed ? c
 // mode 0: the production kernels (v2 unless the grid needs v1); mode 1 / 2: the two ordered-cap
 // passes, always on the literal v1 kernels
 // `L`: the lane the launch goes to (the ordered-cap passes and the literal kernels always get lane 0)
-int launch_same(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, double psi_ref, int mode = 0, const HbtCap *capin = nullptr) {
+int launch_same(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, double psi_ref, int mode = 0, const HbtCap *capin = nullptr,
+                float host_range = -1.f) {
     if (n < 2) return HBT_OK;
     ctx->reduced = false;
     cudaEvent_t e0, e1;
@@ -470,7 +479,7 @@ int launch_same(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, double psi_
             return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld work units", all_units);
         if (sorted) {
             // production: Morton-sorted copy + tile boxes, units that can hold an accepted pair
-            rc = prepare_sorted(ctx, L, d_p, n);
+            rc = prepare_sorted(ctx, L, d_p, n, host_range);
             if (rc) return rc;
             rc = ensure_units(ctx, L, all_units);
             if (rc) return rc;
@@ -597,7 +606,7 @@ int launch_mixed(hbt_ctx *ctx, Lane &L, const double *d_p1, const double *d_p2, 
 // production launch of a whole batch: sort + cull of the same-event list, then one kernel that
 // works through the same-event and the mixed-event units interleaved (hbt_pairs_v3_fused)
 int launch_fused(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg,
-                 size_t nseg, long long nblocks, unsigned long long npairs_mixed, double psi_ref) {
+                 size_t nseg, long long nblocks, unsigned long long npairs_mixed, double psi_ref, float host_range = -1.f) {
     ctx->reduced = false;
     cudaEvent_t e0, e1;
     int rc = get_event_pair(ctx, &e0, &e1);
@@ -610,7 +619,7 @@ int launch_fused(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, const doub
     const long long all_units = hbt_v3_same_units(n, ctx->row_item0);
     if (all_units > 0x7fffffffLL || n > HBT_V3_MAX_SORTED || nblocks + all_units > 0x7fffffffLL)
         return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld work units", all_units + nblocks);
-    rc = prepare_sorted(ctx, L, d_p, n);
+    rc = prepare_sorted(ctx, L, d_p, n, host_range);
     if (rc) return rc;
     rc = ensure_units(ctx, L, all_units);
     if (rc) return rc;
@@ -1347,6 +1356,17 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
         if (nseg) CU(ctx, cudaMemcpyAsync(s->d_seg, s->h_seg, nseg * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, ctx->copy));
     }
     CU(ctx, cudaEventRecord(s->uploaded, ctx->copy));
+    // max(|px|, |py|) of list 1 for the Morton keys of the same-event sort, from the staged copy (as
+    // hbt_sort_range computes it: finite values only)
+    float host_range = -1.f;
+    if (do_same && !ctx->stats && ctx->kernel_version != 1 && n1 > 1) {
+        float m = 0.f;
+        for (int64_t i = 0; i < n1; i++) {
+            const float a = std::max(std::fabs(static_cast<float>(s->h_p[8 * i])), std::fabs(static_cast<float>(s->h_p[8 * i + 1])));
+            if (a == a && a < 3.0e38f) m = std::max(m, a);
+        }
+        host_range = m;
+    }
     const unsigned long long sp_all = n1 > 1 ? static_cast<unsigned long long>(n1) * (n1 - 1) / 2 : 0;
     const bool near_cap = (do_same && cap_may_engage(ctx, false, sp_all)) || (do_mixed && cap_may_engage(ctx, true, npairs));
     Lane &L = pick_lane(ctx, near_cap);
@@ -1373,7 +1393,7 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
             rc = prepare_mixed_sorted(ctx, L, s->d_p, n1 + n2, &d_mix);
             if (rc) return rc;
         }
-        rc = launch_fused(ctx, L, s->d_p, n1, d_mix, d_mix, s->d_seg, nseg, nblocks, npairs, psi_ref);
+        rc = launch_fused(ctx, L, s->d_p, n1, d_mix, d_mix, s->d_seg, nseg, nblocks, npairs, psi_ref, host_range);
         if (rc) return rc;
         do_same = do_mixed = 0;
     }
@@ -1381,7 +1401,8 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
     if (do_same) {
         const unsigned long long sp = sp_all;
         in.mixed = false;
-        rc = cap_may_engage(ctx, false, sp) ? capped_phase(ctx, in, nullptr, 0, 0, sp) : launch_same(ctx, L, s->d_p, n1, psi_ref);
+        rc = cap_may_engage(ctx, false, sp) ? capped_phase(ctx, in, nullptr, 0, 0, sp)
+                                            : launch_same(ctx, L, s->d_p, n1, psi_ref, 0, nullptr, host_range);
         if (rc) return rc;
     }
     if (do_mixed) {

@@ -40,11 +40,12 @@ __global__ void hbt_sort_range(const double *__restrict__ p, long long n, unsign
     if ((threadIdx.x & 31) == 0) atomicMax(rmax, __float_as_uint(m));
 }
 
-__global__ void hbt_sort_keys(const double *__restrict__ p, long long n, const unsigned *__restrict__ rmax,
+// rmax: device word written by hbt_sort_range, or null when the host already knows the range (r_host)
+__global__ void hbt_sort_keys(const double *__restrict__ p, long long n, const unsigned *__restrict__ rmax, float r_host,
                               unsigned *__restrict__ keys, unsigned *__restrict__ idx) {
     const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (i >= n) return;
-    const float R = fmaxf(__uint_as_float(*rmax), 1e-30f) * 1.0001f;
+    const float R = fmaxf(rmax ? __uint_as_float(*rmax) : r_host, 1e-30f) * 1.0001f;
     const float scale = 32767.5f / R;
     const double2 v = *reinterpret_cast<const double2 *>(p + 8 * i);
     const float fx = (static_cast<float>(v.x) + R) * scale, fy = (static_cast<float>(v.y) + R) * scale;
