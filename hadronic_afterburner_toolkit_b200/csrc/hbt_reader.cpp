@@ -1,7 +1,10 @@
 // Fast reader for the particle samples that feed the HBT path.
 //
 // Replaces, for read_in_mode = 10 ("particle_samples.gz": gzipped iSS text), 2 ("particle_list.dat":
-// gzipped UrQMD text) and 21 ("particle_list.bin": UrQMD binary), the chain
+// gzipped UrQMD text), 21 ("particle_list.bin": UrQMD binary), 0 ("OSCAR.DAT": OSCAR1997A text) and 1
+// ("particle_list.dat": UrQMD file-13 style text), the chain
+//   particleSamples::read_in_particle_samples_OSCAR          src/particleSamples.cpp:680-714 (+ header :198-202)
+//   particleSamples::read_in_particle_samples_UrQMD          src/particleSamples.cpp:838-908
 //   particleSamples::read_in_particle_samples_gzipped        src/particleSamples.cpp:1247-1286
 //   particleSamples::read_in_particle_samples_UrQMD_zipped   src/particleSamples.cpp:910-974
 //   particleSamples::read_in_particle_samples_UrQMD_binary   src/particleSamples.cpp:976-1059
@@ -171,7 +174,107 @@ struct hbt_reader {
     }
 
     std::unique_ptr<Batch> read_batch() {
-        return mode == 21 ? read_batch_urqmd_binary() : mode == 2 ? read_batch_urqmd_text() : read_batch_iss();
+        switch (mode) {
+            case 21: return read_batch_urqmd_binary();
+            case 2: return read_batch_urqmd_text();
+            case 1: return read_batch_urqmd_f13();
+            case 0: return read_batch_oscar();
+            default: return read_batch_iss();
+        }
+    }
+
+    // read_in_mode 0, src/particleSamples.cpp:689-712 (the three header lines of the file are skipped when it
+    // is opened, :198-202): "<event id> <n> ..." then n lines "<index> <monval> px py pz E mass x y z t"
+    std::unique_ptr<Batch> read_batch_oscar() {
+        std::unique_ptr<Batch> b(new Batch);
+        b->off.push_back(0);
+        const double ch = std::cosh(rap_shift), sh = std::sinh(rap_shift);
+        int64_t num_particles = 0;
+        while (num_particles < buffer_size) {
+            const char *lb, *le;
+            readline(&lb, &le);
+            if (hit_eof) break;  // inputfile.eof() after the header read (:694)
+            long long event_id = 0, n_particle = 0;
+            const char *q = parse_int(lb, le, &event_id);
+            parse_int(q, le, &n_particle);
+            for (long long ip = 0; ip < n_particle; ip++) {
+                if (!readline(&lb, &le) && hit_eof) {
+                    error = "OSCAR.DAT ends inside an event";
+                    return b;
+                }
+                long long idx = 0, mv = 0;
+                double px, py, pz, E, mass, x, y, z, t;
+                q = parse_int(lb, le, &idx);
+                q = parse_int(q, le, &mv);
+                q = parse_double(q, le, &px);
+                q = parse_double(q, le, &py);
+                q = parse_double(q, le, &pz);
+                q = parse_double(q, le, &E);
+                q = parse_double(q, le, &mass);
+                q = parse_double(q, le, &x);
+                q = parse_double(q, le, &y);
+                q = parse_double(q, le, &z);
+                q = parse_double(q, le, &t);
+                keep(*b, mv, ch, sh, t, x, y, z, E, px, py, pz);
+            }
+            num_particles += n_particle;
+            b->off.push_back(static_cast<int64_t>(b->p.size() / 8));
+        }
+        b->all_particles = num_particles;
+        return b;
+    }
+
+    // read_in_mode 1, src/particleSamples.cpp:849-906: 17 header lines, "<n> ...", one line that is skipped,
+    // then n lines "r0 rx ry rz p0 px py pz m ityp 2i3 chg lcl# ncl or t x y z E px py pz" (the last eight are
+    // the freeze-out coordinates and momenta that are used)
+    std::unique_ptr<Batch> read_batch_urqmd_f13() {
+        std::unique_ptr<Batch> b(new Batch);
+        b->off.push_back(0);
+        const double ch = std::cosh(rap_shift), sh = std::sinh(rap_shift);
+        int64_t num_particles = 0;
+        while (num_particles < buffer_size) {
+            const char *lb, *le;
+            readline(&lb, &le);
+            if (hit_eof) break;  // inputfile.eof() after the first header line (:851)
+            for (int i = 0; i < 16; i++) readline(&lb, &le);
+            readline(&lb, &le);
+            long long n_particle = 0;
+            parse_int(lb, le, &n_particle);
+            if (!readline(&lb, &le) && hit_eof && n_particle > 0) {
+                error = "particle_list.dat ends inside an event";
+                return b;
+            }
+            for (long long ip = 0; ip < n_particle; ip++) {
+                if (!readline(&lb, &le) && hit_eof) {
+                    error = "particle_list.dat ends inside an event";
+                    return b;
+                }
+                double d, mass, t, x, y, z, E, px, py, pz;
+                long long id = 0, iso3 = 0, charge = 0, proc = 0;
+                const char *q = lb;
+                for (int i = 0; i < 8; i++) q = parse_double(q, le, &d);
+                q = parse_double(q, le, &mass);
+                q = parse_int(q, le, &id);
+                q = parse_int(q, le, &iso3);
+                q = parse_int(q, le, &charge);
+                q = parse_double(q, le, &d);
+                q = parse_double(q, le, &d);
+                q = parse_int(q, le, &proc);
+                q = parse_double(q, le, &t);
+                q = parse_double(q, le, &x);
+                q = parse_double(q, le, &y);
+                q = parse_double(q, le, &z);
+                q = parse_double(q, le, &E);
+                q = parse_double(q, le, &px);
+                q = parse_double(q, le, &py);
+                q = parse_double(q, le, &pz);
+                keep(*b, urqmd_to_pdg(id, iso3), ch, sh, t, x, y, z, E, px, py, pz);
+            }
+            num_particles += n_particle;
+            b->off.push_back(static_cast<int64_t>(b->p.size() / 8));
+        }
+        b->all_particles = num_particles;
+        return b;
     }
 
     // read_in_mode 2, src/particleSamples.cpp:921-972: "<n>", one line that is skipped, then n lines
@@ -303,6 +406,10 @@ struct hbt_reader {
     }
 
     void run() {
+        if (mode == 0) {  // the file header of OSCAR1997A (src/particleSamples.cpp:198-202)
+            const char *lb, *le;
+            for (int i = 0; i < 3; i++) readline(&lb, &le);
+        }
         for (;;) {
             std::unique_ptr<Batch> b = read_batch();
             const bool last = b->off.size() == 1 || !error.empty();  // no event: end of the file
@@ -321,7 +428,7 @@ extern "C" int hbt_reader_open(const char *path, int32_t read_in_mode, int32_t p
                                double rap_shift, const hbt_params *rapidity_cut, hbt_reader **out) {
     if (!path || !out) return HBT_ERR_INVALID;
     *out = nullptr;
-    if (read_in_mode != 10 && read_in_mode != 2 && read_in_mode != 21) return HBT_ERR_INVALID;
+    if (read_in_mode != 10 && read_in_mode != 2 && read_in_mode != 21 && read_in_mode != 0 && read_in_mode != 1) return HBT_ERR_INVALID;
     // species groups (9999, 9998, ... : all charged, ...) need the particle table; single species only
     const int32_t a = particle_monval < 0 ? -particle_monval : particle_monval;
     if (a >= 9996 && a <= 99999 && (a <= 9999 || a == 99999)) return HBT_ERR_INVALID;

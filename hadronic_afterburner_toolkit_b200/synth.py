@@ -122,3 +122,34 @@ def write_urqmd_bin(path: str, records) -> None:
                 uid, iso3 = URQMD_IDS[pdg]
                 f.write(np.array([uid, iso3, _URQMD_CHARGE[pdg], 1, 6, 99], dtype=np.int32).tobytes())
                 f.write(np.array([mass, p[7], p[4], p[5], p[6], p[3], p[0], p[1], p[2]], dtype=np.float32).tobytes())
+
+
+def write_oscar(path: str, records) -> None:
+    """read_in_mode=0 text (``OSCAR.DAT``, OSCAR1997A final_id_p_x; ``src/particleSamples.cpp:680-714``): three
+    header lines, then per event ``<event id> <n> 0 0`` and n lines ``<index> <monval> px py pz E mass x y z t``."""
+    with open(path, "w") as f:
+        f.write("OSC1997A\nfinal_id_p_x\n 3DHydro       1.1  (197,    79)+(197,    79)  eqsp  0.1000E+03         1\n")
+        for iev, rows in enumerate(records):
+            f.write("%10d  %10d  %8d  %8d\n" % (iev + 1, len(rows), 0, 0))
+            for k, (pdg, mass, p) in enumerate(rows):
+                f.write("%10d  %10d  %.17g  %.17g  %.17g  %.17g  %.17g  %.17g  %.17g  %.17g  %.17g\n"
+                        % (k + 1, pdg if pdg else 113, p[0], p[1], p[2], p[3], mass, p[4], p[5], p[6], p[7]))
+
+
+def write_urqmd_f13(path: str, records) -> None:
+    """read_in_mode=1 text (UrQMD file-13 style ``particle_list.dat``, ``src/particleSamples.cpp:838-908``): per
+    event 17 header lines, ``<n> <time>``, one line the reader skips, then n lines ``r0 rx ry rz p0 px py pz m ityp
+    2i3 chg lcl# ncl or t x y z E px py pz`` of which the reader uses m, ityp, 2i3 and the last eight."""
+    with open(path, "w") as f:
+        for iev, rows in enumerate(records):
+            f.write("UQMD   version:       30400   1000  30400  output_file  13\n")
+            for k in range(15):
+                f.write("header line %d of event %d\n" % (k + 2, iev + 1))
+            f.write("pvec: r0 rx ry rz p0 px py pz m ityp 2i3 chg lcl# ncl or\n")
+            f.write("%12d %11d\n" % (len(rows), 8000))
+            f.write("      65       4      61       0     221      11       0       0\n")
+            for pdg, mass, p in rows:
+                uid, iso3 = URQMD_IDS[pdg]
+                f.write(" 0.8E+04 1.0 2.0 3.0 %.8E %.8E %.8E %.8E %.17g %d %d %d %d %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n"
+                        % (p[3], p[0], p[1], p[2], mass, uid, iso3, _URQMD_CHARGE[pdg], 6, 1, 99,
+                           p[7], p[4], p[5], p[6], p[3], p[0], p[1], p[2]))

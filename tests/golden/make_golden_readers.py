@@ -1,12 +1,15 @@
 #!/usr/bin/env python
-"""Golden vectors for the fast reader's UrQMD modes: synthetic `particle_list.dat` (read_in_mode 2,
-gzipped text) and `particle_list.bin` (read_in_mode 21) files are pushed through the UNMODIFIED
+"""Golden vectors for the fast reader's formats beyond the iSS one: synthetic `particle_list.dat` (read_in_mode 2,
+gzipped UrQMD text; read_in_mode 1, UrQMD file-13 style text), `particle_list.bin` (read_in_mode 21) and
+`OSCAR.DAT` (read_in_mode 0) files are pushed through the UNMODIFIED
 reference reader (oracle/_ref/ref_driver files: particleSamples + its filter, the loop of
 src/Analysis.cpp:817-835) and the filtered particle lists it produced are committed next to the
 inputs:
 
   tests/golden/urqmd_small.particle_list.dat      mode-2 input (gz)
   tests/golden/urqmd_small.particle_list.bin      mode-21 input
+  tests/golden/urqmd_small.f13.dat                mode-1 input
+  tests/golden/urqmd_small.OSCAR.DAT              mode-0 input
   tests/golden/urqmd_<mode>_<case>.particles.bin  HBTIN001 dumps of the reference reader
 
 Run here (needs /root/reference compiled into oracle/_ref):  python tests/golden/make_golden_readers.py
@@ -41,8 +44,14 @@ def main():
     ftxt, fbin = os.path.join(HERE, "urqmd_small.particle_list.dat"), os.path.join(HERE, "urqmd_small.particle_list.bin")
     synth.write_urqmd_gz(ftxt, records)
     synth.write_urqmd_bin(fbin, records)
+    ff13, fosc = os.path.join(HERE, "urqmd_small.f13.dat"), os.path.join(HERE, "urqmd_small.OSCAR.DAT")
+    # shorter inputs for the two plain-text formats (they are not compressed in the repository)
+    short = records[:5]
+    synth.write_urqmd_f13(ff13, short)
+    synth.write_oscar(fosc, short)
     meta = {}
-    for mode, src, name in ((2, ftxt, "particle_list.dat"), (21, fbin, "particle_list.bin")):
+    for mode, src, name in ((2, ftxt, "particle_list.dat"), (21, fbin, "particle_list.bin"), (1, ff13, "particle_list.dat"),
+                            (0, fosc, "OSCAR.DAT")):
         for case, (monval, buf, shift) in CASES.items():
             with tempfile.TemporaryDirectory() as td:
                 os.makedirs(os.path.join(td, "EOS"))

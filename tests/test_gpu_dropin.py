@@ -87,7 +87,7 @@ def test_fast_driver_refuses_what_it_cannot_read(tmp_path):
     batches = synth.make_batches(44, 1, 2, multiplicity=50)
     gz = str(tmp_path / "input.gz")
     synth.write_iss_gz(gz, batches)
-    for key, value in (("read_in_mode", 1), ("resonance_feed_down_flag", 1), ("particle_monval", 9999),
+    for key, value in (("read_in_mode", 3), ("resonance_feed_down_flag", 1), ("particle_monval", 9999),
                        ("read_in_real_mixed_events", 1)):  # (the last: no mixed-event file in the directory)
         text = P.parameters_dat(event_buffer_size=100, **{key: value})
         with pytest.raises(AssertionError, match="hbt_fast_analysis"):
@@ -114,19 +114,22 @@ def test_real_mixed_events_same_files(tmp_path):
     same_text(want, fast)
 
 
-@pytest.mark.parametrize("mode,input_name", [(2, "particle_list.dat"), (21, "particle_list.bin")])
-def test_urqmd_input_formats_same_files(mode, input_name, tmp_path):
+@pytest.mark.parametrize("mode,input_name,src_name", [(2, "particle_list.dat", "urqmd_small.particle_list.dat"),
+                                                      (21, "particle_list.bin", "urqmd_small.particle_list.bin"),
+                                                      (1, "particle_list.dat", "urqmd_small.f13.dat"),
+                                                      (0, "OSCAR.DAT", "urqmd_small.OSCAR.DAT")])
+def test_urqmd_input_formats_same_files(mode, input_name, src_name, tmp_path):
     """read_in_mode 2 (gzipped UrQMD text) and 21 (UrQMD binary): the reference binary, the drop-in
     binary (reference reader, GPU pair loops) and hbt_fast_analysis.e (our reader, no reference code)
     write the same files from the committed synthetic UrQMD-format inputs."""
-    src = os.path.join(ROOT, "tests", "golden", "urqmd_small." + input_name)
+    src = os.path.join(ROOT, "tests", "golden", src_name)
     P = HBTParams(qnpts=11, KT_min=0.0, KT_max=1.0, n_KT=3, HBTrap_min=-1.0, HBTrap_max=1.0)
     text = P.parameters_dat(read_in_mode=mode, event_buffer_size=400)
     want, _ = run_binary(REF_EXE, str(tmp_path / "ref"), text, src, input_name=input_name)
     got, _ = run_binary(OUR_EXE, str(tmp_path / "ours"), text, src, env={"HBT_B200_DEVICES": "1"}, input_name=input_name)
     same_text(want, got)
     fast, out = run_binary(FAST_EXE, str(tmp_path / "fast"), text, src, input_name=input_name)
-    assert "hbt_fast_analysis: 2 batches, 9 events" in out
+    assert ("hbt_fast_analysis: 2 batches, 9 events" if mode in (2, 21) else "hbt_fast_analysis: 1 batches, 5 events") in out
     same_text(want, fast)
     assert any(float(l.split()[3]) != 0.0 for fn in want for l in want[fn])  # the files hold pairs
 

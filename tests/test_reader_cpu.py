@@ -146,7 +146,7 @@ def test_errors(tmp_path):
     path = tmp_path / "p.gz"
     with gzip.open(path, "wt") as f:
         f.write("2\n211 0.138 1 0 0 0 1 0.1 0.1 0.1\n")  # the event announces 2 particles, holds 1
-    assert L.hbt_reader_open(str(path).encode(), 1, 211, 100, 0.0, None, ctypes.byref(h)) == -1  # modes 10, 2, 21 only
+    assert L.hbt_reader_open(str(path).encode(), 3, 211, 100, 0.0, None, ctypes.byref(h)) == -1  # modes 10, 2, 21, 0, 1 only
     assert L.hbt_reader_open(str(path).encode(), 10, 9999, 100, 0.0, None, ctypes.byref(h)) == -1  # species groups need pdg.dat
     r = hbtio.FastReader(str(path), 211, 100)
     with pytest.raises(capi.HBTError):
@@ -154,7 +154,7 @@ def test_errors(tmp_path):
     r.close()
 
 
-# ---- UrQMD formats (read_in_mode 2 and 21) against the reference reader's own output ------------
+# ---- UrQMD and OSCAR formats (read_in_mode 2, 21, 1, 0) against the reference reader's own output ----
 import json
 import os
 
@@ -166,7 +166,7 @@ READER_CASES = json.load(open(os.path.join(GOLDEN, "reader_cases.json")))
 @pytest.mark.parametrize("name", sorted(READER_CASES))
 def test_urqmd_modes_match_the_reference_reader(name):
     """tests/golden/make_golden_readers.py pushed the committed particle_list.dat (gzipped UrQMD
-    text) / particle_list.bin (UrQMD binary) through the unmodified reference reader and dumped
+    text) / particle_list.bin (UrQMD binary) / f13.dat (UrQMD file-13 text) / OSCAR.DAT through the unmodified reference reader and dumped
     the filtered particle lists per batch; hbt_reader must return the same batches, events and
     doubles (id map, species filter, unknown ids and other species counted for event_buffer_size,
     an empty event, float32 -> double, the rapidity shift)."""
@@ -217,3 +217,23 @@ def test_urqmd_truncated_files_are_errors(tmp_path):
     with pytest.raises(capi.HBTError):
         next(r)
     r.close()
+
+
+REF_FIXTURES = "/root/reference/unit_tests/test_reader_files"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_FIXTURES), reason="the reference's own fixtures are only in the build container")
+@pytest.mark.parametrize("name,mode,fn", [("unit_urqmd_txt", 1, "particle_list.dat"), ("unit_oscar_kplus", 0, "OSCAR.DAT")])
+def test_reference_unit_test_fixtures(name, mode, fn):
+    """The reference's own reader fixtures (unit_tests/test_reader_files: two UrQMD events as file-13 text and as
+    OSCAR1997A) through hbt_reader, against the particle lists the reference reader produced from them
+    (tests/golden/<name>.particles.bin, made by tests/golden/make_golden.py)."""
+    import json as _json
+    meta = _json.load(open(os.path.join(GOLDEN, "cases.json")))[name]
+    want = [b for b in hbtio.read_batches(os.path.join(GOLDEN, name + ".particles.bin")) if len(b.same) > 0]
+    got = collect(os.path.join(REF_FIXTURES, fn), meta["params"]["particle_monval"], 100000, read_in_mode=mode)
+    assert len(got) == len(want) > 0
+    for (evs, _), b in zip(got, want):
+        assert len(evs) == len(b.same)
+        for x, y in zip(evs, b.same):
+            assert x.shape == y.shape and np.array_equal(x, y)
