@@ -1,8 +1,11 @@
 // Fast reader for the particle samples that feed the HBT path.
 //
 // Replaces, for read_in_mode = 10 ("particle_samples.gz": gzipped iSS text), 2 ("particle_list.dat":
-// gzipped UrQMD text), 21 ("particle_list.bin": UrQMD binary), 0 ("OSCAR.DAT": OSCAR1997A text) and 1
-// ("particle_list.dat": UrQMD file-13 style text), the chain
+// gzipped UrQMD text), 21 ("particle_list.bin": UrQMD binary), 0 ("OSCAR.DAT": OSCAR1997A text), 1
+// ("particle_list.dat": UrQMD file-13 style text), 9 ("particle_list.bin": iSS binary) and 7
+// ("particle_list.dat": gzipped SMASH text), the chain
+//   particleSamples::read_in_particle_samples_binary         src/particleSamples.cpp:1203-1245
+//   particleSamples::read_in_particle_samples_SMASH_gzipped  src/particleSamples.cpp:1061-1102
 //   particleSamples::read_in_particle_samples_OSCAR          src/particleSamples.cpp:680-714 (+ header :198-202)
 //   particleSamples::read_in_particle_samples_UrQMD          src/particleSamples.cpp:838-908
 //   particleSamples::read_in_particle_samples_gzipped        src/particleSamples.cpp:1247-1286
@@ -179,8 +182,92 @@ struct hbt_reader {
             case 2: return read_batch_urqmd_text();
             case 1: return read_batch_urqmd_f13();
             case 0: return read_batch_oscar();
+            case 9: return read_batch_iss_binary();
+            case 7: return read_batch_smash_text();
             default: return read_batch_iss();
         }
+    }
+
+    // read_in_mode 9, src/particleSamples.cpp:1208-1243: int n, then per particle int pdg and 9 floats (mass t x
+    // y z E px py pz).  The reference never advances its event index in this routine: every particle of the
+    // batch lands in the batch's FIRST event and the other events stay empty; reproduced as it is.
+    std::unique_ptr<Batch> read_batch_iss_binary() {
+        std::unique_ptr<Batch> b(new Batch);
+        const double ch = std::cosh(rap_shift), sh = std::sinh(rap_shift);
+        int64_t num_particles = 0;
+        int nev = 0;
+        std::vector<unsigned char> rec;
+        while (num_particles < buffer_size) {
+            int32_t n_particle = 0;
+            const size_t got = std::fread(&n_particle, 1, 4, bin);
+            bytes_inflated += got;
+            if (got < 4) break;  // inputfile.eof() after the read of n_particle (:1211)
+            nev++;
+            if (n_particle > 0) {
+                rec.resize(static_cast<size_t>(n_particle) * 40);
+                if (std::fread(rec.data(), 40, static_cast<size_t>(n_particle), bin) != static_cast<size_t>(n_particle)) {
+                    error = "particle_list.bin ends inside an event";
+                    b->off.assign(1, 0);
+                    return b;
+                }
+                bytes_inflated += rec.size();
+            }
+            for (int32_t ip = 0; ip < n_particle; ip++) {
+                int32_t pdg;
+                float v[9];
+                std::memcpy(&pdg, rec.data() + static_cast<size_t>(ip) * 40, 4);
+                std::memcpy(v, rec.data() + static_cast<size_t>(ip) * 40 + 4, 36);
+                keep(*b, pdg, ch, sh, v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+            }
+            num_particles += n_particle;
+        }
+        b->off.assign(1, 0);
+        for (int e = 0; e < nev; e++) b->off.push_back(static_cast<int64_t>(b->p.size() / 8));  // all in event 0
+        b->all_particles = num_particles;
+        return b;
+    }
+
+    // read_in_mode 7, src/particleSamples.cpp:1072-1100: "<n>" then n lines
+    // "pdg charge process mother1 mother2 mass t x y z E px py pz"
+    std::unique_ptr<Batch> read_batch_smash_text() {
+        std::unique_ptr<Batch> b(new Batch);
+        b->off.push_back(0);
+        const double ch = std::cosh(rap_shift), sh = std::sinh(rap_shift);
+        int64_t num_particles = 0;
+        while (num_particles < buffer_size) {
+            const char *lb, *le;
+            readline(&lb, &le);
+            if (hit_eof) break;  // gzeof() after the header read (:1075)
+            long long n_particle = 0;
+            parse_int(lb, le, &n_particle);
+            for (long long ip = 0; ip < n_particle; ip++) {
+                if (!readline(&lb, &le) && hit_eof) {
+                    error = "particle_list.dat ends inside an event";
+                    return b;
+                }
+                long long pdg = 0, charge = 0, proc = 0, m1 = 0, m2 = 0;
+                double mass, t, x, y, z, E, px, py, pz;
+                const char *q = parse_int(lb, le, &pdg);
+                q = parse_int(q, le, &charge);
+                q = parse_int(q, le, &proc);
+                q = parse_int(q, le, &m1);
+                q = parse_int(q, le, &m2);
+                q = parse_double(q, le, &mass);
+                q = parse_double(q, le, &t);
+                q = parse_double(q, le, &x);
+                q = parse_double(q, le, &y);
+                q = parse_double(q, le, &z);
+                q = parse_double(q, le, &E);
+                q = parse_double(q, le, &px);
+                q = parse_double(q, le, &py);
+                q = parse_double(q, le, &pz);
+                keep(*b, pdg, ch, sh, t, x, y, z, E, px, py, pz);
+            }
+            num_particles += n_particle;
+            b->off.push_back(static_cast<int64_t>(b->p.size() / 8));
+        }
+        b->all_particles = num_particles;
+        return b;
     }
 
     // read_in_mode 0, src/particleSamples.cpp:689-712 (the three header lines of the file are skipped when it
@@ -428,13 +515,15 @@ extern "C" int hbt_reader_open(const char *path, int32_t read_in_mode, int32_t p
                                double rap_shift, const hbt_params *rapidity_cut, hbt_reader **out) {
     if (!path || !out) return HBT_ERR_INVALID;
     *out = nullptr;
-    if (read_in_mode != 10 && read_in_mode != 2 && read_in_mode != 21 && read_in_mode != 0 && read_in_mode != 1) return HBT_ERR_INVALID;
+    if (read_in_mode != 10 && read_in_mode != 2 && read_in_mode != 21 && read_in_mode != 0 && read_in_mode != 1 &&
+        read_in_mode != 9 && read_in_mode != 7)
+        return HBT_ERR_INVALID;
     // species groups (9999, 9998, ... : all charged, ...) need the particle table; single species only
     const int32_t a = particle_monval < 0 ? -particle_monval : particle_monval;
     if (a >= 9996 && a <= 99999 && (a <= 9999 || a == 99999)) return HBT_ERR_INVALID;
     gzFile gz = nullptr;
     FILE *bin = nullptr;
-    if (read_in_mode == 21) {
+    if (read_in_mode == 21 || read_in_mode == 9) {
         bin = std::fopen(path, "rb");
         if (!bin) return HBT_ERR_INVALID;
         std::setvbuf(bin, nullptr, _IOFBF, 1 << 20);

@@ -2,7 +2,8 @@
 // (Analysis::HBTAnalysis, /root/reference/src/Analysis.cpp:817-835) end to end on libhbt_b200.so,
 // for the input formats hbt_reader_* reads (read_in_mode = 10: results/particle_samples.gz, the
 // production configs' format; 2: gzipped UrQMD text results/particle_list.dat; 21: UrQMD binary
-// results/particle_list.bin; 0: results/OSCAR.DAT; 1: UrQMD file-13 text results/particle_list.dat):
+// results/particle_list.bin; 0: results/OSCAR.DAT; 1: UrQMD file-13 text results/particle_list.dat; 9: iSS
+// binary results/particle_list.bin; 7: gzipped SMASH text results/particle_list.dat):
 //
 //   reader thread   hbt_reader_*      inflate + parse + species filter, two batches ahead
 //   host            psi_2, rapidity cut, the reference's RNG draws (partner events, rotation angles)
@@ -95,10 +96,12 @@ int main(int argc, char *argv[]) {
 
     if (P.get("analyze_HBT", 0) != 1) die("analyze_HBT is not 1: nothing to do (the other analyses are the reference program's)");
     const int read_in_mode = static_cast<int>(P.get("read_in_mode"));
-    if (read_in_mode != 10 && read_in_mode != 2 && read_in_mode != 21 && read_in_mode != 0 && read_in_mode != 1)
-        die("only read_in_mode = 10 (gzipped iSS samples), 2 (gzipped UrQMD text), 21 (UrQMD binary), 0 (OSCAR) and 1 (UrQMD text) are read here");
+    if (read_in_mode != 10 && read_in_mode != 2 && read_in_mode != 21 && read_in_mode != 0 && read_in_mode != 1 &&
+        read_in_mode != 9 && read_in_mode != 7)
+        die("only read_in_mode = 10 (gzipped iSS samples), 9 (iSS binary), 2 (gzipped UrQMD text), 21 (UrQMD binary), 1 (UrQMD "
+            "text), 0 (OSCAR) and 7 (gzipped SMASH text) are read here");
     // (modes 2 and 21 do not force these off as mode 10 does, src/particleSamples.cpp:409-412)
-    if (read_in_mode != 10 && read_in_mode != 0 && P.get("resonance_weak_feed_down_flag", 0) == 1)
+    if (read_in_mode != 10 && read_in_mode != 0 && read_in_mode != 9 && P.get("resonance_weak_feed_down_flag", 0) == 1)
         die("resonance_weak_feed_down_flag = 1 is not supported here");
     const bool real_mixed = P.get("read_in_real_mixed_events", 0) == 1;
     if (P.get("resonance_feed_down_flag", 0) == 1) die("resonance_feed_down_flag = 1 is not supported here");
@@ -125,7 +128,8 @@ int main(int argc, char *argv[]) {
     if (hbt_rng_create(static_cast<int32_t>(P.get("randomSeed")), &rng) != HBT_OK) die("cannot create the random number generator");
     hbt_reader *rd = nullptr;
     // file names of src/particleSamples.cpp:133-149
-    const std::string file = path + (read_in_mode == 10 ? "/particle_samples.gz" : read_in_mode == 21 ? "/particle_list.bin"
+    const bool bin_file = read_in_mode == 21 || read_in_mode == 9;
+    const std::string file = path + (read_in_mode == 10 ? "/particle_samples.gz" : bin_file ? "/particle_list.bin"
                                      : read_in_mode == 0 ? "/OSCAR.DAT" : "/particle_list.dat");
     if (hbt_reader_open(file.c_str(), read_in_mode, static_cast<int>(P.get("particle_monval")), static_cast<int64_t>(P.get("event_buffer_size")),
                         P.get("rapidity_shift", 0), nullptr, &rd) != HBT_OK)
@@ -133,7 +137,7 @@ int main(int argc, char *argv[]) {
     hbt_reader *rd2 = nullptr;  // the mixed-event file (src/particleSamples.cpp:133-149, :527-535)
     if (real_mixed) {
         const std::string file2 = path + (read_in_mode == 10 ? "/particle_samples_mixed_event.gz"
-                                          : read_in_mode == 21 ? "/particle_list_mixed_event.bin"
+                                          : bin_file ? "/particle_list_mixed_event.bin"
                                           : read_in_mode == 0 ? "/OSCAR_mixed_event.DAT" : "/particle_list_mixed_event.dat");
         if (hbt_reader_open(file2.c_str(), read_in_mode, static_cast<int>(P.get("particle_monval")),
                             static_cast<int64_t>(P.get("event_buffer_size")), P.get("rapidity_shift", 0), nullptr, &rd2) != HBT_OK)

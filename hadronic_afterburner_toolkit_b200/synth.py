@@ -153,3 +153,27 @@ def write_urqmd_f13(path: str, records) -> None:
                 f.write(" 0.8E+04 1.0 2.0 3.0 %.8E %.8E %.8E %.8E %.17g %d %d %d %d %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n"
                         % (p[3], p[0], p[1], p[2], mass, uid, iso3, _URQMD_CHARGE[pdg], 6, 1, 99,
                            p[7], p[4], p[5], p[6], p[3], p[0], p[1], p[2]))
+
+
+def write_iss_bin(path: str, records) -> None:
+    """read_in_mode=9 binary (iSS ``particle_list.bin``, ``src/particleSamples.cpp:1203-1245``): per event int32
+    count, per particle int32 Monte-Carlo number and 9 float32 (mass t x y z E px py pz)."""
+    with open(path, "wb") as f:
+        for rows in records:
+            f.write(np.array([len(rows)], dtype=np.int32).tobytes())
+            for pdg, mass, p in rows:
+                f.write(np.array([pdg if pdg else 113], dtype=np.int32).tobytes())
+                f.write(np.array([mass, p[7], p[4], p[5], p[6], p[3], p[0], p[1], p[2]], dtype=np.float32).tobytes())
+
+
+def write_smash_gz(path: str, records) -> None:
+    """read_in_mode=7 text (gzipped SMASH ``particle_list.dat``, ``src/particleSamples.cpp:1061-1102``): per event
+    the particle count, then ``pdg charge process mother1 mother2 mass t x y z E px py pz`` per particle."""
+    lines = []
+    for rows in records:
+        lines.append(f"{len(rows)}")
+        for pdg, mass, p in rows:
+            lines.append("%d %d %d %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g"
+                         % (pdg if pdg else 113, _URQMD_CHARGE[pdg], 0, 0, 0, mass, p[7], p[4], p[5], p[6], p[3], p[0], p[1], p[2]))
+    with gzip.open(path, "wt", compresslevel=1) as f:
+        f.write("\n".join(lines) + "\n")

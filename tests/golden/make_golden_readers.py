@@ -10,6 +10,8 @@ inputs:
   tests/golden/urqmd_small.particle_list.bin      mode-21 input
   tests/golden/urqmd_small.f13.dat                mode-1 input
   tests/golden/urqmd_small.OSCAR.DAT              mode-0 input
+  tests/golden/urqmd_small.iss.bin                mode-9 input (iSS binary)
+  tests/golden/urqmd_small.smash.dat              mode-7 input (gzipped SMASH text)
   tests/golden/urqmd_<mode>_<case>.particles.bin  HBTIN001 dumps of the reference reader
 
 Run here (needs /root/reference compiled into oracle/_ref):  python tests/golden/make_golden_readers.py
@@ -49,9 +51,12 @@ def main():
     short = records[:5]
     synth.write_urqmd_f13(ff13, short)
     synth.write_oscar(fosc, short)
+    fiss, fsm = os.path.join(HERE, "urqmd_small.iss.bin"), os.path.join(HERE, "urqmd_small.smash.dat")
+    synth.write_iss_bin(fiss, records)
+    synth.write_smash_gz(fsm, short)
     meta = {}
     for mode, src, name in ((2, ftxt, "particle_list.dat"), (21, fbin, "particle_list.bin"), (1, ff13, "particle_list.dat"),
-                            (0, fosc, "OSCAR.DAT")):
+                            (0, fosc, "OSCAR.DAT"), (9, fiss, "particle_list.bin"), (7, fsm, "particle_list.dat")):
         for case, (monval, buf, shift) in CASES.items():
             with tempfile.TemporaryDirectory() as td:
                 os.makedirs(os.path.join(td, "EOS"))
