@@ -2,8 +2,12 @@
 //
 // Replaces, for read_in_mode = 10 ("particle_samples.gz": gzipped iSS text), 2 ("particle_list.dat":
 // gzipped UrQMD text), 21 ("particle_list.bin": UrQMD binary), 0 ("OSCAR.DAT": OSCAR1997A text), 1
-// ("particle_list.dat": UrQMD file-13 style text), 9 ("particle_list.bin": iSS binary) and 7
-// ("particle_list.dat": gzipped SMASH text), the chain
+// ("particle_list.dat": UrQMD file-13 style text; 4: the UrQMD 3.3p header; 3: no header block), 5
+// ("particle_list.dat": JAM text), 9 ("particle_list.bin": iSS binary) and 7 ("particle_list.dat": gzipped
+// SMASH text), the chain
+//   particleSamples::read_in_particle_samples_UrQMD_3p3      src/particleSamples.cpp:1463-1529
+//   particleSamples::read_in_particle_samples_Sangwook       src/particleSamples.cpp:1955-2020
+//   particleSamples::read_in_particle_samples_JAM            src/particleSamples.cpp:716-756 (+ header :205-210)
 //   particleSamples::read_in_particle_samples_binary         src/particleSamples.cpp:1203-1245
 //   particleSamples::read_in_particle_samples_SMASH_gzipped  src/particleSamples.cpp:1061-1102
 //   particleSamples::read_in_particle_samples_OSCAR          src/particleSamples.cpp:680-714 (+ header :198-202)
@@ -180,7 +184,10 @@ struct hbt_reader {
         switch (mode) {
             case 21: return read_batch_urqmd_binary();
             case 2: return read_batch_urqmd_text();
-            case 1: return read_batch_urqmd_f13();
+            case 1: return read_batch_urqmd_f13(16);
+            case 4: return read_batch_urqmd_f13(13);
+            case 3: return read_batch_urqmd_f13(-1);
+            case 5: return read_batch_jam();
             case 0: return read_batch_oscar();
             case 9: return read_batch_iss_binary();
             case 7: return read_batch_smash_text();
@@ -311,10 +318,9 @@ struct hbt_reader {
         return b;
     }
 
-    // read_in_mode 1, src/particleSamples.cpp:849-906: 17 header lines, "<n> ...", one line that is skipped,
-    // then n lines "r0 rx ry rz p0 px py pz m ityp 2i3 chg lcl# ncl or t x y z E px py pz" (the last eight are
-    // the freeze-out coordinates and momenta that are used)
-    std::unique_ptr<Batch> read_batch_urqmd_f13() {
+    // read_in_mode 5, src/particleSamples.cpp:726-754 (the first line of the file is skipped when it is opened,
+    // :205-210): "<char> <event id> <n>" then n lines "monval mass px py pz x y z t"; E from the mass shell
+    std::unique_ptr<Batch> read_batch_jam() {
         std::unique_ptr<Batch> b(new Batch);
         b->off.push_back(0);
         const double ch = std::cosh(rap_shift), sh = std::sinh(rap_shift);
@@ -322,9 +328,55 @@ struct hbt_reader {
         while (num_particles < buffer_size) {
             const char *lb, *le;
             readline(&lb, &le);
-            if (hit_eof) break;  // inputfile.eof() after the first header line (:851)
-            for (int i = 0; i < 16; i++) readline(&lb, &le);
+            if (hit_eof) break;  // inputfile.eof() after the header read (:731)
+            long long event_id = 0, n_particle = 0;
+            const char *q = skip_ws(lb, le);
+            if (q < le) q++;  // operator>>(char): one non-blank character
+            q = parse_int(q, le, &event_id);
+            parse_int(q, le, &n_particle);
+            for (long long ip = 0; ip < n_particle; ip++) {
+                if (!readline(&lb, &le) && hit_eof) {
+                    error = "particle_list.dat ends inside an event";
+                    return b;
+                }
+                long long mv = 0;
+                double mass, px, py, pz, x, y, z, t;
+                q = parse_int(lb, le, &mv);
+                q = parse_double(q, le, &mass);
+                q = parse_double(q, le, &px);
+                q = parse_double(q, le, &py);
+                q = parse_double(q, le, &pz);
+                q = parse_double(q, le, &x);
+                q = parse_double(q, le, &y);
+                q = parse_double(q, le, &z);
+                q = parse_double(q, le, &t);
+                const double E = std::sqrt(mass * mass + px * px + py * py + pz * pz);  // :743-747, as written
+                keep(*b, mv, ch, sh, t, x, y, z, E, px, py, pz);
+            }
+            num_particles += n_particle;
+            b->off.push_back(static_cast<int64_t>(b->p.size() / 8));
+        }
+        b->all_particles = num_particles;
+        return b;
+    }
+
+    // read_in_mode 1, src/particleSamples.cpp:849-906: 17 header lines, "<n> ...", one line that is skipped,
+    // then n lines "r0 rx ry rz p0 px py pz m ityp 2i3 chg lcl# ncl or t x y z E px py pz" (the last eight are
+    // the freeze-out coordinates and momenta that are used).  read_in_mode 4 (:1473-1527) has 14 header lines,
+    // read_in_mode 3 (:1968-2018) none: `skip` = header lines after the first one, -1 = the first line is "<n>".
+    std::unique_ptr<Batch> read_batch_urqmd_f13(int skip) {
+        std::unique_ptr<Batch> b(new Batch);
+        b->off.push_back(0);
+        const double ch = std::cosh(rap_shift), sh = std::sinh(rap_shift);
+        int64_t num_particles = 0;
+        while (num_particles < buffer_size) {
+            const char *lb, *le;
             readline(&lb, &le);
+            if (hit_eof) break;  // inputfile.eof() after the first line (:851, :1475, :1970)
+            if (skip >= 0) {
+                for (int i = 0; i < skip; i++) readline(&lb, &le);
+                readline(&lb, &le);
+            }
             long long n_particle = 0;
             parse_int(lb, le, &n_particle);
             if (!readline(&lb, &le) && hit_eof && n_particle > 0) {
@@ -493,9 +545,9 @@ struct hbt_reader {
     }
 
     void run() {
-        if (mode == 0) {  // the file header of OSCAR1997A (src/particleSamples.cpp:198-202)
+        if (mode == 0 || mode == 5) {  // the file header of OSCAR1997A (src/particleSamples.cpp:198-202), of JAM (:205-210)
             const char *lb, *le;
-            for (int i = 0; i < 3; i++) readline(&lb, &le);
+            for (int i = 0; i < (mode == 0 ? 3 : 1); i++) readline(&lb, &le);
         }
         for (;;) {
             std::unique_ptr<Batch> b = read_batch();
@@ -516,7 +568,7 @@ extern "C" int hbt_reader_open(const char *path, int32_t read_in_mode, int32_t p
     if (!path || !out) return HBT_ERR_INVALID;
     *out = nullptr;
     if (read_in_mode != 10 && read_in_mode != 2 && read_in_mode != 21 && read_in_mode != 0 && read_in_mode != 1 &&
-        read_in_mode != 9 && read_in_mode != 7)
+        read_in_mode != 9 && read_in_mode != 7 && read_in_mode != 3 && read_in_mode != 4 && read_in_mode != 5)
         return HBT_ERR_INVALID;
     // species groups (9999, 9998, ... : all charged, ...) need the particle table; single species only
     const int32_t a = particle_monval < 0 ? -particle_monval : particle_monval;

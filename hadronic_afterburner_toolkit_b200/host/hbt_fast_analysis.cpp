@@ -3,7 +3,8 @@
 // for the input formats hbt_reader_* reads (read_in_mode = 10: results/particle_samples.gz, the
 // production configs' format; 2: gzipped UrQMD text results/particle_list.dat; 21: UrQMD binary
 // results/particle_list.bin; 0: results/OSCAR.DAT; 1: UrQMD file-13 text results/particle_list.dat; 9: iSS
-// binary results/particle_list.bin; 7: gzipped SMASH text results/particle_list.dat):
+// binary results/particle_list.bin; 7: gzipped SMASH text, 4 / 3: UrQMD 3.3p / header-less UrQMD text, 5: JAM
+// text, all results/particle_list.dat):
 //
 //   reader thread   hbt_reader_*      inflate + parse + species filter, two batches ahead
 //   host            psi_2, rapidity cut, the reference's RNG draws (partner events, rotation angles)
@@ -96,10 +97,10 @@ int main(int argc, char *argv[]) {
 
     if (P.get("analyze_HBT", 0) != 1) die("analyze_HBT is not 1: nothing to do (the other analyses are the reference program's)");
     const int read_in_mode = static_cast<int>(P.get("read_in_mode"));
-    if (read_in_mode != 10 && read_in_mode != 2 && read_in_mode != 21 && read_in_mode != 0 && read_in_mode != 1 &&
-        read_in_mode != 9 && read_in_mode != 7)
-        die("only read_in_mode = 10 (gzipped iSS samples), 9 (iSS binary), 2 (gzipped UrQMD text), 21 (UrQMD binary), 1 (UrQMD "
-            "text), 0 (OSCAR) and 7 (gzipped SMASH text) are read here");
+    const bool known_mode = read_in_mode == 10 || read_in_mode == 9 || read_in_mode == 2 || read_in_mode == 21 || read_in_mode == 0 ||
+                            read_in_mode == 1 || read_in_mode == 3 || read_in_mode == 4 || read_in_mode == 5 || read_in_mode == 7;
+    if (!known_mode)
+        die("read_in_mode = 8 (SMASH binary) is not read here: use the drop-in binary, which keeps the reference's reader");
     // (modes 2 and 21 do not force these off as mode 10 does, src/particleSamples.cpp:409-412)
     if (read_in_mode != 10 && read_in_mode != 0 && read_in_mode != 9 && P.get("resonance_weak_feed_down_flag", 0) == 1)
         die("resonance_weak_feed_down_flag = 1 is not supported here");

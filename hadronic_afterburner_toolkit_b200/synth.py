@@ -136,16 +136,18 @@ def write_oscar(path: str, records) -> None:
                         % (k + 1, pdg if pdg else 113, p[0], p[1], p[2], p[3], mass, p[4], p[5], p[6], p[7]))
 
 
-def write_urqmd_f13(path: str, records) -> None:
+def write_urqmd_f13(path: str, records, header_lines=17) -> None:
     """read_in_mode=1 text (UrQMD file-13 style ``particle_list.dat``, ``src/particleSamples.cpp:838-908``): per
     event 17 header lines, ``<n> <time>``, one line the reader skips, then n lines ``r0 rx ry rz p0 px py pz m ityp
     2i3 chg lcl# ncl or t x y z E px py pz`` of which the reader uses m, ityp, 2i3 and the last eight."""
     with open(path, "w") as f:
         for iev, rows in enumerate(records):
-            f.write("UQMD   version:       30400   1000  30400  output_file  13\n")
-            for k in range(15):
-                f.write("header line %d of event %d\n" % (k + 2, iev + 1))
-            f.write("pvec: r0 rx ry rz p0 px py pz m ityp 2i3 chg lcl# ncl or\n")
+            # header_lines: 17 (read_in_mode 1), 14 (read_in_mode 4, UrQMD 3.3p) or 0 (read_in_mode 3)
+            if header_lines:
+                f.write("UQMD   version:       30400   1000  30400  output_file  13\n")
+                for k in range(header_lines - 2):
+                    f.write("header line %d of event %d\n" % (k + 2, iev + 1))
+                f.write("pvec: r0 rx ry rz p0 px py pz m ityp 2i3 chg lcl# ncl or\n")
             f.write("%12d %11d\n" % (len(rows), 8000))
             f.write("      65       4      61       0     221      11       0       0\n")
             for pdg, mass, p in rows:
@@ -177,3 +179,15 @@ def write_smash_gz(path: str, records) -> None:
                          % (pdg if pdg else 113, _URQMD_CHARGE[pdg], 0, 0, 0, mass, p[7], p[4], p[5], p[6], p[3], p[0], p[1], p[2]))
     with gzip.open(path, "wt", compresslevel=1) as f:
         f.write("\n".join(lines) + "\n")
+
+
+def write_jam(path: str, records) -> None:
+    """read_in_mode=5 text (JAM ``particle_list.dat``, ``src/particleSamples.cpp:716-756``): one header line, per
+    event ``# <event id> <n>`` and n lines ``monval mass px py pz x y z t`` (the reader computes E itself)."""
+    with open(path, "w") as f:
+        f.write("# JAM style list written by synth.write_jam\n")
+        for iev, rows in enumerate(records):
+            f.write("# %d %d\n" % (iev + 1, len(rows)))
+            for pdg, mass, p in rows:
+                f.write("%d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n"
+                        % (pdg if pdg else 113, mass, p[0], p[1], p[2], p[4], p[5], p[6], p[7]))

@@ -12,6 +12,7 @@ inputs:
   tests/golden/urqmd_small.OSCAR.DAT              mode-0 input
   tests/golden/urqmd_small.iss.bin                mode-9 input (iSS binary)
   tests/golden/urqmd_small.smash.dat              mode-7 input (gzipped SMASH text)
+  tests/golden/urqmd_small.f13_3p3.dat / f13_nohdr.dat / jam.dat   mode-4 / mode-3 / mode-5 inputs (3 events each)
   tests/golden/urqmd_<mode>_<case>.particles.bin  HBTIN001 dumps of the reference reader
 
 Run here (needs /root/reference compiled into oracle/_ref):  python tests/golden/make_golden_readers.py
@@ -54,9 +55,14 @@ def main():
     fiss, fsm = os.path.join(HERE, "urqmd_small.iss.bin"), os.path.join(HERE, "urqmd_small.smash.dat")
     synth.write_iss_bin(fiss, records)
     synth.write_smash_gz(fsm, short)
+    f3p3, fnoh, fjam = (os.path.join(HERE, "urqmd_small." + n) for n in ("f13_3p3.dat", "f13_nohdr.dat", "jam.dat"))
+    synth.write_urqmd_f13(f3p3, short[:3], header_lines=14)
+    synth.write_urqmd_f13(fnoh, short[:3], header_lines=0)
+    synth.write_jam(fjam, short[:3])
     meta = {}
     for mode, src, name in ((2, ftxt, "particle_list.dat"), (21, fbin, "particle_list.bin"), (1, ff13, "particle_list.dat"),
-                            (0, fosc, "OSCAR.DAT"), (9, fiss, "particle_list.bin"), (7, fsm, "particle_list.dat")):
+                            (0, fosc, "OSCAR.DAT"), (9, fiss, "particle_list.bin"), (7, fsm, "particle_list.dat"),
+                            (4, f3p3, "particle_list.dat"), (3, fnoh, "particle_list.dat"), (5, fjam, "particle_list.dat")):
         for case, (monval, buf, shift) in CASES.items():
             with tempfile.TemporaryDirectory() as td:
                 os.makedirs(os.path.join(td, "EOS"))
