@@ -8,6 +8,7 @@
 //   particleSamples::read_in_particle_samples_UrQMD_3p3      src/particleSamples.cpp:1463-1529
 //   particleSamples::read_in_particle_samples_Sangwook       src/particleSamples.cpp:1955-2020
 //   particleSamples::read_in_particle_samples_JAM            src/particleSamples.cpp:716-756 (+ header :205-210)
+//   particleSamples::open_SMASH_binary / read_in_particle_samples_SMASH_binary   :288-323, :1104-1201  (mode 8)
 //   particleSamples::read_in_particle_samples_binary         src/particleSamples.cpp:1203-1245
 //   particleSamples::read_in_particle_samples_SMASH_gzipped  src/particleSamples.cpp:1061-1102
 //   particleSamples::read_in_particle_samples_OSCAR          src/particleSamples.cpp:680-714 (+ header :198-202)
@@ -78,7 +79,8 @@ int urqmd_to_pdg(long long id, long long iso3) {
 
 struct hbt_reader {
     gzFile gz = nullptr;
-    FILE *bin = nullptr;  // read_in_mode 21
+    FILE *bin = nullptr;  // read_in_mode 21, 9, 8
+    uint16_t smash_version = 0;  // read_in_mode 8: format version of the file header
     int32_t mode = 10;
     int32_t monval = 0;
     int64_t buffer_size = 0;
@@ -188,11 +190,67 @@ struct hbt_reader {
             case 4: return read_batch_urqmd_f13(13);
             case 3: return read_batch_urqmd_f13(-1);
             case 5: return read_batch_jam();
+            case 8: return read_batch_smash_binary();
             case 0: return read_batch_oscar();
             case 9: return read_batch_iss_binary();
             case 7: return read_batch_smash_text();
             default: return read_batch_iss();
         }
+    }
+
+    // read_in_mode 8, src/particleSamples.cpp:1110-1199 (extended SMASH binary; the file header is read when
+    // the file is opened, :296-322): blocks 'f' (end of an event: u32, f64 and, from format version 7 on, one
+    // more byte: skipped) and 'p' (u32 n, then n records of 128 bytes: t x y z m p0 px py pz as f64, pdg id
+    // charge ncoll as i32, two f64, two i32, time_last_coll f64, two i32); anything else ends the batch.  The
+    // particle is moved back along its velocity to the time of its last collision (:1177-1181, as written).
+    std::unique_ptr<Batch> read_batch_smash_binary() {
+        std::unique_ptr<Batch> b(new Batch);
+        b->off.push_back(0);
+        const double ch = std::cosh(rap_shift), sh = std::sinh(rap_shift);
+        int64_t num_particles = 0;
+        std::vector<unsigned char> rec;
+        while (num_particles < buffer_size) {
+            char block_type;
+            if (std::fread(&block_type, 1, 1, bin) != 1) break;  // !SMASH_inputfile (:1113)
+            bytes_inflated += 1;
+            if (block_type == 'f') {
+                unsigned char skip[13];
+                const size_t want = smash_version > 6 ? 13 : 12;
+                const size_t got = std::fread(skip, 1, want, bin);
+                bytes_inflated += got;
+                if (got < want) break;
+                continue;
+            }
+            if (block_type != 'p') break;
+            uint32_t n_part = 0;
+            if (std::fread(&n_part, 4, 1, bin) != 1) {
+                error = "particles_binary.bin ends inside a block";
+                return b;
+            }
+            bytes_inflated += 4;
+            rec.resize(static_cast<size_t>(n_part) * 128);
+            if (n_part && std::fread(rec.data(), 128, n_part, bin) != n_part) {
+                error = "particles_binary.bin ends inside a block";
+                return b;
+            }
+            bytes_inflated += rec.size();
+            for (uint32_t ip = 0; ip < n_part; ip++) {
+                const unsigned char *r = rec.data() + static_cast<size_t>(ip) * 128;
+                double v[9], t_last;  // t x y z m p0 px py pz
+                int32_t pdg;
+                std::memcpy(v, r, 72);
+                std::memcpy(&pdg, r + 72, 4);
+                std::memcpy(&t_last, r + 112, 8);
+                const double vx = v[6] / v[5], vy = v[7] / v[5], vz = v[8] / v[5];
+                const double dt = v[0] - t_last;
+                const double xm = vx * dt, ym = vy * dt, zm = vz * dt;
+                keep(*b, pdg, ch, sh, t_last, v[1] - xm, v[2] - ym, v[3] - zm, v[5], v[6], v[7], v[8]);
+            }
+            num_particles += n_part;
+            b->off.push_back(static_cast<int64_t>(b->p.size() / 8));
+        }
+        b->all_particles = num_particles;
+        return b;
     }
 
     // read_in_mode 9, src/particleSamples.cpp:1208-1243: int n, then per particle int pdg and 9 floats (mass t x
@@ -568,17 +626,31 @@ extern "C" int hbt_reader_open(const char *path, int32_t read_in_mode, int32_t p
     if (!path || !out) return HBT_ERR_INVALID;
     *out = nullptr;
     if (read_in_mode != 10 && read_in_mode != 2 && read_in_mode != 21 && read_in_mode != 0 && read_in_mode != 1 &&
-        read_in_mode != 9 && read_in_mode != 7 && read_in_mode != 3 && read_in_mode != 4 && read_in_mode != 5)
+        read_in_mode != 9 && read_in_mode != 7 && read_in_mode != 3 && read_in_mode != 4 && read_in_mode != 5 && read_in_mode != 8)
         return HBT_ERR_INVALID;
     // species groups (9999, 9998, ... : all charged, ...) need the particle table; single species only
     const int32_t a = particle_monval < 0 ? -particle_monval : particle_monval;
     if (a >= 9996 && a <= 99999 && (a <= 9999 || a == 99999)) return HBT_ERR_INVALID;
     gzFile gz = nullptr;
     FILE *bin = nullptr;
-    if (read_in_mode == 21 || read_in_mode == 9) {
+    uint16_t smash_version = 0;
+    if (read_in_mode == 21 || read_in_mode == 9 || read_in_mode == 8) {
         bin = std::fopen(path, "rb");
         if (!bin) return HBT_ERR_INVALID;
         std::setvbuf(bin, nullptr, _IOFBF, 1 << 20);
+        if (read_in_mode == 8) {  // open_SMASH_binary, src/particleSamples.cpp:296-322
+            char magic[4];
+            uint16_t variant = 0;
+            uint32_t len = 0;
+            bool ok = std::fread(magic, 1, 4, bin) == 4 && std::fread(&smash_version, 2, 1, bin) == 1 &&
+                      std::fread(&variant, 2, 1, bin) == 1 && std::fread(&len, 4, 1, bin) == 1;
+            ok = ok && std::memcmp(magic, "SMSH", 4) == 0 && variant == 1 && len < 4096;  // the extended format only
+            if (ok && len) ok = std::fseek(bin, static_cast<long>(len), SEEK_CUR) == 0;
+            if (!ok) {
+                std::fclose(bin);
+                return HBT_ERR_INVALID;
+            }
+        }
     } else {
         gz = gzopen(path, "rb");
         if (!gz) return HBT_ERR_INVALID;
@@ -587,6 +659,7 @@ extern "C" int hbt_reader_open(const char *path, int32_t read_in_mode, int32_t p
     hbt_reader *r = new hbt_reader;
     r->gz = gz;
     r->bin = bin;
+    r->smash_version = smash_version;
     r->mode = read_in_mode;
     r->monval = particle_monval;
     r->buffer_size = event_buffer_size;

@@ -4,7 +4,7 @@
 // production configs' format; 2: gzipped UrQMD text results/particle_list.dat; 21: UrQMD binary
 // results/particle_list.bin; 0: results/OSCAR.DAT; 1: UrQMD file-13 text results/particle_list.dat; 9: iSS
 // binary results/particle_list.bin; 7: gzipped SMASH text, 4 / 3: UrQMD 3.3p / header-less UrQMD text, 5: JAM
-// text, all results/particle_list.dat):
+// text, all results/particle_list.dat; 8: extended SMASH binary results/particles_binary.bin):
 //
 //   reader thread   hbt_reader_*      inflate + parse + species filter, two batches ahead
 //   host            psi_2, rapidity cut, the reference's RNG draws (partner events, rotation angles)
@@ -98,9 +98,9 @@ int main(int argc, char *argv[]) {
     if (P.get("analyze_HBT", 0) != 1) die("analyze_HBT is not 1: nothing to do (the other analyses are the reference program's)");
     const int read_in_mode = static_cast<int>(P.get("read_in_mode"));
     const bool known_mode = read_in_mode == 10 || read_in_mode == 9 || read_in_mode == 2 || read_in_mode == 21 || read_in_mode == 0 ||
-                            read_in_mode == 1 || read_in_mode == 3 || read_in_mode == 4 || read_in_mode == 5 || read_in_mode == 7;
-    if (!known_mode)
-        die("read_in_mode = 8 (SMASH binary) is not read here: use the drop-in binary, which keeps the reference's reader");
+                            read_in_mode == 1 || read_in_mode == 3 || read_in_mode == 4 || read_in_mode == 5 || read_in_mode == 7 ||
+                            read_in_mode == 8;
+    if (!known_mode) die("unknown read_in_mode (the reference has 0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 21)");
     // (modes 2 and 21 do not force these off as mode 10 does, src/particleSamples.cpp:409-412)
     if (read_in_mode != 10 && read_in_mode != 0 && read_in_mode != 9 && P.get("resonance_weak_feed_down_flag", 0) == 1)
         die("resonance_weak_feed_down_flag = 1 is not supported here");
@@ -131,6 +131,7 @@ int main(int argc, char *argv[]) {
     // file names of src/particleSamples.cpp:133-149
     const bool bin_file = read_in_mode == 21 || read_in_mode == 9;
     const std::string file = path + (read_in_mode == 10 ? "/particle_samples.gz" : bin_file ? "/particle_list.bin"
+                                     : read_in_mode == 8 ? "/particles_binary.bin"
                                      : read_in_mode == 0 ? "/OSCAR.DAT" : "/particle_list.dat");
     if (hbt_reader_open(file.c_str(), read_in_mode, static_cast<int>(P.get("particle_monval")), static_cast<int64_t>(P.get("event_buffer_size")),
                         P.get("rapidity_shift", 0), nullptr, &rd) != HBT_OK)
@@ -139,6 +140,7 @@ int main(int argc, char *argv[]) {
     if (real_mixed) {
         const std::string file2 = path + (read_in_mode == 10 ? "/particle_samples_mixed_event.gz"
                                           : bin_file ? "/particle_list_mixed_event.bin"
+                                          : read_in_mode == 8 ? "/particles_binary_mixed_event.bin"
                                           : read_in_mode == 0 ? "/OSCAR_mixed_event.DAT" : "/particle_list_mixed_event.dat");
         if (hbt_reader_open(file2.c_str(), read_in_mode, static_cast<int>(P.get("particle_monval")),
                             static_cast<int64_t>(P.get("event_buffer_size")), P.get("rapidity_shift", 0), nullptr, &rd2) != HBT_OK)

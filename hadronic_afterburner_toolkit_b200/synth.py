@@ -191,3 +191,24 @@ def write_jam(path: str, records) -> None:
             for pdg, mass, p in rows:
                 f.write("%d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n"
                         % (pdg if pdg else 113, mass, p[0], p[1], p[2], p[4], p[5], p[6], p[7]))
+
+
+def write_smash_bin(path: str, records, rng, format_version: int = 7) -> None:
+    """read_in_mode=8 binary (extended SMASH ``particles_binary.bin``, ``src/particleSamples.cpp:288-323,
+    1104-1201``): header ``SMSH``, u16 format version, u16 variant 1, u32 length + version string; per event a
+    ``p`` block (u32 n, n records of 128 bytes) and an ``f`` block (u32 event, f64 impact parameter, one more
+    byte from format version 7 on).  The particles are written at a later time t > t_last on their straight
+    line, as SMASH does; the reader moves them back to t_last."""
+    import struct
+    with open(path, "wb") as f:
+        ver = b"SMASH-synth"
+        f.write(b"SMSH" + struct.pack("<HHI", format_version, 1, len(ver)) + ver)
+        for iev, rows in enumerate(records):
+            f.write(b"p" + struct.pack("<I", len(rows)))
+            for k, (pdg, mass, p) in enumerate(rows):
+                dt = float(rng.uniform(0.0, 30.0))
+                t = p[7] + dt
+                x, y, z = (p[4 + c] + p[c] / p[3] * dt for c in range(3))
+                f.write(struct.pack("<9d4i2d2id2i", t, x, y, z, mass, p[3], p[0], p[1], p[2], pdg if pdg else 113, k,
+                                    _URQMD_CHARGE[pdg], 3, 0.0, 1.0, 17, 5, p[7], 0, 0))
+            f.write(b"f" + struct.pack("<Id", iev, 0.0) + (b"\x00" if format_version > 6 else b""))

@@ -114,7 +114,8 @@ int32_t hbt_rng_mixed_plan(hbt_rng *rng, int32_t nev, int32_t nev_mixed, int32_t
  * (results/particle_list.dat, gzipped UrQMD text), 21 (results/particle_list.bin, UrQMD binary), 1
  * (results/particle_list.dat, UrQMD file-13 style text), 0 (results/OSCAR.DAT, OSCAR1997A), 9
  * (results/particle_list.bin, iSS binary), 7 (gzipped SMASH text), 4 / 3 (UrQMD 3.3p / header-less UrQMD text)
- * and 5 (JAM text; all three results/particle_list.dat) — every mode of the reference but 8 (SMASH binary) —,
+ * 5 (JAM text; all three results/particle_list.dat) and 8 (results/particles_binary.bin, extended SMASH binary)
+ * — every read_in_mode of the reference —,
  * the reference's reader and the steps between it and the pair loops:
  * read_in_particle_samples_gzipped / _UrQMD_zipped / _UrQMD_binary / _UrQMD / _OSCAR + gz_readline
  * (src/particleSamples.cpp:1247-1286, :910-974, :976-1059, :838-908, :680-714, :2209-2218), the UrQMD id map

@@ -13,6 +13,7 @@ inputs:
   tests/golden/urqmd_small.iss.bin                mode-9 input (iSS binary)
   tests/golden/urqmd_small.smash.dat              mode-7 input (gzipped SMASH text)
   tests/golden/urqmd_small.f13_3p3.dat / f13_nohdr.dat / jam.dat   mode-4 / mode-3 / mode-5 inputs (3 events each)
+  tests/golden/urqmd_small.smash.bin              mode-8 input (extended SMASH binary, 3 events)
   tests/golden/urqmd_<mode>_<case>.particles.bin  HBTIN001 dumps of the reference reader
 
 Run here (needs /root/reference compiled into oracle/_ref):  python tests/golden/make_golden_readers.py
@@ -59,10 +60,13 @@ def main():
     synth.write_urqmd_f13(f3p3, short[:3], header_lines=14)
     synth.write_urqmd_f13(fnoh, short[:3], header_lines=0)
     synth.write_jam(fjam, short[:3])
+    fsmb = os.path.join(HERE, "urqmd_small.smash.bin")
+    synth.write_smash_bin(fsmb, short[:3], np.random.default_rng(8))
     meta = {}
     for mode, src, name in ((2, ftxt, "particle_list.dat"), (21, fbin, "particle_list.bin"), (1, ff13, "particle_list.dat"),
                             (0, fosc, "OSCAR.DAT"), (9, fiss, "particle_list.bin"), (7, fsm, "particle_list.dat"),
-                            (4, f3p3, "particle_list.dat"), (3, fnoh, "particle_list.dat"), (5, fjam, "particle_list.dat")):
+                            (4, f3p3, "particle_list.dat"), (3, fnoh, "particle_list.dat"), (5, fjam, "particle_list.dat"),
+                            (8, fsmb, "particles_binary.bin")):
         for case, (monval, buf, shift) in CASES.items():
             with tempfile.TemporaryDirectory() as td:
                 os.makedirs(os.path.join(td, "EOS"))

@@ -87,7 +87,7 @@ def test_fast_driver_refuses_what_it_cannot_read(tmp_path):
     batches = synth.make_batches(44, 1, 2, multiplicity=50)
     gz = str(tmp_path / "input.gz")
     synth.write_iss_gz(gz, batches)
-    for key, value in (("read_in_mode", 8), ("resonance_feed_down_flag", 1), ("particle_monval", 9999),
+    for key, value in (("read_in_mode", 6), ("resonance_feed_down_flag", 1), ("particle_monval", 9999),
                        ("read_in_real_mixed_events", 1)):  # (the last: no mixed-event file in the directory)
         text = P.parameters_dat(event_buffer_size=100, **{key: value})
         with pytest.raises(AssertionError, match="hbt_fast_analysis"):

@@ -146,7 +146,8 @@ def test_errors(tmp_path):
     path = tmp_path / "p.gz"
     with gzip.open(path, "wt") as f:
         f.write("2\n211 0.138 1 0 0 0 1 0.1 0.1 0.1\n")  # the event announces 2 particles, holds 1
-    assert L.hbt_reader_open(str(path).encode(), 8, 211, 100, 0.0, None, ctypes.byref(h)) == -1  # every mode but 8 (SMASH binary)
+    assert L.hbt_reader_open(str(path).encode(), 6, 211, 100, 0.0, None, ctypes.byref(h)) == -1  # not a read_in_mode of the reference
+    assert L.hbt_reader_open(str(path).encode(), 8, 211, 100, 0.0, None, ctypes.byref(h)) == -1  # not an extended SMASH binary
     assert L.hbt_reader_open(str(path).encode(), 10, 9999, 100, 0.0, None, ctypes.byref(h)) == -1  # species groups need pdg.dat
     r = hbtio.FastReader(str(path), 211, 100)
     with pytest.raises(capi.HBTError):
