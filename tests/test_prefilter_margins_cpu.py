@@ -1,0 +1,100 @@
+"""The packed-FP32 prefilter of the production kernels (v3_run_unit in csrc/hbt_kernels_v3.cuh) may only
+drop a pair that certainly fails the K_T cut or the q_out / q_side window.  Its margins (64 u S on k2, the
+relative margin rho on the window, the k2 floor when rho is too large) are re-stated here in numpy — float32
+operations rounded once, fma as one rounding, directed roundings of the thresholds as in the kernel — and
+checked against the binary64 decision on millions of pairs per case: tiles of 128 x 128 particles of the
+benchmark distribution, with momentum outliers in the tile (x30, x3000: S grows, the margins follow), with
+tiny momenta and a K_T range that starts at 0 (the floor branch)."""
+import numpy as np
+import pytest
+
+F = np.float32
+U = 2.0 ** -24
+
+
+def fma32(a, b, c):
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def f32_ru(x):
+    y = np.float32(x)
+    return np.nextafter(y, np.float32(np.inf)) if float(y) < x else y
+
+
+def f32_rd(x):
+    y = np.float32(x)
+    return np.nextafter(y, np.float32(-np.inf)) if float(y) > x else y
+
+
+def tile(rng, n, scale, outlier):
+    px, py = rng.normal(0, 0.37, n) * scale, rng.normal(0, 0.33, n) * scale
+    if outlier:
+        k = rng.choice(n, 3, replace=False)
+        px[k] *= outlier
+        py[k] *= outlier
+    return px, py
+
+
+CASES = {
+    "benchmark": dict(scale=1.0, outlier=0, ktmin=0.15, ktmax=0.55),
+    "outliers_x30": dict(scale=1.0, outlier=30.0, ktmin=0.15, ktmax=0.55),
+    "outliers_x3000": dict(scale=1.0, outlier=3000.0, ktmin=0.15, ktmax=0.55),
+    "kt_from_0": dict(scale=1.0, outlier=0, ktmin=0.0, ktmax=1.0),
+    "tiny_kt_from_0": dict(scale=1e-3, outlier=0, ktmin=0.0, ktmax=1.0),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_prefilter_never_drops_a_pair_the_exact_test_keeps(case):
+    c = CASES[case]
+    rng = np.random.default_rng(20260600 + sorted(CASES).index(case))
+    dq = 0.4 / 40
+    q_lo, q_hi = -0.2 - dq / 2 + 1e-8, 0.2 + dq / 2 - 1e-8
+    W2 = max(q_lo * q_lo, q_hi * q_hi)
+    Wd = np.sqrt(W2)
+    k2lo, k2hi = 4 * c["ktmin"] ** 2, 4 * c["ktmax"] ** 2
+    kept_exact = dropped_exact = floor_tiles = 0
+    for _ in range(60):
+        ax, ay = tile(rng, 128, c["scale"], c["outlier"])
+        bx, by = tile(rng, 128, c["scale"], c["outlier"])
+        at, bt = ax * ax + ay * ay, bx * bx + by * by
+        S = at.max() + bt.max()
+        # the margins, as the kernel derives them per unit (binary64)
+        Ek = 64.0 * U * S
+        k2e = max(k2lo - Ek, 0.0)
+        rho = 64.0 * U * S / (Wd * np.sqrt(k2e)) + 64.0 * U * S / k2e + 4.0 * U if k2e > 0 else 1.0
+        use_floor = not (rho <= 0.03)
+        k2_floor = 0.0
+        if use_floor:
+            a1, a2 = 64.0 * U * S / (0.015 * Wd), 64.0 * U * S / 0.015
+            k2_floor = max(a1 * a1, a2) + Ek
+            rho = 0.03 + 4.0 * U
+            floor_tiles += 1
+        Wqf = f32_ru(0.25 * W2 * (1.0 + 4.0 * rho + 16.0 * U))
+        klo_f, khi_f, kfloor_f = f32_rd(max(k2lo - Ek, 0.0)), f32_ru(k2hi + Ek), f32_ru(k2_floor)
+        # float prefilter on all 128 x 128 pairs
+        fax, fay, fat = (v.astype(np.float32)[:, None] for v in (ax, ay, 0.5 * at))
+        fbx, fby, fnb = (v.astype(np.float32)[None, :] for v in (bx, by, -0.5 * bt))
+        sx, sy = fax + fbx, fay + fby
+        k2 = fma32(sy, sy, sx * sx)
+        d = fat + fnb
+        x = fma32(np.broadcast_to(fbx, k2.shape), np.broadcast_to(fay, k2.shape), (-fax) * fby)
+        keep = (k2 >= klo_f) & (k2 <= khi_f)
+        inside = np.maximum(d * d, x * x) <= k2 * Wqf
+        if use_floor:
+            inside |= k2 < kfloor_f
+        passed = keep & inside
+        # binary64 decision: K_T cut and both windows (what the drain / the reference decide)
+        SX, SY, QX, QY = ax[:, None] + bx[None, :], ay[:, None] + by[None, :], ax[:, None] - bx[None, :], ay[:, None] - by[None, :]
+        K2 = SX * SX + SY * SY
+        with np.errstate(divide="ignore", invalid="ignore"):
+            QO, QS = (QX * SX + QY * SY) / np.sqrt(K2), (QY * SX - QX * SY) / np.sqrt(K2)
+        exact = (K2 >= k2lo) & (K2 <= k2hi) & (QO > q_lo) & (QO < q_hi) & (QS > q_lo) & (QS < q_hi)
+        assert not np.any(exact & ~passed), (case, int(np.sum(exact & ~passed)))
+        kept_exact += int(exact.sum())
+        dropped_exact += int((~passed).sum())
+    assert kept_exact > 1000                       # the sample does contain accepted pairs
+    if case == "benchmark":
+        assert dropped_exact > 0.5 * 60 * 128 * 128  # ... and the prefilter does discard most of the others
+    if case == "tiny_kt_from_0":
+        assert floor_tiles > 0                     # the floor branch was exercised
