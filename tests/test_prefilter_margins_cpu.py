@@ -98,3 +98,36 @@ def test_prefilter_never_drops_a_pair_the_exact_test_keeps(case):
         assert dropped_exact > 0.5 * 60 * 128 * 128  # ... and the prefilter does discard most of the others
     if case == "tiny_kt_from_0":
         assert floor_tiles > 0                     # the floor branch was exercised
+
+
+@pytest.mark.parametrize("scale", [1.0, 30.0, 1e-3])
+def test_pt_range_restriction_never_excludes_an_accepted_pair(scale):
+    """The production mixed-event units only visit the list-2 particles with (pT_min - W)^2 (1 - 1e-9) <= pT^2 <=
+    (pT_max + W)^2 (1 + 1e-9), pT_min / pT_max over the unit's 128 list-1 particles and W = sqrt(W2) (1 + 1e-9)
+    (v3_run_unit, PTRANGE): every pair with |q_out| inside the window must lie in that stretch, because
+    |q_out| = |pT_i^2 - pT_j^2| / (2 K_perp) >= |pT_i - pT_j|."""
+    rng = np.random.default_rng(int(scale * 1000) + 5)
+    dq = 0.4 / 40
+    q_lo, q_hi = -0.2 - dq / 2 + 1e-8, 0.2 + dq / 2 - 1e-8
+    W2 = max(q_lo * q_lo, q_hi * q_hi)
+    n_in = 0
+    for _ in range(40):
+        ax, ay = tile(rng, 128, scale, 0)
+        ax, ay = (v[np.argsort(ax * ax + ay * ay)[40:168]] if len(v) > 168 else v for v in (ax, ay))
+        bx, by = tile(rng, 1500, scale, 0)
+        at, bt = ax * ax + ay * ay, bx * bx + by * by
+        Wd = np.sqrt(W2) * (1.0 + 1e-9)
+        lo, hi = np.sqrt(at.min()) - Wd, np.sqrt(at.max()) + Wd
+        pt2_lo = lo * lo * (1.0 - 1e-9) if lo > 0 else 0.0
+        pt2_hi = hi * hi * (1.0 + 1e-9)
+        visited = (bt >= pt2_lo) & (bt <= pt2_hi)
+        SX, SY = ax[:, None] + bx[None, :], ay[:, None] + by[None, :]
+        K2 = SX * SX + SY * SY
+        with np.errstate(divide="ignore", invalid="ignore"):
+            QO = ((ax[:, None] - bx[None, :]) * SX + (ay[:, None] - by[None, :]) * SY) / np.sqrt(K2)
+            # the inequality itself, to rounding
+            assert np.all(np.abs(QO) >= np.abs(np.sqrt(at)[:, None] - np.sqrt(bt)[None, :]) * (1 - 1e-12) - 1e-300)
+        inside = (QO > q_lo) & (QO < q_hi)
+        assert not np.any(inside & ~visited[None, :])
+        n_in += int(inside.sum())
+    assert n_in > 1000
