@@ -5,7 +5,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from hadronic_afterburner_toolkit_b200 import synth  # noqa: E402
 from hadronic_afterburner_toolkit_b200.hbt_correlation import HBT_correlation  # noqa: E402
 from hadronic_afterburner_toolkit_b200.params import C3  # noqa: E402

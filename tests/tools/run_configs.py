@@ -3,7 +3,7 @@
 reference (oracle/_ref/ref_driver) on the host cores; check parity on the raw accumulators
 (integers bit-exact, sums <= 1e-10) and print one JSON line per config plus a markdown table.
 
-    python scripts/run_configs.py [--configs C1,C2,C3,C4,C5] [--c5-groups 200] [--out gpurun_out/configs.json]
+    python tests/tools/run_configs.py [--configs C1,C2,C3,C4,C5] [--c5-groups 200] [--out gpurun_out/configs.json]
 
 The reference is run by a pool of single-threaded processes, one per host core, each owning a
 subset of the oversample groups (`only=`: the other groups only advance the shared RNG stream).
@@ -20,7 +20,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from hadronic_afterburner_toolkit_b200 import hbtio, synth  # noqa: E402
