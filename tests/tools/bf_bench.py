@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from hadronic_afterburner_toolkit_b200.balance_function import BalanceFunction  # noqa: E402
 from hadronic_afterburner_toolkit_b200.hbt_correlation import Random  # noqa: E402

@@ -1,6 +1,6 @@
 """Wall-clock of the whole HBT analysis from results/particle_samples.gz to the .dat files:
 the reference binary, the drop-in binary (reference reader + our class) and hbt_fast_analysis.e
-(our reader + driver) on the same input.  Usage: python scripts/e2e_files.py [groups] [events/group]"""
+(our reader + driver) on the same input.  Usage: python tests/tools/e2e_files.py [groups] [events/group]"""
 import json
 import os
 import shutil
@@ -9,7 +9,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from hadronic_afterburner_toolkit_b200 import synth  # noqa: E402
 from hadronic_afterburner_toolkit_b200.params import C3  # noqa: E402
