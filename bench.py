@@ -244,7 +244,7 @@ def main():
     P = C5
     eng = HBT_correlation(P, device=local)
     h = eng._h
-    if os.environ.get("HBT_B200_FUSE", "1") == "0" or os.environ.get("HBT_B200_KERNEL", "2") == "1":
+    if (os.environ.get("HBT_B200_FUSE", "1") == "0" or os.environ.get("HBT_B200_KERNEL", "2") == "1") and "HBT_B200_LANES" not in os.environ:
         # per-loop timings: one compute stream, so that the two kernels of a group do not overlap the next group's
         _check(h, L.hbt_set_option(h, 4, 1))
     if world > 1:  # NCCL communicator of the library itself; torch only ferries the 128-byte id

@@ -749,6 +749,7 @@ struct PhaseInput {
     const double *h1 = nullptr, *h2 = nullptr;  // host copies of list 1 / list 2
     const double *d1 = nullptr, *d2 = nullptr;  // device copies
     int64_t n1 = 0;
+    int64_t base2 = 0;  // offset of list 2 inside the staged device buffer (0 when it aliases list 1)
     const int64_t *off1 = nullptr, *off2 = nullptr;
     int32_t nev1 = 0, nmix = 0;
     const int32_t *ids = nullptr;
@@ -863,10 +864,18 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
     (in.mixed ? ctx->exact_den : ctx->exact_num) = before;
     const size_t nx = crossing.size();
     const int64_t nrows = in.n1;
-    int32_t *d_xidx = nullptr;
-    unsigned *d_rowcnt = nullptr;
-    int64_t *d_cut = nullptr;
-    HbtMixSeg *d_seg1 = nullptr;
+    // scratch of one replay, released on every exit path
+    struct Scratch {
+        int32_t *xidx = nullptr;
+        unsigned *rowcnt = nullptr;
+        int64_t *cut = nullptr;
+        HbtMixSeg *seg1 = nullptr;
+        ~Scratch() { cudaFree(xidx); cudaFree(rowcnt); cudaFree(cut); cudaFree(seg1); }
+    } scratch;
+    int32_t *&d_xidx = scratch.xidx;
+    unsigned *&d_rowcnt = scratch.rowcnt;
+    int64_t *&d_cut = scratch.cut;
+    HbtMixSeg *&d_seg1 = scratch.seg1;
     std::vector<HbtMixSeg> seg1;
     unsigned long long np1 = npairs;
     long long nb1 = 0;
@@ -878,7 +887,7 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
     CU(ctx, cudaMemsetAsync(d_rowcnt, 0, nx * nrows * sizeof(unsigned), ctx->compute));
     if (in.mixed) {  // the literal kernels tile differently: rebuild the segments for them
         seg1.resize(static_cast<size_t>(in.nev1) * in.nmix);
-        nseg1 = build_segments(in.off1, in.nev1, in.off2, in.d2 == in.d1 ? 0 : in.n1, in.ids, in.cs, in.nmix, kTileV1, kTileV1,
+        nseg1 = build_segments(in.off1, in.nev1, in.off2, in.base2, in.ids, in.cs, in.nmix, kTileV1, kTileV1,
                                seg1.data(), &np1, &nb1);
         CU(ctx, cudaMalloc(&d_seg1, std::max<size_t>(nseg1, 1) * sizeof(HbtMixSeg)));
         CU(ctx, cudaMemcpyAsync(d_seg1, seg1.data(), nseg1 * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, ctx->compute));
@@ -935,10 +944,6 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
     rc = resolve_deferred(ctx, &f);
     if (rc) return rc;
     rc = refresh_counts(ctx);
-    cudaFree(d_xidx);
-    cudaFree(d_rowcnt);
-    cudaFree(d_cut);
-    if (d_seg1) cudaFree(d_seg1);
     if (rc) return rc;
     return sync_closed(ctx, in.mixed);
 }
@@ -1085,6 +1090,11 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_fused, hbt_pairs_v3_fused, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed_stats, hbt_pairs_v3<true, true>, 32, 0));
     if (!hbt_v2_supported(g)) ctx->kernel_version = 1;  // q_inv mode, one-sided q windows: literal kernels
+    if (const char *v = getenv("HBT_B200_OCC")) {  // experiments: fewer resident warps per SM than the kernels allow
+        const int cap = std::max(1, atoi(v));
+        ctx->occ_same = std::min(ctx->occ_same, cap); ctx->occ_mixed = std::min(ctx->occ_mixed, cap);
+        ctx->occ_fused = std::min(ctx->occ_fused, cap);
+    }
 
     {
         V2Dev dv;
@@ -1377,6 +1387,7 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
     in.d1 = s->d_p;
     in.d2 = s->d_p;  // segments carry the list-2 base offset
     in.n1 = n1;
+    in.base2 = alias ? 0 : n1;
     in.off1 = off1;
     in.off2 = off2;
     in.nev1 = nev1;

@@ -37,6 +37,9 @@
 #ifndef HBT_V3_WARPS_PER_SM
 #define HBT_V3_WARPS_PER_SM 18
 #endif
+#ifndef HBT_DBG_RED
+#define HBT_DBG_RED 0  // control experiments (profiles/r02_controls.txt); never set in the shipped library
+#endif
 #define HBT_V3_MAX_SORTED ((1ll << 22) - 64)  // unit encoding (row << 16 | tile) of the culled list, gridDim.y
 
 // Units of the sorted same-event list that can hold an accepted pair: row a = particles
@@ -490,18 +493,42 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
     if (closed && closed[slab + (MIXED ? g.nslab : 0)]) return;  // needed_number_of_pairs reached earlier
     const unsigned bin = ((static_cast<unsigned>(slab) * g.nq + b.io) * g.nq + b.is) * g.nq + b.il;  // < 2^31 (hbt_create)
     if (MIXED) {
+#if HBT_DBG_RED == 1
+        if (bin == 0x7fffffffu)
+#endif
         red_inc_u64(&acc.den_count[bin]);
     } else {
-        const double xd = lds_f64(sia + 8 * TI * (4 % NC)) - lds_f64(sja + 8 * TJ * (4 % NC));
-        const double yd = lds_f64(sia + 8 * TI * (5 % NC)) - lds_f64(sja + 8 * TJ * (5 % NC));
-        const double zd = lds_f64(sia + 8 * TI * (6 % NC)) - lds_f64(sja + 8 * TJ * (6 % NC));
-        const double td = lds_f64(sia + 8 * TI * (7 % NC)) - lds_f64(sja + 8 * TJ * (7 % NC));
+#if HBT_DBG_RED == 6  // control: conflict-free reads of the space-time components (wrong cos, same control flow)
+        const unsigned sia2 = sbase + L::SI + 8u * (threadIdx.x & 31), sja2 = sbase + L::SJ + 8u * (threadIdx.x & 31);
+#else
+        const unsigned sia2 = sia, sja2 = sja;
+#endif
+        const double xd = lds_f64(sia2 + 8 * TI * (4 % NC)) - lds_f64(sja2 + 8 * TJ * (4 % NC));
+        const double yd = lds_f64(sia2 + 8 * TI * (5 % NC)) - lds_f64(sja2 + 8 * TJ * (5 % NC));
+        const double zd = lds_f64(sia2 + 8 * TI * (6 % NC)) - lds_f64(sja2 + 8 * TJ * (6 % NC));
+        const double td = lds_f64(sia2 + 8 * TI * (7 % NC)) - lds_f64(sja2 + 8 * TJ * (7 % NC));
         const double cv = v3_cos(g.hbarc_inv * (b.qE * td - b.qx * xd - b.qy * yd - b.qz * zd));  // src :431-433
-        red_inc_u64(&acc.num_count[bin]);
-        red_add_f64(&acc.sum_qo[bin], b.qo);
-        red_add_f64(&acc.sum_qs[bin], b.qs);
-        red_add_f64(&acc.sum_ql[bin], b.ql);
-        red_add_f64(&acc.num_cos[bin], cv);
+#if HBT_DBG_RED == 1    // control: no reductions (values stay live)
+        if (bin == 0x7fffffffu) {
+#elif HBT_DBG_RED == 2  // control: all reductions into 1024 bins
+        const unsigned bin_ = bin;
+        {
+            const unsigned bin = bin_ & 1023u;
+#else
+        {
+#endif
+            red_inc_u64(&acc.num_count[bin]);
+#if HBT_DBG_RED == 3    // control: one reduction per accepted pair instead of five
+            if (bin == 0x7fffffffu) {
+#else
+            {
+#endif
+                red_add_f64(&acc.sum_qo[bin], b.qo);
+                red_add_f64(&acc.sum_qs[bin], b.qs);
+                red_add_f64(&acc.sum_ql[bin], b.ql);
+                red_add_f64(&acc.num_cos[bin], cv);
+            }
+        }
     }
 }
 

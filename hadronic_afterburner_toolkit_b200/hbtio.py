@@ -184,8 +184,14 @@ def compare(ref: Accumulators, got: Accumulators, rtol: float = 1e-10, check_sta
         tol = rtol * np.maximum(np.abs(a), 1e-4 * cnt * scale)
         nz = cnt > 0
         rel = d[nz] / np.maximum(np.abs(a[nz]), 1e-300)
+        # bins that the pure relative test alone would reject and only the conditioning floor accepts, and the
+        # deviation per accumulated pair (SURVEY.md 8c asks for both to be reported)
+        floor_bins = int(np.sum(nz & (d > rtol * np.abs(a)) & (d <= tol)))
+        per_pair = d[nz] / cnt[nz]
         report[name] = {"max_abs": float(d.max()) if d.size else 0.0,
-                        "max_rel": float(rel.max()) if rel.size else 0.0}
+                        "max_rel": float(rel.max()) if rel.size else 0.0,
+                        "floor_bins": floor_bins, "bins": int(nz.sum()),
+                        "max_abs_per_pair": float(per_pair.max()) if per_pair.size else 0.0}
         assert np.all(d <= tol), (f"{name}: {int(np.sum(d > tol))} bins exceed tolerance, "
                                   f"max_abs={d.max():.3e} max_rel={report[name]['max_rel']:.3e}")
     if ref.invariant_radius_flag == 1:

@@ -38,6 +38,33 @@ __global__ void __launch_bounds__(32, 18) k(unsigned long long *cnt, double *f, 
             double *r = f + 4ull * bin;
             red_u64(cnt + bin);
             red_f64(r, v); red_f64(r + 1, v); red_f64(r + 2, v); red_f64(r + 3, v);
+        } else if (MODE == 5) {
+            // TRANSPOSED, 64-byte records of five f64 (the count kept as a double): the 160 reductions of a round of
+            // 32 pairs are issued as 5 instructions in which consecutive lanes take consecutive components of the
+            // same record: 6.4 records (lines) per instruction instead of 32
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int s = k * 32 + threadIdx.x, pr = s / 5, c = s - 5 * pr;
+                const unsigned b = __shfl_sync(0xffffffffu, bin, pr);
+                red_f64(f + 8ull * b + c, v);
+            }
+        } else if (MODE == 6) {
+            // TRANSPOSED, 32-byte records of four f64 (one sector) + the count as a separate spread u64 RED
+            red_u64(cnt + bin);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int s = k * 32 + threadIdx.x, pr = s >> 2, c = s & 3;
+                const unsigned b = __shfl_sync(0xffffffffu, bin, pr);
+                red_f64(f + 4ull * b + c, v);
+            }
+        } else if (MODE == 7) {
+            // TRANSPOSED, 64-byte records, 8 lanes per record (5 live + 3 idle lanes): 4 records per instruction, 8 instructions
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int pr = k * 4 + (threadIdx.x >> 3), c = threadIdx.x & 7;
+                const unsigned b = __shfl_sync(0xffffffffu, bin, pr);
+                if (c < 5) red_f64(f + 8ull * b + c, v);
+            }
         }
     }
 }
@@ -77,6 +104,9 @@ int main() {
         run<2>("AoS 40-byte records", cnt, f, nbins, p.multiProcessorCount, ghz);
         run<4>("AoS 32-byte f64 + count", cnt, f, nbins, p.multiProcessorCount, ghz);
         run<3>("1 RED per pair", cnt, f, nbins, p.multiProcessorCount, ghz);
+        run<5>("transposed 64-byte records", cnt, f, nbins, p.multiProcessorCount, ghz);
+        run<6>("transposed 32-byte + count", cnt, f, nbins, p.multiProcessorCount, ghz);
+        run<7>("transposed 64-byte, 8 lanes", cnt, f, nbins, p.multiProcessorCount, ghz);
     }
     return 0;
 }

@@ -447,6 +447,25 @@ def test_real_mixed_event_lists():
     hbtio.compare(ref, acc, rtol=RTOL, check_stage="cheap")
 
 
+@pytest.mark.parametrize("P", [HBTParams(qnpts=21, needed_number_of_pairs=3000.0),
+                               HBTParams(qnpts=21, invariant_radius_flag=1, needed_number_of_pairs=300.0),
+                               C4.with_(qnpts=11, n_KT=4, n_Kphi=4, needed_number_of_pairs=700.0)],
+                         ids=["3d", "qinv", "az"])
+def test_ordered_cap_with_real_mixed_event_lists(P):
+    """The cap replay when list 2 is a separate buffer (read_in_real_mixed_events = 1): the literal passes must read
+    list 2 at its offset in the staged buffer, like the optimistic pass and the host's row evaluation do."""
+    batches = []
+    for k in range(3):
+        a = synth.make_batches(80 + k, 1, 4, multiplicity=400)[0]
+        b = synth.make_batches(90 + k, 1, 5, multiplicity=350)[0]
+        batches.append(hbtio.Batch(a.same, b.same))
+    ref = run_oracle(P, batches)
+    _, acc = run_product(P, batches)
+    hbtio.compare(ref, acc, rtol=RTOL, check_stage="cheap")
+    lim = int(P.needed_number_of_pairs) + 1
+    assert int(acc.npairs_den.max()) == lim  # the denominator cap engaged on the separate list
+
+
 def test_per_method_interface_matches_batched_call():
     """combine_and_bin_particle_pairs + per-event combine_and_bin_particle_pairs_mixed_events
     (the reference's public methods) give the same result as the one-submission batch call."""
