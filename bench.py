@@ -12,6 +12,13 @@ same-event + mixed-event pairs; ONE STEP = `--groups-per-gpu` such groups on eve
 scaling: each rank owns distinct groups, exactly how config 5 shards its 200 groups; no
 data-path collective) followed by the single NCCL all-reduce of the histograms.
 
+    --config c2|c3|c4|c4k     the other BASELINE configurations' group shapes (c2: 10 events, same-event only; c3: + mixed;
+                              c4 / c4k: 50 events of pi+ / K+, 8 K_T x 8 K_phi bins x 41^3 = 238 MB of histograms)
+    --scaling strong          config 5 as written: `--total-groups` (200) groups sharded round-robin over the ranks, ONE
+                              all-reduce at the end; a step = the whole job, `value` = its pairs / time-to-result
+Every line carries `checksum`: integer sums / a position-weighted hash of the all-reduced num_count and den_count of a
+FIXED job (strong: the job itself; weak: 8 groups sharded over the ranks), so the same value must appear at N = 1, 2, 4, 8.
+
 `value`  = pairs of all ranks / max-over-ranks device time of the step, particles already in HBM.
 `e2e`    = same metric through the reference-facing host call (hbt_accumulate_batch) with the
            particles in pinned HOST memory: staging copy, H2D, mixed-event plan (RNG draws),
@@ -34,11 +41,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from hadronic_afterburner_toolkit_b200 import hbtio, synth  # noqa: E402
-from hadronic_afterburner_toolkit_b200.params import C5, EVENT_MULTIPLICITY, PION_MASS  # noqa: E402
+from hadronic_afterburner_toolkit_b200.params import C2, C3, C4, C5, EVENT_MULTIPLICITY, KAON_MASS, PION_MASS  # noqa: E402
 
 METRIC = "HBT pairs/sec (same+mixed)"
 UNIT = "pairs/s"
 SEED = 20260005
+
+
+# group shapes of BASELINE.json's configurations (C2/C3 10 events x 1500, C4 50 x 1500, C5 100 x 1500)
+CONFIGS = {
+    "c5": dict(P=C5, events=100, mass=PION_MASS, species="pi+", mixed=True, groups=2,
+               desc="config-5-shape oversample groups, same+mixed pairs, 41^3 q grid x 4 K_T bins"),
+    "c3": dict(P=C3, events=10, mass=PION_MASS, species="pi+", mixed=True, groups=32,
+               desc="config-3-shape oversample groups (oversampling 10), same+mixed pairs, 41^3 q grid x 4 K_T bins"),
+    "c2": dict(P=C2, events=10, mass=PION_MASS, species="pi+", mixed=False, groups=32,
+               desc="config-2-shape oversample groups (oversampling 10), same-event pairs only, 41^3 q grid x 4 K_T bins"),
+    "c4": dict(P=C4, events=50, mass=PION_MASS, species="pi+", mixed=True, groups=2,
+               desc="config-4-shape oversample groups (oversampling 50), same+mixed pairs, 8 K_T x 8 K_phi bins x 41^3 (238 MB of histograms)"),
+    "c4k": dict(P=C4, events=50, mass=KAON_MASS, species="K+", mixed=True, groups=2,
+                desc="config-4-shape oversample groups (oversampling 50), same+mixed pairs, 8 K_T x 8 K_phi bins x 41^3 (238 MB of histograms)"),
+}
 
 
 def parse():
@@ -47,66 +69,89 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--groups-per-gpu", type=int, default=2)
-    ap.add_argument("--events-per-group", type=int, default=100)
+    ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--total-groups", type=int, default=200, help="--scaling strong: groups of the whole job (config 5: 200)")
+    ap.add_argument("--groups-per-gpu", type=int, default=None, help="--scaling weak: groups per GPU per step")
+    ap.add_argument("--events-per-group", type=int, default=None)
     ap.add_argument("--multiplicity", type=int, default=EVENT_MULTIPLICITY)
     ap.add_argument("--cpu-events", type=int, default=10, help="events in the CPU baseline's bounded sample group")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    if a.groups_per_gpu is None:
+        a.groups_per_gpu = c["groups"]
+    if a.events_per_group is None:
+        a.events_per_group = c["events"]
+    return a
 
 
 def workload_config(a, world):
+    c = CONFIGS[a.config]
+    P = c["P"]
+    if a.scaling == "strong":
+        per_step = f"{a.total_groups} groups in all, sharded round-robin over the ranks, one all-reduce at the end (a step = the whole job)"
+    else:
+        per_step = f"{a.groups_per_gpu} groups/GPU/step"
     return {
-        "workload": f"config-5-shape oversample groups: {a.events_per_group} events x {a.multiplicity} pi+ "
-                    f"per group, same+mixed pairs, 41^3 q grid x 4 K_T bins; {a.groups_per_gpu} groups/GPU/step",
-        "groups_per_gpu_per_step": a.groups_per_gpu, "events_per_group": a.events_per_group,
-        "multiplicity": a.multiplicity, "qnpts": C5.qnpts, "n_KT": C5.n_KT,
-        "needed_number_of_pairs": C5.needed_number_of_pairs,
+        "workload": f"{c['desc']}: {a.events_per_group} events x {a.multiplicity} {c['species']} per group; {per_step}",
+        "name": a.config, "scaling": a.scaling,
+        "groups_per_gpu_per_step": a.groups_per_gpu if a.scaling == "weak" else None,
+        "total_groups": a.total_groups if a.scaling == "strong" else None,
+        "events_per_group": a.events_per_group,
+        "multiplicity": a.multiplicity, "qnpts": P.qnpts, "n_KT": P.n_KT, "n_Kphi": P.n_Kphi if P.azimuthal_flag else None,
+        "needed_number_of_pairs": P.needed_number_of_pairs,
         "sharding": f"event groups over {world} rank(s), one NCCL all-reduce of the histograms per step",
         "l2": "flushed between timed steps (256 MiB write); accumulators stay resident by design",
+        "reference_arm_sample": f"the reference arm and cpu_baseline time groups of {a.cpu_events} events x {a.multiplicity} particles "
+                                f"(one per host core; {a.cpu_events * a.multiplicity} particles per group against "
+                                f"{a.events_per_group * a.multiplicity} here: a full-size group of config 5 takes the reference 15 min "
+                                "per core); smaller groups have the smaller working set, which favours the reference",
     }
 
 
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's own CPU implementation on the host cores
-def run_cpu_reference(n_events, multiplicity, cores, repeats=1):
-    """One process per core, each pushing one group of n_events x multiplicity pi+ through the
+def run_cpu_reference(a, cores, repeats=1):
+    """One process per core, each pushing one group of n_events x multiplicity particles through the
     UNMODIFIED reference (oracle/_ref/ref_driver mem).  Returns (pairs/s aggregate, pairs per
     process, kind).  Falls back to the C oracle port if the compiled reference is absent."""
     from oracle import oracle_py as O
 
-    P = C5
+    c = CONFIGS[a.config]
+    P, n_events, multiplicity, mass = c["P"], a.cpu_events, a.multiplicity, c["mass"]
     nmix = n_events // 2 + 1
     n = n_events * multiplicity
-    pairs = n * (n - 1) // 2 + n_events * multiplicity * nmix * multiplicity
+    pairs = n * (n - 1) // 2 + (n_events * multiplicity * nmix * multiplicity if c["mixed"] else 0)
     if O.have_reference():
         with tempfile.TemporaryDirectory() as td:
             fpar = os.path.join(td, "parameters.dat")
             with open(fpar, "w") as f:
                 f.write(P.parameters_dat())
             fins = []
-            for c in range(cores):
-                fin = os.path.join(td, f"in{c}.bin")
-                hbtio.write_batches(fin, synth.make_batches(SEED, 1, n_events, PION_MASS, multiplicity, first_group=1000 + c))
+            for k in range(cores):
+                fin = os.path.join(td, f"in{k}.bin")
+                hbtio.write_batches(fin, synth.make_batches(SEED, 1, n_events, mass, multiplicity, first_group=1000 + k))
                 fins.append(fin)
             best = 0.0
             for _ in range(repeats):
                 t0 = time.perf_counter()
-                procs = [subprocess.Popen([O.REF_DRIVER, "mem", fpar, fins[c], os.path.join(td, f"out{c}.bin")],
-                                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for c in range(cores)]
+                procs = [subprocess.Popen([O.REF_DRIVER, "mem", fpar, fins[k], os.path.join(td, f"out{k}.bin")]
+                                          + ([] if c["mixed"] else ["same_only"]),
+                                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for k in range(cores)]
                 rcs = [p.wait() for p in procs]
                 wall = time.perf_counter() - t0
                 assert all(r == 0 for r in rcs), "ref_driver failed"
                 # time inside the reference's two loop functions, slowest process
-                t_loop = max(hbtio.read_accumulators(os.path.join(td, f"out{c}.bin")).t_total for c in range(cores))
+                t_loop = max(hbtio.read_accumulators(os.path.join(td, f"out{k}.bin")).t_total for k in range(cores))
                 best = max(best, cores * pairs / t_loop)
             return best, pairs, "reference", wall
     # port: the C restatement, single-threaded per process (run in-process, one core)
     o = O.Oracle(P)
-    b = synth.make_batches(SEED, 1, n_events, PION_MASS, multiplicity, first_group=1000)[0]
+    b = synth.make_batches(SEED, 1, n_events, mass, multiplicity, first_group=1000)[0]
     t0 = time.perf_counter()
-    o.process_batch(b)
+    o.process_batch(b, do_mixed=c["mixed"])
     wall = time.perf_counter() - t0
     ts, tm = o.times()
     return pairs / (ts + tm), pairs, "port", wall
@@ -125,16 +170,17 @@ def reference_arm(a, rank, world):
     cores = host_cores()
     vals, walls = [], []
     for i in range(a.warmup + a.steps):
-        v, pairs, kind, wall = run_cpu_reference(a.cpu_events, a.multiplicity, cores)
+        v, pairs, kind, wall = run_cpu_reference(a, cores)
         if i >= a.warmup:
             vals.append(v)
             walls.append(wall)
     value = float(np.mean(vals))
-    sample = (f"per step: {cores} processes x 1 group of {a.cpu_events} events x {a.multiplicity} pi+ "
-              f"({pairs:.3e} pairs each), time inside the reference's two pair-loop functions")
+    sample = (f"per step: {cores} processes x 1 group of {a.cpu_events} events x {a.multiplicity} particles "
+              f"({pairs:.3e} pairs each; NOT the {a.events_per_group}-event groups of the GPU arm, see config.reference_arm_sample), "
+              "time inside the reference's two pair-loop functions")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak",
+        "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -215,6 +261,15 @@ def emit(obj) -> None:
         os.write(_REAL_STDOUT, line)
 
 
+def checksum(num_count, den_count):
+    """Integer fingerprint of the two count histograms: sums and a position-weighted hash (exact in Python ints)."""
+    w = (np.arange(num_count.size, dtype=np.uint64) % np.uint64(65521)) + np.uint64(1)
+    M = (1 << 61) - 1
+    hn = int(np.sum((num_count.astype(object) * w.astype(object)))) % M
+    hd = int(np.sum((den_count.astype(object) * w.astype(object)))) % M
+    return {"num_count_sum": int(num_count.sum()), "den_count_sum": int(den_count.sum()), "num_hash": hn, "den_hash": hd}
+
+
 def main():
     global _REAL_STDOUT
     a = parse()
@@ -234,14 +289,16 @@ def main():
     import torch.distributed as dist
 
     from hadronic_afterburner_toolkit_b200 import capi
-    from hadronic_afterburner_toolkit_b200.hbt_correlation import HBT_correlation, Random, _check, gather_rapidity
+    from hadronic_afterburner_toolkit_b200.hbt_correlation import HBT_correlation, Random, _check, gather_rapidity, psi_ref
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU path"
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = capi.lib()
-    P = C5
+    cfg = CONFIGS[a.config]
+    P, mass, do_mixed = cfg["P"], cfg["mass"], cfg["mixed"]
+    az = P.azimuthal_flag == 1
     eng = HBT_correlation(P, device=local)
     h = eng._h
     if (os.environ.get("HBT_B200_FUSE", "1") == "0" or os.environ.get("HBT_B200_KERNEL", "2") == "1") and "HBT_B200_LANES" not in os.environ:
@@ -258,21 +315,45 @@ def main():
         _check(h, L.hbt_comm_init_rank(h, world, rank, ctypes.create_string_buffer(raw, 128)))
 
     # ---- synthetic input: this rank's groups, pinned host copies and HBM-resident copies
-    G, nev, mult = a.groups_per_gpu, a.events_per_group, a.multiplicity
-    host, dev, offs = [], [], []
-    for g in range(G):
-        arr = synth.make_group(SEED, rank * G + g, nev, PION_MASS, mult).reshape(nev * mult, 8)
+    nev, mult = a.events_per_group, a.multiplicity
+    strong = a.scaling == "strong"
+    if strong:
+        my_groups = [g for g in range(a.total_groups) if g % world == rank]  # round-robin, as config 5 shards its groups
+        all_groups = a.total_groups
+    else:
+        my_groups = [rank * a.groups_per_gpu + g for g in range(a.groups_per_gpu)]
+        all_groups = world * a.groups_per_gpu
+    n = nev * mult
+    nmix = nev // 2 + 1
+    off = np.arange(nev + 1, dtype=np.int64) * mult
+    pairs_group = n * (n - 1) // 2 + (nev * mult * nmix * mult if do_mixed else 0)
+
+    def load_group(seed, g):
+        arr = synth.make_group(seed, g, nev, mass, mult).reshape(nev * mult, 8)
         flat = np.ascontiguousarray(np.concatenate([gather_rapidity(P, arr[e * mult:(e + 1) * mult]) for e in range(nev)]))
         assert flat.shape[0] == nev * mult  # |y| < 0.45 < HBTrap: the cut keeps everything
         t = torch.from_numpy(flat).pin_memory()
-        host.append(t)
-        dev.append(t.cuda())
-        offs.append(np.arange(nev + 1, dtype=np.int64) * mult)
-    n = nev * mult
-    nmix = nev // 2 + 1
-    pairs_step_rank = G * (n * (n - 1) // 2 + nev * mult * nmix * mult)
-    rng = Random(P.randomSeed)
-    plans = [rng.mixed_plan(nev, nev) for _ in range(G)]
+        # Psi_2 of the group (azimuthally sensitive configs), glibc on the host as the reference computes it
+        return t, t.cuda(), (psi_ref(arr, 2) if az else 0.0)
+
+    host, dev, psis = [], [], []
+    for g in my_groups:
+        t, d, ps = load_group(SEED, g)
+        host.append(t); dev.append(d); psis.append(ps)
+
+    def make_plans(seed, groups_all, mine):
+        """The reference's draws for the whole job in stream order; a rank keeps the plans of its own groups and
+        only advances the stream past the others (src/HBT_correlation.cpp:200-215)."""
+        rng = Random(seed)
+        plans = {}
+        for g in groups_all:
+            if g in mine:
+                plans[g] = rng.mixed_plan(nev, nev)
+            else:
+                rng.skip_batch(nev, nev)
+        return plans
+
+    plans = make_plans(P.randomSeed, range(all_groups) if strong else my_groups, set(my_groups)) if do_mixed else {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -280,30 +361,43 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        for g in range(G):
-            ids, cs = plans[g]
+    def submit_resident(d_t, psi, plan):
+        if do_mixed:
+            ids, cs = plan
             # one fused launch per group (both loops); separate kernels with HBT_B200_FUSE=0 or stage counters on
-            _check(h, L.hbt_accumulate_batch_dev(h, dev[g].data_ptr(), offs[g].ctypes.data, nev,
-                                                 ids.ctypes.data, cs.ctypes.data, nmix, 0.0))
+            _check(h, L.hbt_accumulate_batch_dev(h, d_t.data_ptr(), off.ctypes.data, nev, ids.ctypes.data, cs.ctypes.data, nmix, psi))
+        else:
+            _check(h, L.hbt_accumulate_same_dev(h, d_t.data_ptr(), n, psi))
+
+    def submit_host(h_t, psi, plan):
+        if do_mixed:
+            ids, cs = plan
+            _check(h, L.hbt_accumulate_batch(h, h_t.data_ptr(), off.ctypes.data, nev, None, None, 0,
+                                             ids.ctypes.data, cs.ctypes.data, nmix, psi, 1, 1))
+        else:
+            _check(h, L.hbt_accumulate_batch(h, h_t.data_ptr(), off.ctypes.data, nev, None, None, 0, None, None, 0, psi, 1, 0))
+
+    def step_resident():
+        for k, g in enumerate(my_groups):
+            submit_resident(dev[k], psis[k], plans.get(g))
         if world > 1:
             _check(h, L.hbt_allreduce(h))
 
     kcount = np.zeros(2 * P.n_slabs, dtype=np.uint64)
+    e2e_rng = Random(P.randomSeed + 1)
 
     def step_e2e():
-        for g in range(G):
-            ids, cs = rng.mixed_plan(nev, nev)  # fresh draws, as the host loop would make them
-            _check(h, L.hbt_accumulate_batch(h, host[g].data_ptr(), offs[g].ctypes.data, nev, None, None, 0,
-                                             ids.ctypes.data, cs.ctypes.data, nmix, 0.0, 1, 1))
+        for k, g in enumerate(my_groups):
+            plan = e2e_rng.mixed_plan(nev, nev) if do_mixed else None  # fresh draws, as the host loop would make them
+            submit_host(host[k], psis[k], plan)
         if world > 1:
             _check(h, L.hbt_allreduce(h))
         # the step's result: per-K_T accepted-pair counters, device -> host
         _check(h, L.hbt_read(h, None, None, None, None, None, None, kcount.ctypes.data, kcount[P.n_slabs:].ctypes.data))
 
-    def timed(step_fn, steps, device_timer):
+    def timed(step_fn, steps, device_timer, after=None):
         total = 0.0
-        for _ in range(steps):
+        for it in range(steps):
             flush.fill_(1)
             barrier()
             if device_timer:
@@ -316,6 +410,8 @@ def main():
             else:
                 t0 = time.perf_counter()
                 step_fn()
+                if after is not None and it == steps - 1:
+                    after()
                 _check(h, L.hbt_synchronize(h))
                 torch.cuda.synchronize()
                 total += time.perf_counter() - t0
@@ -334,8 +430,11 @@ def main():
     # bounding boxes cannot hold an accepted pair and therefore do not see every pair
     _check(h, L.hbt_set_option(h, 1, 1))
     s0 = eng.stage_counters()
-    step_resident()
-    st_step = ((eng.stage_counters() - s0) // np.uint64(world)).astype(np.uint64) if world > 1 else eng.stage_counters() - s0
+    inst_groups = my_groups if not strong else my_groups[:2]  # (strong: two groups, scaled: all groups have the same shape)
+    for k, g in enumerate(inst_groups):
+        submit_resident(dev[k], psis[k], plans.get(g))
+    st_step = eng.stage_counters() - s0
+    st_step = (st_step.astype(np.float64) * (len(my_groups) / max(1, len(inst_groups)))).astype(np.uint64)
     _check(h, L.hbt_set_option(h, 1, 0))
 
     # ---- resident-input measurement (value) ---------------------------------------------
@@ -351,17 +450,29 @@ def main():
     clocks = sampler.stop() if sampler else None
     st1 = eng.stage_counters()
     tm1, l1 = eng.timers(), launches()
-    pairs_total = world * pairs_step_rank * a.steps
+    pairs_step = all_groups * pairs_group
+    pairs_total = pairs_step * a.steps
     value = pairs_total / t_value
 
     # ---- end-to-end measurement (host buffers through the reference-facing call) ----------
     e2e = None
     if not a.no_e2e:
+        nb = P.n_bins
+        full = [np.zeros(nb, dtype=np.uint64)] + [np.zeros(nb, dtype=np.float64) for _ in range(4)] + [np.zeros(nb, dtype=np.uint64)]
+
+        def read_all():
+            # the path's result: all six histograms, read once per analysis (here: once per timed region)
+            _check(h, L.hbt_read(h, full[0].ctypes.data, full[1].ctypes.data, full[2].ctypes.data, full[3].ctypes.data,
+                                 full[4].ctypes.data, full[5].ctypes.data, kcount.ctypes.data, kcount[P.n_slabs:].ctypes.data))
+
         timed(step_e2e, max(1, a.warmup - 1), False)
-        t_e2e = timed(step_e2e, a.steps, False)
+        t_e2e = timed(step_e2e, a.steps, False, after=read_all)
+        blob = sum(x.nbytes for x in full)
         e2e = {"value": pairs_total / t_e2e, "unit": UNIT,
-               "h2d_bytes_per_step": int(G * (n * 64 + nev * nmix * 48)),
-               "d2h_bytes_per_step": int(kcount.nbytes),
+               "h2d_bytes_per_step": int(len(my_groups) * (n * 64 + (nev * nmix * 48 if do_mixed else 0))),
+               "d2h_bytes_per_step": int(kcount.nbytes + blob / a.steps),
+               "d2h_note": f"per step the per-K_T pair counters ({kcount.nbytes} B); the six histograms ({blob} B) are read ONCE, "
+                           f"inside the timed region, after the last step (amortised over the {a.steps} steps)",
                "ms_per_step": 1e3 * t_e2e / a.steps}
 
     # ---- roofline of the pair kernels (rank 0's device) -------------------------------------
@@ -369,36 +480,53 @@ def main():
     _check(None, L.hbt_measure_fp64_peak(local, 300.0, ctypes.byref(peak)))
     # stage populations of this rank over the timed steps = steps x (one instrumented step)
     dst = (st_step * np.uint64(a.steps)).astype(np.uint64)
-    assert int(dst[0]) * world == int(st1[0] - st0[0]) or world > 1  # same pair count in both passes
-    ops_same, ops_mixed = algorithmic_ops(dst, boost=P.long_comoving_boost == 1, az=P.azimuthal_flag == 1)
-    fused = os.environ.get("HBT_B200_FUSE", "1") != "0" and os.environ.get("HBT_B200_KERNEL", "2") != "1"
+    ops_same, ops_mixed = algorithmic_ops(dst, boost=P.long_comoving_boost == 1, az=az)
+    if not do_mixed:
+        ops_mixed = 0.0
+    fused = do_mixed and os.environ.get("HBT_B200_FUSE", "1") != "0" and os.environ.get("HBT_B200_KERNEL", "2") != "1"
     ks = (tm1["same_ms"] - tm0["same_ms"]) * 1e-3
     km = (tm1["mixed_ms"] - tm0["mixed_ms"]) * 1e-3
     ach = (ops_same + ops_mixed) / (ks + km) / 1e12
     traffic = None
     traffic_detail = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch (one C5-shape group)
-        traffic = tj["fused" if fused else "same"]["dram_bytes_per_launch"] + (0 if fused else tj["mixed"]["dram_bytes_per_launch"])
-        traffic_detail = {"unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one C5-shape group per launch)",
-                          "fused": tj["fused"]["dram_bytes_per_launch"], "same": tj["same"]["dram_bytes_per_launch"],
-                          "mixed": tj["mixed"]["dram_bytes_per_launch"],
-                          "algorithmic_bytes_per_launch": tj["fused"]["algorithmic_bytes_per_launch"], "source": tj["source"]}
-    except (OSError, KeyError, ValueError):
-        pass
+    if a.config == "c5":
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch (one C5-shape group)
+            traffic = tj["fused" if fused else "same"]["dram_bytes_per_launch"] + (0 if fused else tj["mixed"]["dram_bytes_per_launch"])
+            traffic_detail = {"kind": "STATIC: a constant read from profiles/traffic.json (one `ncu --set full` capture with a cold L2), "
+                                      "NOT measured in this run",
+                              "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one C5-shape group per launch)",
+                              "fused": tj["fused"]["dram_bytes_per_launch"], "same": tj["same"]["dram_bytes_per_launch"],
+                              "mixed": tj["mixed"]["dram_bytes_per_launch"],
+                              "algorithmic_bytes_per_launch": tj["fused"]["algorithmic_bytes_per_launch"], "source": tj["source"]}
+        except (OSError, KeyError, ValueError):
+            pass
+    # what actually binds (profiles/r02_controls.txt): the spread-address reductions of the accepted same-event
+    # pairs (5 per pair) + 1 per accepted mixed-event pair, against the rate a reductions-only kernel sustains
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    red_lanes = 5.0 * float(dst[4]) + float(dst[10])
+    red_rate = red_lanes / (ks + km) / (sm_mhz * 1e6) / n_sm
+    bound_actual = {
+        "reductions": {"red_lanes_per_clk_per_sm": red_rate, "ceiling_reductions_only_kernel": 0.66,
+                       "frac": red_rate / 0.66, "lanes": "5 per accepted same-event pair + 1 per accepted mixed-event pair",
+                       "ceiling_source": "profiles/r02_red_bench.txt (scripts/micro/red_bench.cu, one lane per bin, spread addresses)"},
+        "issue_slots": {"busy_pct_fused_kernel": 65.3, "kind": "STATIC: ncu capture profiles/r01_ncu_summary_final.txt "
+                        "(smsp__issue_active); 20.3e9 warp instructions per C5-shape fused launch = 17.5 ms at 4/clk/SM"},
+        "controls": "profiles/r02_controls.txt: same-event kernel 15.3 ms with / 10.1 ms without its reductions; fused 27.3 / 23.5",
+    }
     roofline = {
         "bound": "fp64", "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
-        "traffic": traffic, "traffic_detail": traffic_detail,
+        "traffic": traffic, "traffic_detail": traffic_detail, "bound_actual": bound_actual,
         "peak_source": "measured on this device: DFMA dependent-chain microbenchmark (hbt_measure_fp64_peak); "
                        "FP64 is not in MEASURED_PEAKS.json",
         "definition": "algorithmic FP64 ops (SURVEY.md 8d: 7nA+10nB+5nC+17nD+20nE same, ...+3nE mixed; stage populations from an "
                       "instrumented, untimed pass over the same input) / CUDA-event time of the production pair kernels "
                       "(incl. the same-event sort + cull kernels) on the launching stream",
-        "note": "the bound is the FP64 pipe (SURVEY.md 8d), not HBM or tensor cores; the production prefilter runs in packed "
-                "FP32 and mixed-event survivors are binned in FP32 wherever a rigorous error band allows, so the FP64 pipe itself is "
-                "~19 % busy (ncu, fused kernel; issue slots 65 %) while the algorithmic-ops fraction is what is reported; same-event "
-                "units are bounded by their 5 spread-address REDs per accepted pair (DESIGN.md 5)",
+        "note": "the bound SURVEY.md 8d names is the FP64 pipe; it is NOT what binds this design: the production prefilter runs in "
+                "packed FP32 and mixed-event survivors are binned in FP32 wherever a rigorous error band allows, so the FP64 pipe "
+                "itself is ~19 % busy (ncu, fused kernel) and `frac` is an algorithmic-throughput fraction; see bound_actual",
         "kernels": ({
             # one launch per group works through the same-event and the mixed-event units interleaved
             "hbt_pairs_v3_fused": {"ms_per_launch": 1e3 * (ks + km) / max(1, tm1["same_launches"] - tm0["same_launches"]),
@@ -408,9 +536,9 @@ def main():
             "same": {"ms_per_launch": 1e3 * ks / max(1, tm1["same_launches"] - tm0["same_launches"]),
                      "pairs_per_s": float(dst[0]) / ks, "tflops": ops_same / ks / 1e12, "frac": ops_same / ks / 1e12 / peak.value,
                      "ops_per_pair": ops_same / float(dst[0])},
-            "mixed": {"ms_per_launch": 1e3 * km / max(1, tm1["mixed_launches"] - tm0["mixed_launches"]),
-                      "pairs_per_s": float(dst[6]) / km, "tflops": ops_mixed / km / 1e12, "frac": ops_mixed / km / 1e12 / peak.value,
-                      "ops_per_pair": ops_mixed / float(dst[6])},
+            **({"mixed": {"ms_per_launch": 1e3 * km / max(1, tm1["mixed_launches"] - tm0["mixed_launches"]),
+                          "pairs_per_s": float(dst[6]) / km, "tflops": ops_mixed / km / 1e12, "frac": ops_mixed / km / 1e12 / peak.value,
+                          "ops_per_pair": ops_mixed / float(dst[6])}} if do_mixed else {}),
         }),
         "stage_fractions_same": [float(x) / float(dst[0]) for x in dst[:6]],
         "kernel_share_of_step": (ks + km) / (t_value if world == 1 else max(t_value, 1e-12)),
@@ -419,20 +547,42 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cores = host_cores()
-        v, pairs, kind, wall = run_cpu_reference(a.cpu_events, mult, cores)
+        v, pairs, kind, wall = run_cpu_reference(a, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": f"{cores} processes x 1 group of {a.cpu_events} events x {mult} pi+ ({pairs:.3e} pairs each), "
-                         f"time inside the reference's two pair-loop functions; wall {wall:.1f} s",
+               "sample": f"{cores} processes x 1 group of {a.cpu_events} events x {mult} particles ({pairs:.3e} pairs each; the GPU arm's "
+                         f"groups have {nev} events), time inside the reference's two pair-loop functions; wall {wall:.1f} s",
                "per_core": v / cores}
+
+    # ---- checksum of a FIXED job: identical at every N (driver-visible multi-GPU parity) ---------------------
+    _check(h, L.hbt_reset(h))
+    if strong:
+        ck_groups, ck_seed = list(range(a.total_groups)), SEED
+        for k, g in enumerate(my_groups):
+            submit_resident(dev[k], psis[k], plans.get(g))
+    else:
+        ck_groups, ck_seed = list(range(8)), SEED + 77
+        mine = [g for g in ck_groups if g % world == rank]
+        ck_plans = make_plans(P.randomSeed, ck_groups, set(mine)) if do_mixed else {}
+        keep = []
+        for g in mine:
+            t, d, ps = load_group(ck_seed, g)
+            keep.append(d)
+            submit_resident(d, ps, ck_plans.get(g))
+    if world > 1:
+        _check(h, L.hbt_allreduce(h))
+    numc, denc = np.zeros(P.n_bins, dtype=np.uint64), np.zeros(P.n_bins, dtype=np.uint64)
+    _check(h, L.hbt_read(h, numc.ctypes.data, None, None, None, None, denc.ctypes.data, None, None))
+    ck = checksum(numc, denc)
+    ck["job"] = f"{len(ck_groups)} groups (seed {ck_seed}) of {nev} events x {mult} {cfg['species']}, sharded round-robin over {world} rank(s), all-reduced"
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": 1e3 * t_value / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * t_value / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a, world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(l1 - l0), "roofline": roofline, "cpu_baseline": cpu,
-            "pairs_per_step": world * pairs_step_rank, "kernel": os.environ.get("HBT_B200_KERNEL", "default"),
-            "deferred_pairs": eng.deferred_pairs(),
+            "pairs_per_step": pairs_step, "kernel": os.environ.get("HBT_B200_KERNEL", "default"),
+            "deferred_pairs": eng.deferred_pairs(), "checksum": ck,
         }
         emit(out)
     eng.close()

@@ -28,6 +28,9 @@ EXPORTS = (
     "hbt_comm_unique_id", "hbt_comm_init_rank", "hbt_comm_init_all", "hbt_allreduce", "hbt_allreduce_all",
     "hbt_version", "hbt_device_count", "hbt_set_option",
     "hbt_reader_open", "hbt_reader_next", "hbt_reader_error", "hbt_reader_bytes", "hbt_reader_close",
+    "hbt_group_create", "hbt_group_destroy", "hbt_group_last_error", "hbt_group_size", "hbt_group_ctx",
+    "hbt_group_accumulate_batch", "hbt_group_reduce", "hbt_group_ordered_batches",
+    "hbt_cap_channels", "hbt_cap_get_counts", "hbt_cap_set_foreign",
     "hbt_bf_create", "hbt_bf_destroy", "hbt_bf_last_error", "hbt_bf_accumulate", "hbt_bf_read", "hbt_bf_get_timers",
 )
 
@@ -107,6 +110,17 @@ def lib() -> ctypes.CDLL:
         "hbt_reader_error": (ctypes.c_char_p, [vp]),
         "hbt_reader_bytes": (ctypes.c_uint64, [vp]),
         "hbt_reader_close": (None, [vp]),
+        "hbt_group_create": (ctypes.c_int, [pp, i32, vp, ctypes.POINTER(vp)]),
+        "hbt_group_destroy": (None, [vp]),
+        "hbt_group_last_error": (ctypes.c_char_p, [vp]),
+        "hbt_group_size": (i32, [vp]),
+        "hbt_group_ctx": (vp, [vp, i32]),
+        "hbt_group_accumulate_batch": (ctypes.c_int, [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, dbl, i32, i32]),
+        "hbt_group_reduce": (ctypes.c_int, [vp]),
+        "hbt_group_ordered_batches": (ctypes.c_int, [vp, vp]),
+        "hbt_cap_channels": (i32, [vp]),
+        "hbt_cap_get_counts": (ctypes.c_int, [vp, vp, vp]),
+        "hbt_cap_set_foreign": (ctypes.c_int, [vp, vp, vp]),
         "hbt_bf_create": (ctypes.c_int, [i32, dbl, i32, vp]),
         "hbt_bf_destroy": (None, [vp]),
         "hbt_bf_last_error": (ctypes.c_char_p, [vp]),

@@ -164,6 +164,9 @@ struct hbt_ctx {
     // needed_number_of_pairs bookkeeping (ordered cap)
     std::vector<uint64_t> exact_num, exact_den;  // per-slab accepted pairs as of the last refresh
     uint64_t pending_num = 0, pending_den = 0;   // pairs submitted since (upper bound of what they add)
+    // accepted pairs per cap channel accumulated by the OTHER contexts of a group (hbt_cap_set_foreign): the cap is
+    // cumulative over all batches of the analysis, whichever GPU took them
+    std::vector<uint64_t> foreign_num, foreign_den;
     std::vector<unsigned char> closed;           // [2*nslab] slabs whose counter exceeds the cap
     unsigned char *d_closed = nullptr;
     bool any_closed = false;
@@ -757,26 +760,33 @@ struct PhaseInput {
     double psi_ref = 0.;
 };
 
+// pairs of channel c the cap has seen so far: this context's own (as of the last refresh) + the other contexts'
+uint64_t foreign_count(const hbt_ctx *ctx, int c, bool mixed) {
+    const std::vector<uint64_t> &f = mixed ? ctx->foreign_den : ctx->foreign_num;
+    return f.empty() ? 0 : f[c];
+}
+uint64_t have_count(const hbt_ctx *ctx, int c, bool mixed) {
+    const std::vector<uint64_t> &ex = mixed ? ctx->exact_den : ctx->exact_num;
+    return (ex.empty() ? 0 : ex[c]) + foreign_count(ctx, c, mixed);
+}
+
 bool cap_may_engage(const hbt_ctx *ctx, bool mixed, unsigned long long pairs) {
     if (ctx->grid.needed >= (1ull << 56)) return false;
-    const std::vector<uint64_t> &ex = mixed ? ctx->exact_den : ctx->exact_num;
     const uint64_t pend = (mixed ? ctx->pending_den : ctx->pending_num) + pairs;
     const int nch = n_channels(ctx);
     for (int c = 0; c < nch; c++) {
         if (ctx->closed[closed_index(ctx, c, mixed)]) continue;
-        const uint64_t have = ex.empty() ? 0 : ex[c];
-        if (have + pend > channel_quota(ctx, c)) return true;
+        if (have_count(ctx, c, mixed) + pend > channel_quota(ctx, c)) return true;
     }
     return false;
 }
 
 int sync_closed(hbt_ctx *ctx, bool mixed) {
     const int nch = n_channels(ctx);
-    const std::vector<uint64_t> &ex = mixed ? ctx->exact_den : ctx->exact_num;
     bool changed = false;
     for (int c = 0; c < nch; c++) {
         const size_t ci = closed_index(ctx, c, mixed);
-        if (ex[c] >= channel_quota(ctx, c) && !ctx->closed[ci]) { ctx->closed[ci] = 1; changed = true; }
+        if (have_count(ctx, c, mixed) >= channel_quota(ctx, c) && !ctx->closed[ci]) { ctx->closed[ci] = 1; changed = true; }
     }
     if (changed) {
         ctx->any_closed = true;
@@ -852,7 +862,7 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
     std::vector<int32_t> xidx(nch, -1);
     std::vector<int> crossing;
     for (int k = 0; k < nch; k++)
-        if (!ctx->closed[closed_index(ctx, k, in.mixed)] && after[k] > channel_quota(ctx, k)) {
+        if (!ctx->closed[closed_index(ctx, k, in.mixed)] && after[k] + foreign_count(ctx, k, in.mixed) > channel_quota(ctx, k)) {
             xidx[k] = static_cast<int32_t>(crossing.size());
             crossing.push_back(k);
         }
@@ -920,7 +930,8 @@ int capped_phase(hbt_ctx *ctx, const PhaseInput &in, const HbtMixSeg *d_seg, siz
     std::vector<int64_t> cut_row(nch, INT64_MAX), cut_pos(nch, INT64_MAX);
     for (size_t x = 0; x < nx; x++) {
         const int K = crossing[x];
-        uint64_t quota = channel_quota(ctx, K) - before[K];  // >= 1 for an open slab; 0 for q_inv with needed = 0
+        // >= 1 for an open slab; 0 for q_inv with needed = 0
+        uint64_t quota = channel_quota(ctx, K) - std::min<uint64_t>(channel_quota(ctx, K), before[K] + foreign_count(ctx, K, in.mixed));
         if (quota == 0) { cut_row[K] = -1; cut_pos[K] = -1; continue; }
         int64_t row = 0;
         const unsigned *rc_x = rowcnt.data() + x * nrows;
@@ -1711,3 +1722,251 @@ extern "C" int hbt_allreduce_all(hbt_ctx **ctxs, int32_t n) {
 }
 
 extern "C" int hbt_allreduce(hbt_ctx *ctx) { return hbt_allreduce_all(&ctx, 1); }
+
+
+// ---- cap bookkeeping across contexts ---------------------------------------------------------------
+extern "C" int32_t hbt_cap_channels(const hbt_ctx *ctx) { return ctx ? n_channels(ctx) : 0; }
+
+extern "C" int hbt_cap_get_counts(hbt_ctx *ctx, uint64_t *num, uint64_t *den) {
+    if (!ctx) return HBT_ERR_INVALID;
+    int rc = hbt_synchronize(ctx);  // refreshes the exact per-channel counters
+    if (rc) return rc;
+    const size_t nch = static_cast<size_t>(n_channels(ctx));
+    if (num) std::memcpy(num, ctx->exact_num.data(), nch * 8);
+    if (den) std::memcpy(den, ctx->exact_den.data(), nch * 8);
+    return HBT_OK;
+}
+
+extern "C" int hbt_cap_set_foreign(hbt_ctx *ctx, const uint64_t *num, const uint64_t *den) {
+    if (!ctx || !num || !den) return HBT_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = hbt_synchronize(ctx);
+    if (rc) return rc;
+    const size_t nch = static_cast<size_t>(n_channels(ctx));
+    ctx->foreign_num.assign(num, num + nch);
+    ctx->foreign_den.assign(den, den + nch);
+    rc = sync_closed(ctx, false);  // channels another context filled are closed here too
+    if (rc) return rc;
+    return sync_closed(ctx, true);
+}
+
+// ---- group of contexts: one analysis over several GPUs of one process -----------------------------
+namespace {
+__global__ void hbt_add_blob_u64(unsigned long long *__restrict__ dst, const unsigned long long *__restrict__ src, size_t n) {
+    const size_t k = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (k < n) dst[k] += src[k];
+}
+__global__ void hbt_add_blob_f64(double *__restrict__ dst, const double *__restrict__ src, size_t n) {
+    const size_t k = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (k < n) dst[k] += src[k];
+}
+}  // namespace
+
+struct hbt_group {
+    std::vector<hbt_ctx *> ctx;
+    int next = 0;
+    bool distinct = true;      // all contexts on different devices: the sum is one NCCL all-reduce
+    bool cap_possible = false;
+    int nch = 0, nslab = 0;
+    uint64_t needed = 0;
+    std::vector<uint64_t> g_num, g_den;                     // accepted pairs per channel, all contexts, as of the last refresh
+    std::vector<std::vector<uint64_t>> own_num, own_den;    // per context
+    uint64_t pend_num = 0, pend_den = 0;                    // pairs submitted to any context since
+    uint64_t ordered_batches = 0;                           // batches that had to run in sequence (near the cap)
+    std::string err;
+};
+
+namespace {
+int gfail(hbt_group *g, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (g) g->err = buf; else g_create_error = buf;
+    return code;
+}
+uint64_t gquota(const hbt_group *g, int c) { return c < g->nslab ? g->needed + 1 : 50 * g->needed; }
+
+// synchronize every context, sum the exact per-channel counters and tell each context what the others hold
+int group_refresh(hbt_group *g) {
+    const size_t nch = static_cast<size_t>(g->nch);
+    std::fill(g->g_num.begin(), g->g_num.end(), 0);
+    std::fill(g->g_den.begin(), g->g_den.end(), 0);
+    for (size_t i = 0; i < g->ctx.size(); i++) {
+        int rc = hbt_cap_get_counts(g->ctx[i], g->own_num[i].data(), g->own_den[i].data());
+        if (rc) return gfail(g, rc, "%s", hbt_last_error(g->ctx[i]));
+        for (size_t c = 0; c < nch; c++) { g->g_num[c] += g->own_num[i][c]; g->g_den[c] += g->own_den[i][c]; }
+    }
+    std::vector<uint64_t> fn(nch), fd(nch);
+    for (size_t i = 0; i < g->ctx.size(); i++) {
+        for (size_t c = 0; c < nch; c++) { fn[c] = g->g_num[c] - g->own_num[i][c]; fd[c] = g->g_den[c] - g->own_den[i][c]; }
+        int rc = hbt_cap_set_foreign(g->ctx[i], fn.data(), fd.data());
+        if (rc) return gfail(g, rc, "%s", hbt_last_error(g->ctx[i]));
+    }
+    g->pend_num = g->pend_den = 0;
+    return HBT_OK;
+}
+
+bool group_far(const hbt_group *g, uint64_t sp, uint64_t mp) {
+    for (int c = 0; c < g->nch; c++) {
+        const uint64_t q = gquota(g, c);
+        if (sp && g->g_num[c] < q && g->g_num[c] + g->pend_num + sp > q) return false;
+        if (mp && g->g_den[c] < q && g->g_den[c] + g->pend_den + mp > q) return false;
+    }
+    return true;
+}
+}  // namespace
+
+extern "C" int hbt_group_create(const hbt_params *params, int32_t n_devices, const int32_t *devices, hbt_group **out) {
+    if (!params || !out || n_devices < 1) return gfail(nullptr, HBT_ERR_INVALID, "hbt_group_create: bad argument");
+    *out = nullptr;
+    hbt_group *g = new hbt_group;
+    for (int i = 0; i < n_devices; i++) {
+        hbt_ctx *c = nullptr;
+        const int dev = devices ? devices[i] : i;
+        const int rc = hbt_create(params, dev, &c);
+        if (rc) {
+            for (hbt_ctx *x : g->ctx) hbt_destroy(x);
+            delete g;
+            return rc;  // message in hbt_last_error(NULL)
+        }
+        for (hbt_ctx *x : g->ctx) if (x->device == dev) g->distinct = false;
+        g->ctx.push_back(c);
+    }
+    hbt_ctx *c0 = g->ctx[0];
+    g->nch = n_channels(c0);
+    g->nslab = c0->grid.nslab;
+    g->needed = c0->grid.needed;
+    g->cap_possible = g->needed < (1ull << 56);
+    g->g_num.assign(g->nch, 0);
+    g->g_den.assign(g->nch, 0);
+    g->own_num.assign(g->ctx.size(), std::vector<uint64_t>(g->nch, 0));
+    g->own_den.assign(g->ctx.size(), std::vector<uint64_t>(g->nch, 0));
+    if (g->ctx.size() > 1 && g->distinct) {
+        const int rc = hbt_comm_init_all(g->ctx.data(), static_cast<int>(g->ctx.size()));
+        if (rc) {
+            gfail(nullptr, rc, "%s", hbt_last_error(c0));
+            for (hbt_ctx *x : g->ctx) hbt_destroy(x);
+            delete g;
+            return rc;
+        }
+    }
+    *out = g;
+    return HBT_OK;
+}
+
+extern "C" void hbt_group_destroy(hbt_group *g) {
+    if (!g) return;
+    for (hbt_ctx *c : g->ctx) hbt_destroy(c);
+    delete g;
+}
+
+extern "C" const char *hbt_group_last_error(const hbt_group *g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+extern "C" int32_t hbt_group_size(const hbt_group *g) { return g ? static_cast<int32_t>(g->ctx.size()) : 0; }
+extern "C" hbt_ctx *hbt_group_ctx(hbt_group *g, int32_t i) {
+    return (g && i >= 0 && i < static_cast<int32_t>(g->ctx.size())) ? g->ctx[i] : nullptr;
+}
+extern "C" int hbt_group_ordered_batches(const hbt_group *g, uint64_t *n) {
+    if (!g || !n) return HBT_ERR_INVALID;
+    *n = g->ordered_batches;
+    return HBT_OK;
+}
+
+extern "C" int hbt_group_accumulate_batch(hbt_group *g, const double *p1, const int64_t *off1, int32_t nev1,
+                                          const double *p2, const int64_t *off2, int32_t nev2,
+                                          const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
+                                          double psi_ref, int32_t do_same, int32_t do_mixed) {
+    if (!g || nev1 < 0) return gfail(g, HBT_ERR_INVALID, "hbt_group_accumulate_batch: bad argument");
+    if (nev1 == 0) return HBT_OK;
+    if (!off1) return gfail(g, HBT_ERR_INVALID, "hbt_group_accumulate_batch: null offsets");
+    hbt_ctx *c = g->ctx[g->next];
+    g->next = (g->next + 1) % static_cast<int>(g->ctx.size());
+    auto submit = [&]() {
+        const int rc = hbt_accumulate_batch(c, p1, off1, nev1, p2, off2, nev2, partner_ids, cos_sin, nmix, psi_ref, do_same, do_mixed);
+        return rc ? gfail(g, rc, "%s", hbt_last_error(c)) : HBT_OK;
+    };
+    if (!g->cap_possible || g->ctx.size() == 1) return submit();
+    // pairs of this batch (what the loops will visit: an upper bound of what they accept)
+    const uint64_t n1 = static_cast<uint64_t>(off1[nev1]);
+    const uint64_t sp = (do_same && n1 > 1) ? n1 * (n1 - 1) / 2 : 0;
+    uint64_t mp = 0;
+    if (do_mixed && nmix > 0 && partner_ids) {
+        const int64_t *o2 = p2 ? off2 : off1;
+        const int32_t ne2 = p2 ? nev2 : nev1;
+        for (int iev = 0; iev < nev1; iev++)
+            for (int k = 0; k < nmix; k++) {
+                const int id = partner_ids[static_cast<size_t>(iev) * nmix + k];
+                if (id < 0 || id >= ne2) return gfail(g, HBT_ERR_INVALID, "partner id %d out of range", id);
+                mp += static_cast<uint64_t>(off1[iev + 1] - off1[iev]) * static_cast<uint64_t>(o2[id + 1] - o2[id]);
+            }
+    }
+    // Far from the cap the batches stay asynchronous on their GPUs.  The needed_number_of_pairs cap is cumulative
+    // over the batches IN ORDER (src/HBT_correlation.cpp:402-406, :651-655): when this batch could close a channel,
+    // every context is brought up to date first, then the batch runs alone, with the other contexts' counters as
+    // its starting point (hbt_cap_set_foreign), so its own ordered replay cuts at the reference's pair.
+    if (!group_far(g, sp, mp)) {
+        int rc = group_refresh(g);
+        if (rc) return rc;
+        if (!group_far(g, sp, mp)) {
+            rc = submit();
+            if (rc) return rc;
+            g->ordered_batches++;
+            return group_refresh(g);
+        }
+    }
+    g->pend_num += sp;
+    g->pend_den += mp;
+    return submit();
+}
+
+// sum of all contexts' accumulators, readable from context 0 afterwards
+extern "C" int hbt_group_reduce(hbt_group *g) {
+    if (!g) return HBT_ERR_INVALID;
+    const int n = static_cast<int>(g->ctx.size());
+    if (n == 1) return hbt_synchronize(g->ctx[0]) ? gfail(g, HBT_ERR_CUDA, "%s", hbt_last_error(g->ctx[0])) : HBT_OK;
+    if (g->distinct) {  // one NCCL all-reduce over NVLink
+        const int rc = hbt_allreduce_all(g->ctx.data(), n);
+        return rc ? gfail(g, rc, "%s", hbt_last_error(g->ctx[0])) : HBT_OK;
+    }
+    // several contexts share a device (test configurations): NCCL refuses duplicate devices in one communicator;
+    // context 0 adds the others' blobs itself (peer copies where the device differs)
+    for (hbt_ctx *c : g->ctx) {
+        const int rc = hbt_synchronize(c);
+        if (rc) return gfail(g, rc, "%s", hbt_last_error(c));
+    }
+    hbt_ctx *c0 = g->ctx[0];
+    CU(c0, cudaSetDevice(c0->device));
+    if (!c0->red_u64) {
+        CU(c0, cudaMalloc(&c0->red_u64, c0->n_u64 * 8));
+        CU(c0, cudaMalloc(&c0->red_f64, c0->n_f64 * 8));
+    }
+    CU(c0, cudaMemcpyAsync(c0->red_u64, c0->blob_u64, c0->n_u64 * 8, cudaMemcpyDeviceToDevice, c0->compute));
+    CU(c0, cudaMemcpyAsync(c0->red_f64, c0->blob_f64, c0->n_f64 * 8, cudaMemcpyDeviceToDevice, c0->compute));
+    unsigned long long *tmp_u = nullptr;
+    double *tmp_f = nullptr;
+    for (int i = 1; i < n; i++) {
+        hbt_ctx *ci = g->ctx[i];
+        const unsigned long long *su = ci->blob_u64;
+        const double *sf = ci->blob_f64;
+        if (ci->device != c0->device) {
+            if (!tmp_u) {
+                CU(c0, cudaMalloc(&tmp_u, c0->n_u64 * 8));
+                CU(c0, cudaMalloc(&tmp_f, c0->n_f64 * 8));
+            }
+            CU(c0, cudaMemcpyPeerAsync(tmp_u, c0->device, ci->blob_u64, ci->device, c0->n_u64 * 8, c0->compute));
+            CU(c0, cudaMemcpyPeerAsync(tmp_f, c0->device, ci->blob_f64, ci->device, c0->n_f64 * 8, c0->compute));
+            su = tmp_u;
+            sf = tmp_f;
+        }
+        hbt_add_blob_u64<<<static_cast<unsigned>((c0->n_u64 + 255) / 256), 256, 0, c0->compute>>>(c0->red_u64, su, c0->n_u64);
+        hbt_add_blob_f64<<<static_cast<unsigned>((c0->n_f64 + 255) / 256), 256, 0, c0->compute>>>(c0->red_f64, sf, c0->n_f64);
+        c0->kernel_launches += 2;
+        CU(c0, cudaGetLastError());
+        CU(c0, cudaStreamSynchronize(c0->compute));
+    }
+    cudaFree(tmp_u);
+    cudaFree(tmp_f);
+    c0->reduced = true;
+    return HBT_OK;
+}

@@ -84,25 +84,41 @@ class HBT_correlation:
 
     def __init__(self, params: HBTParams, path: str = ".", ran_gen: Optional[Random] = None, device: int = 0,
                  stage_counters: Optional[bool] = None, kernel: Optional[int] = None, fuse: Optional[bool] = None,
-                 lanes: Optional[int] = None, ptsort: Optional[int] = None):
+                 lanes: Optional[int] = None, ptsort: Optional[int] = None, devices: Optional[Sequence[int]] = None):
+        """``devices``: run the analysis on a GROUP of contexts, one per listed CUDA device (``hbt_group_*``; what the
+        C++ class does for ``HBT_B200_DEVICES`` > 1): batches go to the devices in turn, the ordered pair cap stays
+        exact, results are summed when read.  A device may be listed twice (several contexts on one GPU)."""
         self.params = params
         self.path_ = path
         self.ran_gen = ran_gen if ran_gen is not None else Random(params.randomSeed)
         self._L = capi.lib()
         self._cp = params.to_c()
-        h = ctypes.c_void_p()
-        _check(None, self._L.hbt_create(ctypes.byref(self._cp), device, ctypes.byref(h)))
+        self._g = None
+        self._hs = []
+        if devices is not None:
+            g = ctypes.c_void_p()
+            devs = (ctypes.c_int32 * len(devices))(*devices)
+            _check(None, self._L.hbt_group_create(ctypes.byref(self._cp), len(devices), devs, ctypes.byref(g)))
+            self._g = g
+            self._hs = [ctypes.c_void_p(self._L.hbt_group_ctx(g, i)) for i in range(len(devices))]
+            h = self._hs[0]
+        else:
+            h = ctypes.c_void_p()
+            _check(None, self._L.hbt_create(ctypes.byref(self._cp), device, ctypes.byref(h)))
+            self._hs = [h]
         self._h = h
-        if stage_counters is not None:  # HBT_OPT_STAGE_COUNTERS: instrumented run, exact stage populations
-            _check(h, self._L.hbt_set_option(h, 1, int(stage_counters)))
-        if kernel is not None:  # HBT_OPT_KERNEL
-            _check(h, self._L.hbt_set_option(h, 2, int(kernel)))
-        if fuse is not None:  # HBT_OPT_FUSE: one kernel for both loops of a batch (default) or one per loop
-            _check(h, self._L.hbt_set_option(h, 3, int(fuse)))
-        if lanes is not None:  # HBT_OPT_LANES: compute streams that take production batches in turn
-            _check(h, self._L.hbt_set_option(h, 4, int(lanes)))
-        if ptsort is not None:  # HBT_OPT_PTSORT: per-event pT-sorted copy for the mixed-event loops (0 never, 1 auto, 2 always)
-            _check(h, self._L.hbt_set_option(h, 5, int(ptsort)))
+        for h in self._hs:
+            if stage_counters is not None:  # HBT_OPT_STAGE_COUNTERS: instrumented run, exact stage populations
+                _check(h, self._L.hbt_set_option(h, 1, int(stage_counters)))
+            if kernel is not None:  # HBT_OPT_KERNEL
+                _check(h, self._L.hbt_set_option(h, 2, int(kernel)))
+            if fuse is not None:  # HBT_OPT_FUSE: one kernel for both loops of a batch (default) or one per loop
+                _check(h, self._L.hbt_set_option(h, 3, int(fuse)))
+            if lanes is not None:  # HBT_OPT_LANES: compute streams that take production batches in turn
+                _check(h, self._L.hbt_set_option(h, 4, int(lanes)))
+            if ptsort is not None:  # HBT_OPT_PTSORT: per-event pT-sorted copy for the mixed-event loops (0 never, 1 auto, 2 always)
+                _check(h, self._L.hbt_set_option(h, 5, int(ptsort)))
+        h = self._h
         self.psi_ref = 0.0
         self.psi_refs: List[float] = []
         self.particle_list: Optional[Batch] = None
@@ -111,9 +127,34 @@ class HBT_correlation:
 
     # -- lifetime ---------------------------------------------------------------------
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_g", None):
+            self._L.hbt_group_destroy(self._g)
+            self._g = None
+            self._h = None
+        elif getattr(self, "_h", None):
             self._L.hbt_destroy(self._h)
             self._h = None
+
+    def _submit_batch(self, *args) -> None:
+        """hbt_accumulate_batch on the single context, or hbt_group_accumulate_batch on the group."""
+        if self._g is not None:
+            rc = self._L.hbt_group_accumulate_batch(self._g, *args)
+            if rc != capi.HBT_OK:
+                raise capi.HBTError(rc, (self._L.hbt_group_last_error(self._g) or b"").decode())
+        else:
+            _check(self._h, self._L.hbt_accumulate_batch(self._h, *args))
+
+    def _reduce(self) -> None:
+        if self._g is not None:
+            rc = self._L.hbt_group_reduce(self._g)
+            if rc != capi.HBT_OK:
+                raise capi.HBTError(rc, (self._L.hbt_group_last_error(self._g) or b"").decode())
+
+    def ordered_batches(self) -> int:
+        n = ctypes.c_uint64()
+        if self._g is not None:
+            self._L.hbt_group_ordered_batches(self._g, ctypes.byref(n))
+        return n.value
 
     def __del__(self):
         self.close()
@@ -161,13 +202,11 @@ class HBT_correlation:
             nmix = ids.shape[1]
             n2 = np.diff(off2)
             self.pairs_mixed += int(np.sum(np.diff(off1)[:, None] * n2[ids]))
-            _check(self._h, self._L.hbt_accumulate_batch(
-                self._h, p1.ctypes.data, off1.ctypes.data, nev, a2[0], a2[1], a2[2], ids.ctypes.data,
-                cs.ctypes.data, nmix, self.psi_ref, 1, 1))
+            self._submit_batch(p1.ctypes.data, off1.ctypes.data, nev, a2[0], a2[1], a2[2], ids.ctypes.data,
+                               cs.ctypes.data, nmix, self.psi_ref, 1, 1)
         else:
-            _check(self._h, self._L.hbt_accumulate_batch(
-                self._h, p1.ctypes.data, off1.ctypes.data, nev, a2[0], a2[1], a2[2], None, None, 0,
-                self.psi_ref, 1, 0))
+            self._submit_batch(p1.ctypes.data, off1.ctypes.data, nev, a2[0], a2[1], a2[2], None, None, 0,
+                               self.psi_ref, 1, 0)
 
     def combine_and_bin_particle_pairs(self, event_list: Sequence[int]) -> None:
         """``src/HBT_correlation.cpp:251-462``: same-event pairs of the listed events merged."""
@@ -192,10 +231,12 @@ class HBT_correlation:
 
     # -- results ----------------------------------------------------------------------
     def synchronize(self) -> None:
-        _check(self._h, self._L.hbt_synchronize(self._h))
+        for h in self._hs:
+            _check(h, self._L.hbt_synchronize(h))
 
     def accumulators(self) -> Accumulators:
         P = self.params
+        self._reduce()
         nb, ns = P.n_bins, P.n_slabs
         u = lambda n: np.zeros(n, dtype=np.uint64)
         d = lambda n: np.zeros(n, dtype=np.float64)

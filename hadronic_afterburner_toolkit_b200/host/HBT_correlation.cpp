@@ -6,6 +6,7 @@
 // fatal conditions (message + exit(1)).
 #include "HBT_correlation.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <fstream>
@@ -21,19 +22,30 @@ namespace {
 // glibc / iostream print a NaN produced by 0.0/0.0 as "-nan"; nothing to do, ostream<<double
 // does the same here because the same expressions are evaluated.
 
-int device_count_from_env() {
+// HBT_B200_DEVICES: "all", a count ("4": devices 0..3) or an explicit list ("0,2,3"; a device may repeat)
+std::vector<int32_t> devices_from_env() {
+    std::vector<int32_t> devs;
     const char *e = std::getenv("HBT_B200_DEVICES");
-    if (!e || !*e) return 1;
-    if (std::string(e) == "all") return hbt_device_count();
-    const int n = std::atoi(e);
-    return n < 1 ? 1 : n;
+    if (!e || !*e) return std::vector<int32_t>(1, 0);
+    const std::string v(e);
+    if (v == "all") {
+        for (int d = 0; d < hbt_device_count(); d++) devs.push_back(d);
+    } else if (v.find(',') != std::string::npos) {
+        std::stringstream ss(v);
+        std::string tok;
+        while (std::getline(ss, tok, ',')) if (!tok.empty()) devs.push_back(std::atoi(tok.c_str()));
+    } else {
+        for (int d = 0; d < std::max(1, std::atoi(e)); d++) devs.push_back(d);
+    }
+    if (devs.empty()) devs.push_back(0);
+    return devs;
 }
 
 }  // namespace
 
 HBT_correlation::HBT_correlation(ParameterReader &paraRdr, std::string path,
                                  std::shared_ptr<RandomUtil::Random> ran_gen)
-    : paraRdr_(paraRdr), path_(path), next_ctx_(0), reduced_(false), fetched_(false) {
+    : paraRdr_(paraRdr), path_(path), group_(nullptr), fetched_(false) {
     ran_gen_ptr_ = ran_gen;
 
     // same keys, same order as src/HBT_correlation.cpp:22-46 (a missing key exits in getVal)
@@ -80,34 +92,21 @@ HBT_correlation::HBT_correlation(ParameterReader &paraRdr, std::string path,
     p.HBTrap_max = Krap_max_;
     p.needed_number_of_pairs = paraRdr_.getVal("needed_number_of_pairs");
 
-    int ndev = device_count_from_env();
-    if (ndev > 1 && p.needed_number_of_pairs < 1e14) {
-        // the pair cap is cumulative over the batches IN ORDER (src/HBT_correlation.cpp:402-406):
-        // groups spread over several GPUs could not reproduce it, so a run whose cap can
-        // engage stays on one device
-        messager << "needed_number_of_pairs = " << p.needed_number_of_pairs
-                 << " can be reached: the ordered pair cap needs the batches in sequence, using 1 GPU";
-        messager.flush("warning");
-        ndev = 1;
+    // One engine context per GPU, as a group: oversample groups go to the GPUs in turn, and the group keeps the
+    // ordered needed_number_of_pairs cap (src/HBT_correlation.cpp:402-406) exact across them.
+    const std::vector<int32_t> devs = devices_from_env();
+    const int rc = hbt_group_create(&p, static_cast<int32_t>(devs.size()), devs.data(), &group_);
+    if (rc != HBT_OK) {
+        messager << "HBT_correlation: cannot create the GPU engine: " << hbt_group_last_error(nullptr) << hbt_last_error(nullptr);
+        messager.flush("error");
+        exit(1);
     }
-    for (int d = 0; d < ndev; d++) {
-        hbt_ctx *c = nullptr;
-        const int rc = hbt_create(&p, d, &c);
-        if (rc != HBT_OK) {
-            messager << "HBT_correlation: cannot create the GPU engine on device " << d << ": "
-                     << hbt_last_error(nullptr);
-            messager.flush("error");
-            exit(1);
-        }
-        ctx_.push_back(c);
-    }
-    if (ndev > 1) check(ctx_[0], hbt_comm_init_all(ctx_.data(), ndev), "hbt_comm_init_all");
-    messager << "HBT pair loops run on " << ndev << " GPU(s) [" << hbt_version() << "]";
+    messager << "HBT pair loops run on " << devs.size() << " GPU context(s) [" << hbt_version() << "]";
     messager.flush("info");
 }
 
 HBT_correlation::~HBT_correlation() {
-    for (hbt_ctx *c : ctx_) hbt_destroy(c);
+    hbt_group_destroy(group_);
 }
 
 void HBT_correlation::check(hbt_ctx *ctx, int rc, const char *what) {
@@ -117,12 +116,10 @@ void HBT_correlation::check(hbt_ctx *ctx, int rc, const char *what) {
     exit(1);
 }
 
-hbt_ctx *HBT_correlation::pick_context() {
-    hbt_ctx *c = ctx_[next_ctx_];
-    next_ctx_ = (next_ctx_ + 1) % ctx_.size();
-    reduced_ = false;
+// the per-method interface (the reference's unit test drives it) stays on the first context
+hbt_ctx *HBT_correlation::first_context() {
     fetched_ = false;
-    return c;
+    return hbt_group_ctx(group_, 0);
 }
 
 //! Psi_n of the batch, src/HBT_correlation.cpp:233-249 (all filtered particles, no rapidity cut)
@@ -229,12 +226,14 @@ void HBT_correlation::calculate_HBT_correlation_function(std::shared_ptr<particl
         }
     }
     if (nev == 0) return;  // the reader's trailing empty batch: nothing to do, no draws
-    hbt_ctx *c = pick_context();
-    check(c,
-          hbt_accumulate_batch(c, gather1_.data(), reinterpret_cast<const int64_t *>(off1_.data()), nev, p2,
-                               reinterpret_cast<const int64_t *>(o2), real_mixed ? mixed_nev : 0, ids.data(), cs.data(),
-                               do_mixed ? nmix : 0, psi_ref, 1, do_mixed ? 1 : 0),
-          "hbt_accumulate_batch");
+    fetched_ = false;
+    if (hbt_group_accumulate_batch(group_, gather1_.data(), reinterpret_cast<const int64_t *>(off1_.data()), nev, p2,
+                                   reinterpret_cast<const int64_t *>(o2), real_mixed ? mixed_nev : 0, ids.data(), cs.data(),
+                                   do_mixed ? nmix : 0, psi_ref, 1, do_mixed ? 1 : 0) != HBT_OK) {
+        messager << "HBT_correlation: hbt_group_accumulate_batch failed: " << hbt_group_last_error(group_);
+        messager.flush("error");
+        exit(1);
+    }
 }
 
 //! Same-event pairs of the listed events merged into one list, src/HBT_correlation.cpp:251-462
@@ -242,7 +241,7 @@ void HBT_correlation::combine_and_bin_particle_pairs(std::vector<int> event_list
     const long long n = gather_events(false, event_list, gather1_, off1_);
     messager << "number of pairs: " << (n > 0 ? static_cast<unsigned long long>(n) * (n - 1) / 2 : 0);
     messager.flush("info");
-    hbt_ctx *c = pick_context();
+    hbt_ctx *c = first_context();
     check(c, hbt_accumulate_same(c, gather1_.data(), n, psi_ref), "hbt_accumulate_same");
 }
 
@@ -264,7 +263,7 @@ void HBT_correlation::combine_and_bin_particle_pairs_mixed_events(int event_id1,
     }
     messager << "number of mixed pairs: " << static_cast<unsigned long long>(n1) * off2_.back();
     messager.flush("info");
-    hbt_ctx *c = pick_context();
+    hbt_ctx *c = first_context();
     check(c,
           hbt_accumulate_mixed(c, gather1_.data(), reinterpret_cast<const int64_t *>(off1_.data()), 1, gather2_.data(),
                                reinterpret_cast<const int64_t *>(off2_.data()), nmix, ids.data(), cs.data(), nmix,
@@ -273,9 +272,13 @@ void HBT_correlation::combine_and_bin_particle_pairs_mixed_events(int event_id1,
 }
 
 void HBT_correlation::fetch_results() {
-    if (ctx_.size() > 1 && !reduced_) check(ctx_[0], hbt_allreduce_all(ctx_.data(), static_cast<int>(ctx_.size())), "hbt_allreduce_all");
-    reduced_ = true;
-    check(ctx_[0], hbt_fetch_results(ctx_[0], params_, res_), "hbt_read");
+    if (hbt_group_reduce(group_) != HBT_OK) {
+        messager << "HBT_correlation: hbt_group_reduce failed: " << hbt_group_last_error(group_);
+        messager.flush("error");
+        exit(1);
+    }
+    hbt_ctx *c0 = hbt_group_ctx(group_, 0);
+    check(c0, hbt_fetch_results(c0, params_, res_), "hbt_read");
     fetched_ = true;
 }
 

@@ -51,11 +51,10 @@ class HBT_correlation {
     int number_of_oversample_events_;
     unsigned long long int needed_number_of_pairs;
 
-    // one engine context per GPU; batches are dealt round-robin, histograms are summed once
-    // (NCCL all-reduce over NVLink) before the output is written
-    std::vector<hbt_ctx *> ctx_;
-    size_t next_ctx_;
-    bool reduced_;
+    // one engine context per GPU (HBT_B200_DEVICES), as a group of libhbt_b200: batches are dealt round-robin, the
+    // ordered pair cap stays exact across the GPUs, histograms are summed once (NCCL all-reduce over NVLink)
+    // before the output is written
+    hbt_group *group_;
 
     // host copies of the accumulators, filled by fetch_results()
     hbt_params params_;
@@ -67,7 +66,7 @@ class HBT_correlation {
     std::vector<long long> off1_, off2_;
 
     void check(hbt_ctx *ctx, int rc, const char *what);
-    hbt_ctx *pick_context();
+    hbt_ctx *first_context();
     long long gather_events(bool mixed_list, const std::vector<int> &events, std::vector<double> &out,
                             std::vector<long long> &offsets);
     void fetch_results();

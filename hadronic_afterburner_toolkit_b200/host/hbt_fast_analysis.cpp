@@ -19,6 +19,7 @@
 // It does not link any reference code.  Switches it cannot honour (other read_in_mode values,
 // resonance feed-down, species groups) are refused with a message: use the drop-in binary
 // (hadronic_afterburner_tools_b200.e) for those.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -123,8 +124,26 @@ int main(int argc, char *argv[]) {
     hp.HBTrap_max = P.get("HBTrap_max");
     hp.needed_number_of_pairs = P.get("needed_number_of_pairs");
 
-    hbt_ctx *ctx = nullptr;
-    if (hbt_create(&hp, 0, &ctx) != HBT_OK) die(std::string("cannot create the GPU engine: ") + hbt_last_error(nullptr));
+    // HBT_B200_DEVICES as in the drop-in class: "all", a count, or a list of devices; one context per entry, the
+    // batches go to them in turn and the ordered pair cap stays exact across them (hbt_group_*)
+    std::vector<int32_t> devs;
+    if (const char *e = std::getenv("HBT_B200_DEVICES")) {
+        const std::string v(e);
+        if (v == "all") {
+            for (int d = 0; d < hbt_device_count(); d++) devs.push_back(d);
+        } else if (v.find(',') != std::string::npos) {
+            std::stringstream ss(v);
+            std::string tok;
+            while (std::getline(ss, tok, ',')) if (!tok.empty()) devs.push_back(std::atoi(tok.c_str()));
+        } else {
+            for (int d = 0; d < std::max(1, std::atoi(e)); d++) devs.push_back(d);
+        }
+    }
+    if (devs.empty()) devs.push_back(0);
+    hbt_group *grp = nullptr;
+    if (hbt_group_create(&hp, static_cast<int32_t>(devs.size()), devs.data(), &grp) != HBT_OK)
+        die(std::string("cannot create the GPU engine: ") + hbt_group_last_error(nullptr) + hbt_last_error(nullptr));
+    hbt_ctx *ctx = hbt_group_ctx(grp, 0);
     hbt_rng *rng = nullptr;
     if (hbt_rng_create(static_cast<int32_t>(P.get("randomSeed")), &rng) != HBT_OK) die("cannot create the random number generator");
     hbt_reader *rd = nullptr;
@@ -195,9 +214,9 @@ int main(int argc, char *argv[]) {
         ids.resize(static_cast<size_t>(nev) * nmix);
         cs.resize(static_cast<size_t>(nev) * nmix * 2);
         if (nmix) hbt_rng_mixed_plan(rng, nev, nev2, ids.data(), cs.data(), nullptr);
-        check(ctx, hbt_accumulate_batch(ctx, cut.data(), off.data(), nev, rd2 ? cut2.data() : nullptr, rd2 ? off2.data() : nullptr,
-                                        rd2 ? nev2 : 0, ids.data(), cs.data(), nmix, psi_ref, 1, nmix > 0 ? 1 : 0),
-              "hbt_accumulate_batch");
+        if (hbt_group_accumulate_batch(grp, cut.data(), off.data(), nev, rd2 ? cut2.data() : nullptr, rd2 ? off2.data() : nullptr,
+                                       rd2 ? nev2 : 0, ids.data(), cs.data(), nmix, psi_ref, 1, nmix > 0 ? 1 : 0) != HBT_OK)
+            die(std::string("hbt_group_accumulate_batch failed: ") + hbt_group_last_error(grp));
         const unsigned long long n1 = static_cast<unsigned long long>(off.back());
         pairs_same += n1 > 1 ? n1 * (n1 - 1) / 2 : 0;
         for (int e = 0; e < nev; e++)
@@ -208,13 +227,18 @@ int main(int argc, char *argv[]) {
         n_batches++;
         n_events += nev;
     }
-    check(ctx, hbt_synchronize(ctx), "hbt_synchronize");
+    if (hbt_group_reduce(grp) != HBT_OK) die(std::string("hbt_group_reduce failed: ") + hbt_group_last_error(grp));
     const double t_loop = seconds_since(t_start);
     HbtHostResults res;
     check(ctx, hbt_fetch_results(ctx, hp, res), "hbt_read");
     HbtOutputWriter(hp, path, P.get("ecoOutput", 0) == 1).write_all(res);
     double same_ms = 0, mixed_ms = 0;
-    hbt_get_timers(ctx, &same_ms, &mixed_ms, nullptr, nullptr);
+    for (int d = 0; d < hbt_group_size(grp); d++) {  // (sum over the GPUs: they work at the same time)
+        double a = 0, b = 0;
+        hbt_get_timers(hbt_group_ctx(grp, d), &a, &b, nullptr, nullptr);
+        same_ms += a;
+        mixed_ms += b;
+    }
     std::printf("[info] hbt_fast_analysis: %lld batches, %lld events, %llu same + %llu mixed pairs; %.3f s in all "
                 "(%.3f s waiting for the reader, %.1f MB of text, pair kernels %.3f s), output %.3f s\n",
                 n_batches, n_events, pairs_same, pairs_mixed, t_loop, t_wait, hbt_reader_bytes(rd) / 1e6,
@@ -222,6 +246,6 @@ int main(int argc, char *argv[]) {
     hbt_reader_close(rd);
     if (rd2) hbt_reader_close(rd2);
     hbt_rng_destroy(rng);
-    hbt_destroy(ctx);
+    hbt_group_destroy(grp);
     return 0;
 }

@@ -253,6 +253,42 @@ int hbt_comm_init_all(hbt_ctx **ctxs, int32_t n);
 int hbt_allreduce(hbt_ctx *ctx);
 int hbt_allreduce_all(hbt_ctx **ctxs, int32_t n);
 
+/* ---- one analysis over several GPUs of ONE process: a group of contexts ------------------------------
+ * What the drop-in class does when HBT_B200_DEVICES > 1 (host/HBT_correlation.cpp): oversample groups (batches) go to
+ * the GPUs in turn — they are independent of each other (src/Analysis.cpp:821-833) except for ONE coupling, the
+ * needed_number_of_pairs cap, which is cumulative over the batches in order (src/HBT_correlation.cpp:402-406,
+ * :424-428, :651-655, :673-677).  hbt_group_accumulate_batch keeps that exact: while no channel (K_T[,K_phi] slab, q_inv
+ * histogram) can reach its quota with the pairs submitted so far, batches run asynchronously on their GPUs; when a
+ * batch could close a channel, all contexts are synchronised, their exact per-channel counters are summed, and the
+ * batch runs alone on its GPU starting from the other contexts' counts (hbt_cap_set_foreign), so that its ordered
+ * replay stops at the very pair the reference stops at.  The reference's default needed_number_of_pairs = 3e7
+ * therefore gives the reference's files on any number of GPUs.
+ * devices == NULL: devices 0 .. n_devices-1.  A device may be listed more than once (several contexts on one GPU:
+ * used by the tests on single-GPU boxes); the final sum is one NCCL all-reduce when the devices are distinct. */
+typedef struct hbt_group hbt_group;
+int hbt_group_create(const hbt_params *params, int32_t n_devices, const int32_t *devices, hbt_group **out);
+void hbt_group_destroy(hbt_group *group);
+const char *hbt_group_last_error(const hbt_group *group); /* group == NULL: of the last failed hbt_group_create */
+int32_t hbt_group_size(const hbt_group *group);
+hbt_ctx *hbt_group_ctx(hbt_group *group, int32_t i);
+/* same arguments as hbt_accumulate_batch; the batch goes to the next context in turn */
+int hbt_group_accumulate_batch(hbt_group *group, const double *p1, const int64_t *off1, int32_t nev1,
+                               const double *p2, const int64_t *off2, int32_t nev2,
+                               const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
+                               double psi_ref, int32_t do_same, int32_t do_mixed);
+/* sums the accumulators of all contexts; afterwards hbt_read / hbt_read_qinv / hbt_get_stage_counters on
+ * hbt_group_ctx(group, 0) return the totals (until the next accumulate) */
+int hbt_group_reduce(hbt_group *group);
+/* batches that had to run in sequence because the cap could engage */
+int hbt_group_ordered_batches(const hbt_group *group, uint64_t *n);
+/* building blocks of the above, for hosts that drive their contexts themselves (one process per GPU): the cap
+ * channels are the slabs, followed by the n_KT q_inv histograms when invariant_radius_flag = 1.
+ * hbt_cap_get_counts synchronises and returns this context's own accepted pairs per channel (numerator /
+ * denominator); hbt_cap_set_foreign tells it how many pairs the OTHER contexts hold. */
+int32_t hbt_cap_channels(const hbt_ctx *ctx);
+int hbt_cap_get_counts(hbt_ctx *ctx, uint64_t *num, uint64_t *den);
+int hbt_cap_set_foreign(hbt_ctx *ctx, const uint64_t *num, const uint64_t *den);
+
 /* FP64-pipe roofline denominator: runs a dependent-chain DFMA microbenchmark on `device`
  * for about `ms` milliseconds and returns the sustained rate in TFLOP/s (2 flops per DFMA).
  * Measurement aid for bench.py; not part of the reference's interface. */

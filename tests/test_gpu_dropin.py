@@ -73,7 +73,7 @@ def test_same_files_as_reference_binary(name, tmp_path):
     text = P.parameters_dat(event_buffer_size=nev * mult)  # groups of exactly nev events
     want, _ = run_binary(REF_EXE, str(tmp_path / "ref"), text, gz)
     got, out = run_binary(OUR_EXE, str(tmp_path / "ours"), text, gz, env={"HBT_B200_DEVICES": "1"})
-    assert "HBT pair loops run on 1 GPU(s)" in out
+    assert "HBT pair loops run on 1 GPU context(s)" in out
     same_text(want, got)
     assert len(want) == (P.n_KT - 1) * (P.n_Kphi if P.azimuthal_flag else 1) * (2 if P.invariant_radius_flag else 1)
     # third arm: our own reader and driver (no reference code at all) on the same directory layout
@@ -155,18 +155,34 @@ def test_balance_function_operator_same_files(alpha, beta, rap_type, buf, tmp_pa
         assert want[fn] == got[fn], fn
 
 
-def test_groups_sharded_over_all_gpus_of_the_box(tmp_path):
+SHARDED = {
+    "uncapped": C3.with_(qnpts=15),
+    # the ordered pair cap engages in the middle of the run: the group must cut at the reference's pair
+    "capped": C3.with_(qnpts=15, needed_number_of_pairs=6000.0),
+    "capped_qinv": HBTParams(qnpts=21, invariant_radius_flag=1, needed_number_of_pairs=400.0),
+}
+
+
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0", "all"])
+@pytest.mark.parametrize("name", sorted(SHARDED))
+def test_groups_sharded_over_several_contexts_same_files(name, devices, tmp_path):
+    """Oversample groups dealt round-robin to several engine contexts (HBT_B200_DEVICES): one per GPU of the box
+    ("all"; skipped on a single-GPU box), or several on GPU 0 — the same code path, which also runs where the driver
+    has one GPU.  With and without the needed_number_of_pairs cap: same files as the reference binary."""
     from hadronic_afterburner_toolkit_b200 import capi
 
     ndev = capi.lib().hbt_device_count()
-    if ndev < 2:
+    if devices == "all" and ndev < 2:
         pytest.skip("needs >= 2 GPUs")
-    P, ngrp, nev, mult = C3.with_(qnpts=15), 5, 4, 300
+    nctx = ndev if devices == "all" else devices.count(",") + 1
+    P, ngrp, nev, mult = SHARDED[name], 7, 4, 300
     batches = synth.make_batches(43, ngrp, nev, multiplicity=mult)
     gz = str(tmp_path / "input.gz")
     synth.write_iss_gz(gz, batches)
     text = P.parameters_dat(event_buffer_size=nev * mult)
     want, _ = run_binary(REF_EXE, str(tmp_path / "ref"), text, gz)
-    got, out = run_binary(OUR_EXE, str(tmp_path / "ours"), text, gz, env={"HBT_B200_DEVICES": "all"})
-    assert f"HBT pair loops run on {ndev} GPU(s)" in out
+    got, out = run_binary(OUR_EXE, str(tmp_path / "ours"), text, gz, env={"HBT_B200_DEVICES": devices})
+    assert f"HBT pair loops run on {nctx} GPU context(s)" in out
     same_text(want, got)
+    fast, _ = run_binary(FAST_EXE, str(tmp_path / "fast"), text, gz, env={"HBT_B200_DEVICES": devices})
+    same_text(want, fast)
