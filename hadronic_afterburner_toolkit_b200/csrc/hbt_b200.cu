@@ -68,6 +68,30 @@ struct Lane {
     long long *mix_off = nullptr;
     void *mix_tmp = nullptr;
     size_t mix_tmp_bytes = 0, mix_cap = 0, mix_off_cap = 0;
+    // several small batches in one launch (flush_pending): tile limit of every row, the launch's segments
+    unsigned *row_end = nullptr;
+    size_t row_end_cap = 0;
+    HbtMixSeg *mseg = nullptr;
+    size_t mseg_cap = 0;
+};
+
+// Small batches waiting to be launched together (see hbt_sort.cuh, "several small batches in one launch").
+struct PendBatch {
+    const double *d_src;  // device address of the batch's particles
+    int64_t n;
+};
+struct Pending {
+    std::vector<PendBatch> b;
+    std::vector<long long> evoff;   // event boundaries of the logical concatenation (evoff[0] = 0)
+    std::vector<HbtMixSeg> segs;    // mixed-event segments, offsets in the logical concatenation
+    unsigned long long pairs_same = 0, pairs_mixed = 0;
+    long long nblocks = 0, units_bound = 0;
+    int64_t n_logical = 0, n_padded = 0;
+    bool do_mixed = false, host = false;
+    Slot *slot = nullptr;           // host-staged batches: their common staging slot (ONE upload at the flush)
+    size_t staged = 0;              // particles staged in slot->h_p so far
+    float host_range = 0.f;         // max(|px|, |py|) of the staged particles
+    double psi_ref = 0.;
 };
 
 struct TimerRec {
@@ -143,6 +167,9 @@ struct hbt_ctx {
     unsigned long long ptsort_min_pairs = 500000000ull;
     std::vector<long long> evoff;  // event boundaries of the buffer being sorted
     bool fuse = true;  // whole batches run the fused same+mixed kernel (HBT_B200_FUSE=0 / HBT_OPT_FUSE: separate kernels)
+    // small production batches are collected and launched together (HBT_B200_COALESCE=0 / HBT_OPT_COALESCE: one launch each)
+    bool coalesce = true;
+    Pending pend;
     Slot slots[kSlots];
     int next_slot = 0;
     std::vector<TimerRec> timers;
@@ -332,7 +359,7 @@ int ensure_units(hbt_ctx *ctx, Lane &L, long long all_units) {
 // gather, tile boxes): ~4 small kernels, microseconds against the pair kernel's milliseconds
 // host_range: max(|px|, |py|) of the list when the caller has the particles on the host (saves the range
 // kernel and its memset), negative otherwise
-int prepare_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, float host_range = -1.f) {
+int ensure_sort_buffers(hbt_ctx *ctx, Lane &L, int64_t n) {
     if (static_cast<size_t>(n) > L.sort_cap) {
         CU(ctx, cudaStreamSynchronize(L.stream));  // the previous launch of this lane may still read the buffers
         for (int k = 0; k < 2; k++) { cudaFree(L.sort_keys[k]); cudaFree(L.sort_idx[k]); }
@@ -354,6 +381,12 @@ int prepare_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, float ho
         L.sort_tmp_bytes = bytes;
         L.sort_cap = cap;
     }
+    return HBT_OK;
+}
+
+int prepare_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, float host_range = -1.f) {
+    int rc0 = ensure_sort_buffers(ctx, L, n);
+    if (rc0) return rc0;
     const int th = 256;
     const unsigned nb = static_cast<unsigned>((n + th - 1) / th);
     if (host_range >= 0.f) {
@@ -377,14 +410,7 @@ int prepare_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, float ho
 #endif
 
 #ifdef HBT_HAVE_V2
-// Per-event pT order of the buffer the mixed-event loops read (ctx->evoff: its event boundaries):
-// keys, one radix sort of (event, pT^2), gather.  pT is invariant under the partner rotation, so one
-// sort per batch serves every (event, partner) segment; v3_run_unit then skips the list-2 particles
-// whose pT is farther than the q_out window from the sub-tile's pT range.  Returns the sorted copy.
-int prepare_mixed_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, const double **out) {
-    *out = d_p;
-    const int nev = static_cast<int>(ctx->evoff.size()) - 1;
-    if (n < 2 || nev < 1) return HBT_OK;
+int ensure_mix_buffers(hbt_ctx *ctx, Lane &L, int64_t n, size_t n_evoff) {
     if (static_cast<size_t>(n) > L.mix_cap) {
         CU(ctx, cudaStreamSynchronize(L.stream));
         for (int k = 0; k < 2; k++) { cudaFree(L.mix_keys[k]); cudaFree(L.mix_idx[k]); L.mix_keys[k] = nullptr; L.mix_idx[k] = nullptr; }
@@ -403,13 +429,26 @@ int prepare_mixed_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, co
         L.mix_tmp_bytes = bytes;
         L.mix_cap = cap;
     }
-    if (ctx->evoff.size() > L.mix_off_cap) {
+    if (n_evoff > L.mix_off_cap) {
         CU(ctx, cudaStreamSynchronize(L.stream));
         cudaFree(L.mix_off);
         L.mix_off = nullptr;
-        L.mix_off_cap = ctx->evoff.size() * 2;
+        L.mix_off_cap = n_evoff * 2;
         CU(ctx, cudaMalloc(&L.mix_off, L.mix_off_cap * 8));
     }
+    return HBT_OK;
+}
+
+// Per-event pT order of the buffer the mixed-event loops read (ctx->evoff: its event boundaries):
+// keys, one radix sort of (event, pT^2), gather.  pT is invariant under the partner rotation, so one
+// sort per batch serves every (event, partner) segment; v3_run_unit then skips the list-2 particles
+// whose pT is farther than the q_out window from the sub-tile's pT range.  Returns the sorted copy.
+int prepare_mixed_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, const double **out) {
+    *out = d_p;
+    const int nev = static_cast<int>(ctx->evoff.size()) - 1;
+    if (n < 2 || nev < 1) return HBT_OK;
+    int rc0 = ensure_mix_buffers(ctx, L, n, ctx->evoff.size());
+    if (rc0) return rc0;
     // (pageable source: the copy is staged before the call returns, the vector can be reused)
     CU(ctx, cudaMemcpyAsync(L.mix_off, ctx->evoff.data(), ctx->evoff.size() * 8, cudaMemcpyHostToDevice, L.stream));
     const int th = 256;
@@ -644,6 +683,229 @@ int launch_fused(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, const doub
     ctx->pending_den += npairs_mixed;
     return drain_timers(ctx, false);
 }
+#endif
+
+#ifdef HBT_HAVE_V2
+// ---- several small batches in one launch -----------------------------------------------------------
+constexpr size_t kCoalesceBatches = 32;                     // batches per launch (device-resident batches)
+// host batches are staged one after the other by the calling thread: a launch every 8 keeps the GPU working on
+// the previous ones meanwhile
+constexpr size_t kCoalesceBatchesHost = 8;
+constexpr unsigned long long kCoalescePairs = 1500000000ull;  // a batch with fewer pairs than this is "small"
+constexpr unsigned long long kCoalesceFlushPairs = 8000000000ull;
+constexpr size_t kCoalesceSlotParticles = 1u << 17;         // smallest staging slot of a group of host batches (8 MB)
+
+// launches everything that waits in ctx->pend as ONE production launch
+int flush_pending(hbt_ctx *ctx) {
+    Pending &P = ctx->pend;
+    if (P.b.empty()) return HBT_OK;
+    Lane &L = next_lane(ctx);
+    const int nb = static_cast<int>(P.b.size());
+    if (P.host) {
+        CU(ctx, cudaMemcpyAsync(P.slot->d_p, P.slot->h_p, P.staged * 64, cudaMemcpyHostToDevice, ctx->copy));
+        CU(ctx, cudaEventRecord(P.slot->uploaded, ctx->copy));
+        CU(ctx, cudaStreamWaitEvent(L.stream, P.slot->uploaded, 0));
+    }
+    HbtMulti M;
+    M.nb = nb;
+    M.pad = 0;
+    long long c = 0, q = 0;
+    for (int b = 0; b < nb; b++) {
+        M.src[b] = P.b[b].d_src;
+        M.cbase[b] = c;
+        M.pbase[b] = q;
+        c += P.b[b].n;
+        q += (P.b[b].n + 63) & ~63ll;
+    }
+    for (int b = nb; b <= HBT_MULTI_MAX; b++) { M.cbase[b] = c; M.pbase[b] = q; }
+    for (int b = nb; b < HBT_MULTI_MAX; b++) M.src[b] = nullptr;
+    const long long n_log = c, n_pad = q;
+    ctx->reduced = false;
+    cudaEvent_t e0, e1;
+    int rc = get_event_pair(ctx, &e0, &e1);
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(e0, L.stream));
+    rc = ensure_work(ctx, L);
+    if (rc) return rc;
+    CU(ctx, cudaMemsetAsync(L.d_work, 0, 8, L.stream));
+    rc = ensure_sort_buffers(ctx, L, n_pad);
+    if (rc) return rc;
+    rc = ensure_units(ctx, L, P.units_bound);
+    if (rc) return rc;
+    // tile limit of every row: a unit pairs a row only with tiles of its own batch
+    const long long n_rows = n_pad / HBT_V3_SUB_SAME;
+    std::vector<unsigned> row_end(static_cast<size_t>(n_rows));
+    for (int b = 0; b < nb; b++)
+        for (long long a = M.pbase[b] / HBT_V3_SUB_SAME; a < M.pbase[b + 1] / HBT_V3_SUB_SAME; a++)
+            row_end[static_cast<size_t>(a)] = static_cast<unsigned>(M.pbase[b + 1] / HBT_V3_TJ_SAME);
+    if (row_end.size() > L.row_end_cap) {
+        CU(ctx, cudaStreamSynchronize(L.stream));
+        cudaFree(L.row_end);
+        L.row_end = nullptr;
+        L.row_end_cap = row_end.size() * 2;
+        CU(ctx, cudaMalloc(&L.row_end, L.row_end_cap * 4));
+    }
+    // (pageable sources: the copies are staged before the calls return)
+    CU(ctx, cudaMemcpyAsync(L.row_end, row_end.data(), row_end.size() * 4, cudaMemcpyHostToDevice, L.stream));
+    const int th = 256;
+    // ---- same-event list: (batch, Morton) order of the padded slots, boxes, surviving units
+    if (P.host) {
+        hbt_multi_keys<<<static_cast<unsigned>((n_pad + th - 1) / th), th, 0, L.stream>>>(M, nullptr, P.host_range, L.sort_keys[0], L.sort_idx[0]);
+    } else {
+        CU(ctx, cudaMemsetAsync(L.sort_rmax, 0, 4, L.stream));
+        hbt_multi_range<<<static_cast<unsigned>(std::min<long long>((n_log + th - 1) / th, 1184)), th, 0, L.stream>>>(M, L.sort_rmax);
+        hbt_multi_keys<<<static_cast<unsigned>((n_pad + th - 1) / th), th, 0, L.stream>>>(M, L.sort_rmax, 0.f, L.sort_keys[0], L.sort_idx[0]);
+        ctx->kernel_launches++;
+    }
+    int b_bits = 1;
+    while ((1 << b_bits) < nb) b_bits++;
+    size_t bytes = L.sort_tmp_bytes;
+    CU(ctx, cub::DeviceRadixSort::SortPairs(L.sort_tmp, bytes, L.sort_keys[0], L.sort_keys[1], L.sort_idx[0], L.sort_idx[1],
+                                            static_cast<int>(n_pad), 0, 24 + b_bits, L.stream));
+    hbt_multi_gather<<<static_cast<unsigned>((4 * n_pad + th - 1) / th), th, 0, L.stream>>>(M, L.sort_idx[1], n_pad, L.sort_p);
+    hbt_sort_bbox<<<static_cast<unsigned>((n_pad + HBT_BBOX_TILE - 1) / HBT_BBOX_TILE), HBT_BBOX_TILE, 0, L.stream>>>(L.sort_p, n_pad, L.sort_bbox, L.sort_idx[1]);
+    const long long ntj = n_pad / HBT_V3_TJ_SAME;
+    hbt_cull_units<<<dim3(static_cast<unsigned>((ntj + 127) / 128), static_cast<unsigned>(n_rows)), 128, 0, L.stream>>>(
+        L.sort_bbox, n_pad, ctx->v2c.W2, ctx->v2c.k2lo, ctx->v2c.k2hi, L.d_units, L.d_work, L.row_end);
+    ctx->kernel_launches += 5;
+    CU(ctx, cudaGetLastError());
+    if (P.do_mixed) {
+        // ---- mixed-event lists: per-event pT order of the logical concatenation, one contiguous copy
+        const int nev = static_cast<int>(P.evoff.size()) - 1;
+        rc = ensure_mix_buffers(ctx, L, n_log, P.evoff.size());
+        if (rc) return rc;
+        CU(ctx, cudaMemcpyAsync(L.mix_off, P.evoff.data(), P.evoff.size() * 8, cudaMemcpyHostToDevice, L.stream));
+        hbt_multi_mix_keys<<<static_cast<unsigned>((n_log + th - 1) / th), th, 0, L.stream>>>(M, L.mix_off, nev, L.mix_keys[0], L.mix_idx[0]);
+        int ev_bits = 1;
+        while ((1ll << ev_bits) < nev) ev_bits++;
+        bytes = L.mix_tmp_bytes;
+        CU(ctx, cub::DeviceRadixSort::SortPairs(L.mix_tmp, bytes, L.mix_keys[0], L.mix_keys[1], L.mix_idx[0], L.mix_idx[1],
+                                                static_cast<int>(n_log), 8, 32 + ev_bits, L.stream));
+        hbt_multi_gather<<<static_cast<unsigned>((4 * n_log + th - 1) / th), th, 0, L.stream>>>(M, L.mix_idx[1], n_log, L.mix_p);
+        if (P.segs.size() > L.mseg_cap) {
+            CU(ctx, cudaStreamSynchronize(L.stream));
+            cudaFree(L.mseg);
+            L.mseg = nullptr;
+            L.mseg_cap = P.segs.size() * 2;
+            CU(ctx, cudaMalloc(&L.mseg, L.mseg_cap * sizeof(HbtMixSeg)));
+        }
+        CU(ctx, cudaMemcpyAsync(L.mseg, P.segs.data(), P.segs.size() * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, L.stream));
+        ctx->kernel_launches += 3;
+        const unsigned grid = static_cast<unsigned>(ctx->n_sm * ctx->occ_fused);
+        hbt_pairs_v3_fused<<<grid, 32, 0, L.stream>>>(L.sort_p, n_pad, L.d_units, L.sort_idx[1], L.mix_p, L.mix_p,
+                                                          static_cast<long long>(P.segs.size()), L.mseg, static_cast<unsigned>(P.nblocks),
+                                                          L.d_work, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, P.psi_ref, P.pairs_same,
+                                                          P.pairs_mixed, closed_ptr(ctx));
+        ctx->timers.push_back({e0, e1, 2, static_cast<double>(P.pairs_same) / static_cast<double>(P.pairs_same + P.pairs_mixed)});
+        ctx->mixed_launches++;
+    } else {
+        const unsigned grid = static_cast<unsigned>(ctx->n_sm * ctx->occ_same);
+        hbt_pairs_v3<false, false><<<grid, 32, 0, L.stream>>>(
+            L.sort_p, L.sort_p, n_pad, nullptr, nullptr, 0, L.d_units, L.d_work, 0, ctx->grid, ctx->v2c, ctx->d_dv,
+            ctx->acc, P.psi_ref, P.pairs_same, closed_ptr(ctx), L.sort_idx[1]);
+        ctx->timers.push_back({e0, e1, 0, 0.0});
+    }
+    ctx->kernel_launches++;
+    ctx->same_launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaEventRecord(e1, L.stream));
+    if (P.slot) {
+        CU(ctx, cudaEventRecord(P.slot->done, L.stream));
+        P.slot->in_flight = true;
+    }
+    P = Pending();
+    return drain_timers(ctx, false);
+}
+
+// Takes a small production batch into the pending launch (flushing first when it does not fit).  p_host: the
+// batch's particles in host memory (they are staged now), or null with d_src = their device address.
+int append_pending(hbt_ctx *ctx, const double *p_host, const double *d_src, const int64_t *off, int32_t nev,
+                   const int32_t *ids, const double *cs, int32_t nmix, bool do_mixed, double psi_ref,
+                   unsigned long long sp, unsigned long long mp) {
+    Pending &P = ctx->pend;
+    const int64_t n = off[nev];
+    const bool host = p_host != nullptr;
+    if (!P.b.empty() && (P.do_mixed != do_mixed || P.host != host || P.b.size() >= HBT_MULTI_MAX ||
+                         P.n_padded + ((n + 63) & ~63ll) > HBT_V3_MAX_SORTED ||
+                         (host && P.staged + static_cast<size_t>(n) > P.slot->cap))) {
+        int rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
+    if (P.b.empty()) {
+        P.do_mixed = do_mixed;
+        P.host = host;
+        P.psi_ref = psi_ref;  // (only grids without K_phi bins are coalesced: the angle is not read)
+        P.evoff.assign(1, 0);
+        if (host) {
+            int rc = acquire_slot(ctx, &P.slot);
+            if (rc) return rc;
+            // (8 batches of 15 000-30 000 particles; grows with the batches, once)
+            rc = ensure_slot(ctx, *P.slot, std::max<size_t>(static_cast<size_t>(n) * kCoalesceBatchesHost, kCoalesceSlotParticles), 0);
+            if (rc) return rc;
+        }
+    }
+    if (host) {
+        double *dst = P.slot->h_p + 8 * P.staged;
+        std::memcpy(dst, p_host, static_cast<size_t>(n) * 64);
+        float m = P.host_range;
+        for (int64_t i = 0; i < n; i++) {
+            const float a = std::max(std::fabs(static_cast<float>(dst[8 * i])), std::fabs(static_cast<float>(dst[8 * i + 1])));
+            if (a == a && a < 3.0e38f) m = std::max(m, a);
+        }
+        P.host_range = m;
+        d_src = P.slot->d_p + 8 * P.staged;
+        P.staged += static_cast<size_t>(n);
+    }
+    if (do_mixed) {
+        const size_t s0 = P.segs.size();
+        P.segs.resize(s0 + static_cast<size_t>(nev) * nmix);
+        unsigned long long np = 0;
+        long long nblk = 0;
+        const size_t ns = build_segments(off, nev, off, 0, ids, cs, nmix, HBT_V3_SUB_MIXED, HBT_V3_TJ_MIXED, P.segs.data() + s0, &np, &nblk);
+        P.segs.resize(s0 + ns);
+        for (size_t k = s0; k < s0 + ns; k++) {
+            P.segs[k].i0 += P.n_logical;
+            P.segs[k].j0 += P.n_logical;
+            P.segs[k].block0 += P.nblocks;
+        }
+        P.nblocks += nblk;
+    }
+    for (int e = 1; e <= nev; e++) P.evoff.push_back(P.n_logical + off[e]);
+    P.b.push_back({d_src, n});
+    P.n_logical += n;
+    P.n_padded += (n + 63) & ~63ll;
+    {
+        const long long rows = (n + HBT_V3_SUB_SAME - 1) / HBT_V3_SUB_SAME;
+        P.units_bound += rows * (rows + 1) / 2;
+    }
+    P.pairs_same += sp;
+    P.pairs_mixed += mp;
+    ctx->pending_num += sp;
+    ctx->pending_den += mp;
+    if (P.b.size() >= (host ? kCoalesceBatchesHost : kCoalesceBatches) || P.pairs_same + P.pairs_mixed >= kCoalesceFlushPairs)
+        return flush_pending(ctx);
+    return HBT_OK;
+}
+
+unsigned long long mixed_pairs(const int64_t *off1, int32_t nev1, const int64_t *off2, const int32_t *ids, int32_t nmix) {
+    unsigned long long mp = 0;
+    for (int iev = 0; iev < nev1; iev++)
+        for (int k = 0; k < nmix; k++) {
+            const int id = ids[static_cast<size_t>(iev) * nmix + k];
+            mp += static_cast<unsigned long long>(off1[iev + 1] - off1[iev]) * static_cast<unsigned long long>(off2[id + 1] - off2[id]);
+        }
+    return mp;
+}
+
+// may this batch wait for others?  Production mode, list 2 = list 1, no K_phi bins (one psi_ref per launch), far
+// from the pair cap, few pairs.
+bool can_coalesce(const hbt_ctx *ctx, bool do_same, bool do_mixed, bool alias, int64_t n1, unsigned long long sp,
+                  unsigned long long mp, bool near_cap) {
+    return ctx->coalesce && do_same && alias && !ctx->stats && ctx->kernel_version != 1 && !ctx->grid.az && !near_cap &&
+           n1 > 1 && sp + mp < kCoalescePairs && (!do_mixed || (ctx->fuse && ctx->ptsort != 0 && mp > 0));
+}
+#else
+int flush_pending(hbt_ctx *) { return HBT_OK; }
 #endif
 
 int tile_i(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V3_SUB_MIXED; }
@@ -1022,6 +1284,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     if (const char *v = getenv("HBT_B200_KERNEL")) ctx->kernel_version = atoi(v) == 1 ? 1 : 2;
     if (const char *v = getenv("HBT_B200_STATS")) ctx->stats = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_FUSE")) ctx->fuse = atoi(v) != 0;
+    if (const char *v = getenv("HBT_B200_COALESCE")) ctx->coalesce = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_PTSORT")) ctx->ptsort = std::min(2, std::max(0, atoi(v)));
 #define CUC(call)                                                                              \
     do {                                                                                       \
@@ -1163,6 +1426,8 @@ extern "C" void hbt_destroy(hbt_ctx *ctx) {
         if (L.mix_p) cudaFree(L.mix_p);
         if (L.mix_off) cudaFree(L.mix_off);
         if (L.mix_tmp) cudaFree(L.mix_tmp);
+        if (L.row_end) cudaFree(L.row_end);
+        if (L.mseg) cudaFree(L.mseg);
         if (L.tail) cudaEventDestroy(L.tail);
     }
     if (ctx->epoch) cudaEventDestroy(ctx->epoch);
@@ -1206,6 +1471,10 @@ extern "C" int hbt_reset(hbt_ctx *ctx) {
 extern "C" int hbt_synchronize(hbt_ctx *ctx) {
     if (!ctx) return HBT_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
+    {
+        int rc = flush_pending(ctx);  // small batches still waiting for company
+        if (rc) return rc;
+    }
     CU(ctx, cudaStreamSynchronize(ctx->copy));
     for (Lane &L : ctx->lanes) {
         CU(ctx, cudaStreamSynchronize(L.stream));
@@ -1240,6 +1509,18 @@ int mixed_dev_on(hbt_ctx *ctx, Lane &L, const double *d_p1, const int64_t *off1,
 
 extern "C" int hbt_accumulate_same_dev(hbt_ctx *ctx, const double *d_p, int64_t n, double psi_ref) {
     if (!ctx) return HBT_ERR_INVALID;
+#ifdef HBT_HAVE_V2
+    if (d_p && n > 1) {
+        CU(ctx, cudaSetDevice(ctx->device));
+        const unsigned long long sp0 = static_cast<unsigned long long>(n) * (n - 1) / 2;
+        if (can_coalesce(ctx, true, false, true, n, sp0, 0, cap_may_engage(ctx, false, sp0))) {
+            const int64_t off[2] = {0, n};
+            return append_pending(ctx, nullptr, d_p, off, 1, nullptr, nullptr, 0, false, psi_ref, sp0, 0);
+        }
+        int rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
+#endif
     return same_dev_on(ctx, pick_lane(ctx), d_p, n, psi_ref);
 }
 
@@ -1248,6 +1529,10 @@ extern "C" int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const 
                                         const int32_t *partner_ids, const double *cos_sin, int32_t nmix,
                                         double psi_ref) {
     if (!ctx) return HBT_ERR_INVALID;
+    {
+        int rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
     return mixed_dev_on(ctx, pick_lane(ctx), d_p1, off1, nev1, d_p2, off2, nev2, partner_ids, cos_sin, nmix, psi_ref);
 }
 
@@ -1300,9 +1585,20 @@ extern "C" int hbt_accumulate_batch_dev(hbt_ctx *ctx, const double *d_p, const i
     const int64_t n = off[nev];
 #ifdef HBT_HAVE_V2
     const bool do_mixed = nmix > 0 && partner_ids && cos_sin;
-    if (do_mixed && ctx->fuse && !ctx->stats && ctx->kernel_version != 1 && n > 1) {
+    if (do_mixed)
         for (size_t k = 0; k < static_cast<size_t>(nev) * nmix; k++)
             if (partner_ids[k] < 0 || partner_ids[k] >= nev) return fail(ctx, HBT_ERR_INVALID, "partner id %d out of range", partner_ids[k]);
+    {
+        CU(ctx, cudaSetDevice(ctx->device));
+        const unsigned long long sp0 = n > 1 ? static_cast<unsigned long long>(n) * (n - 1) / 2 : 0;
+        const unsigned long long mp0 = do_mixed ? mixed_pairs(off, nev, off, partner_ids, nmix) : 0;
+        const bool near0 = cap_may_engage(ctx, false, sp0) || (do_mixed && cap_may_engage(ctx, true, mp0));
+        if (can_coalesce(ctx, true, do_mixed, true, n, sp0, mp0, near0))
+            return append_pending(ctx, nullptr, d_p, off, nev, partner_ids, cos_sin, nmix, do_mixed, psi_ref, sp0, mp0);
+        int rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
+    if (do_mixed && ctx->fuse && !ctx->stats && ctx->kernel_version != 1 && n > 1) {
         CU(ctx, cudaSetDevice(ctx->device));
         Slot *s;
         int rc = acquire_slot(ctx, &s);
@@ -1359,8 +1655,20 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
             if (partner_ids[k] < 0 || partner_ids[k] >= nev2) return fail(ctx, HBT_ERR_INVALID, "partner id %d out of range", partner_ids[k]);
     }
     CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+#ifdef HBT_HAVE_V2
+    {   // small production batches wait for each other and go out as one launch
+        const unsigned long long sp0 = (do_same && n1 > 1) ? static_cast<unsigned long long>(n1) * (n1 - 1) / 2 : 0;
+        const unsigned long long mp0 = do_mixed ? mixed_pairs(off1, nev1, off2, partner_ids, nmix) : 0;
+        const bool near0 = (do_same && cap_may_engage(ctx, false, sp0)) || (do_mixed && cap_may_engage(ctx, true, mp0));
+        if (can_coalesce(ctx, do_same, do_mixed, alias, n1, sp0, mp0, near0))
+            return append_pending(ctx, p1, nullptr, off1, nev1, partner_ids, cos_sin, nmix, do_mixed, psi_ref, sp0, mp0);
+        rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
+#endif
     Slot *s;
-    int rc = acquire_slot(ctx, &s);
+    rc = acquire_slot(ctx, &s);
     if (rc) return rc;
     rc = ensure_slot(ctx, *s, static_cast<size_t>(n1 + n2), do_mixed ? static_cast<size_t>(nev1) * nmix : 0);
     if (rc) return rc;
@@ -1535,6 +1843,10 @@ extern "C" int hbt_timer_start(hbt_ctx *ctx) {
         CU(ctx, cudaEventCreate(&ctx->sw0));
         CU(ctx, cudaEventCreate(&ctx->sw1));
     }
+    {
+        int rc = flush_pending(ctx);  // what was submitted before the stopwatch starts before it
+        if (rc) return rc;
+    }
     CU(ctx, cudaStreamSynchronize(ctx->copy));
     int rc = join_lanes(ctx);
     if (rc) return rc;
@@ -1546,6 +1858,10 @@ extern "C" int hbt_timer_start(hbt_ctx *ctx) {
 extern "C" int hbt_timer_stop(hbt_ctx *ctx, double *ms) {
     if (!ctx || !ms || !ctx->sw0) return HBT_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
+    {
+        int rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
     CU(ctx, cudaStreamSynchronize(ctx->copy));  // everything uploaded has been handed to a compute lane
     int rc = join_lanes(ctx);
     if (rc) return rc;
@@ -1573,6 +1889,9 @@ extern "C" int hbt_set_option(hbt_ctx *ctx, int32_t option, int32_t value) {
             return HBT_OK;
         case HBT_OPT_FUSE:
             ctx->fuse = value != 0;
+            return HBT_OK;
+        case HBT_OPT_COALESCE:
+            ctx->coalesce = value != 0;
             return HBT_OK;
         case HBT_OPT_PTSORT:
             if (value < 0 || value > 2) return fail(ctx, HBT_ERR_INVALID, "ptsort must be 0, 1 or 2");

@@ -45,13 +45,16 @@
 // Units of the sorted same-event list that can hold an accepted pair: row a = particles
 // [64a, 64a+64), tile t = particles [64t, 64t+64), t >= a (upper triangle incl. the
 // diagonal tiles).  work[1] counts them; work[0] is the pop counter of the pair kernel.
+// row_end (multi-batch lists, else null): row_end[a] = first tile past the batch that row a belongs to.
 __global__ void hbt_cull_units(const HbtBBox *__restrict__ bbox, long long n, double W2, double k2lo, double k2hi,
-                               unsigned *__restrict__ units, unsigned *__restrict__ work) {
+                               unsigned *__restrict__ units, unsigned *__restrict__ work,
+                               const unsigned *__restrict__ row_end = nullptr) {
     constexpr int RB = HBT_V3_SUB_SAME / HBT_BBOX_TILE, TB = HBT_V3_TJ_SAME / HBT_BBOX_TILE;
     const long long nb = (n + HBT_BBOX_TILE - 1) / HBT_BBOX_TILE;
     const int a = blockIdx.y;
     const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    const long long ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
+    long long ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
+    if (row_end) ntj = min(ntj, static_cast<long long>(row_end[a]));
     bool alive = false;
     if (t < ntj && t >= static_cast<long long>(a) * HBT_V3_SUB_SAME / HBT_V3_TJ_SAME) {
         HbtBBox ra = bbox[static_cast<long long>(a) * RB], tb = bbox[t * TB];

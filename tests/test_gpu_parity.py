@@ -20,8 +20,8 @@ RTOL = 1e-10
 
 
 
-def run_product(P, batches, do_mixed=True, stats=False):
-    h = HBT_correlation(P, stage_counters=stats)
+def run_product(P, batches, do_mixed=True, stats=False, coalesce=None):
+    h = HBT_correlation(P, stage_counters=stats, coalesce=coalesce)
     for b in batches:
         h.calculate_HBT_correlation_function(b, do_mixed=do_mixed)
     acc = h.accumulators()
@@ -136,7 +136,7 @@ def test_fused_and_separate_kernels_agree_and_device_resident_batch():
     ref = run_oracle(P, batches)
     res = []
     for fuse in (True, False):
-        h = HBT_correlation(P, fuse=fuse)
+        h = HBT_correlation(P, fuse=fuse, coalesce=False)  # one launch (fused) / two launches per batch
         for b in batches:
             h.calculate_HBT_correlation_function(b)
         res.append(h.accumulators())
@@ -145,6 +145,12 @@ def test_fused_and_separate_kernels_agree_and_device_resident_batch():
         h.close()
     hbtio.compare(ref, res[0], rtol=RTOL, check_stage="cheap")
     hbtio.compare(res[0], res[1], rtol=RTOL, check_stage="cheap")
+    h = HBT_correlation(P)  # default: the two small batches go out as ONE fused launch
+    for b in batches:
+        h.calculate_HBT_correlation_function(b)
+    hbtio.compare(ref, h.accumulators(), rtol=RTOL, check_stage="cheap")
+    assert h.timers()["same_launches"] == 1
+    h.close()
     # device-resident list, same plan as the oracle's draws (the class shares the RNG stream)
     h = HBT_correlation(P)
     keep = []
@@ -179,7 +185,7 @@ def test_batches_in_flight_on_two_lanes(same_only):
     ref = run_oracle(P, batches, do_mixed=not same_only)
     res = []
     for lanes in (2, 1):
-        h = HBT_correlation(P, lanes=lanes)
+        h = HBT_correlation(P, lanes=lanes, coalesce=False)  # one launch per batch: the lanes take them in turn
         assert h._L.hbt_timer_start(h._h) == 0
         for b in batches:
             if same_only:
@@ -391,19 +397,63 @@ SEEDED = {
 }
 
 
-@pytest.mark.parametrize("stats", [False, True], ids=["production", "instrumented"])
+@pytest.mark.parametrize("mode", ["production", "one_launch_per_batch", "instrumented"])
 @pytest.mark.parametrize("name", sorted(SEEDED))
-def test_seeded_against_oracle(name, stats):
-    """production: Morton-sorted same-event list with tile culling; instrumented: every pair
-    through the prefilter, all six stage populations exact."""
+def test_seeded_against_oracle(name, mode):
+    """production: Morton-sorted same-event list with tile culling, small batches launched together;
+    one_launch_per_batch: the same without coalescing; instrumented: every pair through the prefilter, all six
+    stage populations exact."""
+    stats = mode == "instrumented"
     P, ngrp, nev, mult, mass = SEEDED[name]
     batches = synth.make_batches(20260002, ngrp, nev, mass=mass, multiplicity=mult)
     do_mixed = name != "c2_same_only"
     ref = run_oracle(P, batches, do_mixed)
-    h, acc = run_product(P, batches, do_mixed, stats=stats)
+    h, acc = run_product(P, batches, do_mixed, stats=stats, coalesce=False if mode == "one_launch_per_batch" else None)
     rep = hbtio.compare(ref, acc, rtol=RTOL, check_stage=True if stats else "cheap")
     assert int(acc.stage[0]) == h.pairs_same and int(acc.stage[6]) == h.pairs_mixed
     print(name, rep, "deferred", h.deferred_pairs())
+
+
+@pytest.mark.parametrize("resident", [False, True], ids=["host_buffers", "device_resident"])
+@pytest.mark.parametrize("do_mixed", [True, False], ids=["same_mixed", "same_only"])
+def test_small_batches_launched_together(do_mixed, resident):
+    """HBT_OPT_COALESCE: 40 small batches of ragged sizes (event multiplicities that are no multiples of the 64-particle
+    work units, one-particle events, a batch of a single event) go out as two launches of up to 32 batches: same
+    integers as the oracle in every bin, batch by batch in the reference's RNG order."""
+    import torch
+
+    P = HBTParams(qnpts=21)
+    rng = np.random.default_rng(5)
+    batches = []
+    for k in range(40):
+        nev = int(rng.integers(1, 6))
+        evs = [synth.make_group(900 + k, e, 1, multiplicity=int(rng.integers(1, 330)))[0] for e in range(nev)]
+        batches.append(hbtio.Batch(evs))
+    ref = run_oracle(P, batches, do_mixed)
+    h = HBT_correlation(P)
+    keep = []
+    for b in batches:
+        if not resident:
+            h.calculate_HBT_correlation_function(b, do_mixed=do_mixed)
+            continue
+        flat, off = b.flat("same")
+        d = torch.from_numpy(np.ascontiguousarray(flat)).cuda()
+        keep.append(d)  # device buffers stay valid until the context is synchronised
+        nev = len(b.same)
+        if do_mixed:
+            ids, cs = h.ran_gen.mixed_plan(nev, nev)
+            from hadronic_afterburner_toolkit_b200.hbt_correlation import _check
+            _check(h._h, h._L.hbt_accumulate_batch_dev(h._h, d.data_ptr(), off.ctypes.data, nev, ids.ctypes.data, cs.ctypes.data,
+                                                       ids.shape[1], 0.0))
+        else:
+            from hadronic_afterburner_toolkit_b200.hbt_correlation import _check
+            _check(h._h, h._L.hbt_accumulate_same_dev(h._h, d.data_ptr(), int(off[-1]), 0.0))
+    acc = h.accumulators()
+    hbtio.compare(ref, acc, rtol=RTOL)
+    t = h.timers()
+    # 40 batches in 2 launches when device resident, a launch per 8 host batches (one more if a batch did not qualify)
+    assert t["same_launches"] <= (3 if resident else 7), t
+    h.close()
 
 
 def test_empty_and_tiny_batches():
