@@ -4,14 +4,18 @@
 //   BalanceFunction::combine_and_bin_mixed_particle_pairs   src/BalanceFunction.cpp:159-197
 //
 // The loops only histogram (Delta y, Delta phi) of particle pairs of ONE event (or one event and
-// its drawn partner); everything per pair is IEEE add / divide / floor / int cast on values the
-// host computed per particle, so evaluating the reference's expressions literally (__dsub_rn,
-// __ddiv_rn: no FMA contraction, no reciprocal) gives the reference's bin for every pair — no guard
-// bands needed.  One thread block = 128 list-a particles of one event against the partner
+// its drawn partner); per pair the reference does IEEE subtract / add / divide / floor / int cast on
+// values the host computed per particle.  The two divisions are by grid constants, and
+// floor(RN(x / d)) is a monotone step function of the double x: its steps are found ONCE on the host
+// (bisection over doubles on the reference's own expression) and a pair's index is a multiply-estimate
+// corrected against the exact thresholds — the reference's bin for every pair, without a division in
+// the loop (the literal __ddiv_rn chain, ~110 instructions per pair, remains as the fallback for values
+// outside the tables).  One thread block = 128 list-a particles of one event against the partner
 // event's list b staged through shared memory; the [Bnpts][20] histogram is privatised per block
 // in shared memory (u32) and flushed with one u64 atomic per non-empty bin.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -25,12 +29,17 @@ namespace {
 
 constexpr int kTile = 128;
 
+// phi index k = floor((dphi - Bphi_min)/dphi_bin) for |phi_p| <= pi and a rotation in [0, 2 pi): k in [-15, 45]
+constexpr int kPhiLo = -24, kPhiN = 80;   // thresholds for k = kPhiLo .. kPhiLo + kPhiN (inclusive upper sentinel)
+constexpr int kMaxRap = 2048;
+
 struct BfGrid {
     int nrap;         // Bnpts
     double rap_min;   // Brap_min = -|Brap_max| - drap/2
     double drap;
     double phi_min;   // -pi/2
     double dphi;      // 2 pi / 20
+    double inv_dphi, inv_drap;  // estimates only
 };
 
 struct BfSeg {  // one event of list a: its particles, the partner event's particles, the rotation
@@ -41,14 +50,24 @@ struct BfSeg {  // one event of list a: its particles, the partner event's parti
     double rotation;
 };
 
+// thr_phi[i]: smallest double x with floor(x / dphi) >= kPhiLo + i (i = 0 .. kPhiN); thr_rap[k]: smallest double x >= 0
+// with int(x / drap) >= k (k = 0 .. nrap)
 __global__ void __launch_bounds__(kTile) bf_pairs(const double2 *__restrict__ a, const double2 *__restrict__ b,
                                                    const BfSeg *__restrict__ segs, int nseg, BfGrid g,
+                                                   const double *__restrict__ thr_phi, const double *__restrict__ thr_rap,
                                                    unsigned long long *__restrict__ hist) {
-    extern __shared__ unsigned s_hist[];  // [nrap * 20]
+    extern __shared__ __align__(16) unsigned char dyn[];
+    double *const s_tphi = reinterpret_cast<double *>(dyn);     // [kPhiN + 1]
+    double *const s_trap = s_tphi + (kPhiN + 1);                 // [nrap + 1]
+    unsigned *const s_hist = reinterpret_cast<unsigned *>(s_trap + g.nrap + 1);  // [nrap * 20]
+    unsigned char *const s_pbin = reinterpret_cast<unsigned char *>(s_hist + g.nrap * HBT_BF_NPHI);  // [kPhiN]: k -> k mod 20
     __shared__ double2 sb[kTile];
     const int t = threadIdx.x;
     const int nbins = g.nrap * HBT_BF_NPHI;
     for (int k = t; k < nbins; k += kTile) s_hist[k] = 0u;
+    for (int k = t; k <= kPhiN; k += kTile) s_tphi[k] = thr_phi[k];
+    for (int k = t; k <= g.nrap; k += kTile) s_trap[k] = thr_rap[k];
+    for (int k = t; k < kPhiN; k += kTile) s_pbin[k] = static_cast<unsigned char>(((kPhiLo + k) % HBT_BF_NPHI + HBT_BF_NPHI) % HBT_BF_NPHI);
     int lo = 0, hi = nseg - 1;  // the event that owns this block
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -67,16 +86,34 @@ __global__ void __launch_bounds__(kTile) bf_pairs(const double2 *__restrict__ a,
         const int nj = min(kTile, sg.nb - j0);
         for (int j = 0; j < nj; j++) {
             const double2 pb = sb[j];
-            // :134-139 / :175-180 — (a.phi - b.phi) + rotation, then floor((. - Bphi_min)/dphi) % Bnphi
-            const double dphi_local = __dadd_rn(__dsub_rn(pa.x, pb.x), sg.rotation);
-            int phi_idx = static_cast<int>(floor(__ddiv_rn(__dsub_rn(dphi_local, g.phi_min), g.dphi))) % HBT_BF_NPHI;
-            if (phi_idx < 0) phi_idx += HBT_BF_NPHI;
-            // :141-151 / :182-192
+            // :141-151 / :182-192 first: most rejected pairs leave here
             const double dy = __dsub_rn(pa.y, pb.y);
             if (fabs(dy) < 1e-10) continue;
             if (dy < g.rap_min) continue;
-            const int y_idx = static_cast<int>(__ddiv_rn(__dsub_rn(dy, g.rap_min), g.drap));
-            if (y_idx >= 0 && y_idx < g.nrap) atomicAdd(&s_hist[y_idx * HBT_BF_NPHI + phi_idx], 1u);
+            const double xr = __dsub_rn(dy, g.rap_min);  // >= 0
+            int y_idx = __double2int_rz(xr * g.inv_drap);
+            if (y_idx >= 0 && y_idx <= g.nrap) {  // estimate within one step of int(RN(xr / drap)): settle it on the thresholds
+                if (y_idx > 0 && xr < s_trap[y_idx]) y_idx--;
+                else if (y_idx < g.nrap && xr >= s_trap[y_idx + 1]) y_idx++;
+            } else {
+                y_idx = (xr * g.inv_drap > static_cast<double>(g.nrap)) ? g.nrap : __double2int_rz(__ddiv_rn(xr, g.drap));  // far outside / NaN
+            }
+            if (!(y_idx >= 0 && y_idx < g.nrap)) continue;
+            // :134-139 / :175-180 — (a.phi - b.phi) + rotation, then floor((. - Bphi_min)/dphi) % Bnphi
+            const double dphi_local = __dadd_rn(__dsub_rn(pa.x, pb.x), sg.rotation);
+            const double xp = __dsub_rn(dphi_local, g.phi_min);
+            int phi_idx;
+            const int ke = __double2int_rd(xp * g.inv_dphi) - kPhiLo;  // table position of the estimate
+            if (ke >= 1 && ke < kPhiN - 1) {
+                int kk = ke;
+                if (xp < s_tphi[kk]) kk--;
+                else if (xp >= s_tphi[kk + 1]) kk++;
+                phi_idx = s_pbin[kk];
+            } else {  // outside the tables (|phi_p| > pi, NaN, ...): the reference's expression as written
+                phi_idx = static_cast<int>(floor(__ddiv_rn(xp, g.dphi))) % HBT_BF_NPHI;
+                if (phi_idx < 0) phi_idx += HBT_BF_NPHI;
+            }
+            atomicAdd(&s_hist[y_idx * HBT_BF_NPHI + phi_idx], 1u);
         }
     }
     __syncthreads();
@@ -91,6 +128,7 @@ struct hbt_bf {
     BfGrid grid{};
     cudaStream_t stream = nullptr;
     unsigned long long *d_hist = nullptr;  // [8][nrap][20]
+    double *d_thr = nullptr;               // [kPhiN + 1] phi thresholds, then [nrap + 1] rapidity thresholds
     double2 *d_a = nullptr, *d_b = nullptr;
     BfSeg *d_seg = nullptr;
     size_t cap_a = 0, cap_b = 0, cap_seg = 0;
@@ -130,6 +168,23 @@ int bf_reserve(hbt_bf *bf, T **p, size_t *cap, size_t n) {
 }
 }  // namespace
 
+namespace {
+// smallest double x in [lo, hi] with pred(x) true (pred monotone: false ... false true ... true; pred(hi) true)
+template <typename F>
+double first_true(double lo, double hi, F pred) {
+    if (pred(lo)) return lo;
+    // bisection on the ordered bit patterns of non-negative / negative doubles
+    auto key = [](double v) { int64_t b; std::memcpy(&b, &v, 8); return b < 0 ? static_cast<int64_t>(0x8000000000000000ull) - b : b; };
+    auto val = [](int64_t k) { int64_t b = k < 0 ? static_cast<int64_t>(0x8000000000000000ull) - k : k; double v; std::memcpy(&v, &b, 8); return v; };
+    int64_t a = key(lo), c = key(hi);  // pred(val(a)) false, pred(val(c)) true
+    while (c - a > 1) {
+        const int64_t m = a + (c - a) / 2;
+        if (pred(val(m))) c = m; else a = m;
+    }
+    return val(c);
+}
+}  // namespace
+
 extern "C" const char *hbt_bf_last_error(const hbt_bf *bf) { return bf ? bf->err.c_str() : g_bf_error.c_str(); }
 
 extern "C" int hbt_bf_create(int32_t Bnpts, double Brap_max, int32_t device, hbt_bf **out) {
@@ -155,6 +210,21 @@ extern "C" int hbt_bf_create(int32_t Bnpts, double Brap_max, int32_t device, hbt
     const size_t n = static_cast<size_t>(HBT_BF_NHIST) * Bnpts * HBT_BF_NPHI;
     BFCU(bf, cudaMalloc(&bf->d_hist, n * 8));
     BFCU(bf, cudaMemset(bf->d_hist, 0, n * 8));
+    // steps of the two index expressions (src/BalanceFunction.cpp:135-137, :149-150), exact: the host divides as
+    // the reference does (IEEE, round to nearest)
+    bf->grid.inv_dphi = 1.0 / bf->grid.dphi;
+    bf->grid.inv_drap = 1.0 / bf->grid.drap;
+    std::vector<double> thr(static_cast<size_t>(kPhiN + 1) + Bnpts + 1);
+    const double dphi = bf->grid.dphi, drap = bf->grid.drap;
+    for (int i = 0; i <= kPhiN; i++) {
+        const int k = kPhiLo + i;
+        thr[i] = first_true((k - 2) * dphi, (k + 2) * dphi, [&](double x) { return std::floor(x / dphi) >= k; });
+    }
+    thr[kPhiN + 1] = 0.0;  // int(x / drap) >= 0 for every x >= 0
+    for (int k = 1; k <= Bnpts; k++)
+        thr[kPhiN + 1 + k] = first_true(std::max(0.0, (k - 2) * drap), (k + 2) * drap, [&](double x) { return static_cast<int>(x / drap) >= k; });
+    BFCU(bf, cudaMalloc(&bf->d_thr, thr.size() * 8));
+    BFCU(bf, cudaMemcpy(bf->d_thr, thr.data(), thr.size() * 8, cudaMemcpyHostToDevice));
     return HBT_OK;
 }
 
@@ -163,6 +233,7 @@ extern "C" void hbt_bf_destroy(hbt_bf *bf) {
     cudaSetDevice(bf->device);
     if (bf->stream) cudaStreamSynchronize(bf->stream);
     cudaFree(bf->d_hist);
+    cudaFree(bf->d_thr);
     cudaFree(bf->d_a);
     cudaFree(bf->d_b);
     cudaFree(bf->d_seg);
@@ -214,8 +285,10 @@ extern "C" int hbt_bf_accumulate(hbt_bf *bf, int32_t hist, const double *a, cons
     BFCU(bf, cudaMemcpyAsync(bf->d_seg, segs.data(), segs.size() * sizeof(BfSeg), cudaMemcpyHostToDevice, bf->stream));
     const size_t nbins = static_cast<size_t>(bf->grid.nrap) * HBT_BF_NPHI;
     BFCU(bf, cudaEventRecord(bf->e0, bf->stream));
-    bf_pairs<<<static_cast<unsigned>(blocks), kTile, nbins * sizeof(unsigned), bf->stream>>>(
-        bf->d_a, bf->d_b, bf->d_seg, static_cast<int>(segs.size()), bf->grid, bf->d_hist + static_cast<size_t>(hist) * nbins);
+    const size_t smem = (static_cast<size_t>(kPhiN + 1) + bf->grid.nrap + 1) * 8 + nbins * sizeof(unsigned) + kPhiN;
+    bf_pairs<<<static_cast<unsigned>(blocks), kTile, smem, bf->stream>>>(
+        bf->d_a, bf->d_b, bf->d_seg, static_cast<int>(segs.size()), bf->grid, bf->d_thr, bf->d_thr + kPhiN + 1,
+        bf->d_hist + static_cast<size_t>(hist) * nbins);
     BFCU(bf, cudaGetLastError());
     BFCU(bf, cudaEventRecord(bf->e1, bf->stream));
     BFCU(bf, cudaStreamSynchronize(bf->stream));  // segs / a / b may be freed by the caller on return

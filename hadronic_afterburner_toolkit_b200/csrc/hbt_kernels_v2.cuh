@@ -77,13 +77,18 @@ __host__ inline V2Const hbt_v2_consts(const HbtGrid &g) {
     return c;
 }
 
-// v2 handles the 3-D histograms with a window that is symmetric about zero; everything else
-// (q_inv mode, one-sided windows) runs on the literal v1 kernels
+// The tuned kernels handle the 3-D histograms; q_inv mode runs on the literal v1 kernels.  The window need not be
+// symmetric about zero: the prefilter, the culling and the pT range restriction test |q_out|, |q_side| against
+// W = max(|q_lo|, |q_hi|) — a superset of any window [q_lo, q_hi] — and the drain decides in bin units
+// u = (q - q_base)/delta_q, where the window is [eps, nq - eps] whatever its position.  The float decision of
+// mixed-event survivors budgets 8 x 2^-24 x (nq + 2) for the rounding of u and of the offset -q_base/delta_q, so a
+// window that lies many bin-counts away from zero (|q_base|/delta_q > 4 (nq + 2)) goes to the literal kernels.
 __host__ inline bool hbt_v2_supported(const HbtGrid &g) {
     // K_T bins at least 1e-4 of KT_max wide: the float estimate of the K_T bin is then within one
     // bin (relative error of the estimate ~4e-7); bin index in 32 bits
     const double kt_max = g.KT_min + g.dKT * g.nKT;
-    return !g.qinv && hbt_v2_consts(g).symmetric && g.dq > 1e-6 && g.dKT > 1e-4 * kt_max && g.nbins < (1ll << 31);
+    const V2Const c = hbt_v2_consts(g);
+    return !g.qinv && fabs(c.ub) <= 4.0 * (c.nq_d + 2.0) && g.dq > 1e-6 && g.dKT > 1e-4 * kt_max && g.nbins < (1ll << 31);
 }
 
 // global-memory copy of everything the non-inlined device functions need (passing the

@@ -511,7 +511,11 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
         const double zd = lds_f64(sia2 + 8 * TI * (6 % NC)) - lds_f64(sja2 + 8 * TJ * (6 % NC));
         const double td = lds_f64(sia2 + 8 * TI * (7 % NC)) - lds_f64(sja2 + 8 * TJ * (7 % NC));
         const double cv = v3_cos(g.hbarc_inv * (b.qE * td - b.qx * xd - b.qy * yd - b.qz * zd));  // src :431-433
-#if HBT_DBG_RED == 1    // control: no reductions (values stay live)
+#if HBT_DBG_RED == 1    // control: no reductions; the compiler sinks the cos chain into the dead branch, so this
+                        // also removes ~1/4 of the drain's arithmetic (see HBT_DBG_RED == 7)
+        if (bin == 0x7fffffffu) {
+#elif HBT_DBG_RED == 7  // control: no reductions, the four sums still evaluated (their bits feed a counter)
+        n.nE += static_cast<unsigned>(__double2hiint(cv) ^ __double2hiint(b.qo) ^ __double2hiint(b.qs) ^ __double2hiint(b.ql)) >> 31;
         if (bin == 0x7fffffffu) {
 #elif HBT_DBG_RED == 2  // control: all reductions into 1024 bins
         const unsigned bin_ = bin;
@@ -797,7 +801,9 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                             const int dd = __double2hiint(d2) - hw;               // d^2   vs W^2 k2
                             const int dx = __double2hiint(x2) + 0x00200000 - hw;  // 4 x^2 vs W^2 k2
                             bool rej_o = dd > 1;                 // q_out certainly outside the window
-                            bool rej_s = (dd < -1) && (dx > 1);  // q_out certainly inside, q_side certainly outside
+                            // q_out certainly inside, q_side certainly outside.  Only a window symmetric about zero lets
+                            // |q_out| < W stand for "passed the q_out cut" in the stage counters: otherwise the drain decides
+                            bool rej_s = (dd < -1) && (dx > 1) && c.symmetric;
                             if (FLOOR) {
                                 const bool tiny = k2 < k2_floor;
                                 rej_o = rej_o && !tiny;

@@ -192,8 +192,12 @@ def compare(ref: Accumulators, got: Accumulators, rtol: float = 1e-10, check_sta
                         "max_rel": float(rel.max()) if rel.size else 0.0,
                         "floor_bins": floor_bins, "bins": int(nz.sum()),
                         "max_abs_per_pair": float(per_pair.max()) if per_pair.size else 0.0}
-        assert np.all(d <= tol), (f"{name}: {int(np.sum(d > tol))} bins exceed tolerance, "
-                                  f"max_abs={d.max():.3e} max_rel={report[name]['max_rel']:.3e}")
+        if not np.all(d <= tol):
+            bad = np.flatnonzero(~(d <= tol).ravel())
+            k = bad[0]
+            raise AssertionError(f"{name}: {bad.size} bins exceed tolerance, max_abs={d.max():.3e} "
+                                 f"max_rel={report[name]['max_rel']:.3e}; first bin {k}: count={cnt.ravel()[k]:.0f} "
+                                 f"ref={a.ravel()[k]!r} got={b.ravel()[k]!r} tol={tol.ravel()[k]:.3e}")
     if ref.invariant_radius_flag == 1:
         for name in ("qinv_count", "qinv_den", "npairs_num_qinv", "npairs_den_qinv"):
             a, b = np.asarray(getattr(ref, name)), np.asarray(getattr(got, name))

@@ -392,7 +392,10 @@ SEEDED = {
     "noboost": (HBTParams(long_comoving_boost=0), 1, 3, 800, 0.138),
     "ragged_tiles": (HBTParams(qnpts=21), 2, 3, 257, 0.138),   # tile edges: 257 = 2*128 + 1
     "single_event": (HBTParams(qnpts=21), 1, 1, 700, 0.138),   # mixed_nev == 1: self pairing
+    # one-sided windows run on the tuned kernels too (the prefilter tests against max(|q_lo|, |q_hi|))
     "asym_window": (HBTParams(qnpts=16, q_min=-0.05, q_max=0.25), 1, 4, 600, 0.138),
+    "positive_window": (HBTParams(qnpts=13, q_min=0.02, q_max=0.14), 1, 4, 600, 0.138),
+    "negative_window_noboost": (HBTParams(qnpts=11, q_min=-0.2, q_max=-0.01, long_comoving_boost=0), 1, 4, 600, 0.138),
     "kt_from_zero": (HBTParams(qnpts=21, KT_min=0.0, KT_max=1.0, n_KT=6), 1, 3, 600, 0.138),
 }
 
