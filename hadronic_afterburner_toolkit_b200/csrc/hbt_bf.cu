@@ -31,7 +31,6 @@ constexpr int kTile = 128;
 
 // phi index k = floor((dphi - Bphi_min)/dphi_bin) for |phi_p| <= pi and a rotation in [0, 2 pi): k in [-15, 45]
 constexpr int kPhiLo = -24, kPhiN = 80;   // thresholds for k = kPhiLo .. kPhiLo + kPhiN (inclusive upper sentinel)
-constexpr int kMaxRap = 2048;
 
 struct BfGrid {
     int nrap;         // Bnpts
@@ -40,6 +39,11 @@ struct BfGrid {
     double phi_min;   // -pi/2
     double dphi;      // 2 pi / 20
     double inv_dphi, inv_drap;  // estimates only
+    // binary32 decision (see bf_pairs): bin units u_y = (dy - rap_min) / drap, u_phi = (dphi + rotation - phi_min) / dphi
+    float rap_min_f, inv_drap_f, inv_dphi_f;
+    float ky, k0y;  // |u_y(float) - u_y| <= ky (|y_a| + |y_b|) + k0y
+    float kp;       // |u_phi(float) - u_phi| <= kp (|phi_a| + |phi_b|) + k0p, k0p = kp0a |rotation - phi_min| + kp0b
+    float kp0a, kp0b;
 };
 
 struct BfSeg {  // one event of list a: its particles, the partner event's particles, the rotation
@@ -52,6 +56,54 @@ struct BfSeg {  // one event of list a: its particles, the partner event's parti
 
 // thr_phi[i]: smallest double x with floor(x / dphi) >= kPhiLo + i (i = 0 .. kPhiN); thr_rap[k]: smallest double x >= 0
 // with int(x / drap) >= k (k = 0 .. nrap)
+// The reference's bin of one pair, every operation in binary64 as written there; -1 = not binned.
+__device__ __forceinline__ int bf_pair_exact(const BfGrid &g, const double2 pa, const double2 pb, const double rotation,
+                                             const double *s_tphi, const double *s_trap, const unsigned char *s_pbin) {
+    // :141-151 / :182-192
+    const double dy = __dsub_rn(pa.y, pb.y);
+    if (fabs(dy) < 1e-10) return -1;
+    if (dy < g.rap_min) return -1;
+    const double xr = __dsub_rn(dy, g.rap_min);  // >= 0
+    int y_idx = __double2int_rz(xr * g.inv_drap);
+    if (y_idx >= 0 && y_idx <= g.nrap) {  // estimate within one step of int(RN(xr / drap)): settle it on the thresholds
+        if (y_idx > 0 && xr < s_trap[y_idx]) y_idx--;
+        else if (y_idx < g.nrap && xr >= s_trap[y_idx + 1]) y_idx++;
+    } else {
+        y_idx = (xr * g.inv_drap > static_cast<double>(g.nrap)) ? g.nrap : __double2int_rz(__ddiv_rn(xr, g.drap));  // far outside / NaN
+    }
+    if (!(y_idx >= 0 && y_idx < g.nrap)) return -1;
+    // :134-139 / :175-180 — (a.phi - b.phi) + rotation, then floor((. - Bphi_min)/dphi) % Bnphi
+    const double dphi_local = __dadd_rn(__dsub_rn(pa.x, pb.x), rotation);
+    const double xp = __dsub_rn(dphi_local, g.phi_min);
+    int phi_idx;
+    const int ke = __double2int_rd(xp * g.inv_dphi) - kPhiLo;  // table position of the estimate
+    if (ke >= 1 && ke < kPhiN - 1) {
+        int kk = ke;
+        if (xp < s_tphi[kk]) kk--;
+        else if (xp >= s_tphi[kk + 1]) kk++;
+        phi_idx = s_pbin[kk];
+    } else {  // outside the tables (|phi_p| > pi, NaN, ...): the reference's expression as written
+        phi_idx = static_cast<int>(floor(__ddiv_rn(xp, g.dphi))) % HBT_BF_NPHI;
+        if (phi_idx < 0) phi_idx += HBT_BF_NPHI;
+    }
+    return y_idx * HBT_BF_NPHI + phi_idx;
+}
+
+// floor(u) and |u - rint(u)| for |u| < 2^22 (u + 1.5 * 2^23 holds rint(u) in its mantissa); NaN / inf give far = false
+__device__ __forceinline__ void bf_classify(float u, float band, int &i, bool &far) {
+    const float magic = 12582912.f;
+    const float t = u + magic;
+    const float d = u - (t - magic);
+    i = __float_as_int(t) - 0x4B400000 - (d < 0.f ? 1 : 0);
+    far = fabsf(d) > band;
+}
+
+// Per pair the bin is first evaluated in binary32 from float copies of (phi, rapidity): in bin units the bin edges are
+// the integers, and the float value differs from the exact one by at most `band` (every input rounding and every
+// operation accounted for, x2; constants in BfGrid, derivation in hbt_bf_create).  A pair farther than its band from
+// every integer in both coordinates (and with |dy| safely above the reference's 1e-10 self-pair test) has the
+// reference's bin — or is certainly outside the rapidity range — without any binary64 operation; the others
+// (~1e-5 of the pairs) take bf_pair_exact.
 __global__ void __launch_bounds__(kTile) bf_pairs(const double2 *__restrict__ a, const double2 *__restrict__ b,
                                                    const BfSeg *__restrict__ segs, int nseg, BfGrid g,
                                                    const double *__restrict__ thr_phi, const double *__restrict__ thr_rap,
@@ -62,6 +114,7 @@ __global__ void __launch_bounds__(kTile) bf_pairs(const double2 *__restrict__ a,
     unsigned *const s_hist = reinterpret_cast<unsigned *>(s_trap + g.nrap + 1);  // [nrap * 20]
     unsigned char *const s_pbin = reinterpret_cast<unsigned char *>(s_hist + g.nrap * HBT_BF_NPHI);  // [kPhiN]: k -> k mod 20
     __shared__ double2 sb[kTile];
+    __shared__ float2 sbf[kTile];
     const int t = threadIdx.x;
     const int nbins = g.nrap * HBT_BF_NPHI;
     for (int k = t; k < nbins; k += kTile) s_hist[k] = 0u;
@@ -78,42 +131,39 @@ __global__ void __launch_bounds__(kTile) bf_pairs(const double2 *__restrict__ a,
     const bool live = ia < sg.na;
     double2 pa = make_double2(0.0, 0.0);
     if (live) pa = a[sg.a0 + ia];
+    const float paf_x = static_cast<float>(pa.x), paf_y = static_cast<float>(pa.y);
+    const double rotm = sg.rotation - g.phi_min;
+    const float rotm_f = static_cast<float>(rotm);
+    const float k0p = fmaf(fabsf(rotm_f), g.kp0a, g.kp0b);
+    const unsigned nrap = static_cast<unsigned>(g.nrap);
     for (int j0 = 0; j0 < sg.nb; j0 += kTile) {
         __syncthreads();
-        if (j0 + t < sg.nb) sb[t] = b[sg.b0 + j0 + t];
+        if (j0 + t < sg.nb) {
+            const double2 v = b[sg.b0 + j0 + t];
+            sb[t] = v;
+            sbf[t] = make_float2(static_cast<float>(v.x), static_cast<float>(v.y));
+        }
         __syncthreads();
         if (!live) continue;
         const int nj = min(kTile, sg.nb - j0);
         for (int j = 0; j < nj; j++) {
-            const double2 pb = sb[j];
-            // :141-151 / :182-192 first: most rejected pairs leave here
-            const double dy = __dsub_rn(pa.y, pb.y);
-            if (fabs(dy) < 1e-10) continue;
-            if (dy < g.rap_min) continue;
-            const double xr = __dsub_rn(dy, g.rap_min);  // >= 0
-            int y_idx = __double2int_rz(xr * g.inv_drap);
-            if (y_idx >= 0 && y_idx <= g.nrap) {  // estimate within one step of int(RN(xr / drap)): settle it on the thresholds
-                if (y_idx > 0 && xr < s_trap[y_idx]) y_idx--;
-                else if (y_idx < g.nrap && xr >= s_trap[y_idx + 1]) y_idx++;
+            const float2 pbf = sbf[j];
+            const float ysum = fabsf(paf_y) + fabsf(pbf.y);
+            const float dyf = paf_y - pbf.y;
+            int iy, ip;
+            bool far_y, far_p;
+            bf_classify((dyf - g.rap_min_f) * g.inv_drap_f, fmaf(ysum, g.ky, g.k0y), iy, far_y);
+            bf_classify(((paf_x - pbf.x) + rotm_f) * g.inv_dphi_f, fmaf(fabsf(paf_x) + fabsf(pbf.x), g.kp, k0p), ip, far_p);
+            const bool not_self = fabsf(dyf) > fmaf(ysum, 2.4e-7f, 1e-9f);  // |dy| certainly >= 1e-10 (:141 / :182)
+            int bin;
+            if (far_y && not_self && static_cast<unsigned>(iy) >= nrap) continue;  // certainly outside the rapidity range
+            if (far_y && not_self && far_p && static_cast<unsigned>(ip + 160) < 320u) {
+                bin = iy * HBT_BF_NPHI + static_cast<int>(static_cast<unsigned>(ip + 160) % HBT_BF_NPHI);
             } else {
-                y_idx = (xr * g.inv_drap > static_cast<double>(g.nrap)) ? g.nrap : __double2int_rz(__ddiv_rn(xr, g.drap));  // far outside / NaN
+                bin = bf_pair_exact(g, pa, sb[j], sg.rotation, s_tphi, s_trap, s_pbin);
+                if (bin < 0) continue;
             }
-            if (!(y_idx >= 0 && y_idx < g.nrap)) continue;
-            // :134-139 / :175-180 — (a.phi - b.phi) + rotation, then floor((. - Bphi_min)/dphi) % Bnphi
-            const double dphi_local = __dadd_rn(__dsub_rn(pa.x, pb.x), sg.rotation);
-            const double xp = __dsub_rn(dphi_local, g.phi_min);
-            int phi_idx;
-            const int ke = __double2int_rd(xp * g.inv_dphi) - kPhiLo;  // table position of the estimate
-            if (ke >= 1 && ke < kPhiN - 1) {
-                int kk = ke;
-                if (xp < s_tphi[kk]) kk--;
-                else if (xp >= s_tphi[kk + 1]) kk++;
-                phi_idx = s_pbin[kk];
-            } else {  // outside the tables (|phi_p| > pi, NaN, ...): the reference's expression as written
-                phi_idx = static_cast<int>(floor(__ddiv_rn(xp, g.dphi))) % HBT_BF_NPHI;
-                if (phi_idx < 0) phi_idx += HBT_BF_NPHI;
-            }
-            atomicAdd(&s_hist[y_idx * HBT_BF_NPHI + phi_idx], 1u);
+            atomicAdd(&s_hist[bin], 1u);
         }
     }
     __syncthreads();
@@ -214,6 +264,23 @@ extern "C" int hbt_bf_create(int32_t Bnpts, double Brap_max, int32_t device, hbt
     // the reference does (IEEE, round to nearest)
     bf->grid.inv_dphi = 1.0 / bf->grid.dphi;
     bf->grid.inv_drap = 1.0 / bf->grid.drap;
+    {   // Error bands of the binary32 decision, u = 2^-24.  With y_a, y_b rounded to float, dy_f = fl(y_a - y_b),
+        // t = fl(dy_f - fl(rap_min)), u_y = fl(t * fl(1/drap)):
+        //   |u_y(float) - u_y| <= (u / drap) (3 (|y_a| + |y_b|) + 2 |rap_min|) + 2 u |u_y|
+        // and the same with (phi_a, phi_b, rotation - phi_min, dphi).  |u_y| <= nrap + 1 and |u_phi| <= 160 wherever a
+        // decision inside the grid is taken (beyond that only "certainly outside" is concluded, which the relative
+        // term cannot overturn).  Everything x2, plus 1e-9 for the roundings of the reference's own binary64 chain.
+        const double u = 5.9604644775390625e-8, S = 2.0;
+        BfGrid &g = bf->grid;
+        g.rap_min_f = static_cast<float>(g.rap_min);
+        g.inv_drap_f = static_cast<float>(g.inv_drap);
+        g.inv_dphi_f = static_cast<float>(g.inv_dphi);
+        g.ky = static_cast<float>(S * 3.0 * u * g.inv_drap * 1.001);
+        g.k0y = static_cast<float>((S * (2.0 * std::fabs(g.rap_min) * g.inv_drap * u + 2.0 * u * (Bnpts + 1)) + 1e-9) * 1.001);
+        g.kp = static_cast<float>(S * 3.0 * u * g.inv_dphi * 1.001);
+        g.kp0a = static_cast<float>(S * 2.0 * u * g.inv_dphi * 1.001);
+        g.kp0b = static_cast<float>((S * 2.0 * u * 160.0 + 1e-9) * 1.001);
+    }
     std::vector<double> thr(static_cast<size_t>(kPhiN + 1) + Bnpts + 1);
     const double dphi = bf->grid.dphi, drap = bf->grid.drap;
     for (int i = 0; i <= kPhiN; i++) {

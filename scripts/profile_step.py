@@ -25,7 +25,7 @@ ap.add_argument("--launches", type=int, default=2)
 ap.add_argument("--events", type=int, default=100)
 ap.add_argument("--shape", default="C5")
 a = ap.parse_args()
-P = {"C2": C2, "C3": C3, "C4": C4.with_(qnpts=31), "C5": C5}[a.shape]
+P = {"C2": C2, "C3": C3, "C4": C4.with_(qnpts=31), "C4_41": C4, "C5": C5}[a.shape]
 nev, mult = a.events, 1500
 arr = synth.make_group(20260005, 0, nev, PION_MASS, mult).reshape(nev * mult, 8)
 flat = np.ascontiguousarray(np.concatenate([gather_rapidity(P, arr[e * mult:(e + 1) * mult]) for e in range(nev)]))
@@ -35,7 +35,7 @@ h = HBT_correlation(P)
 ids, cs = Random(P.randomSeed).mixed_plan(nev, nev)
 for _ in range(a.launches):
     _check(h._h, h._L.hbt_accumulate_batch_dev(h._h, d.data_ptr(), off.ctypes.data, nev, ids.ctypes.data, cs.ctypes.data,
-                                               ids.shape[1], 0.0))
+                                               ids.shape[1], 0.3 if P.azimuthal_flag else 0.0))
 h.synchronize()
 t = h.timers()
 print({k: v for k, v in t.items()})

@@ -70,6 +70,49 @@ def test_seeded_batches_against_oracle(rap_type):
     bf.close()
 
 
+def test_float_decision_bands_hold_next_to_bin_edges():
+    """The kernel bins a pair in binary32 when it is farther than a proven error band from every bin edge and takes
+    the reference's binary64 chain otherwise.  Pairs are placed 1e-9 ... 1e-3 bin widths on either side of rapidity
+    and azimuth bin edges (and of the two ends of the rapidity range, and at |Delta y| around the 1e-10 self-pair
+    test), at small and large |y| / |phi|: the histograms must equal the oracle's integers."""
+    Bnpts, Brap_max = 21, 2.0
+    args = (Bnpts, Brap_max, 0.2, 3.0, 1)
+    drap = 2. * Brap_max / (Bnpts - 1)
+    rap_min = -Brap_max - 0.5 * drap
+    dphi = 2. * np.pi / 20
+    rng = np.random.default_rng(7)
+    eps = np.concatenate([[0.0], 10.0 ** np.arange(-9.0, -2.5, 0.5)])
+    eps = np.concatenate([eps, -eps])
+    nev, n = 4, 640
+    def lists_for(rot_free):
+        ev_a, ev_b = [], []
+        for e in range(nev):
+            yb = rng.uniform(-3.0, 3.0, n) * (30.0 if e == 3 else 1.0)   # e == 3: large |y| (wide bands)
+            pb = rng.uniform(-np.pi, np.pi, n)
+            k = rng.integers(0, Bnpts + 1, n)            # rapidity edges 0 .. Bnpts (both ends of the range included)
+            m = rng.integers(-14, 15, n)                 # azimuth edges
+            ya = yb + rap_min + (k + rng.choice(eps, n)) * drap
+            pa = pb - np.pi / 2 + (m + rng.choice(eps, n)) * dphi
+            pa = np.clip(pa, -np.pi, np.pi)
+            if e == 2:                                   # |Delta y| around the self-pair threshold
+                ya = yb + rng.choice([0.0, 5e-11, 1.5e-10, -5e-11, -1.5e-10, 1e-9, 1e-7], n)
+            pT = np.full(n, 1.0)
+            ev_a.append({"pT": pT, "phi": pa, "rap_y": ya, "rap_eta": ya})
+            ev_b.append({"pT": pT, "phi": pb, "rap_y": yb, "rap_eta": yb})
+        return {"a": ev_a, "abar": ev_b, "b": ev_b, "bbar": ev_a}
+    seed = 3
+    o = bf_oracle.BFOracle(*args, oracle_py.Oracle(HBTParams(randomSeed=seed)))
+    bf = BalanceFunction(211, -211, *args, ran_gen=Random(seed))
+    for _ in range(2):
+        lists = lists_for(True)
+        o.calculate_balance_function(lists)
+        bf.calculate_balance_function(lists)
+    got, want = bf.histograms(), o.histograms()
+    assert want.sum() > 1e6
+    assert np.array_equal(got, want)
+    bf.close()
+
+
 def test_bad_arguments():
     import ctypes
 
