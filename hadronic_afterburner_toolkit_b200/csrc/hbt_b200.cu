@@ -201,6 +201,10 @@ struct hbt_ctx {
     bool stats = false;                          // exact stage populations B, C, D (no culling)
     int n_sm = 148;
     int occ_same = 12, occ_same_stats = 12, occ_mixed = 12, occ_mixed_stats = 12, occ_fused = 12;  // resident warps per SM
+    int occ_same_q = 12, occ_mixed_q = 12;       // q_inv mode
+    double *d_qinv_thr = nullptr;                // q_inv mode: exact bin thresholds in s space (V2Const::qinv_thr)
+    unsigned long long *d_qrep_u64 = nullptr;    // q_inv mode: replicated accumulators (V2Const::qrep_*)
+    double *d_qrep_f64 = nullptr;
     std::vector<int> row_item0;                  // same-event unit prefix per row (instrumented runs)
     int *d_rows = nullptr;
     size_t d_rows_cap = 0;
@@ -475,10 +479,27 @@ void set_evoff(hbt_ctx *ctx, const int64_t *off1, int32_t nev1, const int64_t *o
 }
 
 bool production_mixed(const hbt_ctx *ctx, unsigned long long npairs) {
-    return (ctx->ptsort == 2 || (ctx->ptsort == 1 && npairs >= ctx->ptsort_min_pairs)) && !ctx->stats && ctx->kernel_version != 1;
+    return (ctx->ptsort == 2 || (ctx->ptsort == 1 && npairs >= ctx->ptsort_min_pairs)) && !ctx->stats && ctx->kernel_version != 1 &&
+           !ctx->grid.qinv;  // (the pT range restriction rests on the q_out window, which q_inv does not respect)
 }
 
 const unsigned char *closed_ptr(const hbt_ctx *ctx) { return ctx->any_closed ? ctx->d_closed : nullptr; }
+
+// the literal kernels: when asked for, when the grid needs them, for the two ordered-cap passes, and for
+// instrumented runs in q_inv mode (the tuned q_inv kernels keep no stage counters)
+bool use_literal(const hbt_ctx *ctx, int mode) {
+    return ctx->kernel_version == 1 || mode != 0 || (ctx->grid.qinv && ctx->stats);
+}
+
+#ifdef HBT_HAVE_V2
+// q_inv mode: the replicas of the q_inv accumulators go into the histograms after every launch (same stream)
+int fold_qinv(hbt_ctx *ctx, Lane &L) {
+    hbt_qinv_fold<<<static_cast<unsigned>(ctx->grid.nKT * ctx->grid.nq), 128, 0, L.stream>>>(ctx->v2c, ctx->acc, ctx->grid.nKT, ctx->grid.nq);
+    ctx->kernel_launches++;
+    CU(ctx, cudaGetLastError());
+    return HBT_OK;
+}
+#endif
 
 // mode 0: the production kernels (v2 unless the grid needs v1); mode 1 / 2: the two ordered-cap
 // passes, always on the literal v1 kernels
@@ -495,7 +516,7 @@ int launch_same(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, double psi_
     HbtCap cap{};
     if (capin) cap = *capin;
     cap.closed = closed_ptr(ctx);
-    if (ctx->kernel_version == 1 || mode != 0) {
+    if (use_literal(ctx, mode)) {
         const long long T = (n + kTileV1 - 1) / kTileV1;
         const long long blocks = T * (T + 1) / 2;
         if (blocks > 0x7fffffffLL) return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld tiles", blocks);
@@ -514,8 +535,9 @@ int launch_same(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, double psi_
         rc = ensure_work(ctx, L);
         if (rc) return rc;
         CU(ctx, cudaMemsetAsync(L.d_work, 0, 8, L.stream));
-        const bool sorted = !ctx->stats;
-        const unsigned grid = static_cast<unsigned>(ctx->n_sm * (sorted ? ctx->occ_same : ctx->occ_same_stats));
+        const bool qinv = ctx->grid.qinv != 0;
+        const bool sorted = !ctx->stats && !qinv;
+        const unsigned grid = static_cast<unsigned>(ctx->n_sm * (qinv ? ctx->occ_same_q : sorted ? ctx->occ_same : ctx->occ_same_stats));
         const long long all_units = hbt_v3_same_units(n, ctx->row_item0);
         if (all_units > 0x7fffffffLL || n > HBT_V3_MAX_SORTED)  // 8.8e12 pairs in one same-event list
             return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld work units", all_units);
@@ -543,9 +565,18 @@ int launch_same(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, double psi_
             // (pageable source: the copy is staged before the call returns, the vector can be reused)
             CU(ctx, cudaMemcpyAsync(ctx->d_rows, ctx->row_item0.data(), rb, cudaMemcpyHostToDevice, L.stream));
             const int n_rows = static_cast<int>(ctx->row_item0.size()) - 1;
-            hbt_pairs_v3<false, true><<<grid, 32, 0, L.stream>>>(
-                d_p, d_p, n, nullptr, ctx->d_rows, n_rows, nullptr, L.d_work, static_cast<unsigned>(all_units), ctx->grid,
-                ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
+            if (qinv) {
+                // q_inv mode: every unit of the upper triangle (the transverse window does not bound q_inv: no culling)
+                hbt_pairs_v3<false, false, true><<<grid, 32, 0, L.stream>>>(
+                    d_p, d_p, n, nullptr, ctx->d_rows, n_rows, nullptr, L.d_work, static_cast<unsigned>(all_units), ctx->grid,
+                    ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
+                rc = fold_qinv(ctx, L);
+                if (rc) return rc;
+            } else {
+                hbt_pairs_v3<false, true><<<grid, 32, 0, L.stream>>>(
+                    d_p, d_p, n, nullptr, ctx->d_rows, n_rows, nullptr, L.d_work, static_cast<unsigned>(all_units), ctx->grid,
+                    ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
+            }
         }
         ctx->kernel_launches++;
         if (rc) return fail(ctx, rc, "v2 same-event launch failed");
@@ -605,7 +636,7 @@ int launch_mixed(hbt_ctx *ctx, Lane &L, const double *d_p1, const double *d_p2, 
     HbtCap cap{};
     if (capin) cap = *capin;
     cap.closed = closed_ptr(ctx);
-    if (ctx->kernel_version == 1 || mode != 0) {
+    if (use_literal(ctx, mode)) {
         const unsigned nb = static_cast<unsigned>(nblocks);
         const size_t sm = dyn_smem_bytes(ctx->grid);
         const long long ns = static_cast<long long>(nseg);
@@ -623,8 +654,14 @@ int launch_mixed(hbt_ctx *ctx, Lane &L, const double *d_p1, const double *d_p2, 
         if (rc) return rc;
         CU(ctx, cudaMemsetAsync(L.d_work, 0, 8, L.stream));
         const unsigned grid = static_cast<unsigned>(std::min<long long>(
-            nblocks, static_cast<long long>(ctx->n_sm) * (ctx->stats ? ctx->occ_mixed_stats : ctx->occ_mixed)));
-        if (ctx->stats)
+            nblocks, static_cast<long long>(ctx->n_sm) * (ctx->grid.qinv ? ctx->occ_mixed_q : ctx->stats ? ctx->occ_mixed_stats : ctx->occ_mixed)));
+        if (ctx->grid.qinv) {
+            hbt_pairs_v3<true, false, true><<<grid, 32, 0, L.stream>>>(
+                d_p1, d_p2, static_cast<long long>(nseg), d_seg, nullptr, 0, nullptr, L.d_work, static_cast<unsigned>(nblocks), ctx->grid,
+                ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
+            rc = fold_qinv(ctx, L);
+            if (rc) return rc;
+        } else if (ctx->stats)
             hbt_pairs_v3<true, true><<<grid, 32, 0, L.stream>>>(
                 d_p1, d_p2, static_cast<long long>(nseg), d_seg, nullptr, 0, nullptr, L.d_work, static_cast<unsigned>(nblocks), ctx->grid,
                 ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
@@ -901,7 +938,7 @@ unsigned long long mixed_pairs(const int64_t *off1, int32_t nev1, const int64_t 
 // from the pair cap, few pairs.
 bool can_coalesce(const hbt_ctx *ctx, bool do_same, bool do_mixed, bool alias, int64_t n1, unsigned long long sp,
                   unsigned long long mp, bool near_cap) {
-    return ctx->coalesce && do_same && alias && !ctx->stats && ctx->kernel_version != 1 && !ctx->grid.az && !near_cap &&
+    return ctx->coalesce && do_same && alias && !ctx->stats && ctx->kernel_version != 1 && !ctx->grid.az && !ctx->grid.qinv && !near_cap &&
            n1 > 1 && sp + mp < kCoalescePairs && (!do_mixed || (ctx->fuse && ctx->ptsort != 0 && mp > 0));
 }
 #else
@@ -1363,7 +1400,25 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed, hbt_pairs_v3<true, false>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_fused, hbt_pairs_v3_fused, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed_stats, hbt_pairs_v3<true, true>, 32, 0));
-    if (!hbt_v2_supported(g)) ctx->kernel_version = 1;  // q_inv mode, one-sided q windows: literal kernels
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same_q, hbt_pairs_v3<false, false, true>, 32, 0));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed_q, hbt_pairs_v3<true, false, true>, 32, 0));
+    if (!hbt_v2_supported(g)) ctx->kernel_version = 1;  // grids the fast path's guards do not cover: literal kernels
+    if (g.qinv) {  // thresholds of the q_inv tests and the replicated q_inv accumulators (hbt_kernels_v3.cuh: v3_qinv_pair)
+        std::vector<double> thr(static_cast<size_t>(g.nq) + 1);
+        hbt_qinv_thresholds(&g, &ctx->v2c.qinv_s_lo, &ctx->v2c.qinv_s_hi, thr.data());
+        CUC(cudaMalloc(&ctx->d_qinv_thr, thr.size() * 8));
+        CUC(cudaMemcpy(ctx->d_qinv_thr, thr.data(), thr.size() * 8, cudaMemcpyHostToDevice));
+        const int R = 256;
+        const size_t nrep = static_cast<size_t>(R) * 2 * nqi;
+        CUC(cudaMalloc(&ctx->d_qrep_u64, nrep * 8));
+        CUC(cudaMalloc(&ctx->d_qrep_f64, nrep * 8));
+        CUC(cudaMemset(ctx->d_qrep_u64, 0, nrep * 8));
+        CUC(cudaMemset(ctx->d_qrep_f64, 0, nrep * 8));
+        ctx->v2c.qinv_thr = ctx->d_qinv_thr;
+        ctx->v2c.qrep_u64 = ctx->d_qrep_u64;
+        ctx->v2c.qrep_f64 = ctx->d_qrep_f64;
+        ctx->v2c.qrep_n = R;
+    }
     if (const char *v = getenv("HBT_B200_OCC")) {  // experiments: fewer resident warps per SM than the kernels allow
         const int cap = std::max(1, atoi(v));
         ctx->occ_same = std::min(ctx->occ_same, cap); ctx->occ_mixed = std::min(ctx->occ_mixed, cap);
@@ -1414,6 +1469,9 @@ extern "C" void hbt_destroy(hbt_ctx *ctx) {
     if (ctx->h_defcount) cudaFreeHost(ctx->h_defcount);
     if (ctx->d_corr) cudaFree(ctx->d_corr);
     if (ctx->d_closed) cudaFree(ctx->d_closed);
+    if (ctx->d_qinv_thr) cudaFree(ctx->d_qinv_thr);
+    if (ctx->d_qrep_u64) cudaFree(ctx->d_qrep_u64);
+    if (ctx->d_qrep_f64) cudaFree(ctx->d_qrep_f64);
     for (Lane &L : ctx->lanes) {
         for (int k = 0; k < 2; k++) { if (L.sort_keys[k]) cudaFree(L.sort_keys[k]); if (L.sort_idx[k]) cudaFree(L.sort_idx[k]); }
         if (L.sort_p) cudaFree(L.sort_p);
@@ -1598,7 +1656,7 @@ extern "C" int hbt_accumulate_batch_dev(hbt_ctx *ctx, const double *d_p, const i
         int rc = flush_pending(ctx);
         if (rc) return rc;
     }
-    if (do_mixed && ctx->fuse && !ctx->stats && ctx->kernel_version != 1 && n > 1) {
+    if (do_mixed && ctx->fuse && !ctx->stats && ctx->kernel_version != 1 && !ctx->grid.qinv && n > 1) {
         CU(ctx, cudaSetDevice(ctx->device));
         Slot *s;
         int rc = acquire_slot(ctx, &s);
@@ -1715,7 +1773,7 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
     in.cs = cos_sin;
     in.psi_ref = psi_ref;
 #ifdef HBT_HAVE_V2
-    if (do_same && do_mixed && ctx->fuse && !ctx->stats && ctx->kernel_version != 1 && n1 > 1 && nseg > 0 && nblocks > 0 &&
+    if (do_same && do_mixed && ctx->fuse && !ctx->stats && ctx->kernel_version != 1 && !ctx->grid.qinv && n1 > 1 && nseg > 0 && nblocks > 0 &&
         !near_cap) {
         const double *d_mix = s->d_p;
         if (production_mixed(ctx, npairs)) {

@@ -112,6 +112,7 @@ int hbt_host_derive_grid(const hbt_params *p, HbtGrid *g, char *err, int errlen)
 int hbt_host_pair_literal(const HbtGrid *g, const double *a, const double *b, int mixed,
                           double psi_ref, HbtCorrection *c, uint64_t *stage);
 int hbt_host_pair_qinv(const HbtGrid *g, const double *a, const double *b, int *iK, int *iq);
+void hbt_qinv_thresholds(const HbtGrid *g, double *s_lo, double *s_hi, double *thr /* [nq + 1] */);
 #ifdef __cplusplus
 }
 #endif

@@ -167,6 +167,42 @@ extern "C" int32_t hbt_rng_mixed_plan(hbt_rng *rng, int32_t nev, int32_t nev_mix
 // q_inv branch of one pair, literally (src/HBT_correlation.cpp:326-356 / :590-607): 1 when the pair
 // enters the q_inv histogram of K_T bin *iK (window and index tests; the 50*needed cap is the
 // caller's business), with its bin in *iq.
+// q_inv mode on the tuned kernels: the steps of the reference's tests on q_inv = sqrt(s), in s space (s >= 0;
+// sqrt, the comparisons, the subtraction of a constant, the division by a positive constant and the truncation are
+// all monotone in s).  s_lo / s_hi: q_inv > q_lo <=> s >= s_lo, q_inv < q_hi <=> s < s_hi (src :342-343, :597-598);
+// thr[k], k = 0 .. nq: smallest s >= s_lo with int((sqrt(s) - q_base) / delta_q) >= k (:344-345), +inf when no s
+// below s_hi reaches bin k; thr[0] = s_lo.  Bisection on the ordered bit patterns of non-negative doubles.
+namespace {
+template <typename F>
+double first_nonneg_true(double hi_start, F pred) {  // smallest s >= 0 with pred(s); pred monotone; +inf if pred(hi_start) is false
+    if (pred(0.0)) return 0.0;
+    if (!pred(hi_start)) return INFINITY;
+    uint64_t lo = 0, hi;
+    std::memcpy(&hi, &hi_start, 8);
+    while (hi - lo > 1) {  // invariant: !pred(lo), pred(hi)
+        const uint64_t mid = lo + (hi - lo) / 2;
+        double x;
+        std::memcpy(&x, &mid, 8);
+        if (pred(x)) hi = mid; else lo = mid;
+    }
+    double r;
+    std::memcpy(&r, &hi, 8);
+    return r;
+}
+}  // namespace
+
+extern "C" void hbt_qinv_thresholds(const HbtGrid *g, double *s_lo, double *s_hi, double *thr) {
+    const double q_lo = g->q_lo, q_hi = g->q_hi, q_base = g->q_base, dq = g->dq;
+    const double top = 4.0 * (q_hi > 1.0 ? q_hi * q_hi : 1.0) + 4.0;  // sqrt(top) > q_hi
+    *s_lo = first_nonneg_true(top, [&](double s) { return std::sqrt(s) > q_lo; });
+    *s_hi = first_nonneg_true(top, [&](double s) { return !(std::sqrt(s) < q_hi); });  // +inf never happens: sqrt(top) > q_hi
+    for (int k = 0; k <= g->nq; k++) {
+        thr[k] = first_nonneg_true(top, [&](double s) { return std::sqrt(s) > q_lo && static_cast<int>((std::sqrt(s) - q_base) / dq) >= k; });
+        if (!(thr[k] < *s_hi)) thr[k] = INFINITY;
+    }
+    thr[0] = *s_lo;
+}
+
 extern "C" int hbt_host_pair_qinv(const HbtGrid *g, const double *a, const double *b, int *iK, int *iq) {
     const double Kx = 0.5 * (a[0] + b[0]);
     const double Ky = 0.5 * (a[1] + b[1]);

@@ -40,6 +40,21 @@ struct V2Const {
     float f_nkphi;            // n_Kphi as a float (conditioning test of the float K_phi estimate)
     float ktf[HBT_MAX_KT + 1];  // K_T thresholds in k2 space as floats: [0] = k2lo, [k] = kt4[k], [nKT] = k2hi
     int f32_mixed;            // 1: the float path is enabled (HBT_B200_F32MIX=0 disables it)
+    // ---- q_inv mode (invariant_radius_flag = 1) on the tuned kernels, see v3_qinv_pair.  With s = -(q_E^2 - q_x^2 -
+    // q_y^2 - q_z^2) evaluated as the reference does, its tests on q_inv = sqrt(s) (src :340-346, :597-600) are
+    // monotone step functions of the double s; their steps are found once on the host by bisection over doubles on
+    // the reference's own expressions (hbt_qinv_thresholds), like the K_T bins.
+    double qinv_s_lo;         // q_inv > q_lo  <=>  s >= qinv_s_lo
+    double qinv_s_hi;         // q_inv < q_hi  <=>  s <  qinv_s_hi
+    const double *qinv_thr;   // device, [nq + 1]: thr[k] = smallest s (>= qinv_s_lo) whose bin index is >= k; thr[0] = qinv_s_lo
+    float qinv_w2_f;          // max(q_hi, 0)^2 rounded up: the float prefilter keeps s_f <= qinv_w2_f + margin
+    float f_qbase;            // q_base as a float (bin estimate only)
+    // replicated q_inv accumulators (the histograms have n_KT x nq bins: reductions from every warp of the device
+    // into a few hundred addresses would serialise in the L2); lane l of CTA b adds into replica (32 b + l) mod R,
+    // hbt_qinv_fold sums the replicas into the histograms after each launch
+    unsigned long long *qrep_u64;  // [R][2][nKT * nq]: same-event count, mixed-event count
+    double *qrep_f64;              // [R][2][nKT * nq]: sum q_inv, sum cos
+    int qrep_n;                    // R (a power of two, >= 32)
 };
 
 __host__ inline V2Const hbt_v2_consts(const HbtGrid &g) {
@@ -73,12 +88,18 @@ __host__ inline V2Const hbt_v2_consts(const HbtGrid &g) {
     c.ktf[0] = static_cast<float>(c.k2lo);
     for (int k = 1; k < nkt; k++) c.ktf[k] = static_cast<float>(c.kt4[k]);
     c.ktf[nkt] = static_cast<float>(c.k2hi);
-    c.f32_mixed = 1;
+    c.f32_mixed = g.qinv ? 0 : 1;  // (q_inv mode evaluates every survivor in binary64: the q_inv histograms need s)
+    c.qinv_s_lo = 0.0; c.qinv_s_hi = 0.0; c.qinv_thr = nullptr;
+    {
+        const double wq = g.q_hi > 0.0 ? g.q_hi : 0.0;
+        c.qinv_w2_f = static_cast<float>(wq * wq * (1.0 + 2.4e-7));
+    }
+    c.f_qbase = static_cast<float>(g.q_base);
+    c.qrep_u64 = nullptr; c.qrep_f64 = nullptr; c.qrep_n = 0;
     return c;
 }
 
-// The tuned kernels handle the 3-D histograms; q_inv mode runs on the literal v1 kernels.  The window need not be
-// symmetric about zero: the prefilter, the culling and the pT range restriction test |q_out|, |q_side| against
+// The window need not be symmetric about zero: the prefilter, the culling and the pT range restriction test |q_out|, |q_side| against
 // W = max(|q_lo|, |q_hi|) — a superset of any window [q_lo, q_hi] — and the drain decides in bin units
 // u = (q - q_base)/delta_q, where the window is [eps, nq - eps] whatever its position.  The float decision of
 // mixed-event survivors budgets 8 x 2^-24 x (nq + 2) for the rounding of u and of the offset -q_base/delta_q, so a
@@ -88,7 +109,7 @@ __host__ inline bool hbt_v2_supported(const HbtGrid &g) {
     // bin (relative error of the estimate ~4e-7); bin index in 32 bits
     const double kt_max = g.KT_min + g.dKT * g.nKT;
     const V2Const c = hbt_v2_consts(g);
-    return !g.qinv && fabs(c.ub) <= 4.0 * (c.nq_d + 2.0) && g.dq > 1e-6 && g.dKT > 1e-4 * kt_max && g.nbins < (1ll << 31);
+    return fabs(c.ub) <= 4.0 * (c.nq_d + 2.0) && g.dq > 1e-6 && g.dKT > 1e-4 * kt_max && g.nbins < (1ll << 31);
 }
 
 // global-memory copy of everything the non-inlined device functions need (passing the

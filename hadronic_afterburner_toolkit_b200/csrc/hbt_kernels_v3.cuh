@@ -37,6 +37,9 @@
 #ifndef HBT_V3_WARPS_PER_SM
 #define HBT_V3_WARPS_PER_SM 18
 #endif
+#ifndef HBT_V3_WARPS_PER_SM_QINV
+#define HBT_V3_WARPS_PER_SM_QINV 16  // q_inv mode keeps two more packed float operands per list-1 pair: 128 registers
+#endif
 #ifndef HBT_DBG_RED
 #define HBT_DBG_RED 0  // control experiments (profiles/r02_controls.txt); never set in the shipped library
 #endif
@@ -83,17 +86,21 @@ __global__ void hbt_cull_units(const HbtBBox *__restrict__ bbox, long long n, do
 // Shared memory of one warp, as byte offsets from one base address that the kernel keeps in a
 // register (every array is then an immediate offset of an LDS/STS; cvta of separate __shared__
 // arrays is recomputed at each use: S2UR + ULEA).
-template <bool MIXED, bool STATS>
+// QINV: invariant_radius_flag = 1 (the 1-D q_inv histograms next to the 3-D ones): no sorted / culled unit list and
+// no pT range restriction (both rest on the transverse window alone, which q_inv does not respect), two more float
+// arrays (-p_z, -E) for the prefilter's q_inv^2 test.
+template <bool MIXED, bool STATS, bool QINV = false>
 struct V3Smem {
     static constexpr int NC = MIXED ? 4 : 8;  // doubles kept per particle (mixed-event pairs need no x^mu)
     static constexpr int SUB = MIXED ? HBT_V3_SUB_MIXED : HBT_V3_SUB_SAME, TJ = MIXED ? HBT_V3_TJ_MIXED : HBT_V3_TJ_SAME;
-    static constexpr bool SORTED = !MIXED && !STATS;
+    static constexpr bool SORTED = !MIXED && !STATS && !QINV;
+    static constexpr int NF = QINV ? 5 : 3;
     static constexpr int SI = 0;                                 // double [NC][SUB]  list-1 sub-tile, SoA
-    // float [3][TJ] px, py, -pT^2/2 of the list-2 tile (float prefilter).  It sits BEFORE the FP64 tile: the
-    // prefilter loads particle j+1 while it works on j, and the slot past the last array is then sj[0],
+    // float [NF][TJ] px, py, -pT^2/2 (, -pz, -E) of the list-2 tile (float prefilter).  It sits BEFORE the FP64
+    // tile: the prefilter loads particle j+1 while it works on j, and the slot past the last array is then sj[0],
     // which nobody writes during the pair loop
     static constexpr int SJF = SI + 8 * NC * SUB;
-    static constexpr int SJ = SJF + (STATS ? 0 : 4 * 3 * TJ);    // double [NC][TJ]   list-2 tile, SoA
+    static constexpr int SJ = SJF + (STATS ? 0 : 4 * NF * TJ);   // double [NC][TJ]   list-2 tile, SoA
     static constexpr int SJT = SJ + 8 * NC * TJ;                 // double [TJ]       pT^2 of the list-2 tile (FP64 prefilter)
     static constexpr int SIO = SJT + (STATS ? 8 * TJ : 0);       // u32    [SUB]      gather-order index (sorted lists)
     static constexpr int SJO = SIO + (SORTED ? 4 * SUB : 0);     // u32    [TJ]
@@ -417,16 +424,105 @@ __device__ __forceinline__ int v3_mixed_f32(const HbtGrid &g, const V2Const &c, 
     return 1;
 }
 
-template <bool MIXED, bool STATS>
+// ---- q_inv branch of one queued survivor (src :323-356 same event, :585-607 mixed event) -------------------
+// Everything that decides is the reference's own binary64 chain: k2 = 4 K_perp_sq exactly as it rounds (the K_T
+// cut and, through the host's thresholds, the K_T bin), s = -(q_E^2 - q_x^2 - q_y^2 - q_z^2) with its operation
+// order, and the window / bin tests of q_inv = sqrt(s) as comparisons of s with the host's exact thresholds
+// (V2Const::qinv_s_lo / qinv_s_hi / qinv_thr).  Accepted pairs go to this lane's replica of the q_inv
+// accumulators; sqrt and cos are evaluated only for them.
+template <bool MIXED, int NC, int TI, int TJ>
+__device__ __forceinline__ void v3_qinv_pair(const HbtGrid &g, const V2Const &c, const unsigned char *__restrict__ closed,
+                                             unsigned sia, unsigned sja) {
+    const double ax = lds_f64(sia), ay = lds_f64(sia + 8 * TI), bx = lds_f64(sja), by = lds_f64(sja + 8 * TJ);
+    const double sx = __dadd_rn(ax, bx), sy = __dadd_rn(ay, by);
+    const double k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+    if (!((k2 >= c.k2lo) && (k2 <= c.k2hi))) return;  // :319-321 / :581-583
+    const double az = lds_f64(sia + 16 * TI), aE = lds_f64(sia + 24 * TI), bz = lds_f64(sja + 16 * TJ), bE = lds_f64(sja + 24 * TJ);
+    const double qx = __dsub_rn(ax, bx), qy = __dsub_rn(ay, by), qz = __dsub_rn(az, bz), qE = __dsub_rn(aE, bE);
+    const double m2 = __dsub_rn(__dsub_rn(__dsub_rn(__dmul_rn(qE, qE), __dmul_rn(qx, qx)), __dmul_rn(qy, qy)), __dmul_rn(qz, qz));
+    const double s = -m2;
+    if (!((s >= c.qinv_s_lo) && (s < c.qinv_s_hi))) return;  // q_inv outside (q_lo, q_hi), or NaN (s < 0)
+    // bin: float estimate, settled on the exact thresholds
+    const int nq = g.nq;
+    int iq = static_cast<int>((sqrtf(static_cast<float>(s)) - c.f_qbase) * c.f_inv_dq);
+    iq = max(0, min(iq, nq));
+    while (iq > 0 && s < c.qinv_thr[iq]) iq--;
+    while (iq < nq && s >= c.qinv_thr[iq + 1]) iq++;
+    if (iq >= nq) return;  // (:599; the same-event loop would index past its array there)
+    const int iK = v3_kt_bin(g, c, k2);
+    if (closed && closed[2 * g.nslab + iK + (MIXED ? g.nKT : 0)]) return;  // 50 x needed_number_of_pairs reached earlier
+    const unsigned nb = static_cast<unsigned>(g.nKT * nq);
+    const unsigned rep = (blockIdx.x * 32u + (threadIdx.x & 31u)) & static_cast<unsigned>(c.qrep_n - 1);
+    const unsigned at = (rep * 2u + (MIXED ? 1u : 0u)) * nb + static_cast<unsigned>(iK * nq + iq);
+    red_inc_u64(c.qrep_u64 + at);
+    if (!MIXED) {
+        const double xd = lds_f64(sia + 8 * TI * (4 % NC)) - lds_f64(sja + 8 * TJ * (4 % NC));
+        const double yd = lds_f64(sia + 8 * TI * (5 % NC)) - lds_f64(sja + 8 * TJ * (5 % NC));
+        const double zd = lds_f64(sia + 8 * TI * (6 % NC)) - lds_f64(sja + 8 * TJ * (6 % NC));
+        const double td = lds_f64(sia + 8 * TI * (7 % NC)) - lds_f64(sja + 8 * TJ * (7 % NC));
+        const double cv = v3_cos(g.hbarc_inv * (qE * td - qx * xd - qy * yd - qz * zd));  // :347-350
+        double *f = c.qrep_f64 + static_cast<size_t>(rep) * 2u * nb + static_cast<unsigned>(iK * nq + iq);
+        red_add_f64(f, __dsqrt_rn(s));  // q_inv as the reference has it
+        red_add_f64(f + nb, cv);
+    }
+}
+
+// Sums the replicas of the q_inv accumulators into the histograms and the per-K_T pair counters, and clears them
+// (atomic exchange: another lane's launch may be adding meanwhile).  One block per q_inv bin, one thread per replica.
+__global__ void hbt_qinv_fold(const V2Const c, const HbtAccum acc, int nKT, int nq) {
+    const unsigned nb = static_cast<unsigned>(nKT * nq);
+    const unsigned bin = blockIdx.x;
+    unsigned long long cnt = 0, den = 0;
+    double sq = 0.0, sc = 0.0;
+    for (int r = threadIdx.x; r < c.qrep_n; r += blockDim.x) {
+        unsigned long long *u = c.qrep_u64 + static_cast<size_t>(r) * 2u * nb + bin;
+        double *f = c.qrep_f64 + static_cast<size_t>(r) * 2u * nb + bin;
+        // each of the four taken on its own: another lane's running launch may have counted a pair whose sums have
+        // not landed yet; they are picked up by the fold that follows that launch
+        if (__ldcg(u)) cnt += atomicExch(u, 0ull);
+        if (__ldcg(u + nb)) den += atomicExch(u + nb, 0ull);
+        if (__ldcg(f) != 0.0) sq += __longlong_as_double(static_cast<long long>(atomicExch(reinterpret_cast<unsigned long long *>(f), 0ull)));
+        if (__ldcg(f + nb) != 0.0) sc += __longlong_as_double(static_cast<long long>(atomicExch(reinterpret_cast<unsigned long long *>(f + nb), 0ull)));
+    }
+    __shared__ unsigned long long s_u[2][32];
+    __shared__ double s_f[2][32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        den += __shfl_xor_sync(0xffffffffu, den, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        sc += __shfl_xor_sync(0xffffffffu, sc, o);
+    }
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) { s_u[0][w] = cnt; s_u[1][w] = den; s_f[0][w] = sq; s_f[1][w] = sc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < nw; k++) { cnt += s_u[0][k]; den += s_u[1][k]; sq += s_f[0][k]; sc += s_f[1][k]; }
+        const int iK = static_cast<int>(bin) / nq;
+        if (cnt) {
+            atomicAdd(&acc.qinv_count[bin], cnt);
+            atomicAdd(&acc.npairs_num_qinv[iK], cnt);
+        }
+        if (sq != 0.0) atomicAdd(&acc.qinv_sum[bin], sq);
+        if (sc != 0.0) atomicAdd(&acc.qinv_cos[bin], sc);
+        if (den) {
+            atomicAdd(&acc.qinv_den[bin], den);
+            atomicAdd(&acc.npairs_den_qinv[iK], den);
+        }
+    }
+}
+
+template <bool MIXED, bool STATS, bool QINV = false>
 __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
                                               const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv,
                                               unsigned sbase, unsigned entry, double psi_ref, V2Counters &n) {
-    using L = V3Smem<MIXED, STATS>;
+    using L = V3Smem<MIXED, STATS, QINV>;
     constexpr int NC = L::NC, TI = L::SUB, TJ = L::TJ;
     constexpr bool ORIENT = L::SORTED;
     const unsigned il4 = (entry >> 14) & ~3u, jl4 = (entry & 0xffffu) << 2;  // 4 x list-1 / list-2 slot
     const unsigned sia = sbase + L::SI + 2 * il4, sja = sbase + L::SJ + 2 * jl4;
-    if (MIXED && !STATS && c.f32_mixed) {
+    if (QINV) v3_qinv_pair<MIXED, NC, TI, TJ>(g, c, closed, sia, sja);  // independent of what the 3-D chain below decides
+    if (MIXED && !STATS && !QINV && c.f32_mixed) {
         int fslab;
         unsigned fbin;
         const int fs = v3_mixed_f32<TI, TJ>(g, c, sia, sja, psi_ref, fslab, fbin);
@@ -542,7 +638,7 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
 // One work unit (a list-1 sub-tile against one list-2 tile): stage the tiles, prefilter every
 // pair, compact the survivors and drain them.  The warp's survivor queue is empty on entry and on
 // return.  smem/sbase: this warp's shared memory (layout V3Smem<MIXED, STATS>).
-template <bool MIXED, bool STATS>
+template <bool MIXED, bool STATS, bool QINV = false>
 __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned sbase, const int lane, const unsigned u,
                                             const double *__restrict__ p1, const double *__restrict__ p2, const long long n_same,
                                             const HbtMixSeg *__restrict__ segs, const int *__restrict__ row_item0, const int n_rows,
@@ -550,9 +646,10 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                                             const V2Dev *__restrict__ dv, const HbtAccum &acc, const double psi_ref,
                                             const unsigned char *__restrict__ closed, const unsigned *__restrict__ orig,
                                             V2Counters &n, unsigned &cntKT, unsigned &cntRS, unsigned &kept) {
-    using L = V3Smem<MIXED, STATS>;
+    using L = V3Smem<MIXED, STATS, QINV>;
     constexpr int NC = L::NC, SUB = L::SUB, TJ = L::TJ, IPL = SUB / 32;
     constexpr bool SORTED = L::SORTED;
+    static_assert(!(QINV && STATS), "instrumented q_inv runs use the literal kernels");
     double *const si = reinterpret_cast<double *>(smem + L::SI);
     double *const sj = reinterpret_cast<double *>(smem + L::SJ);
     double *const sjt = reinterpret_cast<double *>(smem + L::SJT);
@@ -605,6 +702,8 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
 
     // ---- list-1 sub-tile: shared memory (SoA, NaN padding) + this lane's 4 particles -------
     double ax[IPL], ay[IPL], at[IPL];
+    float azq[QINV ? IPL : 1], aEq[QINV ? IPL : 1];  // q_inv mode: float p_z, E of this lane's particles
+    float Zm1 = 0.f, Em1 = 0.f;                        // q_inv mode: largest |p_z|, |E| of the sub-tile
     unsigned ent[IPL];
     long long ig[IPL];
     double S1 = 0.0, L1 = __longlong_as_double(0x7ff0000000000000ll);  // largest / smallest pT^2 of the sub-tile
@@ -627,7 +726,12 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
             at[s] = fma(v0.x, v0.x, v0.y * v0.y);
             S1 = fmax(S1, at[s]);
             L1 = fmin(L1, at[s]);
+            if (QINV) {
+                azq[s] = static_cast<float>(v1.x); aEq[s] = static_cast<float>(v1.y);
+                Zm1 = fmaxf(Zm1, fabsf(azq[s])); Em1 = fmaxf(Em1, fabsf(aEq[s]));
+            }
         } else {
+            if (QINV) { azq[s] = 0.f; aEq[s] = 0.f; }  // (NaN px, py already fail the K_T test)
 #pragma unroll
             for (int q = 0; q < NC; q++) si[q * SUB + il] = nan;
             if (SORTED) si_o[il] = 0u;
@@ -642,7 +746,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
     // loops a copy in which every event is sorted by pT (rotation invariant), so those particles sit
     // at the two ends of the tile: the pair loop runs over [j_first, j_last] only.  (Positions, not
     // counts: nothing is assumed about the order, an unsorted list just skips less.)
-    constexpr bool PTRANGE = MIXED && !STATS;
+    constexpr bool PTRANGE = MIXED && !STATS && !QINV;
     double pt2_lo = 0.0, pt2_hi = 0.0;
     if (PTRANGE) {
 #pragma unroll
@@ -654,6 +758,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
         if (!(L1 <= S1)) { pt2_lo = 0.0; pt2_hi = __longlong_as_double(0x7ff0000000000000ll); }  // empty / NaN rows: no restriction
     }
     float2 axf[IPL / 2], naxf[IPL / 2], ayf[IPL / 2], atf[IPL / 2];
+    float2 azf[QINV ? IPL / 2 : 1], aEf[QINV ? IPL / 2 : 1];
     if (!STATS) {
 #pragma unroll
         for (int h = 0; h < IPL / 2; h++) {
@@ -661,6 +766,17 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
             naxf[h] = make_float2(-axf[h].x, -axf[h].y);
             ayf[h] = make_float2(static_cast<float>(ay[2 * h]), static_cast<float>(ay[2 * h + 1]));
             atf[h] = make_float2(static_cast<float>(0.5 * at[2 * h]), static_cast<float>(0.5 * at[2 * h + 1]));
+            if (QINV) {
+                azf[h] = make_float2(azq[2 * h], azq[2 * h + 1]);
+                aEf[h] = make_float2(aEq[2 * h], aEq[2 * h + 1]);
+            }
+        }
+    }
+    if (QINV) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            Zm1 = fmaxf(Zm1, __shfl_xor_sync(0xffffffffu, Zm1, o));
+            Em1 = fmaxf(Em1, __shfl_xor_sync(0xffffffffu, Em1, o));
         }
     }
 
@@ -669,6 +785,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
         const int nj = static_cast<int>(min(static_cast<long long>(TJ), jcount - jl0));
         // ---- stage the list-2 tile (the queue is empty here: entries index this unit) --------
         double S2 = 0.0;
+        float Zm2 = 0.f, Em2 = 0.f;
         int j_first = TJ, j_last = -1;  // first position with pT^2 >= pt2_lo, last position with pT^2 <= pt2_hi
         for (int k = lane; k < nj; k += 32) {
             const double2 *src = reinterpret_cast<const double2 *>(p2 + 8 * (jbase + jl0 + k));
@@ -687,6 +804,11 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                 if (!(pt2 > pt2_hi)) j_last = k;                  // k increases along the loop
             }
             if (!STATS) { sjf[k] = static_cast<float>(x); sjf[TJ + k] = static_cast<float>(y); sjf[2 * TJ + k] = static_cast<float>(-0.5 * pt2); }
+            if (QINV) {
+                const float zf = static_cast<float>(v1.x), ef = static_cast<float>(v1.y);
+                sjf[3 * TJ + k] = -zf; sjf[4 * TJ + k] = -ef;
+                Zm2 = fmaxf(Zm2, fabsf(zf)); Em2 = fmaxf(Em2, fabsf(ef));
+            }
             if (SORTED) sj_o[k] = orig[jl0 + k];
             if (!MIXED) {
                 const double2 v2 = src[2], v3 = src[3];
@@ -696,6 +818,13 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) S2 = fmax(S2, __shfl_xor_sync(0xffffffffu, S2, o));
+        if (QINV) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                Zm2 = fmaxf(Zm2, __shfl_xor_sync(0xffffffffu, Zm2, o));
+                Em2 = fmaxf(Em2, __shfl_xor_sync(0xffffffffu, Em2, o));
+            }
+        }
         int j_begin = 0, j_end = nj;
         if (PTRANGE) {
 #pragma unroll
@@ -734,6 +863,17 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
             khi_f = __double2float_ru(k2hi + Ek);
             kfloor_f = __double2float_ru(k2_floor);
         }
+        // q_inv mode: a pair whose q_inv may lie below q_hi is kept whatever its transverse components.  In floats,
+        //   s = q_T^2 + q_z^2 - q_E^2,   q_T^2 = 2 (pT_i^2 + pT_j^2) - k2 = 4 e - k2,   e = pT_i^2/2 + pT_j^2/2,
+        // tested as  4 e + q_z^2 <= q_E^2 + k2 + B.  Errors (u = 2^-24; Z, E = largest |p_z|, |E| of tile 1 + tile 2):
+        // |k2_f - k2| <= 64 u S, |4 e_f - 4 e| <= 8 u S, |q_z,f^2 - q_z^2| <= 5 u Z^2, same for E, and u (|lhs| + |rhs|)
+        // <= u (9 S + Z^2 + E^2 + B) for the two final roundings: B = max(q_hi, 0)^2 + 2 u (81 S + 6 Z^2 + 6 E^2) (x2).
+        float Bq = 0.f;
+        if (QINV) {
+            const double u = 5.9604644775390625e-8;
+            const double Zs = static_cast<double>(Zm1) + static_cast<double>(Zm2), Es = static_cast<double>(Em1) + static_cast<double>(Em2);
+            Bq = __double2float_ru(static_cast<double>(c.qinv_w2_f) * (1.0 + 4.0 * u) + 2.0 * u * (81.0 * S + 6.0 * Zs * Zs + 6.0 * Es * Es));
+        }
         const bool diag = !MIXED && (jl0 < i0 + SUB);  // tile reaches back to the diagonal: j > i only
 
         // the pair loop, specialised on (unit touches the diagonal, error floor active)
@@ -746,18 +886,22 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
             int j = j_begin;
             // the float copy of list-2 particle j is loaded one trip ahead (LDS latency off the loop's
             // critical path; the last trip reads the first slot of the next array, see V3Smem)
-            float pbx = 0.f, pby = 0.f, pnb = 0.f;
+            float pbx = 0.f, pby = 0.f, pnb = 0.f, pnz = 0.f, pnE = 0.f;
             if (!STATS) {
                 const unsigned ja0 = sjf_addr + 4u * static_cast<unsigned>(j_begin);
                 pbx = lds_f32(ja0); pby = lds_f32(ja0 + 4 * TJ); pnb = lds_f32(ja0 + 8 * TJ);
+                if (QINV) { pnz = lds_f32(ja0 + 12 * TJ); pnE = lds_f32(ja0 + 16 * TJ); }
             }
             for (;;) {
                 const bool final = (j >= j_end);  // one extra trip: the per-unit final flush shares the call site
                 if (!final) {
                     if (!STATS) {
-                        const float bxs = pbx, bys = pby, nbh = pnb;
+                        const float bxs = pbx, bys = pby, nbh = pnb, nbz = pnz, nbE = pnE;
                         const unsigned ja = sjf_addr + 4u * static_cast<unsigned>(j + 1);
                         pbx = lds_f32(ja); pby = lds_f32(ja + 4 * TJ); pnb = lds_f32(ja + 8 * TJ);
+                        if (QINV) { pnz = lds_f32(ja + 12 * TJ); pnE = lds_f32(ja + 16 * TJ); }
+                        const float2 nbz2 = make_float2(nbz, nbz), nbE2 = make_float2(nbE, nbE), pbt2 = make_float2(-nbh, -nbh);
+                        const float2 four2 = make_float2(4.f, 4.f), Bq2 = make_float2(Bq, Bq);
                         const float2 bx2 = make_float2(bxs, bxs), by2 = make_float2(bys, bys), nbt2 = make_float2(nbh, nbh);
                         const float2 Wq2 = make_float2(Wqf, Wqf);
                         const unsigned ej = lane16 + static_cast<unsigned>(j);
@@ -768,6 +912,13 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                             const float2 d = __fadd2_rn(atf[h], nbt2);  // (pT_i^2 - pT_j^2) / 2 = K_perp q_out
                             const float2 x = __ffma2_rn(bx2, ayf[h], __fmul2_rn(naxf[h], by2));  // K_perp q_side
                             const float2 d2 = __fmul2_rn(d, d), x2 = __fmul2_rn(x, x), w = __fmul2_rn(k2, Wq2);
+                            float2 ql = make_float2(0.f, 0.f), qr = make_float2(0.f, 0.f);
+                            if (QINV) {
+                                const float2 qz = __fadd2_rn(azf[h], nbz2), qE = __fadd2_rn(aEf[h], nbE2);
+                                const float2 e2 = __fadd2_rn(atf[h], pbt2);
+                                ql = __ffma2_rn(e2, four2, __fmul2_rn(qz, qz));
+                                qr = __ffma2_rn(qE, qE, __fadd2_rn(k2, Bq2));
+                            }
 #pragma unroll
                             for (int e = 0; e < 2; e++) {
                                 const int s = 2 * h + e;
@@ -779,6 +930,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                                 const float m = fmaxf(e ? d2.y : d2.x, e ? x2.y : x2.x);
                                 bool in = m <= (e ? w.y : w.x);
                                 if (FLOOR) in = in || (k2e < kfloor_f);
+                                if (QINV) in = in || ((e ? ql.y : ql.x) <= (e ? qr.y : qr.x));
                                 // the next slot's address goes to a NEW register: advancing the cursor in place
                                 // would wait for the STS to release its address operand (WAR, short scoreboard)
                                 const unsigned slot = Q.cur;
@@ -847,7 +999,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                             const int take = min(32, Q.qcount);
                             const int base = Q.qcount - take;
                             const unsigned next_entry = lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(max(base - 32, 0) + lane));
-                            if (lane < take) v3_drain_pair<MIXED, STATS>(g, c, acc, closed, dv, sbase, entry, psi_ref, n);
+                            if (lane < take) v3_drain_pair<MIXED, STATS, QINV>(g, c, acc, closed, dv, sbase, entry, psi_ref, n);
                             entry = next_entry;
                             Q.qcount = base;
                             __syncwarp();
@@ -865,15 +1017,15 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
     }
 }
 
-template <bool MIXED, bool STATS>
-__global__ void __launch_bounds__(32, HBT_V3_WARPS_PER_SM)
+template <bool MIXED, bool STATS, bool QINV = false>
+__global__ void __launch_bounds__(32, QINV ? HBT_V3_WARPS_PER_SM_QINV : HBT_V3_WARPS_PER_SM)
 hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long long n_same,
              const HbtMixSeg *__restrict__ segs, const int *__restrict__ row_item0, int n_rows,
              const unsigned *__restrict__ units, unsigned *__restrict__ work, unsigned n_units,
              const HbtGrid g, const V2Const c, const V2Dev *__restrict__ dv, const HbtAccum acc,
              const double psi_ref, const unsigned long long total_pairs,
              const unsigned char *__restrict__ closed, const unsigned *__restrict__ orig) {
-    using L = V3Smem<MIXED, STATS>;
+    using L = V3Smem<MIXED, STATS, QINV>;
     __shared__ __align__(16) unsigned char smem[L::BYTES];
     const int lane = threadIdx.x;
     // kept in a register: no per-use S2UR/ULEA
@@ -888,7 +1040,7 @@ hbt_pairs_v3(const double *__restrict__ p1, const double *__restrict__ p2, long 
         const unsigned u = __shfl_sync(0xffffffffu, popped, 0);
         if (u >= total_units) break;
         if (lane == 0) popped = atomicAdd(&work[0], 1u);
-        v3_run_unit<MIXED, STATS>(smem, sbase, lane, u, p1, p2, n_same, segs, row_item0, n_rows, units, g, c, dv, acc, psi_ref,
+        v3_run_unit<MIXED, STATS, QINV>(smem, sbase, lane, u, p1, p2, n_same, segs, row_item0, n_rows, units, g, c, dv, acc, psi_ref,
                                   closed, orig, n, cntKT, cntRS, kept);
     }
 

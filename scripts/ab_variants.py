@@ -23,7 +23,7 @@ def worker(a):
     from hadronic_afterburner_toolkit_b200.hbt_correlation import HBT_correlation, Random, _check, gather_rapidity
     from hadronic_afterburner_toolkit_b200.params import C2, C3, C4, C5, KAON_MASS, PION_MASS
 
-    P = {"C2": C2, "C3": C3, "C4": C4, "C4_31": C4.with_(qnpts=31), "C5": C5}[a.shape]
+    P = {"C2": C2, "C3": C3, "C4": C4, "C4_31": C4.with_(qnpts=31), "C5": C5, "C5_QINV": C5.with_(invariant_radius_flag=1)}[a.shape]
     nev, mult = a.events, a.multiplicity
     mass = KAON_MASS if a.kaons else PION_MASS
     arr = synth.make_group(20260005, 0, nev, mass, mult).reshape(nev * mult, 8)
@@ -36,7 +36,7 @@ def worker(a):
     nmix = ids.shape[1]
     n = flat.shape[0]
     psi = 0.3 if P.azimuthal_flag else 0.0
-    out = {"variant": a.worker, "occ": os.environ.get("HBT_B200_OCC"), "shape": a.shape, "n": n,
+    out = {"variant": a.worker, "occ": os.environ.get("HBT_B200_OCC"), "kernel": os.environ.get("HBT_B200_KERNEL"), "shape": a.shape, "n": n,
            "pairs_same": n * (n - 1) // 2, "pairs_mixed": nev * mult * nmix * mult}
 
     def run(kind, reps):
@@ -55,7 +55,7 @@ def worker(a):
         return (t1["same_ms"] + t1["mixed_ms"] - t0["same_ms"] - t0["mixed_ms"]) / reps
 
     _check(hh, L.hbt_set_option(hh, 4, 1))  # one lane: launches do not overlap
-    for kind in ("same", "mixed", "fused"):
+    for kind in (("same", "mixed") if a.no_fused else ("same", "mixed", "fused")):
         run(kind, 1)
         out[kind + "_ms"] = round(run(kind, a.reps), 4)
     st = h.stage_counters()
@@ -75,6 +75,8 @@ def main():
     ap.add_argument("--multiplicity", type=int, default=1500)
     ap.add_argument("--kaons", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--no-fused", action="store_true")
+    ap.add_argument("--env", action="append", default=[], help="KEY=VALUE for the workers")
     a = ap.parse_args()
     if a.worker:
         return worker(a)
@@ -83,10 +85,13 @@ def main():
         lib = os.path.join(pkg, "libhbt_b200.so") if v == "base" else os.path.join(pkg, "variants", f"libhbt_b200_{v}.so")
         for occ in (a.occ.split(",") if a.occ else [""]):
             env = dict(os.environ, HBT_B200_LIB=lib)
+            for kv in a.env:
+                k, v_ = kv.split("=", 1)
+                env[k] = v_
             if occ:
                 env["HBT_B200_OCC"] = occ
             cmd = [sys.executable, os.path.abspath(__file__), "--worker", v, "--shape", a.shape, "--events", str(a.events),
-                   "--multiplicity", str(a.multiplicity), "--reps", str(a.reps)] + (["--kaons"] if a.kaons else [])
+                   "--multiplicity", str(a.multiplicity), "--reps", str(a.reps)] + (["--kaons"] if a.kaons else []) + (["--no-fused"] if a.no_fused else [])
             r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
             sys.stdout.write(r.stdout if r.returncode == 0 else json.dumps({"variant": v, "occ": occ, "error": r.stderr[-800:]}) + "\n")
             sys.stdout.flush()

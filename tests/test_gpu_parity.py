@@ -389,6 +389,10 @@ SEEDED = {
     "c4_az_pions": (C4.with_(qnpts=21), 1, 6, 800, 0.138),
     "c4_az_kaons": (C4.with_(qnpts=21), 1, 6, 800, KAON_MASS),
     "qinv": (HBTParams(invariant_radius_flag=1, qnpts=31), 1, 4, 800, 0.138),
+    # q_inv mode on the tuned kernels (v3_qinv_pair): windows that start below / above zero, kaons, with K_phi slabs
+    "qinv_positive_window": (HBTParams(invariant_radius_flag=1, qnpts=13, q_min=0.02, q_max=0.14), 1, 4, 600, 0.138),
+    "qinv_wide_kaons": (HBTParams(invariant_radius_flag=1, qnpts=41, q_min=-0.4, q_max=0.4, KT_min=0.1, KT_max=1.2, n_KT=7), 1, 4, 700, KAON_MASS),
+    "qinv_az": (C4.with_(qnpts=11, n_KT=4, n_Kphi=4, invariant_radius_flag=1), 1, 5, 500, 0.138),
     "noboost": (HBTParams(long_comoving_boost=0), 1, 3, 800, 0.138),
     "ragged_tiles": (HBTParams(qnpts=21), 2, 3, 257, 0.138),   # tile edges: 257 = 2*128 + 1
     "single_event": (HBTParams(qnpts=21), 1, 1, 700, 0.138),   # mixed_nev == 1: self pairing
@@ -415,6 +419,47 @@ def test_seeded_against_oracle(name, mode):
     rep = hbtio.compare(ref, acc, rtol=RTOL, check_stage=True if stats else "cheap")
     assert int(acc.stage[0]) == h.pairs_same and int(acc.stage[6]) == h.pairs_mixed
     print(name, rep, "deferred", h.deferred_pairs())
+
+
+def test_qinv_edges_decided_like_the_reference():
+    """q_inv mode on the tuned kernels decides the q_inv window and bin by comparing s = -(q.q), evaluated with the
+    reference's operation order, with thresholds found on the host.  Partners are placed so that q_inv lands
+    1e-13 ... 1e-4 (relative) on either side of every bin edge and of the window's upper end, in both loops; all
+    integers must be the oracle's."""
+    P = HBTParams(invariant_radius_flag=1, qnpts=21)
+    dq = (P.q_max - P.q_min) / (P.qnpts - 1)
+    q_base = P.q_min - dq / 2
+    rng = np.random.default_rng(11)
+    m = 0.138
+    evs = []
+    for e in range(4):
+        n = 500
+        base = synth.make_group(4242, e, 1, multiplicity=n // 2)[0]
+        part = base.copy()
+        k = rng.integers(P.qnpts // 2, P.qnpts + 1, n // 2)          # edges at q_inv >= 0 up to the window's end
+        eps = rng.choice(np.concatenate([[0.0], 10.0 ** np.arange(-13.0, -3.5, 0.5)]), n // 2) * rng.choice([-1.0, 1.0], n // 2)
+        target = np.maximum((q_base + k * dq) * (1.0 + eps), 1e-6)
+        # partner = the particle with its momentum scaled so that q_inv hits the target (bisection in the scale)
+        p = base[:, 0:3]
+        lo, hi = np.ones(n // 2), np.full(n // 2, 3.0)
+        for _ in range(200):
+            mid = 0.5 * (lo + hi)
+            pm = p * mid[:, None]
+            Em = np.sqrt(m * m + (pm * pm).sum(1))
+            dqv = p - pm
+            qinv = np.sqrt(np.maximum((dqv * dqv).sum(1) - (base[:, 3] - Em) ** 2, 0.0))
+            lo = np.where(qinv < target, mid, lo)
+            hi = np.where(qinv < target, hi, mid)
+        part[:, 0:3] = p * hi[:, None]
+        part[:, 3] = np.sqrt(m * m + (part[:, 0:3] ** 2).sum(1))
+        evs.append(np.concatenate([base, part]))
+    batches = [hbtio.Batch(evs)]
+    ref = run_oracle(P, batches, True)
+    assert int(ref.qinv_count.sum()) > 5000
+    for coalesce in (None,):
+        h, acc = run_product(P, batches, True, coalesce=coalesce)
+        hbtio.compare(ref, acc, rtol=RTOL, check_stage="cheap")
+        h.close()
 
 
 @pytest.mark.parametrize("resident", [False, True], ids=["host_buffers", "device_resident"])

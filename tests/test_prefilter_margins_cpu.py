@@ -131,3 +131,66 @@ def test_pt_range_restriction_never_excludes_an_accepted_pair(scale):
         assert not np.any(inside & ~visited[None, :])
         n_in += int(inside.sum())
     assert n_in > 1000
+
+
+QINV_CASES = {
+    # momentum scale, outlier factor, rapidity spread, mass: the margin follows the largest |p_z|, |E| of the tiles
+    "pions": dict(scale=1.0, outlier=0, ymax=0.5, m=0.138),
+    "pions_wide_rapidity": dict(scale=1.0, outlier=0, ymax=3.0, m=0.138),
+    "kaons_outliers": dict(scale=1.0, outlier=30.0, ymax=0.5, m=0.494),
+    "soft": dict(scale=0.4, outlier=0, ymax=0.5, m=0.138),
+}
+
+
+@pytest.mark.parametrize("case", sorted(QINV_CASES))
+def test_qinv_prefilter_never_drops_a_pair_inside_the_qinv_window(case):
+    """q_inv mode (v3_run_unit<.., QINV = true>): a pair is also kept when, in floats,
+    4 e + q_z^2 <= q_E^2 + k2 + B with e = pT_i^2/2 + pT_j^2/2 and B = max(q_hi, 0)^2 (1 + 4u) +
+    2u (81 S + 6 Z^2 + 6 E^2).  Every pair that passes the K_T cut and has s = -(q.q) < q_hi^2 in binary64 must
+    pass (K_T cut with its own margin, as above)."""
+    c = QINV_CASES[case]
+    rng = np.random.default_rng(20260700 + sorted(QINV_CASES).index(case))
+    dq = 0.4 / 40
+    q_hi = 0.2 + dq / 2 - 1e-8
+    w2f = np.float32(q_hi * q_hi * (1.0 + 2.4e-7))
+    k2lo, k2hi = 4 * 0.15 ** 2, 4 * 0.55 ** 2
+    n_in = n_dropped = 0
+    for _ in range(60):
+        def full(n):
+            px, py = tile(rng, n, c["scale"], c["outlier"])
+            y = rng.uniform(-c["ymax"], c["ymax"], n)
+            mt = np.sqrt(c["m"] ** 2 + px * px + py * py)
+            return px, py, mt * np.sinh(y), mt * np.cosh(y)
+        ax, ay, az, aE = full(128)
+        bx, by, bz, bE = full(128)
+        at, bt = ax * ax + ay * ay, bx * bx + by * by
+        S = at.max() + bt.max()
+        Ek = 64.0 * U * S
+        klo_f, khi_f = f32_rd(max(k2lo - Ek, 0.0)), f32_ru(k2hi + Ek)
+        f = lambda v: v.astype(np.float32)
+        Zs = float(np.abs(f(az)).max()) + float(np.abs(f(bz)).max())
+        Es = float(np.abs(f(aE)).max()) + float(np.abs(f(bE)).max())
+        Bq = f32_ru(float(w2f) * (1.0 + 4.0 * U) + 2.0 * U * (81.0 * S + 6.0 * Zs * Zs + 6.0 * Es * Es))
+        fax, fay, fat, faz, faE = (f(v)[:, None] for v in (ax, ay, 0.5 * at, az, aE))
+        fbx, fby, fnb, fnz, fnE = (f(v)[None, :] for v in (bx, by, -0.5 * bt, bz, bE))
+        fnz, fnE = -fnz, -fnE  # the tile stores -p_z, -E
+        sx, sy = fax + fbx, fay + fby
+        k2 = fma32(sy, sy, sx * sx)
+        qz, qE = faz + fnz, faE + fnE
+        e2 = fat + (-fnb)
+        lhs = fma32(e2, np.float32(4.0) * np.ones_like(e2), qz * qz)
+        rhs = fma32(qE, qE, k2 + Bq)
+        passed = (k2 >= klo_f) & (k2 <= khi_f) & (lhs <= rhs)
+        # binary64: the reference's s and its window test
+        SX, SY = ax[:, None] + bx[None, :], ay[:, None] + by[None, :]
+        K2 = SX * SX + SY * SY
+        QX, QY, QZ, QE = (u[:, None] - v[None, :] for u, v in ((ax, bx), (ay, by), (az, bz), (aE, bE)))
+        s = -(QE * QE - QX * QX - QY * QY - QZ * QZ)
+        with np.errstate(invalid="ignore"):
+            exact = (K2 >= k2lo) & (K2 <= k2hi) & (np.sqrt(s) < q_hi)
+        assert not np.any(exact & ~passed), (case, int(np.sum(exact & ~passed)))
+        n_in += int(exact.sum())
+        n_dropped += int((~passed).sum())
+    assert n_in > 1000
+    if case == "pions":
+        assert n_dropped > 0.5 * 60 * 128 * 128
