@@ -502,19 +502,28 @@ def main():
                               "algorithmic_bytes_per_launch": tj["fused"]["algorithmic_bytes_per_launch"], "source": tj["source"]}
         except (OSError, KeyError, ValueError):
             pass
-    # what actually binds (profiles/r02_controls.txt): the spread-address reductions of the accepted same-event
-    # pairs (5 per pair) + 1 per accepted mixed-event pair, against the rate a reductions-only kernel sustains
+    # what actually binds (profiles/r02_controls.txt, corrected control of session 2; profiles/r02_ncu_summary.txt):
+    # instruction issue at 4.5 resident warps per scheduler (latency of the dependent binary64 chains of the drain)
+    # and the LSU data pipe; the reductions (5 per accepted same-event pair, 1 per accepted mixed-event pair) cost
+    # 1.8 ms of the fused launch's 27.3 and run below both of their ceilings
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
     red_lanes = 5.0 * float(dst[4]) + float(dst[10])
     red_rate = red_lanes / (ks + km) / (sm_mhz * 1e6) / n_sm
     bound_actual = {
-        "reductions": {"red_lanes_per_clk_per_sm": red_rate, "ceiling_reductions_only_kernel": 0.66,
-                       "frac": red_rate / 0.66, "lanes": "5 per accepted same-event pair + 1 per accepted mixed-event pair",
-                       "ceiling_source": "profiles/r02_red_bench.txt (scripts/micro/red_bench.cu, one lane per bin, spread addresses)"},
-        "issue_slots": {"busy_pct_fused_kernel": 65.3, "kind": "STATIC: ncu capture profiles/r01_ncu_summary_final.txt "
-                        "(smsp__issue_active); 20.3e9 warp instructions per C5-shape fused launch = 17.5 ms at 4/clk/SM"},
-        "controls": "profiles/r02_controls.txt: same-event kernel 15.3 ms with / 10.1 ms without its reductions; fused 27.3 / 23.5",
+        "issue_slots": {"busy_pct_fused_kernel": 64.6, "warp_instructions_per_c5_group": 20.25e9,
+                        "ms_at_full_issue": 17.4, "resident_warps_per_scheduler": 4.5,
+                        "kind": "STATIC: ncu capture profiles/r02_ncu_summary.txt (smsp__issue_active, smsp__inst_executed; "
+                                "stalls per issue: wait 2.14, short_scoreboard 1.33, not_selected 0.88)"},
+        "lsu_data_pipe": {"busy_pct_fused_kernel": 75.7,
+                          "kind": "STATIC: same capture, l1tex__data_pipe_lsu_wavefronts: shared-memory loads 29.5 %, stores 8.0 %, "
+                                  "global (reductions: 16 wavefronts per 64-bit RED with 32 spread addresses) the rest"},
+        "reductions": {"red_lanes_per_clk_per_sm": red_rate, "ceiling_all_sms_busy": 0.68, "ceiling_per_sm": 0.94,
+                       "frac": red_rate / 0.68, "lanes": "5 per accepted same-event pair + 1 per accepted mixed-event pair",
+                       "ceiling_source": "profiles/r02_tma_red_bench.txt (scripts/micro/tma_red_bench.cu: spread REDs from every SM / "
+                                         "from a quarter of the SMs)"},
+        "controls": "profiles/r02_controls.txt: fused launch 27.25 ms; 25.44 ms with the reductions predicated off and all four sums "
+                    "still evaluated (HBT_DBG_RED=7); the earlier 23.5 ms control also dropped the cos chain",
     }
     roofline = {
         "bound": "fp64", "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,

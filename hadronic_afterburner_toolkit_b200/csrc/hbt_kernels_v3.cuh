@@ -29,11 +29,15 @@
 #ifndef HBT_V3_SUB_SAME
 #define HBT_V3_SUB_SAME 64   // list-1 particles per warp, same-event (2 per lane: more resident warps, finer culling)
 #endif
+#ifndef HBT_V3_SUB_MIXED
 #define HBT_V3_SUB_MIXED 128  // list-1 particles per warp, mixed-event (4 per lane)
+#endif
 #ifndef HBT_V3_TJ_SAME
 #define HBT_V3_TJ_SAME 64    // list-2 tile, same-event (finer culling)
 #endif
+#ifndef HBT_V3_TJ_MIXED
 #define HBT_V3_TJ_MIXED 128  // list-2 tile, mixed-event (no culling: fewer partial drains)
+#endif
 #ifndef HBT_V3_WARPS_PER_SM
 #define HBT_V3_WARPS_PER_SM 18
 #endif
@@ -43,7 +47,8 @@
 #ifndef HBT_DBG_RED
 #define HBT_DBG_RED 0  // control experiments (profiles/r02_controls.txt); never set in the shipped library
 #endif
-#define HBT_V3_MAX_SORTED ((1ll << 22) - 64)  // unit encoding (row << 16 | tile) of the culled list, gridDim.y
+// unit encoding (row << 16 | tile) of the culled list, gridDim.y: fewer than 65536 rows and tiles
+#define HBT_V3_MAX_SORTED (65536ll * (HBT_V3_TJ_SAME < HBT_V3_SUB_SAME ? HBT_V3_TJ_SAME : HBT_V3_SUB_SAME) - 64)
 
 // Units of the sorted same-event list that can hold an accepted pair: row a = particles
 // [64a, 64a+64), tile t = particles [64t, 64t+64), t >= a (upper triangle incl. the
