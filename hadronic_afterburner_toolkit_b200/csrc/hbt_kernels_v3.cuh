@@ -153,8 +153,13 @@ __constant__ double v3_cos_tab[2][8] = {
 __constant__ double v3_cos_red[4] = {6.36619772367581382433e-01, 1.57079632673412561417e+00, 6.07710050650619224932e-11,
                                      2.02226624879595063154e-21};
 
+__device__ __forceinline__ double v3_cos_core(double x);
 __device__ __forceinline__ double v3_cos(double x) {
     if (!(fabs(x) < 1.0e5)) return cos(x);
+    return v3_cos_core(x);
+}
+// the branch-free part, |x| < 1e5
+__device__ __forceinline__ double v3_cos_core(double x) {
     const double nd = rint(x * v3_cos_red[0]);
     double r = fma(-nd, v3_cos_red[1], x);
     r = fma(-nd, v3_cos_red[2], r);
@@ -567,7 +572,7 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
                 const double u = __ddiv_rn(dphi, g.dKphi);
                 const int iphi = __double2int_rz(u);
                 if (fabs(u - rint(u)) < 1e-9) stage = -1;  // the literal path hands it to the host
-                else if (iphi < 0 || iphi >= g.nKphi) stage = 5;  // counted through q_long, then dropped
+                else if (!(u == u) || iphi < 0 || iphi >= g.nKphi) stage = 5;  // counted through q_long, then dropped (NaN angle too)
                 else slab = slab * g.nKphi + iphi;
             }
         }

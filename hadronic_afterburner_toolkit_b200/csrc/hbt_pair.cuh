@@ -81,6 +81,7 @@ __device__ __forceinline__ int pair_literal(const HbtGrid &g, double px1, double
         while (dphi < 0.) dphi = __dadd_rn(dphi, g.two_pi);
         while (dphi > g.two_pi) dphi = __dsub_rn(dphi, g.two_pi);
         const double u = __ddiv_rn(dphi, g.dKphi);
+        if (!(u == u)) return PAIR_REJ_PHI;  // NaN angle (a NaN momentum or psi_ref): the reference's int cast gives INT_MIN, :417-423
         if (fabs(u - rint(u)) < 1e-9) return PAIR_DEFER;
         const int iphi = __double2int_rz(u);
         if (iphi < 0 || iphi >= g.nKphi) return PAIR_REJ_PHI;

@@ -108,6 +108,11 @@ int main(int argc, char *argv[]) {
     const bool real_mixed = P.get("read_in_real_mixed_events", 0) == 1;
     if (P.get("resonance_feed_down_flag", 0) == 1) die("resonance_feed_down_flag = 1 is not supported here");
     if (P.get("readRapidityShiftFromFile", 0) == 1) die("readRapidityShiftFromFile = 1 is not supported here");
+    // particle_monval = 333: for the UrQMD / SMASH / JAM formats the reference keeps reconst_flag = 1 and appends phi
+    // mesons RECONSTRUCTED from K+ K- pairs to the list (src/particleSamples.cpp:116-119, 1303-1307, 2200); hbt_reader
+    // would hand out the primary phi(1020) only
+    if (static_cast<int>(P.get("particle_monval")) == 333 && read_in_mode != 10 && read_in_mode != 9 && read_in_mode != 0)
+        die("particle_monval = 333 with this read_in_mode needs the reference's phi-meson reconstruction: use the drop-in binary");
 
     hbt_params hp;
     hp.qnpts = static_cast<int>(P.get("qnpts"));
