@@ -179,6 +179,12 @@ class HBT_correlation:
         if cut:
             off[1:] = np.cumsum([len(c) for c in cut])
         flat = np.ascontiguousarray(np.concatenate(cut)) if cut else np.zeros((0, 8))
+        if getattr(self, "pin_host", False) and flat.size:
+            # page-locked gather buffers (the library then uploads them without a staging copy)
+            import torch
+            t = torch.from_numpy(flat).pin_memory()
+            self._pinned = getattr(self, "_pinned", [])[-7:] + [t]  # (kept alive past the call)
+            flat = t.numpy()
         return flat, off
 
     def calculate_HBT_correlation_function(self, particle_list: Batch, do_mixed: bool = True) -> None:

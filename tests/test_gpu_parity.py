@@ -421,6 +421,24 @@ def test_seeded_against_oracle(name, mode):
     print(name, rep, "deferred", h.deferred_pairs())
 
 
+@pytest.mark.parametrize("name", ["c3_same_mixed", "c4_az_pions", "qinv"])
+def test_page_locked_caller_buffers_are_uploaded_directly(name):
+    """hbt_accumulate_batch hands page-locked caller buffers to the DMA engine without its staging copy (and returns
+    once they are free again); separate mixed-event lists included.  Same integers as the oracle."""
+    P, ngrp, nev, mult, mass = SEEDED[name]
+    batches = synth.make_batches(20260002, ngrp, nev, mass=mass, multiplicity=mult)
+    other = synth.make_batches(20260009, ngrp, nev + 1, mass=mass, multiplicity=mult - 37)
+    batches = batches + [hbtio.Batch(x.same, y.same) for x, y in zip(batches, other)]  # read_in_real_mixed_events = 1
+    ref = run_oracle(P, batches, True)
+    h = HBT_correlation(P, coalesce=False)
+    h.pin_host = True
+    for b in batches:
+        h.calculate_HBT_correlation_function(b)
+    acc = h.accumulators()
+    hbtio.compare(ref, acc, rtol=RTOL, check_stage="cheap")
+    h.close()
+
+
 def test_qinv_edges_decided_like_the_reference():
     """q_inv mode on the tuned kernels decides the q_inv window and bin by comparing s = -(q.q), evaluated with the
     reference's operation order, with thresholds found on the host.  Partners are placed so that q_inv lands
