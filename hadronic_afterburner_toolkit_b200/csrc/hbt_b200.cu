@@ -88,6 +88,7 @@ struct Pending {
     long long nblocks = 0, units_bound = 0;
     int64_t n_logical = 0, n_padded = 0;
     bool do_mixed = false, host = false;
+    bool direct = false;            // host batches in page-locked caller buffers: uploaded one by one as they arrive, no staging copy
     Slot *slot = nullptr;           // host-staged batches: their common staging slot (ONE upload at the flush)
     size_t staged = 0;              // particles staged in slot->h_p so far
     float host_range = 0.f;         // max(|px|, |py|) of the staged particles
@@ -750,7 +751,7 @@ int flush_pending(hbt_ctx *ctx) {
     Lane &L = next_lane(ctx);
     const int nb = static_cast<int>(P.b.size());
     if (P.host) {
-        CU(ctx, cudaMemcpyAsync(P.slot->d_p, P.slot->h_p, P.staged * 64, cudaMemcpyHostToDevice, ctx->copy));
+        if (!P.direct) CU(ctx, cudaMemcpyAsync(P.slot->d_p, P.slot->h_p, P.staged * 64, cudaMemcpyHostToDevice, ctx->copy));
         CU(ctx, cudaEventRecord(P.slot->uploaded, ctx->copy));
         CU(ctx, cudaStreamWaitEvent(L.stream, P.slot->uploaded, 0));
     }
@@ -873,7 +874,8 @@ int append_pending(hbt_ctx *ctx, const double *p_host, const double *d_src, cons
     Pending &P = ctx->pend;
     const int64_t n = off[nev];
     const bool host = p_host != nullptr;
-    if (!P.b.empty() && (P.do_mixed != do_mixed || P.host != host || P.b.size() >= HBT_MULTI_MAX ||
+    const bool direct = host && ctx->direct_upload && is_page_locked(p_host);
+    if (!P.b.empty() && (P.do_mixed != do_mixed || P.host != host || P.direct != direct || P.b.size() >= HBT_MULTI_MAX ||
                          P.n_padded + ((n + 63) & ~63ll) > HBT_V3_MAX_SORTED ||
                          (host && P.staged + static_cast<size_t>(n) > P.slot->cap))) {
         int rc = flush_pending(ctx);
@@ -882,6 +884,7 @@ int append_pending(hbt_ctx *ctx, const double *p_host, const double *d_src, cons
     if (P.b.empty()) {
         P.do_mixed = do_mixed;
         P.host = host;
+        P.direct = direct;
         P.psi_ref = psi_ref;  // (only grids without K_phi bins are coalesced: the angle is not read)
         P.evoff.assign(1, 0);
         if (host) {
@@ -893,8 +896,13 @@ int append_pending(hbt_ctx *ctx, const double *p_host, const double *d_src, cons
         }
     }
     if (host) {
-        double *dst = P.slot->h_p + 8 * P.staged;
-        std::memcpy(dst, p_host, static_cast<size_t>(n) * 64);
+        const double *dst = p_host;
+        if (direct) {  // straight from the caller's page-locked buffer; waited for below, the caller may reuse it on return
+            CU(ctx, cudaMemcpyAsync(P.slot->d_p + 8 * P.staged, p_host, static_cast<size_t>(n) * 64, cudaMemcpyHostToDevice, ctx->copy));
+        } else {
+            std::memcpy(P.slot->h_p + 8 * P.staged, p_host, static_cast<size_t>(n) * 64);
+            dst = P.slot->h_p + 8 * P.staged;
+        }
         float m = P.host_range;
         for (int64_t i = 0; i < n; i++) {
             const float a = std::max(std::fabs(static_cast<float>(dst[8 * i])), std::fabs(static_cast<float>(dst[8 * i + 1])));
@@ -903,6 +911,7 @@ int append_pending(hbt_ctx *ctx, const double *p_host, const double *d_src, cons
         P.host_range = m;
         d_src = P.slot->d_p + 8 * P.staged;
         P.staged += static_cast<size_t>(n);
+        if (direct) CU(ctx, cudaStreamSynchronize(ctx->copy));  // (the range loop above ran beside the copy)
     }
     if (do_mixed) {
         const size_t s0 = P.segs.size();

@@ -421,8 +421,9 @@ def test_seeded_against_oracle(name, mode):
     print(name, rep, "deferred", h.deferred_pairs())
 
 
+@pytest.mark.parametrize("coalesce", [False, None], ids=["one_launch_per_batch", "small_batches_together"])
 @pytest.mark.parametrize("name", ["c3_same_mixed", "c4_az_pions", "qinv"])
-def test_page_locked_caller_buffers_are_uploaded_directly(name):
+def test_page_locked_caller_buffers_are_uploaded_directly(name, coalesce):
     """hbt_accumulate_batch hands page-locked caller buffers to the DMA engine without its staging copy (and returns
     once they are free again); separate mixed-event lists included.  Same integers as the oracle."""
     P, ngrp, nev, mult, mass = SEEDED[name]
@@ -430,7 +431,12 @@ def test_page_locked_caller_buffers_are_uploaded_directly(name):
     other = synth.make_batches(20260009, ngrp, nev + 1, mass=mass, multiplicity=mult - 37)
     batches = batches + [hbtio.Batch(x.same, y.same) for x, y in zip(batches, other)]  # read_in_real_mixed_events = 1
     ref = run_oracle(P, batches, True)
-    h = HBT_correlation(P, coalesce=False)
+    if coalesce is None:  # more, smaller batches: several of them per launch, each uploaded as it arrives
+        more = synth.make_batches(20260010, 6, 3, mass=mass, multiplicity=300)
+        ref = None
+        batches = more[:3] + batches + more[3:]
+        ref = run_oracle(P, batches, True)
+    h = HBT_correlation(P, coalesce=coalesce)
     h.pin_host = True
     for b in batches:
         h.calculate_HBT_correlation_function(b)
