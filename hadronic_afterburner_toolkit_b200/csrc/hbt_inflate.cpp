@@ -16,6 +16,7 @@
 
 #include <zlib.h>  // crc32()
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
