@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <fstream>
 #include <iomanip>
 #include <sstream>
@@ -60,6 +61,19 @@ struct HbtOutputWriter {
         for (int i = 0; i < p.n_Kphi; i++) Kphi_array.push_back(i * dKphi);
     }
 
+    //! One row as the reference's stream prints it: `output << std::scientific << std::setw(18) << std::setprecision(8)`
+    //! in front of the first value only (setw does not persist), four blanks between values, std::endl.  libstdc++
+    //! formats a double in scientific notation through the C library's "%.8e", so snprintf gives the same characters;
+    //! the rows of a file are collected and written once (the reference's std::endl flushes every row: one write
+    //! system call per row, 69 000 per 41^3 table).
+    static void append_row(std::string &buf, const double *v, int n) {
+        char line[256];
+        int len = std::snprintf(line, sizeof(line), "%18.8e", v[0]);
+        for (int k = 1; k < n; k++) len += std::snprintf(line + len, sizeof(line) - static_cast<size_t>(len), "    %.8e", v[k]);
+        line[len++] = '\n';
+        buf.append(line, static_cast<size_t>(len));
+    }
+
     //! src/HBT_correlation.cpp:694-724
     void write_inv(const HbtHostResults &r) const {
         for (int iK = 0; iK < p.n_KT - 1; iK++) {
@@ -67,19 +81,17 @@ struct HbtOutputWriter {
             std::ostringstream filename;
             filename << path << "/HBT_correlation_function_inv_KT_" << KT_array[iK] << "_" << KT_array[iK + 1] << ".dat";
             std::ofstream output(filename.str().c_str());
+            std::string buf;
             for (int iq = 0; iq < p.qnpts; iq++) {
                 const size_t k = static_cast<size_t>(iK) * p.qnpts + iq;
                 const double count = static_cast<double>(r.inv_count[k]);
                 const double q_inv_local = r.inv_sum[k] / count;
                 const double correl_fun_num = r.inv_cos[k];
                 const double correl_fun_denorm = static_cast<double>(r.inv_den[k]) * npair_ratio;
-                output << std::scientific << std::setw(18) << std::setprecision(8);
-                if (eco) {
-                    output << correl_fun_num << "    " << correl_fun_denorm << std::endl;
-                } else {
-                    output << q_inv_local << "    " << correl_fun_num << "    " << correl_fun_denorm << std::endl;
-                }
+                const double row[3] = {q_inv_local, correl_fun_num, correl_fun_denorm};
+                if (eco) append_row(buf, row + 1, 2); else append_row(buf, row, 3);
             }
+            output.write(buf.data(), static_cast<std::streamsize>(buf.size()));
             output.close();
         }
     }
@@ -90,6 +102,8 @@ struct HbtOutputWriter {
         std::ofstream output(filename.c_str());
         const int qnpts = p.qnpts;
         const size_t q3 = static_cast<size_t>(qnpts) * qnpts * qnpts;
+        std::string buf;
+        buf.reserve(q3 * (eco ? 40 : 96));
         for (int iqlong = 0; iqlong < qnpts; iqlong++) {
             for (int iqout = 0; iqout < qnpts; iqout++) {
                 for (int iqside = 0; iqside < qnpts; iqside++) {
@@ -111,16 +125,12 @@ struct HbtOutputWriter {
                         correl_fun_num = r.num_cos[bin];
                         correl_fun_denorm = npair_ratio * static_cast<double>(r.den_count[bin]);
                     }
-                    output << std::scientific << std::setw(18) << std::setprecision(8);
-                    if (eco) {
-                        output << correl_fun_num << "    " << correl_fun_denorm << std::endl;
-                    } else {
-                        output << q_out_local << "    " << q_side_local << "    " << q_long_local << "    "
-                               << correl_fun_num << "    " << correl_fun_denorm << std::endl;
-                    }
+                    const double row[5] = {q_out_local, q_side_local, q_long_local, correl_fun_num, correl_fun_denorm};
+                    if (eco) append_row(buf, row + 3, 2); else append_row(buf, row, 5);
                 }
             }
         }
+        output.write(buf.data(), static_cast<std::streamsize>(buf.size()));
         output.close();
     }
 
