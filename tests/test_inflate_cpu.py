@@ -218,3 +218,30 @@ def test_large_text_file_matches_gzip(tmp_path):
         h.write(data)
     got, err = inflate_file(f, 4 << 20)
     assert err is None and got == data
+
+
+def test_randomised_sweep_against_zlib(tmp_path):
+    """random sizes, entropies, levels, strategies, window sizes, memory levels and read sizes"""
+    rng = np.random.default_rng(123)
+    f = tmp_path / "x.gz"
+    for case in range(90):
+        kind = case % 6
+        size = int(rng.integers(0, 400000))
+        if kind == 0:
+            data = rng.integers(0, 256, size, dtype=np.uint8).tobytes()
+        elif kind == 1:
+            data = bytes(rng.integers(48, 58, size, dtype=np.uint8))  # digits: one short match after the other
+        elif kind == 2:
+            data = (b"abcdefgh" * (size // 8 + 1))[:size]
+        elif kind == 3:
+            data = bytes(rng.integers(0, 4, size, dtype=np.uint8) * int(rng.integers(1, 60)))
+        elif kind == 4:
+            words = [bytes(rng.integers(97, 123, int(rng.integers(1, 12)), dtype=np.uint8)) for _ in range(200)]
+            data = b" ".join(words[i] for i in rng.integers(0, 200, size // 6 + 1))[:size]
+        else:
+            data = bytes(np.repeat(rng.integers(0, 256, size // 50 + 1, dtype=np.uint8), rng.integers(1, 100, size // 50 + 1)))[:size]
+        level = int(rng.integers(0, 10))
+        strategy = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED][int(rng.integers(0, 5))]
+        f.write_bytes(gz_wrap(deflate_raw(data, level, strategy, -int(rng.integers(9, 16)), int(rng.integers(1, 10))), data))
+        got, err = inflate_file(f, int(rng.integers(1, 1 << 20)))
+        assert err is None and got == data, (case, kind, size, level, strategy, err)
