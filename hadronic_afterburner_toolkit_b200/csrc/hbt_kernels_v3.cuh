@@ -440,15 +440,13 @@ __device__ __forceinline__ int v3_mixed_f32(const HbtGrid &g, const V2Const &c, 
 // order, and the window / bin tests of q_inv = sqrt(s) as comparisons of s with the host's exact thresholds
 // (V2Const::qinv_s_lo / qinv_s_hi / qinv_thr).  Accepted pairs go to this lane's replica of the q_inv
 // accumulators; sqrt and cos are evaluated only for them.
+// k2, iK and the four momentum differences come from the 3-D fast path (v3_fast_bins_all evaluates k2 with the
+// reference's operations, the K_T bin from the exact thresholds, and q = p_1 - p_2 as single IEEE subtractions; q_inv
+// mode has no sorted lists, so the differences are in the reference's orientation).
 template <bool MIXED, int NC, int TI, int TJ>
 __device__ __forceinline__ void v3_qinv_pair(const HbtGrid &g, const V2Const &c, const unsigned char *__restrict__ closed,
-                                             unsigned sia, unsigned sja) {
-    const double ax = lds_f64(sia), ay = lds_f64(sia + 8 * TI), bx = lds_f64(sja), by = lds_f64(sja + 8 * TJ);
-    const double sx = __dadd_rn(ax, bx), sy = __dadd_rn(ay, by);
-    const double k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+                                             unsigned sia, unsigned sja, double k2, int iK, double qx, double qy, double qz, double qE) {
     if (!((k2 >= c.k2lo) && (k2 <= c.k2hi))) return;  // :319-321 / :581-583
-    const double az = lds_f64(sia + 16 * TI), aE = lds_f64(sia + 24 * TI), bz = lds_f64(sja + 16 * TJ), bE = lds_f64(sja + 24 * TJ);
-    const double qx = __dsub_rn(ax, bx), qy = __dsub_rn(ay, by), qz = __dsub_rn(az, bz), qE = __dsub_rn(aE, bE);
     const double m2 = __dsub_rn(__dsub_rn(__dsub_rn(__dmul_rn(qE, qE), __dmul_rn(qx, qx)), __dmul_rn(qy, qy)), __dmul_rn(qz, qz));
     const double s = -m2;
     if (!((s >= c.qinv_s_lo) && (s < c.qinv_s_hi))) return;  // q_inv outside (q_lo, q_hi), or NaN (s < 0)
@@ -459,7 +457,6 @@ __device__ __forceinline__ void v3_qinv_pair(const HbtGrid &g, const V2Const &c,
     while (iq > 0 && s < c.qinv_thr[iq]) iq--;
     while (iq < nq && s >= c.qinv_thr[iq + 1]) iq++;
     if (iq >= nq) return;  // (:599; the same-event loop would index past its array there)
-    const int iK = v3_kt_bin(g, c, k2);
     if (closed && closed[2 * g.nslab + iK + (MIXED ? g.nKT : 0)]) return;  // 50 x needed_number_of_pairs reached earlier
     const unsigned nb = static_cast<unsigned>(g.nKT * nq);
     const unsigned rep = (blockIdx.x * 32u + (threadIdx.x & 31u)) & static_cast<unsigned>(c.qrep_n - 1);
@@ -531,7 +528,6 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
     constexpr bool ORIENT = L::SORTED;
     const unsigned il4 = (entry >> 14) & ~3u, jl4 = (entry & 0xffffu) << 2;  // 4 x list-1 / list-2 slot
     const unsigned sia = sbase + L::SI + 2 * il4, sja = sbase + L::SJ + 2 * jl4;
-    if (QINV) v3_qinv_pair<MIXED, NC, TI, TJ>(g, c, closed, sia, sja);  // independent of what the 3-D chain below decides
     if (MIXED && !STATS && !QINV && c.f32_mixed) {
         int fslab;
         unsigned fbin;
@@ -550,6 +546,8 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
     int slab = 0;
     int stage = STATS ? v3_fast_bins<MIXED, ORIENT, TI, TJ>(g, c, sia, sja, flip, k2, b)
                       : v3_fast_bins_all<MIXED, ORIENT, TI, TJ>(g, c, sia, sja, flip, k2, slab, b);
+    // q_inv histograms: independent of what the 3-D chain decided (slab = the K_T bin here: K_phi comes later)
+    if (QINV) v3_qinv_pair<MIXED, NC, TI, TJ>(g, c, closed, sia, sja, k2, slab, b.qx, b.qy, b.qz, b.qE);
     if (stage == 4) {
         if (STATS) slab = v3_kt_bin(g, c, k2);
         if (g.az) {
