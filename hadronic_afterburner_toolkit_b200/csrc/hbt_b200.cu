@@ -1798,7 +1798,13 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
     const bool near_cap = (do_same && cap_may_engage(ctx, false, sp_all)) || (do_mixed && cap_may_engage(ctx, true, npairs));
     Lane &L = pick_lane(ctx, near_cap);
     CU(ctx, cudaStreamWaitEvent(L.stream, s->uploaded, 0));
-    if (direct) CU(ctx, cudaEventSynchronize(s->uploaded));  // the caller's buffers are free again (the kernels below are not waited for)
+    // the caller's buffers must be free again when the call returns — but not before: the launches below are enqueued
+    // while the DMA engine still reads them (the kernels themselves are not waited for)
+    struct UploadWait {
+        cudaEvent_t e;
+        bool on;
+        ~UploadWait() { if (on) cudaEventSynchronize(e); }
+    } upload_wait{s->uploaded, direct};
     PhaseInput in;
     in.h1 = h1;
     in.h2 = alias ? h1 : h2;
