@@ -20,6 +20,7 @@
 #include "hbt_kernels_v1.cuh"
 #ifdef HBT_HAVE_V2
 #include "hbt_kernels_v3.cuh"
+#include "hbt_kernels_v4.cuh"
 #else
 #define HBT_V3_SUB_MIXED 128
 #define HBT_V3_TJ_MIXED 128
@@ -168,6 +169,11 @@ struct hbt_ctx {
     unsigned long long ptsort_min_pairs = 500000000ull;
     std::vector<long long> evoff;  // event boundaries of the buffer being sorted
     bool fuse = true;  // whole batches run the fused same+mixed kernel (HBT_B200_FUSE=0 / HBT_OPT_FUSE: separate kernels)
+    // production mixed-event loops run hbt_pairs_v4_mixed (binary32 tiles, 24 resident warps; HBT_B200_MIXED4=0: the v3 kernel)
+    bool mixed4 = true;
+    // a whole batch = the same-event kernel followed by the v4 mixed-event kernel on the same stream, each with its own
+    // registers / shared memory / resident warps (HBT_B200_SPLIT=0: the fused v3 kernel, one allocation for both)
+    bool split = true;
     // small production batches are collected and launched together (HBT_B200_COALESCE=0 / HBT_OPT_COALESCE: one launch each)
     bool coalesce = true;
     Pending pend;
@@ -202,7 +208,7 @@ struct hbt_ctx {
     // production mode of the v2 same-event kernel: Morton-sorted copy of the list + tile boxes
     bool stats = false;                          // exact stage populations B, C, D (no culling)
     int n_sm = 148;
-    int occ_same = 12, occ_same_stats = 12, occ_mixed = 12, occ_mixed_stats = 12, occ_fused = 12;  // resident warps per SM
+    int occ_same = 12, occ_same_stats = 12, occ_mixed = 12, occ_mixed_stats = 12, occ_fused = 12, occ_mixed4 = 12;  // resident warps per SM
     int occ_same_q = 12, occ_mixed_q = 12;       // q_inv mode
     double *d_qinv_thr = nullptr;                // q_inv mode: exact bin thresholds in s space (V2Const::qinv_thr)
     unsigned long long *d_qrep_u64 = nullptr;    // q_inv mode: replicated accumulators (V2Const::qrep_*)
@@ -346,7 +352,7 @@ size_t dyn_smem_bytes(const HbtGrid &g) {
 // ---- launches ------------------------------------------------------------------------
 #ifdef HBT_HAVE_V2
 int ensure_work(hbt_ctx *ctx, Lane &L) {
-    if (!L.d_work) CU(ctx, cudaMalloc(&L.d_work, 8));
+    if (!L.d_work) CU(ctx, cudaMalloc(&L.d_work, 16));  // [0] pop counter, [1] units kept by the culling, [2] pop counter of the v4 mixed-event kernel
     return HBT_OK;
 }
 
@@ -503,6 +509,16 @@ bool use_literal(const hbt_ctx *ctx, int mode) {
     return ctx->kernel_version == 1 || mode != 0 || (ctx->grid.qinv && ctx->stats);
 }
 
+// production mixed-event loops on the v4 kernel (binary32 tiles): not instrumented runs, not q_inv mode (both need the
+// binary64 values), not when the FP32 decision is switched off
+bool use_mixed4(const hbt_ctx *ctx) {
+#ifdef HBT_HAVE_V2
+    return ctx->mixed4 && ctx->kernel_version != 1 && !ctx->stats && !ctx->grid.qinv && ctx->v2c.f32_mixed;
+#else
+    return false;
+#endif
+}
+
 #ifdef HBT_HAVE_V2
 // q_inv mode: the replicas of the q_inv accumulators go into the histograms after every launch (same stream)
 int fold_qinv(hbt_ctx *ctx, Lane &L) {
@@ -546,7 +562,7 @@ int launch_same(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, double psi_
 #ifdef HBT_HAVE_V2
         rc = ensure_work(ctx, L);
         if (rc) return rc;
-        CU(ctx, cudaMemsetAsync(L.d_work, 0, 8, L.stream));
+        CU(ctx, cudaMemsetAsync(L.d_work, 0, 16, L.stream));
         const bool qinv = ctx->grid.qinv != 0;
         const bool sorted = !ctx->stats && !qinv;
         const unsigned grid = static_cast<unsigned>(ctx->n_sm * (qinv ? ctx->occ_same_q : sorted ? ctx->occ_same : ctx->occ_same_stats));
@@ -664,7 +680,7 @@ int launch_mixed(hbt_ctx *ctx, Lane &L, const double *d_p1, const double *d_p2, 
 #ifdef HBT_HAVE_V2
         rc = ensure_work(ctx, L);
         if (rc) return rc;
-        CU(ctx, cudaMemsetAsync(L.d_work, 0, 8, L.stream));
+        CU(ctx, cudaMemsetAsync(L.d_work, 0, 16, L.stream));
         const unsigned grid = static_cast<unsigned>(std::min<long long>(
             nblocks, static_cast<long long>(ctx->n_sm) * (ctx->grid.qinv ? ctx->occ_mixed_q : ctx->stats ? ctx->occ_mixed_stats : ctx->occ_mixed)));
         if (ctx->grid.qinv) {
@@ -677,6 +693,10 @@ int launch_mixed(hbt_ctx *ctx, Lane &L, const double *d_p1, const double *d_p2, 
             hbt_pairs_v3<true, true><<<grid, 32, 0, L.stream>>>(
                 d_p1, d_p2, static_cast<long long>(nseg), d_seg, nullptr, 0, nullptr, L.d_work, static_cast<unsigned>(nblocks), ctx->grid,
                 ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs, cap.closed, nullptr);
+        else if (use_mixed4(ctx))
+            hbt_pairs_v4_mixed<<<static_cast<unsigned>(std::min<long long>(nblocks, static_cast<long long>(ctx->n_sm) * ctx->occ_mixed4)), 32, 0, L.stream>>>(
+                d_p1, d_p2, static_cast<int>(nseg), d_seg, L.d_work + 2, static_cast<unsigned>(nblocks), ctx->grid, ctx->v2c, ctx->d_dv,
+                ctx->acc, psi_ref, npairs, cap.closed);
         else
             hbt_pairs_v3<true, false><<<grid, 32, 0, L.stream>>>(
                 d_p1, d_p2, static_cast<long long>(nseg), d_seg, nullptr, 0, nullptr, L.d_work, static_cast<unsigned>(nblocks), ctx->grid,
@@ -706,7 +726,7 @@ int launch_fused(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, const doub
     const unsigned long long npairs_same = static_cast<unsigned long long>(n) * (n - 1) / 2;
     rc = ensure_work(ctx, L);
     if (rc) return rc;
-    CU(ctx, cudaMemsetAsync(L.d_work, 0, 8, L.stream));
+    CU(ctx, cudaMemsetAsync(L.d_work, 0, 16, L.stream));
     const long long all_units = hbt_v3_same_units(n, ctx->row_item0);
     if (all_units > 0x7fffffffLL || n > HBT_V3_MAX_SORTED || nblocks + all_units > 0x7fffffffLL)
         return fail(ctx, HBT_ERR_INVALID, "batch too large: %lld work units", all_units + nblocks);
@@ -717,11 +737,21 @@ int launch_fused(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, const doub
     const long long n_rows = (n + HBT_V3_SUB_SAME - 1) / HBT_V3_SUB_SAME, ntj = (n + HBT_V3_TJ_SAME - 1) / HBT_V3_TJ_SAME;
     hbt_cull_units<<<dim3(static_cast<unsigned>((ntj + 127) / 128), static_cast<unsigned>(n_rows)), 128, 0, L.stream>>>(
         L.sort_bbox, n, ctx->v2c.W2, ctx->v2c.k2lo, ctx->v2c.k2hi, L.d_units, L.d_work);
-    const unsigned grid = static_cast<unsigned>(ctx->n_sm * ctx->occ_fused);
-    hbt_pairs_v3_fused<<<grid, 32, 0, L.stream>>>(L.sort_p, n, L.d_units, L.sort_idx[1], d_p1, d_p2,
-                                                      static_cast<long long>(nseg), d_seg, static_cast<unsigned>(nblocks), L.d_work,
-                                                      ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs_same, npairs_mixed,
-                                                      closed_ptr(ctx));
+    if (ctx->split && use_mixed4(ctx)) {
+        hbt_pairs_v3<false, false><<<static_cast<unsigned>(ctx->n_sm * ctx->occ_same), 32, 0, L.stream>>>(
+            L.sort_p, L.sort_p, n, nullptr, nullptr, 0, L.d_units, L.d_work, 0, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref,
+            npairs_same, closed_ptr(ctx), L.sort_idx[1]);
+        hbt_pairs_v4_mixed<<<static_cast<unsigned>(std::min<long long>(nblocks, static_cast<long long>(ctx->n_sm) * ctx->occ_mixed4)), 32, 0, L.stream>>>(
+            d_p1, d_p2, static_cast<int>(nseg), d_seg, L.d_work + 2, static_cast<unsigned>(nblocks), ctx->grid, ctx->v2c, ctx->d_dv,
+            ctx->acc, psi_ref, npairs_mixed, closed_ptr(ctx));
+        ctx->kernel_launches++;
+    } else {
+        const unsigned grid = static_cast<unsigned>(ctx->n_sm * ctx->occ_fused);
+        hbt_pairs_v3_fused<<<grid, 32, 0, L.stream>>>(L.sort_p, n, L.d_units, L.sort_idx[1], d_p1, d_p2,
+                                                          static_cast<long long>(nseg), d_seg, static_cast<unsigned>(nblocks), L.d_work,
+                                                          ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, npairs_same, npairs_mixed,
+                                                          closed_ptr(ctx));
+    }
     ctx->kernel_launches += 2;
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaEventRecord(e1, L.stream));
@@ -776,7 +806,7 @@ int flush_pending(hbt_ctx *ctx) {
     CU(ctx, cudaEventRecord(e0, L.stream));
     rc = ensure_work(ctx, L);
     if (rc) return rc;
-    CU(ctx, cudaMemsetAsync(L.d_work, 0, 8, L.stream));
+    CU(ctx, cudaMemsetAsync(L.d_work, 0, 16, L.stream));
     rc = ensure_sort_buffers(ctx, L, n_pad);
     if (rc) return rc;
     rc = ensure_units(ctx, L, P.units_bound);
@@ -840,11 +870,21 @@ int flush_pending(hbt_ctx *ctx) {
         }
         CU(ctx, cudaMemcpyAsync(L.mseg, P.segs.data(), P.segs.size() * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, L.stream));
         ctx->kernel_launches += 3;
-        const unsigned grid = static_cast<unsigned>(ctx->n_sm * ctx->occ_fused);
-        hbt_pairs_v3_fused<<<grid, 32, 0, L.stream>>>(L.sort_p, n_pad, L.d_units, L.sort_idx[1], L.mix_p, L.mix_p,
-                                                          static_cast<long long>(P.segs.size()), L.mseg, static_cast<unsigned>(P.nblocks),
-                                                          L.d_work, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, P.psi_ref, P.pairs_same,
-                                                          P.pairs_mixed, closed_ptr(ctx));
+        if (ctx->split && use_mixed4(ctx)) {
+            hbt_pairs_v3<false, false><<<static_cast<unsigned>(ctx->n_sm * ctx->occ_same), 32, 0, L.stream>>>(
+                L.sort_p, L.sort_p, n_pad, nullptr, nullptr, 0, L.d_units, L.d_work, 0, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc,
+                P.psi_ref, P.pairs_same, closed_ptr(ctx), L.sort_idx[1]);
+            hbt_pairs_v4_mixed<<<static_cast<unsigned>(std::min<long long>(P.nblocks, static_cast<long long>(ctx->n_sm) * ctx->occ_mixed4)), 32, 0, L.stream>>>(
+                L.mix_p, L.mix_p, static_cast<int>(P.segs.size()), L.mseg, L.d_work + 2, static_cast<unsigned>(P.nblocks), ctx->grid,
+                ctx->v2c, ctx->d_dv, ctx->acc, P.psi_ref, P.pairs_mixed, closed_ptr(ctx));
+            ctx->kernel_launches++;
+        } else {
+            const unsigned grid = static_cast<unsigned>(ctx->n_sm * ctx->occ_fused);
+            hbt_pairs_v3_fused<<<grid, 32, 0, L.stream>>>(L.sort_p, n_pad, L.d_units, L.sort_idx[1], L.mix_p, L.mix_p,
+                                                              static_cast<long long>(P.segs.size()), L.mseg, static_cast<unsigned>(P.nblocks),
+                                                              L.d_work, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, P.psi_ref, P.pairs_same,
+                                                              P.pairs_mixed, closed_ptr(ctx));
+        }
         ctx->timers.push_back({e0, e1, 2, static_cast<double>(P.pairs_same) / static_cast<double>(P.pairs_same + P.pairs_mixed)});
         ctx->mixed_launches++;
     } else {
@@ -1341,6 +1381,8 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     if (const char *v = getenv("HBT_B200_KERNEL")) ctx->kernel_version = atoi(v) == 1 ? 1 : 2;
     if (const char *v = getenv("HBT_B200_STATS")) ctx->stats = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_FUSE")) ctx->fuse = atoi(v) != 0;
+    if (const char *v = getenv("HBT_B200_MIXED4")) ctx->mixed4 = atoi(v) != 0;
+    if (const char *v = getenv("HBT_B200_SPLIT")) ctx->split = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_DIRECT")) ctx->direct_upload = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_COALESCE")) ctx->coalesce = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_PTSORT")) ctx->ptsort = std::min(2, std::max(0, atoi(v)));
@@ -1420,6 +1462,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same_stats, hbt_pairs_v3<false, true>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed, hbt_pairs_v3<true, false>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_fused, hbt_pairs_v3_fused, 32, 0));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed4, hbt_pairs_v4_mixed, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed_stats, hbt_pairs_v3<true, true>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same_q, hbt_pairs_v3<false, false, true>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed_q, hbt_pairs_v3<true, false, true>, 32, 0));
@@ -1445,6 +1488,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
         ctx->occ_same = std::min(ctx->occ_same, cap); ctx->occ_mixed = std::min(ctx->occ_mixed, cap);
         ctx->occ_fused = std::min(ctx->occ_fused, cap);
     }
+    if (const char *v = getenv("HBT_B200_OCC4")) ctx->occ_mixed4 = std::min(ctx->occ_mixed4, std::max(1, atoi(v)));
 
     {
         V2Dev dv;

@@ -367,13 +367,10 @@ __device__ __forceinline__ void v3_classify_f32(float u, float gb, unsigned nq, 
     out = far && !in_grid;
 }
 
-template <int TI, int TJ>
-__device__ __forceinline__ int v3_mixed_f32(const HbtGrid &g, const V2Const &c, unsigned sia, unsigned sja, double psi_ref,
-                                            int &slab, unsigned &bin) {
-    const float ax = static_cast<float>(lds_f64(sia)), ay = static_cast<float>(lds_f64(sia + 8 * TI));
-    const float az = static_cast<float>(lds_f64(sia + 16 * TI)), aE = static_cast<float>(lds_f64(sia + 24 * TI));
-    const float bx = static_cast<float>(lds_f64(sja)), by = static_cast<float>(lds_f64(sja + 8 * TJ));
-    const float bz = static_cast<float>(lds_f64(sja + 16 * TJ)), bE = static_cast<float>(lds_f64(sja + 24 * TJ));
+// (the arithmetic on the eight rounded components; hbt_kernels_v4.cuh calls it on tiles that are kept in binary32)
+__device__ __forceinline__ int v3_mixed_f32_core(const HbtGrid &g, const V2Const &c, const float ax, const float ay, const float az,
+                                                 const float aE, const float bx, const float by, const float bz, const float bE,
+                                                 double psi_ref, int &slab, unsigned &bin) {
     const float u8 = 4.76837158203125e-7f;  // 8 * 2^-24
     // transverse plane: k2 = 4 K_perp^2, q_out = d r, q_side = e r
     const float sx = ax + bx, sy = ay + by, qx = ax - bx, qy = ay - by;
@@ -432,6 +429,16 @@ __device__ __forceinline__ int v3_mixed_f32(const HbtGrid &g, const V2Const &c, 
     }
     bin = ((static_cast<unsigned>(slab) * nq + io) * nq + is) * nq + il;
     return 1;
+}
+
+template <int TI, int TJ>
+__device__ __forceinline__ int v3_mixed_f32(const HbtGrid &g, const V2Const &c, unsigned sia, unsigned sja, double psi_ref,
+                                            int &slab, unsigned &bin) {
+    const float ax = static_cast<float>(lds_f64(sia)), ay = static_cast<float>(lds_f64(sia + 8 * TI));
+    const float az = static_cast<float>(lds_f64(sia + 16 * TI)), aE = static_cast<float>(lds_f64(sia + 24 * TI));
+    const float bx = static_cast<float>(lds_f64(sja)), by = static_cast<float>(lds_f64(sja + 8 * TJ));
+    const float bz = static_cast<float>(lds_f64(sja + 16 * TJ)), bE = static_cast<float>(lds_f64(sja + 24 * TJ));
+    return v3_mixed_f32_core(g, c, ax, ay, az, aE, bx, by, bz, bE, psi_ref, slab, bin);
 }
 
 // ---- q_inv branch of one queued survivor (src :323-356 same event, :585-607 mixed event) -------------------
