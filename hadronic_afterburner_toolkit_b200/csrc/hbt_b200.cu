@@ -52,6 +52,8 @@ struct Slot {
 // carries everything ordered (cap replay, reductions, the all-reduce, the stopwatch).
 struct Lane {
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;                 // the v4 mixed-event kernel of a whole batch, next to the same-event kernel (co-run)
+    cudaEvent_t fork = nullptr, join = nullptr;  // side waits for fork (the batch's preparation), stream waits for join (side's kernel)
     cudaEvent_t tail = nullptr;                  // last submission (joins into ctx->compute)
     bool busy = false;                           // something was enqueued since the last join
     unsigned *d_work = nullptr;                  // [0] unit pop counter, [1] number of units (culled list)
@@ -174,6 +176,14 @@ struct hbt_ctx {
     // a whole batch = the same-event kernel followed by the v4 mixed-event kernel on the same stream, each with its own
     // registers / shared memory / resident warps (HBT_B200_SPLIT=0: the fused v3 kernel, one allocation for both)
     bool split = true;
+    // split batches: the two kernels run at the same time, the mixed-event kernel on the lane's side stream.  The
+    // same-event kernel alone is bound by its reductions into the L2 (5 per accepted pair), the mixed-event kernel by
+    // instruction issue: next to each other they fill each other's gaps, each with its own registers and shared memory.
+    // corun_same = resident same-event warps per SM during the co-run (the mixed-event kernel is launched with its full
+    // grid and grows into whatever the same-event kernel leaves, and into all of the SM once it has finished).
+    // HBT_B200_CORUN=0: one after the other; HBT_B200_CORUN_SAME=n
+    bool corun = true;
+    int corun_same = 12, corun_mixed = 8;
     // small production batches are collected and launched together (HBT_B200_COALESCE=0 / HBT_OPT_COALESCE: one launch each)
     bool coalesce = true;
     Pending pend;
@@ -714,6 +724,64 @@ int launch_mixed(hbt_ctx *ctx, Lane &L, const double *d_p1, const double *d_p2, 
 }
 
 #ifdef HBT_HAVE_V2
+// the two kernels of a split batch (everything they read has been enqueued on L.stream).
+// Co-run: the same-event kernel with corun_same warps per SM on the lane's stream and the mixed-event kernel with
+// corun_mixed warps per SM on its side stream share every SM.  Both are persistent (a warp leaves when its unit list is
+// empty), so whichever list is finished first frees its share at once: a second launch of the OTHER kernel, queued behind
+// it in stream order with the warps that make up that kernel's full grid, then joins the work that is left (it pops the
+// same unit counter; if nothing is left its warps leave immediately).
+int launch_split_pair(hbt_ctx *ctx, Lane &L, const double *d_same, long long n_same, const double *d_p1, const double *d_p2,
+                      const HbtMixSeg *d_seg, size_t nseg, long long nblocks, double psi_ref, unsigned long long npairs_same,
+                      unsigned long long npairs_mixed) {
+    const bool corun = ctx->corun && ctx->corun_same < ctx->occ_same && ctx->corun_mixed < ctx->occ_mixed4;
+    auto same = [&](cudaStream_t st, int warps, unsigned long long np) {
+        hbt_pairs_v3<false, false><<<static_cast<unsigned>(ctx->n_sm * warps), 32, 0, st>>>(
+            d_same, d_same, n_same, nullptr, nullptr, 0, L.d_units, L.d_work, 0, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref, np,
+            closed_ptr(ctx), L.sort_idx[1]);
+        ctx->kernel_launches++;
+    };
+    auto mixed = [&](cudaStream_t st, int warps, unsigned long long np) {
+        hbt_pairs_v4_mixed<<<static_cast<unsigned>(std::min<long long>(nblocks, static_cast<long long>(ctx->n_sm) * warps)), 32, 0, st>>>(
+            d_p1, d_p2, static_cast<int>(nseg), d_seg, L.d_work + 2, static_cast<unsigned>(nblocks), ctx->grid, ctx->v2c, ctx->d_dv,
+            ctx->acc, psi_ref, np, closed_ptr(ctx));
+        ctx->kernel_launches++;
+    };
+    if (!corun) {
+        same(L.stream, ctx->occ_same, npairs_same);
+        mixed(L.stream, ctx->occ_mixed4, npairs_mixed);
+        ctx->kernel_launches--;  // (the caller counts one of the two)
+        return HBT_OK;
+    }
+    static const bool trace = getenv("HBT_B200_CORUN_TRACE") != nullptr;  // experiments: when does each of the four launches end
+    cudaEvent_t te[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (trace) for (cudaEvent_t &e : te) CU(ctx, cudaEventCreate(&e));
+    CU(ctx, cudaEventRecord(L.fork, L.stream));
+    CU(ctx, cudaStreamWaitEvent(L.side, L.fork, 0));
+    if (trace) CU(ctx, cudaEventRecord(te[0], L.stream));
+    same(L.stream, ctx->corun_same, npairs_same);
+    if (trace) CU(ctx, cudaEventRecord(te[1], L.stream));
+    mixed(L.side, ctx->corun_mixed, npairs_mixed);
+    if (trace) CU(ctx, cudaEventRecord(te[2], L.side));
+    same(L.side, ctx->occ_same - ctx->corun_same, 0);        // after the mixed-event list is empty
+    if (trace) CU(ctx, cudaEventRecord(te[3], L.side));
+    mixed(L.stream, ctx->occ_mixed4 - ctx->corun_mixed, 0);  // after the same-event list is empty
+    if (trace) CU(ctx, cudaEventRecord(te[4], L.stream));
+    CU(ctx, cudaEventRecord(L.join, L.side));
+    CU(ctx, cudaStreamWaitEvent(L.stream, L.join, 0));
+    if (trace) {
+        CU(ctx, cudaEventSynchronize(te[3]));
+        CU(ctx, cudaEventSynchronize(te[4]));
+        float t[5] = {0, 0, 0, 0, 0};
+        for (int k = 1; k < 5; k++) cudaEventElapsedTime(&t[k], te[0], te[k]);
+        fprintf(stderr, "[corun %d:%d] same(%d) ends %.2f ms, mixed(%d) ends %.2f, late same(%d) ends %.2f, late mixed(%d) ends %.2f\n",
+                ctx->corun_same, ctx->corun_mixed, ctx->corun_same, t[1], ctx->corun_mixed, t[2], ctx->occ_same - ctx->corun_same, t[3],
+                ctx->occ_mixed4 - ctx->corun_mixed, t[4]);
+        for (cudaEvent_t e : te) cudaEventDestroy(e);
+    }
+    ctx->kernel_launches--;
+    return HBT_OK;
+}
+
 // production launch of a whole batch: sort + cull of the same-event list, then one kernel that
 // works through the same-event and the mixed-event units interleaved (hbt_pairs_v3_fused)
 int launch_fused(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, const double *d_p1, const double *d_p2, const HbtMixSeg *d_seg,
@@ -738,13 +806,8 @@ int launch_fused(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, const doub
     hbt_cull_units<<<dim3(static_cast<unsigned>((ntj + 127) / 128), static_cast<unsigned>(n_rows)), 128, 0, L.stream>>>(
         L.sort_bbox, n, ctx->v2c.W2, ctx->v2c.k2lo, ctx->v2c.k2hi, L.d_units, L.d_work);
     if (ctx->split && use_mixed4(ctx)) {
-        hbt_pairs_v3<false, false><<<static_cast<unsigned>(ctx->n_sm * ctx->occ_same), 32, 0, L.stream>>>(
-            L.sort_p, L.sort_p, n, nullptr, nullptr, 0, L.d_units, L.d_work, 0, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc, psi_ref,
-            npairs_same, closed_ptr(ctx), L.sort_idx[1]);
-        hbt_pairs_v4_mixed<<<static_cast<unsigned>(std::min<long long>(nblocks, static_cast<long long>(ctx->n_sm) * ctx->occ_mixed4)), 32, 0, L.stream>>>(
-            d_p1, d_p2, static_cast<int>(nseg), d_seg, L.d_work + 2, static_cast<unsigned>(nblocks), ctx->grid, ctx->v2c, ctx->d_dv,
-            ctx->acc, psi_ref, npairs_mixed, closed_ptr(ctx));
-        ctx->kernel_launches++;
+        rc = launch_split_pair(ctx, L, L.sort_p, n, d_p1, d_p2, d_seg, nseg, nblocks, psi_ref, npairs_same, npairs_mixed);
+        if (rc) return rc;
     } else {
         const unsigned grid = static_cast<unsigned>(ctx->n_sm * ctx->occ_fused);
         hbt_pairs_v3_fused<<<grid, 32, 0, L.stream>>>(L.sort_p, n, L.d_units, L.sort_idx[1], d_p1, d_p2,
@@ -871,13 +934,9 @@ int flush_pending(hbt_ctx *ctx) {
         CU(ctx, cudaMemcpyAsync(L.mseg, P.segs.data(), P.segs.size() * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, L.stream));
         ctx->kernel_launches += 3;
         if (ctx->split && use_mixed4(ctx)) {
-            hbt_pairs_v3<false, false><<<static_cast<unsigned>(ctx->n_sm * ctx->occ_same), 32, 0, L.stream>>>(
-                L.sort_p, L.sort_p, n_pad, nullptr, nullptr, 0, L.d_units, L.d_work, 0, ctx->grid, ctx->v2c, ctx->d_dv, ctx->acc,
-                P.psi_ref, P.pairs_same, closed_ptr(ctx), L.sort_idx[1]);
-            hbt_pairs_v4_mixed<<<static_cast<unsigned>(std::min<long long>(P.nblocks, static_cast<long long>(ctx->n_sm) * ctx->occ_mixed4)), 32, 0, L.stream>>>(
-                L.mix_p, L.mix_p, static_cast<int>(P.segs.size()), L.mseg, L.d_work + 2, static_cast<unsigned>(P.nblocks), ctx->grid,
-                ctx->v2c, ctx->d_dv, ctx->acc, P.psi_ref, P.pairs_mixed, closed_ptr(ctx));
-            ctx->kernel_launches++;
+            rc = launch_split_pair(ctx, L, L.sort_p, n_pad, L.mix_p, L.mix_p, L.mseg, P.segs.size(), P.nblocks, P.psi_ref, P.pairs_same,
+                                   P.pairs_mixed);
+            if (rc) return rc;
         } else {
             const unsigned grid = static_cast<unsigned>(ctx->n_sm * ctx->occ_fused);
             hbt_pairs_v3_fused<<<grid, 32, 0, L.stream>>>(L.sort_p, n_pad, L.d_units, L.sort_idx[1], L.mix_p, L.mix_p,
@@ -1383,6 +1442,9 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     if (const char *v = getenv("HBT_B200_FUSE")) ctx->fuse = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_MIXED4")) ctx->mixed4 = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_SPLIT")) ctx->split = atoi(v) != 0;
+    if (const char *v = getenv("HBT_B200_CORUN")) ctx->corun = atoi(v) != 0;
+    if (const char *v = getenv("HBT_B200_CORUN_SAME")) ctx->corun_same = std::max(1, atoi(v));
+    if (const char *v = getenv("HBT_B200_CORUN_MIXED")) ctx->corun_mixed = std::max(1, atoi(v));
     if (const char *v = getenv("HBT_B200_DIRECT")) ctx->direct_upload = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_COALESCE")) ctx->coalesce = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_PTSORT")) ctx->ptsort = std::min(2, std::max(0, atoi(v)));
@@ -1406,7 +1468,10 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     ctx->n_sm = prop.multiProcessorCount;
     for (Lane &L : ctx->lanes) {
         CUC(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CUC(cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking));
         CUC(cudaEventCreateWithFlags(&L.tail, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming));
     }
     ctx->compute = ctx->lanes[0].stream;
     if (const char *v = getenv("HBT_B200_LANES")) ctx->n_lanes = std::min(kLanes, std::max(1, atoi(v)));
@@ -1462,6 +1527,12 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same_stats, hbt_pairs_v3<false, true>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed, hbt_pairs_v3<true, false>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_fused, hbt_pairs_v3_fused, 32, 0));
+    // the same-event kernel and the v4 mixed-event kernel share the SMs (launch_split_pair): two kernels are resident
+    // on one SM only under the same shared-memory carveout, and left to itself the driver sizes each kernel's to its own
+    // full occupancy (228 KB for one, 196 KB for the other)
+    CUC(cudaFuncSetAttribute(hbt_pairs_v3<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUC(cudaFuncSetAttribute(hbt_pairs_v4_mixed, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same, hbt_pairs_v3<false, false>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed4, hbt_pairs_v4_mixed, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_mixed_stats, hbt_pairs_v3<true, true>, 32, 0));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_same_q, hbt_pairs_v3<false, false, true>, 32, 0));
@@ -1562,7 +1633,12 @@ extern "C" void hbt_destroy(hbt_ctx *ctx) {
 #endif
     if (ctx->sw0) cudaEventDestroy(ctx->sw0);
     if (ctx->sw1) cudaEventDestroy(ctx->sw1);
-    for (Lane &L : ctx->lanes) if (L.stream) cudaStreamDestroy(L.stream);
+    for (Lane &L : ctx->lanes) {
+        if (L.stream) cudaStreamDestroy(L.stream);
+        if (L.side) cudaStreamDestroy(L.side);
+        if (L.fork) cudaEventDestroy(L.fork);
+        if (L.join) cudaEventDestroy(L.join);
+    }
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
     delete ctx;
 }

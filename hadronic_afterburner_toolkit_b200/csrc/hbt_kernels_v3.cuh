@@ -160,11 +160,16 @@ __device__ __forceinline__ double v3_cos(double x) {
 }
 // the branch-free part, |x| < 1e5
 __device__ __forceinline__ double v3_cos_core(double x) {
-    const double nd = rint(x * v3_cos_red[0]);
+    // n = rint(x 2/pi) and its low bits without FRND / F2I (XU pipe, long latency): x 2/pi + 1.5*2^52 holds n in its
+    // low word (|n| < 2^31 for |x| < 1e5); a tie may round the other way than rint() of the rounded product would,
+    // which moves r across pi/4 by a rounding error only
+    const double magic = __hiloint2double(0x43380000, 0);
+    const double tn = fma(x, v3_cos_red[0], magic);
+    const double nd = tn - magic;
     double r = fma(-nd, v3_cos_red[1], x);
     r = fma(-nd, v3_cos_red[2], r);
     r = fma(-nd, v3_cos_red[3], r);
-    const int nq = __double2int_rn(nd);
+    const int nq = __double2loint(tn);
     const double z = r * r;
     const double *t = v3_cos_tab[nq & 1];
     // Estrin's scheme: three dependent FMAs after z instead of seven (the drain is bound by the
@@ -329,6 +334,9 @@ __device__ __forceinline__ int v3_fast_bins_all(const HbtGrid &g, const V2Const 
 // exact thresholds of int((sqrt(K_perp_sq) - KT_min)/dKT) in k2 space (V2Const::kt4, found by
 // bisection on the host)
 __device__ __forceinline__ int v3_kt_bin(const HbtGrid &g, const V2Const &c, double k2) {
+    // up to four bins (the reference's default): the bin is the number of thresholds at or below k2 (unused ones are
+    // +inf) — three compares against constant-bank operands instead of the estimate's F2F / MUFU / F2I and its fix-up
+    if (g.nKT <= 4) return (k2 >= c.kt4[1] ? 1 : 0) + (k2 >= c.kt4[2] ? 1 : 0) + (k2 >= c.kt4[3] ? 1 : 0);
     const float k2f = static_cast<float>(k2);
     // (one MUFU: rsqrtf() adds denormal scaling; an estimate only, k2 below 1e-30 lands in bin 0 either way)
     const float kp = 0.5f * k2f * v3_rsqrt_f32(fmaxf(k2f, 1e-30f));
@@ -526,6 +534,114 @@ __global__ void hbt_qinv_fold(const V2Const c, const HbtAccum acc, int nKT, int 
     }
 }
 
+// ---- production same-event survivor (sorted lists, no stage counters, no q_inv): v3_fast_bins_all + the
+// accumulation of v3_drain_pair in one straight line.  Same arithmetic, same guards; what differs is bookkeeping:
+// the three classifications are combined as predicates (no stage code built up by selects), the orientation sign is
+// an XOR on the high word of the two reciprocal square roots, and the tile addresses come straight from the two
+// halves of the queue entry.
+template <int NC, int TI, int TJ, int SI, int SJ, int SIO, int SJO>
+__device__ __forceinline__ void v3_same_pair(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
+                                             const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv,
+                                             unsigned sbase, unsigned entry, double psi_ref, V2Counters &n) {
+    const unsigned il = entry >> 16, jl = entry & 0xffffu;
+    const unsigned sia = sbase + SI + 8u * il, sja = sbase + SJ + 8u * jl;
+    const bool flip = lds_u32(sbase + SIO + 4u * il) > lds_u32(sbase + SJO + 4u * jl);
+    const double ax = lds_f64(sia), ay = lds_f64(sia + 8 * TI), bx = lds_f64(sja), by = lds_f64(sja + 8 * TJ);
+    const double az = lds_f64(sia + 16 * TI), aE = lds_f64(sia + 24 * TI), bz = lds_f64(sja + 16 * TJ), bE = lds_f64(sja + 24 * TJ);
+    const double sx = __dadd_rn(ax, bx), sy = __dadd_rn(ay, by);
+    const double k2 = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+    const bool kt = (k2 >= c.k2lo) && (k2 <= c.k2hi);  // exact K_T cut (the float prefilter only pre-screens it)
+    int slab = v3_kt_bin(g, c, k2);
+    const double qx = ax - bx, qy = ay - by, qz = az - bz, qE = aE - bE;
+    const double d = fma(qx, sx, qy * sy);     // 2 K_perp q_out
+    const double e = fma(qy, sx, -(qx * sy));  // 2 K_perp q_side
+    const double r = v3_rsqrt(k2);             // 1 / (2 K_perp)
+    // the pair may be stored the other way round than the reference takes it: q_out, q_side, q_long change sign with
+    // it (a sign folded into the factor: d * (-r) == -(d * r) exactly)
+    const int sgn = flip ? static_cast<int>(0x80000000u) : 0;
+    const double rs = __hiloint2double(__double2hiint(r) ^ sgn, __double2loint(r));
+    const double qo = d * rs, qs = e * rs;
+    const double gb = fma(fabs(qx) + fabs(qy), c.gq, c.g0);
+    const unsigned nq = static_cast<unsigned>(g.nq);
+    double ql;
+    int io, is, il_;
+    bool ok_o, out_o, ok_s, out_s, ok_l, out_l;
+    if (g.boost) {
+        // q_long = gamma (q_z - beta q_E) = (K_E q_z - K_z q_E) / Mt, src :383-390
+        const double sz = az + bz, sE = aE + bE;
+        const double m2 = (sE - sz) * (sE + sz);  // 4 Mt^2 without cancellation
+        const double r2 = v3_rsqrt(m2);
+        const double t1 = sE * qz, t2 = sz * qE;
+        ql = (t1 - t2) * __hiloint2double(__double2hiint(r2) ^ sgn, __double2loint(r2));
+        const double ch = sE * r2;  // cosh of the pair rapidity amplifies the rounding of Mt
+        const double gbl = fma((fabs(t1) + fabs(t2)) * r2 * fma(2.0 * ch, ch, 1.0), c.gl, c.g0);
+        v3_classify(c, nq, ql, gbl, il_, ok_l, out_l);
+        if (!(m2 > 0.0)) { ok_l = false; out_l = false; }  // undecided
+    } else {
+        // q_long = q_z exactly as the reference has it: its own comparisons and index expression
+        ql = flip ? -qz : qz;
+        il_ = __double2int_rz(__ddiv_rn(__dsub_rn(ql, g.q_base), g.dq));
+        ok_l = in_window(ql, g.q_lo, g.q_hi, false) && (il_ < g.nq);
+        out_l = !ok_l;
+    }
+    v3_classify(c, nq, qo, gb, io, ok_o, out_o);
+    v3_classify(c, nq, qs, gb, is, ok_s, out_s);
+    if (!kt || out_o || out_s || out_l) return;  // the K_T cut or some component certainly outside the window
+    bool undecided = !(ok_o && ok_s && ok_l);
+    bool dropped = false;  // K_phi out of range: counted through q_long, then dropped (:417-423)
+    if (!undecided && g.az) {
+        const double Kx = 0.5 * sx, Ky = 0.5 * sy;  // (exact halvings of the reference's sums)
+        // K_phi bin (:392-400).  First a float estimate: atan2f (<= 3 ulp) of the float-rounded K gives
+        // Delta phi / dK_phi within ~2e-6 n_Kphi/8 of the reference's value; farther than 1e-4 from every
+        // integer (bin edges, both ends of the range) the bin is decided.  Otherwise the double-precision
+        // expression, and within 1e-9 of an edge the host (glibc atan2).
+        double de = static_cast<double>(atan2f(static_cast<float>(Ky), static_cast<float>(Kx))) - psi_ref;
+        de = de < 0. ? de + g.two_pi : de;
+        de = de > g.two_pi ? de - g.two_pi : de;
+        const double ue = de * c.inv_dkphi;
+        const double fe = ue - floor(ue);
+        if (fe > 1e-4 && fe < 1.0 - 1e-4 && ue > 0. && ue < static_cast<double>(g.nKphi) && g.nKphi <= 256) {
+            slab = slab * g.nKphi + static_cast<int>(ue);
+        } else {
+            double dphi = __dsub_rn(atan2(Ky, Kx), psi_ref);
+            while (dphi < 0.) dphi = __dadd_rn(dphi, g.two_pi);
+            while (dphi > g.two_pi) dphi = __dsub_rn(dphi, g.two_pi);
+            const double u = __ddiv_rn(dphi, g.dKphi);
+            const int iphi = __double2int_rz(u);
+            if (fabs(u - rint(u)) < 1e-9) undecided = true;  // the literal path hands it to the host
+            else if (!(u == u) || iphi < 0 || iphi >= g.nKphi) dropped = true;
+            else slab = slab * g.nKphi + iphi;
+        }
+    }
+    if (undecided) {  // literal chain (roles swapped back into the reference's order)
+        double a8[8], b8[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double va = lds_f64(sia + 8 * TI * k), vb = lds_f64(sja + 8 * TJ * k);
+            a8[k] = flip ? vb : va;
+            b8[k] = flip ? va : vb;
+        }
+        V2Counters tmp = {0, 0, 0, 0};  // keeps n itself out of local memory
+        v2_slow_pair<false>(dv, a8, b8, psi_ref, tmp);
+        n.nE += tmp.nE;
+        return;
+    }
+    n.nE++;
+    if (dropped) return;
+    if (closed && closed[slab]) return;  // needed_number_of_pairs reached earlier
+    const unsigned bin = ((static_cast<unsigned>(slab) * g.nq + io) * g.nq + is) * g.nq + il_;  // < 2^31 (hbt_create)
+    const double xd = lds_f64(sia + 8 * TI * 4) - lds_f64(sja + 8 * TJ * 4);
+    const double yd = lds_f64(sia + 8 * TI * 5) - lds_f64(sja + 8 * TJ * 5);
+    const double zd = lds_f64(sia + 8 * TI * 6) - lds_f64(sja + 8 * TJ * 6);
+    const double td = lds_f64(sia + 8 * TI * 7) - lds_f64(sja + 8 * TJ * 7);
+    const double cv = v3_cos(g.hbarc_inv * (qE * td - qx * xd - qy * yd - qz * zd));  // src :431-433
+    red_inc_u64(&acc.num_count[bin]);
+    red_add_f64(&acc.sum_qo[bin], qo);
+    red_add_f64(&acc.sum_qs[bin], qs);
+    red_add_f64(&acc.sum_ql[bin], ql);
+    red_add_f64(&acc.num_cos[bin], cv);
+}
+
 template <bool MIXED, bool STATS, bool QINV = false>
 __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
                                               const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv,
@@ -533,6 +649,12 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
     using L = V3Smem<MIXED, STATS, QINV>;
     constexpr int NC = L::NC, TI = L::SUB, TJ = L::TJ;
     constexpr bool ORIENT = L::SORTED;
+#if !HBT_DBG_RED && !defined(HBT_V3_NO_LEAN_SAME)
+    if constexpr (L::SORTED) {  // production same-event units
+        v3_same_pair<NC, TI, TJ, L::SI, L::SJ, L::SIO, L::SJO>(g, c, acc, closed, dv, sbase, entry, psi_ref, n);
+        return;
+    }
+#endif
     const unsigned il4 = (entry >> 14) & ~3u, jl4 = (entry & 0xffffu) << 2;  // 4 x list-1 / list-2 slot
     const unsigned sia = sbase + L::SI + 2 * il4, sja = sbase + L::SJ + 2 * jl4;
     if (MIXED && !STATS && !QINV && c.f32_mixed) {
