@@ -160,8 +160,8 @@ __device__ __noinline__ void v2_slow_pair(const V2Dev *__restrict__ dv, const do
 
 // state of one warp's survivor bookkeeping
 struct V2Queue {
-    unsigned list_addr;   // shared-memory address of this lane's private list: entry m at list_addr + 128 m
-    unsigned cur;         // shared-memory address of the next free slot (advances by 128 bytes)
+    unsigned list_addr;   // shared-memory address of this lane's private list: entry m at list_addr + 64 m
+    unsigned cur;         // shared-memory address of the next free slot (advances by 64 bytes)
     int qcount;           // entries in the warp's linear queue (warp-uniform)
 };
 
@@ -181,6 +181,16 @@ __device__ __forceinline__ unsigned lds_u32(unsigned addr) {
     unsigned v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
+}
+
+// survivor-queue entries are 16 bits: list-1 slot << 8 | list-2 position (tiles of at most 256 x 256)
+__device__ __forceinline__ unsigned lds_u16(unsigned addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(unsigned addr, unsigned v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)) : "memory");
 }
 
 __device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) {

@@ -100,18 +100,26 @@ struct V3Smem {
     static constexpr int SUB = MIXED ? HBT_V3_SUB_MIXED : HBT_V3_SUB_SAME, TJ = MIXED ? HBT_V3_TJ_MIXED : HBT_V3_TJ_SAME;
     static constexpr bool SORTED = !MIXED && !STATS && !QINV;
     static constexpr int NF = QINV ? 5 : 3;
-    static constexpr int SI = 0;                                 // double [NC][SUB]  list-1 sub-tile, SoA
+    // list-1 sub-tile, SoA, swizzled: lane l keeps particles l, l + 32, ... (s = 0, 1, ...), which sit in the same
+    // banks, and a half-warp of a drain round gathers the particles of a few neighbouring lanes: two wavefronts per
+    // half-warp for every LDS.64 (ncu: 3.9 per instruction, 1.2 for the list-2 gathers).  Particle il = l + 32 s is kept
+    // in slot il ^ (s * SWZ): the s-th particles of neighbouring lanes move SWZ 8-byte banks away from the others.
+    // Queue entries carry the slot.
+    static constexpr int SWZ = 16 / (SUB / 32);
+    static constexpr int SUBP = SUB;                             // stride of the list-1 component arrays
+    static constexpr int SI = 0;                                 // double [NC][SUBP]
     // float [NF][TJ] px, py, -pT^2/2 (, -pz, -E) of the list-2 tile (float prefilter).  It sits BEFORE the FP64
     // tile: the prefilter loads particle j+1 while it works on j, and the slot past the last array is then sj[0],
     // which nobody writes during the pair loop
-    static constexpr int SJF = SI + 8 * NC * SUB;
+    static constexpr int SJF = SI + 8 * NC * SUBP;
     static constexpr int SJ = SJF + (STATS ? 0 : 4 * NF * TJ);   // double [NC][TJ]   list-2 tile, SoA
     static constexpr int SJT = SJ + 8 * NC * TJ;                 // double [TJ]       pT^2 of the list-2 tile (FP64 prefilter)
-    static constexpr int SIO = SJT + (STATS ? 8 * TJ : 0);       // u32    [SUB]      gather-order index (sorted lists)
-    static constexpr int SJO = SIO + (SORTED ? 4 * SUB : 0);     // u32    [TJ]
-    static constexpr int LQ = SJO + (SORTED ? 4 * TJ : 0);       // u32    [LCAP][32] per-lane survivor lists
-    static constexpr int WQ = LQ + 4 * HBT_V2_LCAP * 32;         // u32    [QCAP]     linear warp queue
-    static constexpr int BYTES = WQ + 4 * HBT_V2_QCAP;
+    static constexpr int SIO = SJT + (STATS ? 8 * TJ : 0);       // u32    [SUBP]     gather-order index (sorted lists), by slot
+    static constexpr int SJO = SIO + (SORTED ? 4 * SUBP : 0);    // u32    [TJ]
+    static constexpr int LQ = SJO + (SORTED ? 4 * TJ : 0);       // u16    [LCAP][32] per-lane survivor lists (slot << 8 | position)
+    static constexpr int WQ = LQ + 2 * HBT_V2_LCAP * 32;         // u16    [QCAP]     linear warp queue
+    static constexpr int BYTES = (WQ + 2 * HBT_V2_QCAP + 15) & ~15;
+    static_assert(SUB <= 256 && TJ <= 256, "16-bit queue entries");
 };
 
 // ---- guarded fast path for one queued survivor ---------------------------------------------
@@ -543,7 +551,7 @@ template <int NC, int TI, int TJ, int SI, int SJ, int SIO, int SJO>
 __device__ __forceinline__ void v3_same_pair(const HbtGrid &g, const V2Const &c, const HbtAccum &acc,
                                              const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv,
                                              unsigned sbase, unsigned entry, double psi_ref, V2Counters &n) {
-    const unsigned il = entry >> 16, jl = entry & 0xffffu;
+    const unsigned il = entry >> 8, jl = entry & 0xffu;
     const unsigned sia = sbase + SI + 8u * il, sja = sbase + SJ + 8u * jl;
     const bool flip = lds_u32(sbase + SIO + 4u * il) > lds_u32(sbase + SJO + 4u * jl);
     const double ax = lds_f64(sia), ay = lds_f64(sia + 8 * TI), bx = lds_f64(sja), by = lds_f64(sja + 8 * TJ);
@@ -647,15 +655,15 @@ __device__ __forceinline__ void v3_drain_pair(const HbtGrid &g, const V2Const &c
                                               const unsigned char *__restrict__ closed, const V2Dev *__restrict__ dv,
                                               unsigned sbase, unsigned entry, double psi_ref, V2Counters &n) {
     using L = V3Smem<MIXED, STATS, QINV>;
-    constexpr int NC = L::NC, TI = L::SUB, TJ = L::TJ;
+    constexpr int NC = L::NC, TI = L::SUBP, TJ = L::TJ;  // TI: stride of the list-1 component arrays
     constexpr bool ORIENT = L::SORTED;
 #if !HBT_DBG_RED && !defined(HBT_V3_NO_LEAN_SAME)
     if constexpr (L::SORTED) {  // production same-event units
-        v3_same_pair<NC, TI, TJ, L::SI, L::SJ, L::SIO, L::SJO>(g, c, acc, closed, dv, sbase, entry, psi_ref, n);
+        v3_same_pair<NC, TI, TJ, L::SI, L::SJ, L::SIO, L::SJO>(g, c, acc, closed, dv, sbase, entry, psi_ref, n);  // (TI = SUBP)
         return;
     }
 #endif
-    const unsigned il4 = (entry >> 14) & ~3u, jl4 = (entry & 0xffffu) << 2;  // 4 x list-1 / list-2 slot
+    const unsigned il4 = (entry >> 6) & ~3u, jl4 = (entry & 0xffu) << 2;  // 4 x list-1 / list-2 slot
     const unsigned sia = sbase + L::SI + 2 * il4, sja = sbase + L::SJ + 2 * jl4;
     if (MIXED && !STATS && !QINV && c.f32_mixed) {
         int fslab;
@@ -784,7 +792,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                                             const unsigned char *__restrict__ closed, const unsigned *__restrict__ orig,
                                             V2Counters &n, unsigned &cntKT, unsigned &cntRS, unsigned &kept) {
     using L = V3Smem<MIXED, STATS, QINV>;
-    constexpr int NC = L::NC, SUB = L::SUB, TJ = L::TJ, IPL = SUB / 32;
+    constexpr int NC = L::NC, SUB = L::SUB, SUBP = L::SUBP, TJ = L::TJ, IPL = SUB / 32;
     constexpr bool SORTED = L::SORTED;
     static_assert(!(QINV && STATS), "instrumented q_inv runs use the literal kernels");
     double *const si = reinterpret_cast<double *>(smem + L::SI);
@@ -797,10 +805,10 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     const double k2lo = c.k2lo, k2hi = c.k2hi, W2 = c.W2;
     V2Queue Q;
-    Q.list_addr = sbase + L::LQ + 4u * static_cast<unsigned>(lane);
+    Q.list_addr = sbase + L::LQ + 2u * static_cast<unsigned>(lane);
     Q.cur = Q.list_addr;
     Q.qcount = 0;
-    const unsigned lim = opaque_u32(Q.list_addr + 128u * (HBT_V2_LCAP - IPL));
+    const unsigned lim = opaque_u32(Q.list_addr + 64u * (HBT_V2_LCAP - IPL));
 
     long long i0, jbase, jcount;  // list-2 particles [jbase, jbase + jcount) belong to this row/segment
     int ni, jt;
@@ -847,18 +855,19 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
 #pragma unroll
     for (int s = 0; s < IPL; s++) {
         const int il = s * 32 + lane;
-        ent[s] = static_cast<unsigned>(il) << 16;
+        const int sl = il ^ (s * L::SWZ);  // slot in the swizzled arrays
+        ent[s] = static_cast<unsigned>(sl) << 8;
         ig[s] = i0 + il;
         if (il < ni) {
             const double2 *src = reinterpret_cast<const double2 *>(p1 + 8 * (i0 + il));
             const double2 v0 = src[0], v1 = src[1];
-            si[il] = v0.x; si[SUB + il] = v0.y; si[2 * SUB + il] = v1.x; si[3 * SUB + il] = v1.y;
+            si[sl] = v0.x; si[SUBP + sl] = v0.y; si[2 * SUBP + sl] = v1.x; si[3 * SUBP + sl] = v1.y;
             if (!MIXED) {
                 const double2 v2 = src[2], v3 = src[3];
-                si[(4 % NC) * SUB + il] = v2.x; si[(5 % NC) * SUB + il] = v2.y;
-                si[(6 % NC) * SUB + il] = v3.x; si[(7 % NC) * SUB + il] = v3.y;
+                si[(4 % NC) * SUBP + sl] = v2.x; si[(5 % NC) * SUBP + sl] = v2.y;
+                si[(6 % NC) * SUBP + sl] = v3.x; si[(7 % NC) * SUBP + sl] = v3.y;
             }
-            if (SORTED) si_o[il] = orig[i0 + il];
+            if (SORTED) si_o[sl] = orig[i0 + il];
             ax[s] = v0.x; ay[s] = v0.y;
             at[s] = fma(v0.x, v0.x, v0.y * v0.y);
             S1 = fmax(S1, at[s]);
@@ -870,8 +879,8 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
         } else {
             if (QINV) { azq[s] = 0.f; aEq[s] = 0.f; }  // (NaN px, py already fail the K_T test)
 #pragma unroll
-            for (int q = 0; q < NC; q++) si[q * SUB + il] = nan;
-            if (SORTED) si_o[il] = 0u;
+            for (int q = 0; q < NC; q++) si[q * SUBP + sl] = nan;
+            if (SORTED) si_o[sl] = 0u;
             ax[s] = nan; ay[s] = nan; at[s] = nan;
         }
     }
@@ -1019,7 +1028,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
             int jthr[IPL];  // DIAG: pair (i, j) is taken when j > i, i.e. local j > jthr
 #pragma unroll
             for (int s = 0; s < IPL; s++) jthr[s] = DIAG ? static_cast<int>(ig[s] - jl0) : 0;
-            const unsigned lane16 = static_cast<unsigned>(lane) << 16;
+            const unsigned lane16 = static_cast<unsigned>(lane) << 8;  // (lane in the slot half of a queue entry)
             int j = j_begin;
             // the float copy of list-2 particle j is loaded one trip ahead (LDS latency off the loop's
             // critical path; the last trip reads the first slot of the next array, see V3Smem)
@@ -1071,8 +1080,9 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                                 // the next slot's address goes to a NEW register: advancing the cursor in place
                                 // would wait for the STS to release its address operand (WAR, short scoreboard)
                                 const unsigned slot = Q.cur;
-                                Q.cur = slot + ((keep && in) ? 128u : 0u);
-                                if (keep && in) sts_u32(slot, ej + (static_cast<unsigned>(s) << 21));
+                                Q.cur = slot + ((keep && in) ? 64u : 0u);
+                                // entry: list-1 slot (lane ^ s SWZ) + 32 s, list-2 position
+                                if (keep && in) sts_u16(slot, (ej ^ (static_cast<unsigned>(s * L::SWZ) << 8)) + (static_cast<unsigned>(s) << 13));
                             }
                         }
                     } else {
@@ -1103,8 +1113,8 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                             inc_if(cntKT, kt);
                             inc_if(cntRS, kt && rej_s);
                             if (keep) {
-                                sts_u32(Q.cur, ent[s] | static_cast<unsigned>(j));
-                                Q.cur += 128u;
+                                sts_u16(Q.cur, ent[s] | static_cast<unsigned>(j));
+                                Q.cur += 64u;
                             }
                         }
                     }
@@ -1113,7 +1123,7 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                 }
                 {
                     // compact the per-lane lists into the linear queue and drain it 32 at a time
-                    const int cnt = static_cast<int>(Q.cur - Q.list_addr) >> 7;
+                    const int cnt = static_cast<int>(Q.cur - Q.list_addr) >> 6;
                     int incl = cnt;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -1121,8 +1131,8 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                         if (lane >= o) incl += v;
                     }
                     const int total = __shfl_sync(0xffffffffu, incl, 31);
-                    const unsigned dst = sbase + L::WQ + 4u * static_cast<unsigned>(Q.qcount + (incl - cnt));
-                    for (int m = 0; m < cnt; m++) sts_u32(dst + 4u * m, lds_u32(Q.list_addr + 128u * m));
+                    const unsigned dst = sbase + L::WQ + 2u * static_cast<unsigned>(Q.qcount + (incl - cnt));
+                    for (int m = 0; m < cnt; m++) sts_u16(dst + 2u * m, lds_u16(Q.list_addr + 64u * m));
                     Q.cur = Q.list_addr;
                     Q.qcount += total;
                     kept += static_cast<unsigned>(total);
@@ -1131,11 +1141,11 @@ __device__ __forceinline__ void v3_run_unit(unsigned char *smem, const unsigned 
                     // loaded before this round's pair is evaluated (one LDS round trip off the chain)
                     // (every queue read is followed by a __syncwarp before the next flush writes the queue)
                     if (Q.qcount >= 32 || (final && Q.qcount > 0)) {
-                        unsigned entry = lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(max(Q.qcount - 32, 0) + lane));
+                        unsigned entry = lds_u16(sbase + L::WQ + 2u * static_cast<unsigned>(max(Q.qcount - 32, 0) + lane));
                         do {
                             const int take = min(32, Q.qcount);
                             const int base = Q.qcount - take;
-                            const unsigned next_entry = lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(max(base - 32, 0) + lane));
+                            const unsigned next_entry = lds_u16(sbase + L::WQ + 2u * static_cast<unsigned>(max(base - 32, 0) + lane));
                             if (lane < take) v3_drain_pair<MIXED, STATS, QINV>(g, c, acc, closed, dv, sbase, entry, psi_ref, n);
                             entry = next_entry;
                             Q.qcount = base;

@@ -31,14 +31,20 @@
 
 struct V4Smem {
     static constexpr int TI = 128, TJ = 128;
-    static constexpr int SI = 0;                              // float4 [TI]    list-1 sub-tile {px, py, pz, E}
+    // list-1 sub-tile {px, py, pz, E}, two slots of padding after every 32 records: lane l keeps particles l, l + 32,
+    // l + 64, l + 96 (s = 0 .. 3), whose 16-byte records would share their four banks — and a quarter-warp of a drain
+    // round reads the records of two or three neighbouring lanes (4-way bank conflicts on every gather).  Particle
+    // l + 32 s is kept in slot l + 34 s; queue entries carry the slot.  (Padding, not an XOR swizzle: one base register
+    // and immediates in the staging stores.)
+    static constexpr int TIP = TI + 2 * (TI / 32 - 1);
+    static constexpr int SI = 0;                              // float4 [TIP]
     // float [3][TJ] px, py, -pT^2/2 of the rotated list-2 tile (prefilter; the slot past the last array is read one
     // trip ahead: it is SJ4[0], which nobody writes during the pair loop)
-    static constexpr int SJF = SI + 16 * TI;
+    static constexpr int SJF = SI + 16 * TIP;
     static constexpr int SJ4 = SJF + 12 * TJ;                 // float4 [TJ]    the same particles {px, py, pz, E} (drain)
-    static constexpr int LQ = SJ4 + 16 * TJ;                  // u32 [LCAP][32] per-lane survivor lists
-    static constexpr int WQ = LQ + 4 * HBT_V2_LCAP * 32;      // u32 [QCAP]     linear warp queue
-    static constexpr int PK = WQ + 4 * HBT_V2_QCAP;           // u32 [3][PARK]  parked pairs: list-1 index, list-2 index, segment
+    static constexpr int LQ = SJ4 + 16 * TJ;                  // u16 [LCAP][32] per-lane survivor lists (slot << 8 | position)
+    static constexpr int WQ = LQ + 2 * HBT_V2_LCAP * 32;      // u16 [QCAP]     linear warp queue
+    static constexpr int PK = (WQ + 2 * HBT_V2_QCAP + 3) & ~3;  // u32 [3][PARK]  parked pairs: list-1 index, list-2 index, segment
     static constexpr int BYTES = PK + 12 * HBT_V4_PARK;
 };
 
@@ -135,8 +141,8 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
     float4 *const sj4 = reinterpret_cast<float4 *>(smem + L::SJ4);
     const unsigned sjf_addr = sbase + L::SJF;
     const double k2lo = c.k2lo, k2hi = c.k2hi, W2 = c.W2;
-    const unsigned list_addr = sbase + L::LQ + 4u * static_cast<unsigned>(lane);
-    const unsigned lim = opaque_u32(list_addr + 128u * (HBT_V2_LCAP - IPL));
+    const unsigned list_addr = sbase + L::LQ + 2u * static_cast<unsigned>(lane);
+    const unsigned lim = opaque_u32(list_addr + 64u * (HBT_V2_LCAP - IPL));
     unsigned nE = 0;
     int parked = 0;  // pairs in the warp's parked list (warp-uniform)
     int seg_hint = 0;
@@ -178,7 +184,7 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
 #pragma unroll
             for (int s = 0; s < IPL; s++) {
                 const int il = s * 32 + lane;
-                const unsigned ra = sbase + L::SI + 16u * static_cast<unsigned>(il);
+                const unsigned ra = sbase + L::SI + 16u * static_cast<unsigned>(il + 2 * s);  // slot
                 if (il < ni) {
                     const double2 *src = reinterpret_cast<const double2 *>(p1 + 8 * (i0 + il));
                     const double2 v0 = src[0], v1 = src[1];
@@ -197,9 +203,11 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
             }
 #pragma unroll
             for (int h = 0; h < IPL / 2; h++) {
-                axf[h] = p2_pack_once(fx[2 * h], fx[2 * h + 1]);
-                ayf[h] = p2_pack_once(fy[2 * h], fy[2 * h + 1]);
-                atf[h] = p2_pack_once(ft[2 * h], ft[2 * h + 1]);
+                // (through an identity shuffle: values ptxas cannot re-create from the registers the staging stores pinned
+                // — it would re-pack the pairs from there in every trip of the pair loop, 20 moves per trip)
+                axf[h] = p2_pack_once(__shfl_sync(0xffffffffu, fx[2 * h], lane), __shfl_sync(0xffffffffu, fx[2 * h + 1], lane));
+                ayf[h] = p2_pack_once(__shfl_sync(0xffffffffu, fy[2 * h], lane), __shfl_sync(0xffffffffu, fy[2 * h + 1], lane));
+                atf[h] = p2_pack_once(__shfl_sync(0xffffffffu, ft[2 * h], lane), __shfl_sync(0xffffffffu, ft[2 * h + 1], lane));
             }
         }
 #pragma unroll
@@ -278,7 +286,7 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
         // ---- the pair loop, specialised on (error floor active)
         auto tile_loop = [&](auto floor_c) {
             constexpr bool FLOOR = decltype(floor_c)::value;
-            const unsigned lane16 = opaque_u32(static_cast<unsigned>(lane) << 16);
+            const unsigned lane16 = opaque_u32(static_cast<unsigned>(lane) << 8);  // (lane in the slot half of a queue entry)
             unsigned cur = list_addr;
             int qcount = 0;
             int j = j_begin;
@@ -314,8 +322,8 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
                             // the next slot's address goes to a NEW register: advancing the cursor in place would wait
                             // for the STS to release its address operand (WAR, short scoreboard)
                             const unsigned slot = cur;
-                            cur = slot + ((keep && in) ? 128u : 0u);
-                            if (keep && in) sts_u32(slot, ej + (static_cast<unsigned>(s) << 21));
+                            cur = slot + ((keep && in) ? 64u : 0u);
+                            if (keep && in) sts_u16(slot, ej + static_cast<unsigned>(s) * 0x2200u);  // list-1 slot lane + 34 s, list-2 position
                         }
                     }
                     j++;
@@ -323,7 +331,7 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
                 }
                 {
                     // compact the per-lane lists into the linear queue and drain it 32 at a time
-                    const int cnt = static_cast<int>(cur - list_addr) >> 7;
+                    const int cnt = static_cast<int>(cur - list_addr) >> 6;
                     int incl = cnt;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -331,8 +339,8 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
                         if (lane >= o) incl += v;
                     }
                     const int total = __shfl_sync(0xffffffffu, incl, 31);
-                    const unsigned dst = sbase + L::WQ + 4u * static_cast<unsigned>(qcount + (incl - cnt));
-                    for (int m = 0; m < cnt; m++) sts_u32(dst + 4u * m, lds_u32(list_addr + 128u * m));
+                    const unsigned dst = sbase + L::WQ + 2u * static_cast<unsigned>(qcount + (incl - cnt));
+                    for (int m = 0; m < cnt; m++) sts_u16(dst + 2u * m, lds_u16(list_addr + 64u * m));
                     cur = list_addr;
                     qcount += total;
                     __syncwarp();
@@ -340,13 +348,13 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
                     // this round's pair is evaluated (every queue read is followed by a __syncwarp before the next
                     // flush writes the queue)
                     if (qcount >= 32 || (final && qcount > 0)) {
-                        unsigned entry = lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(max(qcount - 32, 0) + lane));
+                        unsigned entry = lds_u16(sbase + L::WQ + 2u * static_cast<unsigned>(max(qcount - 32, 0) + lane));
                         do {
                             const int take = min(32, qcount);
                             const int base = qcount - take;
-                            const unsigned next_entry = lds_u32(sbase + L::WQ + 4u * static_cast<unsigned>(max(base - 32, 0) + lane));
+                            const unsigned next_entry = lds_u16(sbase + L::WQ + 2u * static_cast<unsigned>(max(base - 32, 0) + lane));
                             // every lane evaluates (idle lanes on a stale entry of this unit: the tiles are there)
-                            const unsigned il = (entry >> 16) & static_cast<unsigned>(TI - 1), jl = entry & static_cast<unsigned>(TJ - 1);
+                            const unsigned il = min(entry >> 8, static_cast<unsigned>(L::TIP - 1)), jl = entry & static_cast<unsigned>(TJ - 1);  // il: slot
                             const float4 a = lds_f32x4(sbase + L::SI + 16u * il), b = lds_f32x4(sbase + L::SJ4 + 16u * jl);
                             int slab;
                             unsigned bin;
@@ -361,7 +369,7 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
                             if (um) {
                                 if (fs < 0) {
                                     const unsigned at = sbase + L::PK + 4u * static_cast<unsigned>(parked + __popc(um & ((1u << lane) - 1u)));
-                                    sts_u32(at, static_cast<unsigned>(i0) + il);
+                                    sts_u32(at, static_cast<unsigned>(i0) + il - 2u * (il / 34u));  // slot -> particle
                                     sts_u32(at + 4 * HBT_V4_PARK, static_cast<unsigned>(j0) + jl);
                                     sts_u32(at + 8 * HBT_V4_PARK, static_cast<unsigned>(si));
                                 }
