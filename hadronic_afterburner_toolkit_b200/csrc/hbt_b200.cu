@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "hbt_common.h"
@@ -55,6 +56,13 @@ struct Lane {
     cudaStream_t side = nullptr;                 // the v4 mixed-event kernel of a whole batch, next to the same-event kernel (co-run)
     cudaEvent_t fork = nullptr, join = nullptr;  // side waits for fork (the batch's preparation), stream waits for join (side's kernel)
     cudaEvent_t tail = nullptr;                  // last submission (joins into ctx->compute)
+    // page-locked staging of the small per-launch tables (event offsets, segments, row limits).  cudaMemcpyAsync from
+    // PAGEABLE memory first waits for everything queued on its stream — the host would sit out the lane's previous pair
+    // kernel at every launch; from here the copy is only enqueued.
+    unsigned char *h_meta = nullptr;
+    size_t h_meta_cap = 0, h_meta_used = 0;
+    cudaEvent_t meta_done = nullptr;             // the copies out of h_meta have been made (it may be overwritten)
+    bool meta_pending = false;
     bool busy = false;                           // something was enqueued since the last join
     unsigned *d_work = nullptr;                  // [0] unit pop counter, [1] number of units (culled list)
     unsigned *d_units = nullptr;                 // surviving units of the sorted same-event list
@@ -173,6 +181,7 @@ struct hbt_ctx {
     bool fuse = true;  // whole batches run the fused same+mixed kernel (HBT_B200_FUSE=0 / HBT_OPT_FUSE: separate kernels)
     // production mixed-event loops run hbt_pairs_v4_mixed (binary32 tiles, 24 resident warps; HBT_B200_MIXED4=0: the v3 kernel)
     bool mixed4 = true;
+    size_t coalesce_host = 8;  // host batches per launch (HBT_B200_COALESCE_HOST)
     // a whole batch = the same-event kernel followed by the v4 mixed-event kernel on the same stream, each with its own
     // registers / shared memory / resident warps (HBT_B200_SPLIT=0: the fused v3 kernel, one allocation for both)
     bool split = true;
@@ -360,6 +369,39 @@ size_t dyn_smem_bytes(const HbtGrid &g) {
 }
 
 // ---- launches ------------------------------------------------------------------------
+// small host tables go to the device through the lane's page-locked staging buffer: meta_begin (once per launch, waits
+// for the previous launch's copies out of the buffer — done long ago unless the GPU is a whole launch behind), any
+// number of meta_upload, meta_end
+int meta_begin(hbt_ctx *ctx, Lane &L, size_t bytes_needed) {
+    if (L.meta_pending) {
+        CU(ctx, cudaEventSynchronize(L.meta_done));
+        L.meta_pending = false;
+    }
+    if (bytes_needed > L.h_meta_cap) {
+        if (L.h_meta) cudaFreeHost(L.h_meta);
+        L.h_meta = nullptr;
+        L.h_meta_cap = std::max<size_t>(bytes_needed * 2, 1u << 16);
+        CU(ctx, cudaHostAlloc(&L.h_meta, L.h_meta_cap, cudaHostAllocDefault));
+    }
+    L.h_meta_used = 0;
+    return HBT_OK;
+}
+int meta_upload(hbt_ctx *ctx, Lane &L, void *dst_dev, const void *src, size_t bytes) {
+    if (!bytes) return HBT_OK;
+    if (L.h_meta_used + bytes > L.h_meta_cap) return fail(ctx, HBT_ERR_STATE, "staging buffer of the launch tables too small");
+    unsigned char *at = L.h_meta + L.h_meta_used;
+    std::memcpy(at, src, bytes);
+    L.h_meta_used += (bytes + 15) & ~static_cast<size_t>(15);
+    CU(ctx, cudaMemcpyAsync(dst_dev, at, bytes, cudaMemcpyHostToDevice, L.stream));
+    return HBT_OK;
+}
+int meta_end(hbt_ctx *ctx, Lane &L) {
+    if (!L.meta_done) CU(ctx, cudaEventCreateWithFlags(&L.meta_done, cudaEventDisableTiming));
+    CU(ctx, cudaEventRecord(L.meta_done, L.stream));
+    L.meta_pending = true;
+    return HBT_OK;
+}
+
 #ifdef HBT_HAVE_V2
 int ensure_work(hbt_ctx *ctx, Lane &L) {
     if (!L.d_work) CU(ctx, cudaMalloc(&L.d_work, 16));  // [0] pop counter, [1] units kept by the culling, [2] pop counter of the v4 mixed-event kernel
@@ -471,8 +513,12 @@ int prepare_mixed_sorted(hbt_ctx *ctx, Lane &L, const double *d_p, int64_t n, co
     if (n < 2 || nev < 1) return HBT_OK;
     int rc0 = ensure_mix_buffers(ctx, L, n, ctx->evoff.size());
     if (rc0) return rc0;
-    // (pageable source: the copy is staged before the call returns, the vector can be reused)
-    CU(ctx, cudaMemcpyAsync(L.mix_off, ctx->evoff.data(), ctx->evoff.size() * 8, cudaMemcpyHostToDevice, L.stream));
+    rc0 = meta_begin(ctx, L, ctx->evoff.size() * 8 + 16);
+    if (rc0) return rc0;
+    rc0 = meta_upload(ctx, L, L.mix_off, ctx->evoff.data(), ctx->evoff.size() * 8);
+    if (rc0) return rc0;
+    rc0 = meta_end(ctx, L);
+    if (rc0) return rc0;
     const int th = 256;
     hbt_mix_keys<<<static_cast<unsigned>((n + th - 1) / th), th, 0, L.stream>>>(d_p, n, L.mix_off, nev, L.mix_keys[0], L.mix_idx[0]);
     int ev_bits = 1;
@@ -837,10 +883,42 @@ constexpr unsigned long long kCoalescePairs = 1500000000ull;  // a batch with fe
 constexpr unsigned long long kCoalesceFlushPairs = 8000000000ull;
 constexpr size_t kCoalesceSlotParticles = 1u << 17;         // smallest staging slot of a group of host batches (8 MB)
 
+// host-side time of the small-batch path by section (HBT_B200_HOSTPROF=1: printed at hbt_destroy)
+struct HostProf {
+    double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool on = getenv("HBT_B200_HOSTPROF") != nullptr;
+    ~HostProf() {
+        if (!on) return;
+        static const char *name[8] = {"append: upload enqueue", "append: key range", "append: wait for the upload", "append: segments + bookkeeping",
+                                      "flush: until the sort", "flush: sorts + helper launches", "flush: pair kernels + events", "append: page-locked query"};
+        for (int k = 0; k < 8; k++) if (n[k]) fprintf(stderr, "[hostprof] %-34s %8.1f us per call, %llu calls\n", name[k], 1e6 * t[k] / n[k], n[k]);
+    }
+};
+HostProf g_hostprof;
+struct HostProfScope {
+    int k;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostProfScope(int k_) : k(k_), t0(std::chrono::steady_clock::now()) {}
+    ~HostProfScope() {
+        if (!g_hostprof.on) return;
+        g_hostprof.t[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        g_hostprof.n[k]++;
+    }
+};
+
 // launches everything that waits in ctx->pend as ONE production launch
 int flush_pending(hbt_ctx *ctx) {
     Pending &P = ctx->pend;
     if (P.b.empty()) return HBT_OK;
+    auto hp_t = std::chrono::steady_clock::now();
+    auto hp_mark = [&](int k) {
+        if (!g_hostprof.on) return;
+        const auto now = std::chrono::steady_clock::now();
+        g_hostprof.t[k] += std::chrono::duration<double>(now - hp_t).count();
+        g_hostprof.n[k]++;
+        hp_t = now;
+    };
     Lane &L = next_lane(ctx);
     const int nb = static_cast<int>(P.b.size());
     if (P.host) {
@@ -887,11 +965,14 @@ int flush_pending(hbt_ctx *ctx) {
         L.row_end_cap = row_end.size() * 2;
         CU(ctx, cudaMalloc(&L.row_end, L.row_end_cap * 4));
     }
-    // (pageable sources: the copies are staged before the calls return)
-    CU(ctx, cudaMemcpyAsync(L.row_end, row_end.data(), row_end.size() * 4, cudaMemcpyHostToDevice, L.stream));
+    rc = meta_begin(ctx, L, row_end.size() * 4 + P.evoff.size() * 8 + P.segs.size() * sizeof(HbtMixSeg) + 64);
+    if (rc) return rc;
+    rc = meta_upload(ctx, L, L.row_end, row_end.data(), row_end.size() * 4);
+    if (rc) return rc;
     const int th = 256;
+    hp_mark(4);
     // ---- same-event list: (batch, Morton) order of the padded slots, boxes, surviving units
-    if (P.host) {
+    if (P.host && !P.direct) {
         hbt_multi_keys<<<static_cast<unsigned>((n_pad + th - 1) / th), th, 0, L.stream>>>(M, nullptr, P.host_range, L.sort_keys[0], L.sort_idx[0]);
     } else {
         CU(ctx, cudaMemsetAsync(L.sort_rmax, 0, 4, L.stream));
@@ -916,7 +997,8 @@ int flush_pending(hbt_ctx *ctx) {
         const int nev = static_cast<int>(P.evoff.size()) - 1;
         rc = ensure_mix_buffers(ctx, L, n_log, P.evoff.size());
         if (rc) return rc;
-        CU(ctx, cudaMemcpyAsync(L.mix_off, P.evoff.data(), P.evoff.size() * 8, cudaMemcpyHostToDevice, L.stream));
+        rc = meta_upload(ctx, L, L.mix_off, P.evoff.data(), P.evoff.size() * 8);
+        if (rc) return rc;
         hbt_multi_mix_keys<<<static_cast<unsigned>((n_log + th - 1) / th), th, 0, L.stream>>>(M, L.mix_off, nev, L.mix_keys[0], L.mix_idx[0]);
         int ev_bits = 1;
         while ((1ll << ev_bits) < nev) ev_bits++;
@@ -931,8 +1013,12 @@ int flush_pending(hbt_ctx *ctx) {
             L.mseg_cap = P.segs.size() * 2;
             CU(ctx, cudaMalloc(&L.mseg, L.mseg_cap * sizeof(HbtMixSeg)));
         }
-        CU(ctx, cudaMemcpyAsync(L.mseg, P.segs.data(), P.segs.size() * sizeof(HbtMixSeg), cudaMemcpyHostToDevice, L.stream));
+        rc = meta_upload(ctx, L, L.mseg, P.segs.data(), P.segs.size() * sizeof(HbtMixSeg));
+        if (rc) return rc;
         ctx->kernel_launches += 3;
+        rc = meta_end(ctx, L);
+        if (rc) return rc;
+        hp_mark(5);
         if (ctx->split && use_mixed4(ctx)) {
             rc = launch_split_pair(ctx, L, L.sort_p, n_pad, L.mix_p, L.mix_p, L.mseg, P.segs.size(), P.nblocks, P.psi_ref, P.pairs_same,
                                    P.pairs_mixed);
@@ -947,6 +1033,9 @@ int flush_pending(hbt_ctx *ctx) {
         ctx->timers.push_back({e0, e1, 2, static_cast<double>(P.pairs_same) / static_cast<double>(P.pairs_same + P.pairs_mixed)});
         ctx->mixed_launches++;
     } else {
+        rc = meta_end(ctx, L);
+        if (rc) return rc;
+        hp_mark(5);
         const unsigned grid = static_cast<unsigned>(ctx->n_sm * ctx->occ_same);
         hbt_pairs_v3<false, false><<<grid, 32, 0, L.stream>>>(
             L.sort_p, L.sort_p, n_pad, nullptr, nullptr, 0, L.d_units, L.d_work, 0, ctx->grid, ctx->v2c, ctx->d_dv,
@@ -962,7 +1051,9 @@ int flush_pending(hbt_ctx *ctx) {
         P.slot->in_flight = true;
     }
     P = Pending();
-    return drain_timers(ctx, false);
+    rc = drain_timers(ctx, false);
+    hp_mark(6);
+    return rc;
 }
 
 // Takes a small production batch into the pending launch (flushing first when it does not fit).  p_host: the
@@ -973,7 +1064,11 @@ int append_pending(hbt_ctx *ctx, const double *p_host, const double *d_src, cons
     Pending &P = ctx->pend;
     const int64_t n = off[nev];
     const bool host = p_host != nullptr;
-    const bool direct = host && ctx->direct_upload && is_page_locked(p_host);
+    bool direct;
+    {
+        HostProfScope hp(7);
+        direct = host && ctx->direct_upload && is_page_locked(p_host);
+    }
     if (!P.b.empty() && (P.do_mixed != do_mixed || P.host != host || P.direct != direct || P.b.size() >= HBT_MULTI_MAX ||
                          P.n_padded + ((n + 63) & ~63ll) > HBT_V3_MAX_SORTED ||
                          (host && P.staged + static_cast<size_t>(n) > P.slot->cap))) {
@@ -990,28 +1085,38 @@ int append_pending(hbt_ctx *ctx, const double *p_host, const double *d_src, cons
             int rc = acquire_slot(ctx, &P.slot);
             if (rc) return rc;
             // (8 batches of 15 000-30 000 particles; grows with the batches, once)
-            rc = ensure_slot(ctx, *P.slot, std::max<size_t>(static_cast<size_t>(n) * kCoalesceBatchesHost, kCoalesceSlotParticles), 0);
+            rc = ensure_slot(ctx, *P.slot, std::max<size_t>(static_cast<size_t>(n) * ctx->coalesce_host, kCoalesceSlotParticles), 0);
             if (rc) return rc;
         }
     }
     if (host) {
         const double *dst = p_host;
-        if (direct) {  // straight from the caller's page-locked buffer; waited for below, the caller may reuse it on return
-            CU(ctx, cudaMemcpyAsync(P.slot->d_p + 8 * P.staged, p_host, static_cast<size_t>(n) * 64, cudaMemcpyHostToDevice, ctx->copy));
-        } else {
-            std::memcpy(P.slot->h_p + 8 * P.staged, p_host, static_cast<size_t>(n) * 64);
-            dst = P.slot->h_p + 8 * P.staged;
+        {
+            HostProfScope hp(0);
+            if (direct) {  // straight from the caller's page-locked buffer; waited for below, the caller may reuse it on return
+                CU(ctx, cudaMemcpyAsync(P.slot->d_p + 8 * P.staged, p_host, static_cast<size_t>(n) * 64, cudaMemcpyHostToDevice, ctx->copy));
+            } else {
+                std::memcpy(P.slot->h_p + 8 * P.staged, p_host, static_cast<size_t>(n) * 64);
+                dst = P.slot->h_p + 8 * P.staged;
+            }
         }
-        float m = P.host_range;
-        for (int64_t i = 0; i < n; i++) {
-            const float a = std::max(std::fabs(static_cast<float>(dst[8 * i])), std::fabs(static_cast<float>(dst[8 * i + 1])));
-            if (a == a && a < 3.0e38f) m = std::max(m, a);
+        if (!direct) {  // key range of the staged copy (in cache); page-locked batches are not touched: the device finds it
+            HostProfScope hp(1);
+            float m = P.host_range;
+            for (int64_t i = 0; i < n; i++) {
+                const float a = std::max(std::fabs(static_cast<float>(dst[8 * i])), std::fabs(static_cast<float>(dst[8 * i + 1])));
+                if (a == a && a < 3.0e38f) m = std::max(m, a);
+            }
+            P.host_range = m;
         }
-        P.host_range = m;
         d_src = P.slot->d_p + 8 * P.staged;
         P.staged += static_cast<size_t>(n);
-        if (direct) CU(ctx, cudaStreamSynchronize(ctx->copy));  // (the range loop above ran beside the copy)
+        {
+            HostProfScope hp(2);
+            if (direct) CU(ctx, cudaStreamSynchronize(ctx->copy));  // (the range loop above ran beside the copy)
+        }
     }
+    HostProfScope hp3(3);
     if (do_mixed) {
         const size_t s0 = P.segs.size();
         P.segs.resize(s0 + static_cast<size_t>(nev) * nmix);
@@ -1038,7 +1143,7 @@ int append_pending(hbt_ctx *ctx, const double *p_host, const double *d_src, cons
     P.pairs_mixed += mp;
     ctx->pending_num += sp;
     ctx->pending_den += mp;
-    if (P.b.size() >= (host ? kCoalesceBatchesHost : kCoalesceBatches) || P.pairs_same + P.pairs_mixed >= kCoalesceFlushPairs)
+    if (P.b.size() >= (host ? ctx->coalesce_host : kCoalesceBatches) || P.pairs_same + P.pairs_mixed >= kCoalesceFlushPairs)
         return flush_pending(ctx);
     return HBT_OK;
 }
@@ -1441,6 +1546,7 @@ extern "C" int hbt_create(const hbt_params *params, int32_t device, hbt_ctx **ou
     if (const char *v = getenv("HBT_B200_STATS")) ctx->stats = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_FUSE")) ctx->fuse = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_MIXED4")) ctx->mixed4 = atoi(v) != 0;
+    if (const char *v = getenv("HBT_B200_COALESCE_HOST")) ctx->coalesce_host = static_cast<size_t>(std::min(32, std::max(1, atoi(v))));
     if (const char *v = getenv("HBT_B200_SPLIT")) ctx->split = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_CORUN")) ctx->corun = atoi(v) != 0;
     if (const char *v = getenv("HBT_B200_CORUN_SAME")) ctx->corun_same = std::max(1, atoi(v));
@@ -1636,6 +1742,8 @@ extern "C" void hbt_destroy(hbt_ctx *ctx) {
     for (Lane &L : ctx->lanes) {
         if (L.stream) cudaStreamDestroy(L.stream);
         if (L.side) cudaStreamDestroy(L.side);
+        if (L.h_meta) cudaFreeHost(L.h_meta);
+        if (L.meta_done) cudaEventDestroy(L.meta_done);
         if (L.fork) cudaEventDestroy(L.fork);
         if (L.join) cudaEventDestroy(L.join);
     }
@@ -1905,8 +2013,10 @@ extern "C" int hbt_accumulate_batch(hbt_ctx *ctx, const double *p1, const int64_
     CU(ctx, cudaEventRecord(s->uploaded, ctx->copy));
     // max(|px|, |py|) of list 1 for the Morton keys of the same-event sort, from the host copy (as
     // hbt_sort_range computes it: finite values only)
+    // (only of a copy this thread has just made: a page-locked caller buffer is left to the DMA engine, and the device
+    // finds the range — one small kernel — instead of 1 ms of the calling thread per 150 000 particles before the launch)
     float host_range = -1.f;
-    if (do_same && !ctx->stats && ctx->kernel_version != 1 && n1 > 1) {
+    if (do_same && !ctx->stats && ctx->kernel_version != 1 && n1 > 1 && !direct) {
         float m = 0.f;
         for (int64_t i = 0; i < n1; i++) {
             const float a = std::max(std::fabs(static_cast<float>(h1[8 * i])), std::fabs(static_cast<float>(h1[8 * i + 1])));
