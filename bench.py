@@ -364,7 +364,7 @@ def main():
     def submit_resident(d_t, psi, plan):
         if do_mixed:
             ids, cs = plan
-            # one fused launch per group (both loops); separate kernels with HBT_B200_FUSE=0 or stage counters on
+            # one whole-batch call per group (both loops: two kernels next to each other); separate calls with HBT_B200_FUSE=0 or stage counters on
             _check(h, L.hbt_accumulate_batch_dev(h, d_t.data_ptr(), off.ctypes.data, nev, ids.ctypes.data, cs.ctypes.data, nmix, psi))
         else:
             _check(h, L.hbt_accumulate_same_dev(h, d_t.data_ptr(), n, psi))
@@ -484,6 +484,9 @@ def main():
     if not do_mixed:
         ops_mixed = 0.0
     fused = do_mixed and os.environ.get("HBT_B200_FUSE", "1") != "0" and os.environ.get("HBT_B200_KERNEL", "2") != "1"
+    # a whole batch = the same-event kernel and the v4 mixed-event kernel next to each other on two streams
+    # (HBT_B200_SPLIT=0: the one fused v3 kernel of rounds 1-2)
+    split = fused and os.environ.get("HBT_B200_SPLIT", "1") != "0" and os.environ.get("HBT_B200_MIXED4", "1") != "0"
     ks = (tm1["same_ms"] - tm0["same_ms"]) * 1e-3
     km = (tm1["mixed_ms"] - tm0["mixed_ms"]) * 1e-3
     ach = (ops_same + ops_mixed) / (ks + km) / 1e12
@@ -493,7 +496,8 @@ def main():
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch (one C5-shape group)
-            traffic = tj["fused" if fused else "same"]["dram_bytes_per_launch"] + (0 if fused else tj["mixed"]["dram_bytes_per_launch"])
+            one = fused and not split
+            traffic = tj["fused" if one else "same"]["dram_bytes_per_launch"] + (0 if one else tj["mixed"]["dram_bytes_per_launch"])
             traffic_detail = {"kind": "STATIC: a constant read from profiles/traffic.json (one `ncu --set full` capture with a cold L2), "
                                       "NOT measured in this run",
                               "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one C5-shape group per launch)",
@@ -502,28 +506,32 @@ def main():
                               "algorithmic_bytes_per_launch": tj["fused"]["algorithmic_bytes_per_launch"], "source": tj["source"]}
         except (OSError, KeyError, ValueError):
             pass
-    # what actually binds (profiles/r02_controls.txt, corrected control of session 2; profiles/r02_ncu_summary.txt):
-    # instruction issue at 4.5 resident warps per scheduler (latency of the dependent binary64 chains of the drain)
-    # and the LSU data pipe; the reductions (5 per accepted same-event pair, 1 per accepted mixed-event pair) cost
-    # 1.8 ms of the fused launch's 27.3 and run below both of their ceilings
+    # what actually binds (profiles/r03_ncu_summary.txt, profiles/r03_controls_corun.txt): the same-event kernel ALONE
+    # is held by its reductions into the L2 (5 per accepted pair: 15.3 ms, 11.6 ms without them, and neither fewer
+    # instructions nor fewer shared-memory wavefronts nor 20 instead of 18 warps move it); the mixed-event kernel by
+    # instruction issue (80 % of the slots).  Next to each other the mixed-event warps fill the same-event warps'
+    # reduction stalls: 24.4 ms for a C5 group against 26.4 one after the other (and 27.1 for the fused v3 kernel);
+    # with the reductions off both ways take ~23 ms, i.e. what is left is the sum of two issue-bound kernels
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
     red_lanes = 5.0 * float(dst[4]) + float(dst[10])
     red_rate = red_lanes / (ks + km) / (sm_mhz * 1e6) / n_sm
     bound_actual = {
-        "issue_slots": {"busy_pct_fused_kernel": 64.6, "warp_instructions_per_c5_group": 20.25e9,
-                        "ms_at_full_issue": 17.4, "resident_warps_per_scheduler": 4.5,
-                        "kind": "STATIC: ncu capture profiles/r02_ncu_summary.txt (smsp__issue_active, smsp__inst_executed; "
-                                "stalls per issue: wait 2.14, short_scoreboard 1.33, not_selected 0.88)"},
-        "lsu_data_pipe": {"busy_pct_fused_kernel": 75.7,
-                          "kind": "STATIC: same capture, l1tex__data_pipe_lsu_wavefronts: shared-memory loads 29.5 %, stores 8.0 %, "
-                                  "global (reductions: 16 wavefronts per 64-bit RED with 32 spread addresses) the rest"},
+        "issue_slots": {"busy_pct_same_event_kernel_alone": 51.9, "busy_pct_mixed_event_kernel_alone": 80.5,
+                        "warp_instructions_per_c5_group": 9.29e9 + 10.25e9, "ms_at_full_issue": 16.8,
+                        "kind": "STATIC: ncu captures profiles/r03_ncu_summary.txt of the two kernels of a batch, each alone "
+                                "(smsp__issue_active, smsp__inst_executed); under ncu they cannot run next to each other"},
+        "lsu_data_pipe": {"busy_pct_same_event_kernel_alone": 70.7, "busy_pct_mixed_event_kernel_alone": 62.0,
+                          "kind": "STATIC: same captures, l1tex__data_pipe_lsu_wavefronts (same-event: 58 % of the wavefronts are the "
+                                  "reductions, 14 per 64-bit RED of 27 lanes with spread addresses)"},
         "reductions": {"red_lanes_per_clk_per_sm": red_rate, "ceiling_all_sms_busy": 0.68, "ceiling_per_sm": 0.94,
                        "frac": red_rate / 0.68, "lanes": "5 per accepted same-event pair + 1 per accepted mixed-event pair",
                        "ceiling_source": "profiles/r02_tma_red_bench.txt (scripts/micro/tma_red_bench.cu: spread REDs from every SM / "
                                          "from a quarter of the SMs)"},
-        "controls": "profiles/r02_controls.txt: fused launch 27.25 ms; 25.44 ms with the reductions predicated off and all four sums "
-                    "still evaluated (HBT_DBG_RED=7); the earlier 23.5 ms control also dropped the cos chain",
+        "controls": "profiles/r03_controls_corun.txt (one C5-shape group): the two kernels next to each other 24.3 ms, one after the "
+                    "other 26.4 (same-event 15.3 + mixed-event 11.1); same-event reductions predicated off with all four sums still "
+                    "evaluated (HBT_DBG_RED=7): 23.2 / 22.7 (same-event kernel alone 11.6); profiles/r02_controls.txt has the "
+                    "controls of the fused v3 kernel (27.25 ms; 25.44 without reductions)",
     }
     roofline = {
         "bound": "fp64", "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
@@ -535,10 +543,13 @@ def main():
                       "(incl. the same-event sort + cull kernels) on the launching stream",
         "note": "the bound SURVEY.md 8d names is the FP64 pipe; it is NOT what binds this design: the production prefilter runs in "
                 "packed FP32 and mixed-event survivors are binned in FP32 wherever a rigorous error band allows, so the FP64 pipe "
-                "itself is ~19 % busy (ncu, fused kernel) and `frac` is an algorithmic-throughput fraction; see bound_actual",
+                "itself is 31 % busy in the same-event kernel and 2 % in the mixed-event kernel (ncu) and `frac` is an "
+                "algorithmic-throughput fraction; see bound_actual",
         "kernels": ({
-            # one launch per group works through the same-event and the mixed-event units interleaved
-            "hbt_pairs_v3_fused": {"ms_per_launch": 1e3 * (ks + km) / max(1, tm1["same_launches"] - tm0["same_launches"]),
+            # per group: the same-event kernel and the v4 mixed-event kernel share the SMs on two streams (split), or one
+            # fused v3 kernel works through both unit lists interleaved (HBT_B200_SPLIT=0); timed from the first to the
+            # last of them on the launching stream (the second stream joins it)
+            ("hbt_pairs_v3<same-event> || hbt_pairs_v4_mixed" if split else "hbt_pairs_v3_fused"): {"ms_per_launch": 1e3 * (ks + km) / max(1, tm1["same_launches"] - tm0["same_launches"]),
                                    "pairs_per_s": float(dst[0] + dst[6]) / (ks + km), "tflops": ach, "frac": ach / peak.value,
                                    "ops_per_pair_same": ops_same / float(dst[0]), "ops_per_pair_mixed": ops_mixed / float(dst[6])},
         } if fused else {
