@@ -27,6 +27,10 @@
 #ifndef HBT_V4_WARPS_PER_SM
 #define HBT_V4_WARPS_PER_SM 24
 #endif
+#ifndef HBT_V4_LCAP
+#define HBT_V4_LCAP 16  // per-lane survivor list capacity: the lists are compacted and drained when one of them holds more than LCAP - 4
+#endif
+#define HBT_V4_QCAP (32 + 32 * HBT_V4_LCAP)
 #define HBT_V4_PARK 64  // parked (undecided) pairs per warp: a drain round adds at most 32, 32 are evaluated as soon as they are there
 
 struct V4Smem {
@@ -43,8 +47,8 @@ struct V4Smem {
     static constexpr int SJF = SI + 16 * TIP;
     static constexpr int SJ4 = SJF + 12 * TJ;                 // float4 [TJ]    the same particles {px, py, pz, E} (drain)
     static constexpr int LQ = SJ4 + 16 * TJ;                  // u16 [LCAP][32] per-lane survivor lists (slot << 8 | position)
-    static constexpr int WQ = LQ + 2 * HBT_V2_LCAP * 32;      // u16 [QCAP]     linear warp queue
-    static constexpr int PK = (WQ + 2 * HBT_V2_QCAP + 3) & ~3;  // u32 [3][PARK]  parked pairs: list-1 index, list-2 index, segment
+    static constexpr int WQ = LQ + 2 * HBT_V4_LCAP * 32;      // u16 [QCAP]     linear warp queue
+    static constexpr int PK = (WQ + 2 * HBT_V4_QCAP + 3) & ~3;  // u32 [3][PARK]  parked pairs: list-1 index, list-2 index, segment
     static constexpr int BYTES = PK + 12 * HBT_V4_PARK;
 };
 
@@ -142,7 +146,7 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
     const unsigned sjf_addr = sbase + L::SJF;
     const double k2lo = c.k2lo, k2hi = c.k2hi, W2 = c.W2;
     const unsigned list_addr = sbase + L::LQ + 2u * static_cast<unsigned>(lane);
-    const unsigned lim = opaque_u32(list_addr + 64u * (HBT_V2_LCAP - IPL));
+    const unsigned lim = opaque_u32(list_addr + 64u * (HBT_V4_LCAP - IPL));
     unsigned nE = 0;
     int parked = 0;  // pairs in the warp's parked list (warp-uniform)
     int seg_hint = 0;
