@@ -171,7 +171,8 @@ int hbt_accumulate_mixed_dev(hbt_ctx *ctx, const double *d_p1, const int64_t *of
 
 /* One whole batch with list 2 = list 1 (the events of d_p are each other's mixing partners):
  * body of calculate_HBT_correlation_function (:177-218) on a device-resident list.  Both loops
- * run in one fused kernel (HBT_OPT_FUSE). */
+ * are launched together (HBT_OPT_FUSE): the same-event kernel and the mixed-event kernel share
+ * the SMs on two streams. */
 int hbt_accumulate_batch_dev(hbt_ctx *ctx, const double *d_p, const int64_t *off, int32_t nev,
                              const int32_t *partner_ids, const double *cos_sin, int32_t nmix, double psi_ref);
 
@@ -208,10 +209,14 @@ int hbt_get_timers(hbt_ctx *ctx, double *same_ms, double *mixed_ms, uint64_t *sa
  *   (reported as 0); all pairs [0], passed q_long [4] and accepted [5] stay exact, and so does
  *   every histogram.  Default can be changed with the environment variable HBT_B200_STATS=1.
  * HBT_OPT_KERNEL: 2 = tuned kernels (default), 1 = literal kernels (cross-check).
- * HBT_OPT_FUSE: 1 (default) = a whole batch (hbt_accumulate_batch with both halves) runs as one
- *   kernel that works through the same-event and the mixed-event units interleaved; 0 = one
- *   kernel per loop.  Environment: HBT_B200_FUSE.  hbt_get_timers splits the time of a fused
- *   launch between same_ms and mixed_ms by the pairs of each kind.
+ * HBT_OPT_FUSE: 1 (default) = a whole batch (hbt_accumulate_batch with both halves) is ONE
+ *   launch group: the same-event kernel and the mixed-event kernel (hbt_pairs_v4_mixed) run next
+ *   to each other on two streams, each with its own registers and shared memory; 0 = one loop
+ *   after the other.  Environment: HBT_B200_FUSE.  hbt_get_timers splits the time of such a
+ *   launch group between same_ms and mixed_ms by the pairs of each kind.  (Environment only:
+ *   HBT_B200_SPLIT=0 = the single fused kernel of earlier versions, HBT_B200_CORUN=0 = the two
+ *   kernels one after the other, HBT_B200_CORUN_SAME / HBT_B200_CORUN_MIXED = resident warps per
+ *   SM of each during the co-run, HBT_B200_MIXED4=0 = mixed-event loops on the v3 kernel.)
  * HBT_OPT_LANES: 2 (default) = consecutive production batches go to two compute streams in turn,
  *   each with its own scratch, so the sort / cull helpers and the first units of batch k+1 run
  *   under the tail of batch k (batches commute: every accumulation is an atomic add into the
