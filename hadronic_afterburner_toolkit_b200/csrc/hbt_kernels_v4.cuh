@@ -7,18 +7,22 @@
 //  * the tiles are kept in binary32 only: list 1 as float4 {px, py, pz, E}, list 2 (rotated in
 //    binary64 as the reference does, :522-523, then rounded once) as the prefilter's float [3][TJ]
 //    and a float4 copy for the drain.  The drain reads two LDS.128 per survivor instead of eight
-//    LDS.64 + eight F2F.F32.F64; 7.6 KB of shared memory per warp instead of 11.6;
+//    LDS.64 + eight F2F.F32.F64; 8.6 KB of shared memory per warp instead of 11.6;
 //  * no binary64 chain in the kernel body.  The ~1e-3 of the survivors the FP32 bands leave open
 //    are parked — (list-1 index, list-2 index, segment) in a small per-warp list — and evaluated
 //    32 at a time, all lanes busy, by the literal chain out of line (v2_slow_pair: the reference's
 //    own operations on the binary64 particles, re-read from global memory and rotated again), so
 //    every bin index still equals the reference's.  With the chain out of the way the kernel needs
 //    80 registers and 24 warps are resident per SM (v3: 96 registers, 18 warps; the mixed-event
-//    units are latency bound and want warps: profiles/r02_controls.txt).
+//    units are latency bound and want warps: profiles/r02_controls.txt);
+//  * 16-bit queue entries (list-1 slot << 8 | list-2 position), per-lane lists of 16 entries.
 //
 // Accumulation is a commutative integer count, so parking changes nothing in the result.  Used far
 // from the needed-pairs cap only (like every tuned kernel); q_inv mode, instrumented runs and
-// HBT_B200_F32MIX=0 stay on v3.
+// HBT_B200_F32MIX=0 stay on v3.  A whole batch launches it NEXT TO the same-event kernel
+// (hbt_b200.cu: launch_split_pair): both carry cudaFuncAttributePreferredSharedMemoryCarveout =
+// max, without which the two would not be resident on the same SM.  DESIGN.md 5, "Two kernels
+// next to each other"; numbers in profiles/r03_*.
 #ifndef HBT_KERNELS_V4_CUH_
 #define HBT_KERNELS_V4_CUH_
 
