@@ -142,7 +142,8 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
     using L = V4Smem;
     constexpr int TI = L::TI, TJ = L::TJ, IPL = TI / 32;
     __shared__ __align__(16) unsigned char smem[L::BYTES];
-    const int lane = threadIdx.x;
+    // (through an identity shuffle: a value ptxas keeps in a register instead of re-reading SR_TID in every trip)
+    const int lane = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x), static_cast<int>(threadIdx.x));
     const unsigned sbase = opaque_u32(static_cast<unsigned>(__cvta_generic_to_shared(smem)));  // kept in a register: no per-use S2UR/ULEA
     if (blockIdx.x == 0 && lane == 0) atomicAdd(&acc.stage[6], total_pairs);
     float *const sjf = reinterpret_cast<float *>(smem + L::SJF);
