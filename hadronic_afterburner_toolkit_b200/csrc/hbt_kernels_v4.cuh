@@ -310,7 +310,9 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
                     pbx = lds_f32(ja); pby = lds_f32(ja + 4 * TJ); pnb = lds_f32(ja + 8 * TJ);
                     const f32x2_t bx2 = p2_pack(bxs, bxs), by2 = p2_pack(bys, bys), nby2 = p2_pack(-bys, -bys);
                     const f32x2_t nbt2 = p2_pack(nbh, nbh), Wq2 = p2_pack(Wqf, Wqf);
-                    const unsigned ej = lane16 + static_cast<unsigned>(j);
+                    // (one add per trip, not one multiply-add under every survivor's predicate: volatile keeps it here)
+                    unsigned ej;
+                    asm volatile("add.u32 %0, %1, %2;" : "=r"(ej) : "r"(lane16), "r"(static_cast<unsigned>(j)));
 #pragma unroll
                     for (int h = 0; h < IPL / 2; h++) {
                         const f32x2_t sx = p2_add(axf[h], bx2), sy = p2_add(ayf[h], by2);
@@ -363,7 +365,9 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
                             const int base = qcount - take;
                             const unsigned next_entry = lds_u16(sbase + L::WQ + 2u * static_cast<unsigned>(max(base - 32, 0) + lane));
                             // every lane evaluates (idle lanes on a stale entry of this unit: the tiles are there)
-                            const unsigned il = min(entry >> 8, static_cast<unsigned>(L::TIP - 1)), jl = entry & static_cast<unsigned>(TJ - 1);  // il: slot
+                            // il: slot (< 256 even in a stale entry of an idle lane: inside this warp's shared memory)
+                            const unsigned il = entry >> 8, jl = entry & static_cast<unsigned>(TJ - 1);
+                            static_assert(16 * 256 <= L::BYTES, "a stale slot must stay inside the warp's shared memory");
                             const float4 a = lds_f32x4(sbase + L::SI + 16u * il), b = lds_f32x4(sbase + L::SJ4 + 16u * jl);
                             int slab;
                             unsigned bin;
