@@ -1,4 +1,4 @@
-for c in c2 c3; do for k in 8 16 32; do
+for c in c2 c3; do for k in 4 8 12 16; do
 HBT_B200_COALESCE_HOST=$k python bench.py --config $c --no-cpu-baseline --steps 10 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
