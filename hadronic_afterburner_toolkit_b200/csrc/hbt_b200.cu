@@ -182,15 +182,14 @@ struct hbt_ctx {
     // production mixed-event loops run hbt_pairs_v4_mixed (binary32 tiles, 24 resident warps; HBT_B200_MIXED4=0: the v3 kernel)
     bool mixed4 = true;
     size_t coalesce_host = 8;  // host batches per launch (HBT_B200_COALESCE_HOST)
-    // a whole batch = the same-event kernel followed by the v4 mixed-event kernel on the same stream, each with its own
-    // registers / shared memory / resident warps (HBT_B200_SPLIT=0: the fused v3 kernel, one allocation for both)
+    // a whole batch = the same-event kernel and the v4 mixed-event kernel, each with its own registers / shared memory /
+    // resident warps (HBT_B200_SPLIT=0: the fused v3 kernel, one allocation for both)
     bool split = true;
-    // split batches: the two kernels run at the same time, the mixed-event kernel on the lane's side stream.  The
-    // same-event kernel alone is bound by its reductions into the L2 (5 per accepted pair), the mixed-event kernel by
-    // instruction issue: next to each other they fill each other's gaps, each with its own registers and shared memory.
-    // corun_same = resident same-event warps per SM during the co-run (the mixed-event kernel is launched with its full
-    // grid and grows into whatever the same-event kernel leaves, and into all of the SM once it has finished).
-    // HBT_B200_CORUN=0: one after the other; HBT_B200_CORUN_SAME=n
+    // ... next to each other (launch_split_pair): the same-event kernel alone is held by its reductions into the L2 (5
+    // per accepted pair), the mixed-event kernel by instruction issue, so the mixed-event warps fill the issue slots the
+    // same-event warps leave.  corun_same / corun_mixed = resident warps per SM of the first launch of each kernel; a
+    // second launch of each, behind the OTHER kernel in stream order, brings it to its full grid once that one is done.
+    // HBT_B200_CORUN=0: one after the other; HBT_B200_CORUN_SAME / HBT_B200_CORUN_MIXED
     bool corun = true;
     int corun_same = 12, corun_mixed = 8;
     // small production batches are collected and launched together (HBT_B200_COALESCE=0 / HBT_OPT_COALESCE: one launch each)
