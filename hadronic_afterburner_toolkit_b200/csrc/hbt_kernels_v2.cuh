@@ -13,7 +13,9 @@
 #define HBT_V2_TILE_I (32 * HBT_V2_IPL * HBT_V2_WARPS)  // 512
 #define HBT_V2_TILE_J 128
 #define HBT_V2_SUB (HBT_V2_TILE_I / HBT_V2_TILE_J)  // list-2 sub-tiles per 512 x 512 super-tile
-#define HBT_V2_LCAP 8                                // per-lane survivor list capacity
+#ifndef HBT_V2_LCAP
+#define HBT_V2_LCAP 8                                // per-lane survivor list capacity (v3 kernels; the v4 kernel has its own)
+#endif
 #define HBT_V2_QCAP (32 + 32 * HBT_V2_LCAP)          // linear warp queue capacity
 
 // constants of the fast path, derived on the host from HbtGrid
