@@ -25,6 +25,7 @@
 #else
 #define HBT_V3_SUB_MIXED 128
 #define HBT_V3_TJ_MIXED 128
+#define HBT_V4_TI 128
 #endif
 
 namespace {
@@ -563,6 +564,8 @@ bool is_page_locked(const void *p) {
 bool use_literal(const hbt_ctx *ctx, int mode) {
     return ctx->kernel_version == 1 || mode != 0 || (ctx->grid.qinv && ctx->stats);
 }
+
+int tile_i(const hbt_ctx *ctx);  // list-1 particles per mixed-event unit of the kernel this context launches
 
 // production mixed-event loops on the v4 kernel (binary32 tiles): not instrumented runs, not q_inv mode (both need the
 // binary64 values), not when the FP32 decision is switched off
@@ -1121,7 +1124,7 @@ int append_pending(hbt_ctx *ctx, const double *p_host, const double *d_src, cons
         P.segs.resize(s0 + static_cast<size_t>(nev) * nmix);
         unsigned long long np = 0;
         long long nblk = 0;
-        const size_t ns = build_segments(off, nev, off, 0, ids, cs, nmix, HBT_V3_SUB_MIXED, HBT_V3_TJ_MIXED, P.segs.data() + s0, &np, &nblk);
+        const size_t ns = build_segments(off, nev, off, 0, ids, cs, nmix, tile_i(ctx), HBT_V3_TJ_MIXED, P.segs.data() + s0, &np, &nblk);
         P.segs.resize(s0 + ns);
         for (size_t k = s0; k < s0 + ns; k++) {
             P.segs[k].i0 += P.n_logical;
@@ -1168,7 +1171,7 @@ bool can_coalesce(const hbt_ctx *ctx, bool do_same, bool do_mixed, bool alias, i
 int flush_pending(hbt_ctx *) { return HBT_OK; }
 #endif
 
-int tile_i(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V3_SUB_MIXED; }
+int tile_i(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : use_mixed4(ctx) ? HBT_V4_TI : HBT_V3_SUB_MIXED; }
 int tile_j(const hbt_ctx *ctx) { return ctx->kernel_version == 1 ? kTileV1 : HBT_V3_TJ_MIXED; }
 
 // host literal evaluation of the pairs the device deferred; leaves the stream idle

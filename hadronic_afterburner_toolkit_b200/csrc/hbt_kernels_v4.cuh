@@ -35,10 +35,14 @@
 #define HBT_V4_LCAP 16  // per-lane survivor list capacity: the lists are compacted and drained when one of them holds more than LCAP - 4
 #endif
 #define HBT_V4_QCAP (32 + 32 * HBT_V4_LCAP)
+#ifndef HBT_V4_TI
+#define HBT_V4_TI 128  // list-1 particles per unit (4 per lane)
+#endif
 #define HBT_V4_PARK 64  // parked (undecided) pairs per warp: a drain round adds at most 32, 32 are evaluated as soon as they are there
 
 struct V4Smem {
-    static constexpr int TI = 128, TJ = 128;
+    static constexpr int TI = HBT_V4_TI, TJ = 128;
+    static constexpr int ESH = 7;  // queue entry = list-1 slot << 7 | list-2 position (slots below 512)
     // list-1 sub-tile {px, py, pz, E}, two slots of padding after every 32 records: lane l keeps particles l, l + 32,
     // l + 64, l + 96 (s = 0 .. 3), whose 16-byte records would share their four banks — and a quarter-warp of a drain
     // round reads the records of two or three neighbouring lanes (4-way bank conflicts on every gather).  Particle
@@ -151,6 +155,7 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
     const unsigned sjf_addr = sbase + L::SJF;
     const double k2lo = c.k2lo, k2hi = c.k2hi, W2 = c.W2;
     const unsigned list_addr = sbase + L::LQ + 2u * static_cast<unsigned>(lane);
+    static_assert(HBT_V4_LCAP > IPL && L::TIP <= 512 && TJ == 128, "queue entries: 9 bits of slot, 7 bits of position");
     const unsigned lim = opaque_u32(list_addr + 64u * (HBT_V4_LCAP - IPL));
     unsigned nE = 0;
     int parked = 0;  // pairs in the warp's parked list (warp-uniform)
@@ -295,7 +300,7 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
         // ---- the pair loop, specialised on (error floor active)
         auto tile_loop = [&](auto floor_c) {
             constexpr bool FLOOR = decltype(floor_c)::value;
-            const unsigned lane16 = opaque_u32(static_cast<unsigned>(lane) << 8);  // (lane in the slot half of a queue entry)
+            const unsigned lane16 = opaque_u32(static_cast<unsigned>(lane) << L::ESH);  // (lane in the slot part of a queue entry)
             unsigned cur = list_addr;
             int qcount = 0;
             int j = j_begin;
@@ -334,7 +339,7 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
                             // for the STS to release its address operand (WAR, short scoreboard)
                             const unsigned slot = cur;
                             cur = slot + ((keep && in) ? 64u : 0u);
-                            if (keep && in) sts_u16(slot, ej + static_cast<unsigned>(s) * 0x2200u);  // list-1 slot lane + 34 s, list-2 position
+                            if (keep && in) sts_u16(slot, ej + static_cast<unsigned>(s) * (34u << L::ESH));  // list-1 slot lane + 34 s, list-2 position
                         }
                     }
                     j++;
@@ -365,9 +370,9 @@ hbt_pairs_v4_mixed(const double *__restrict__ p1, const double *__restrict__ p2,
                             const int base = qcount - take;
                             const unsigned next_entry = lds_u16(sbase + L::WQ + 2u * static_cast<unsigned>(max(base - 32, 0) + lane));
                             // every lane evaluates (idle lanes on a stale entry of this unit: the tiles are there)
-                            // il: slot (< 256 even in a stale entry of an idle lane: inside this warp's shared memory)
-                            const unsigned il = entry >> 8, jl = entry & static_cast<unsigned>(TJ - 1);
-                            static_assert(16 * 256 <= L::BYTES, "a stale slot must stay inside the warp's shared memory");
+                            // il: slot (< 512 even in a stale entry of an idle lane: inside this warp's shared memory)
+                            const unsigned il = entry >> L::ESH, jl = entry & static_cast<unsigned>(TJ - 1);
+                            static_assert(16 * 512 <= L::BYTES, "a stale slot must stay inside the warp's shared memory");
                             const float4 a = lds_f32x4(sbase + L::SI + 16u * il), b = lds_f32x4(sbase + L::SJ4 + 16u * jl);
                             int slab;
                             unsigned bin;

@@ -50,8 +50,8 @@ def test_v4_padded_slots_and_entries():
     for l in range(32):
         for s in range(4):
             for j in (0, 77, 127):
-                e = ((l << 8) + j + s * 0x2200) & 0xFFFF
-                sl = e >> 8
+                e = ((l << 7) + j + s * (34 << 7)) & 0xFFFF  # V4Smem::ESH = 7: nine bits of slot, seven of position
+                sl = e >> 7
                 assert sl == v4_slot(l, s) and e & 0x7F == j
                 assert sl - 2 * (sl // 34) == l + 32 * s  # slot -> particle (parked pairs)
     # 16-byte records, 8 per 128-byte row: the four particles of two neighbouring lanes in eight different bank groups
